@@ -1,0 +1,251 @@
+// C[M,N] = A[M,K] * W[N,K]^T (+ fused epilogue) on the 5th-gen tensor cores.
+//
+// One kernel serves every dense contraction on the path: the ViT patch-embed,
+// QKV / out-proj / MLP GEMMs (reference: transformers/models/vit/modeling_vit.py
+// :151,228-230,266,297-311), the once-per-crop cross-attention K/V projection
+// (models/bert/modeling_bert.py:252-267) and the small-M decoder GEMMs incl. the
+// LM head (modeling_bert.py:179-181,250,295,340-355,482-500).
+//
+// Design (sm_100a):
+//   * persistent CTAs, static tile schedule (tile = blockIdx.x + i*gridDim.x);
+//   * warp 0: TMA producer (cp.async.bulk.tensor, 128-byte swizzle, K-major tiles,
+//     out-of-bounds rows zero-filled so ragged M needs no special case);
+//   * warp 1: single-thread tcgen05.mma issuer, UMMA 128 x BN x 16, fp32
+//     accumulators in TMEM, double-buffered (2 x BN columns) so the epilogue of
+//     tile i overlaps the main loop of tile i+1;
+//   * warps 2-5: epilogue - tcgen05.ld (32 lanes x 32 columns per warp), fused
+//     bias / erf-GELU / fp32 residual / position-embedding / arg-max, direct
+//     vectorised global stores.
+#pragma once
+#include "common.cuh"
+
+namespace mocr {
+
+enum GemmEpilogue : int {
+  EPI_BF16 = 0,        // out(bf16) = acc + bias
+  EPI_BF16_GELU = 1,   // out(bf16) = gelu_erf(acc + bias)
+  EPI_F32_RESID = 2,   // out(f32)  = acc + bias + resid(f32)      (resid may alias out)
+  EPI_PATCH = 3,       // ViT embeddings: out(f32)[b*197+1+p] = acc + bias + pos[1+p]
+  EPI_ARGMAX = 4,      // LM head: per-row (max, argmax) over this tile's columns; logits optional
+};
+
+struct GemmArgs {
+  int M, N, K;
+  const float* bias;     // [N]
+  void* out;             // bf16 or f32, row stride ldo elements
+  int ldo;
+  const float* resid;    // EPI_F32_RESID: [M, ldr] f32
+  int ldr;
+  const float* pos;      // EPI_PATCH: position table [197, 768] f32
+  float* part_max;       // EPI_ARGMAX: [M, N/BN]
+  int* part_idx;         // EPI_ARGMAX: [M, N/BN]
+  float* logits;         // EPI_ARGMAX: optional [M, N] f32 tap for parity tests (may be null)
+};
+
+constexpr int kGemmBM = 128;
+constexpr int kGemmBK = 64;
+constexpr int kGemmThreads = 192;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStageBytesA = kGemmBM * kGemmBK * 2;
+  static constexpr int kStageBytesB = BN * kGemmBK * 2;
+  static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
+  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;     // power of two for BN in {16..256}
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmArgs args) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);   // SWIZZLE_128B tiles need 1024-B alignment
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * Cfg::kStageBytesA;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;                    // [kStages]  TMA -> MMA
+  uint64_t* empty_bar = bars + kStages;         // [kStages]  MMA -> TMA
+  uint64_t* acc_full = bars + 2 * kStages;      // [2]        MMA -> epilogue
+  uint64_t* acc_empty = bars + 2 * kStages + 2; // [2]        epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_tiles = (args.M + kGemmBM - 1) / kGemmBM;
+  const int n_tiles = args.N / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int k_blocks = args.K / kGemmBK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------ TMA producer ----------
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / n_tiles) * kGemmBM;
+      const int n0 = (tile % n_tiles) * BN;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        if (lane == 0) {
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          tma_load_2d(smem_a + stage * Cfg::kStageBytesA, &tmap_a, &full_bar[stage], kb * kGemmBK, m0);
+          tma_load_2d(smem_b + stage * Cfg::kStageBytesB, &tmap_b, &full_bar[stage], kb * kGemmBK, n0);
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer ------------
+    constexpr uint32_t idesc = umma_idesc_bf16(kGemmBM, BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1u;
+      mbar_wait(&acc_empty[as], aphase ^ 1u);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * BN);
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint64_t da = umma_desc_k_sw128(smem_u32(smem_a + stage * Cfg::kStageBytesA));
+          const uint64_t db = umma_desc_k_sw128(smem_u32(smem_b + stage * Cfg::kStageBytesB));
+#pragma unroll
+          for (int k = 0; k < kGemmBK / 16; ++k) {
+            // advance 16 bf16 = 32 B along K inside the 128-B swizzle atom: +2 in 16-B units
+            umma_bf16(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
+                      static_cast<uint32_t>((kb | k) != 0));
+          }
+          umma_commit(&empty_bar[stage]);                 // smem slot free once these MMAs retire
+          if (kb == k_blocks - 1) umma_commit(&acc_full[as]);  // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else {
+    // ------------------------------------------------ epilogue --------------
+    const int quad = warp & 3;                    // TMEM lane quadrant this warp may access
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1u;
+      const int m0 = (tile / n_tiles) * kGemmBM;
+      const int nt = tile % n_tiles;
+      const int n0 = nt * BN;
+      const int row = m0 + quad * 32 + lane;
+      const bool row_ok = row < args.M;
+      mbar_wait(&acc_full[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * BN);
+
+      float best = -INFINITY;
+      int best_i = 0;
+      int out_row = row;
+      const float* extra = nullptr;               // per-row fp32 addend (residual or position row)
+      if (EPI == EPI_F32_RESID) extra = args.resid + static_cast<size_t>(row) * args.ldr;
+      if (EPI == EPI_PATCH) {
+        const int b = row / kPatches, p = row % kPatches;
+        out_row = b * kEncTokens + 1 + p;
+        extra = args.pos + static_cast<size_t>(1 + p) * kD;
+      }
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(taddr + static_cast<uint32_t>(c * 32), v);
+        tmem_ld_wait();
+        const int col0 = n0 + c * 32;
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(args.bias + col0 + j));
+          f[j] = __uint_as_float(v[j]) + bb.x;
+          f[j + 1] = __uint_as_float(v[j + 1]) + bb.y;
+          f[j + 2] = __uint_as_float(v[j + 2]) + bb.z;
+          f[j + 3] = __uint_as_float(v[j + 3]) + bb.w;
+        }
+        if (EPI == EPI_BF16 || EPI == EPI_BF16_GELU) {
+          if (EPI == EPI_BF16_GELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+          }
+          if (row_ok) {
+            uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(args.out) + static_cast<size_t>(row) * args.ldo + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 q;
+              q.x = pack_bf16(f[8 * j + 0], f[8 * j + 1]);
+              q.y = pack_bf16(f[8 * j + 2], f[8 * j + 3]);
+              q.z = pack_bf16(f[8 * j + 4], f[8 * j + 5]);
+              q.w = pack_bf16(f[8 * j + 6], f[8 * j + 7]);
+              dst[j] = q;
+            }
+          }
+        } else if (EPI == EPI_F32_RESID || EPI == EPI_PATCH) {
+          if (row_ok) {
+            const float4* ex = reinterpret_cast<const float4*>(extra + col0);
+            float4* dst = reinterpret_cast<float4*>(static_cast<float*>(args.out) + static_cast<size_t>(out_row) * args.ldo + col0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 e = ex[j];
+              dst[j] = make_float4(f[4 * j] + e.x, f[4 * j + 1] + e.y, f[4 * j + 2] + e.z, f[4 * j + 3] + e.w);
+            }
+          }
+        } else {  // EPI_ARGMAX
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (f[j] > best) { best = f[j]; best_i = col0 + j; }   // strict > keeps the lowest index on ties
+          }
+          if (args.logits != nullptr && row_ok) {
+            float4* dst = reinterpret_cast<float4*>(args.logits + static_cast<size_t>(row) * args.N + col0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          }
+        }
+      }
+      if (EPI == EPI_ARGMAX && row_ok) {
+        args.part_max[static_cast<size_t>(row) * n_tiles + nt] = best;
+        args.part_idx[static_cast<size_t>(row) * n_tiles + nt] = best_i;
+      }
+      tc_fence_before();
+      mbar_arrive(&acc_empty[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+}  // namespace mocr

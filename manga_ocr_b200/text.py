@@ -1,0 +1,109 @@
+"""Token ids -> string: the host-side tail of ``MangaOcr.__call__``.
+
+Follows the reference path:
+  * ``tokenizer.decode(ids, skip_special_tokens=True)`` of a character-level
+    BERT-Japanese tokenizer = drop special ids, ``" ".join(tokens)``
+    (transformers/models/bert_japanese/tokenization_bert_japanese.py:256-261);
+  * upstream ``manga_ocr.ocr.post_process``: remove all whitespace, ``…`` ->
+    ``...``, runs of ``[・.]{2,}`` -> same-length run of ``.``, then
+    ``jaconv.h2z(text, ascii=True, digit=True)``.
+
+Neither the ``manga-ocr`` package nor ``jaconv`` nor the real ``vocab.txt`` is
+available offline, so the vocabulary is the deterministic synthetic one defined
+here and ``h2z`` is restated from jaconv's published behaviour (half-width
+ASCII / digits / katakana -> full-width).  Both are assumptions recorded in
+DESIGN.md; swapping in the real ``vocab.txt`` is ``Vocab.from_file``.
+"""
+from __future__ import annotations
+
+import re
+from typing import Iterable, List, Sequence
+
+from .weights import VOCAB
+
+SPECIAL_TOKENS = ["[PAD]", "[UNK]", "[CLS]", "[SEP]", "[MASK]"]
+NUM_SPECIAL = len(SPECIAL_TOKENS)
+
+
+def _synthetic_tokens() -> List[str]:
+    toks = list(SPECIAL_TOKENS)
+    seen = set()
+
+    def add(chars: Iterable[str]) -> None:
+        for ch in chars:
+            if ch not in seen and len(toks) < VOCAB:
+                seen.add(ch)
+                toks.append(ch)
+
+    add(chr(c) for c in range(0x3041, 0x3097))        # hiragana
+    add(chr(c) for c in range(0x30A1, 0x30FB))        # katakana
+    add("ー…・。、「」『』！？")
+    add(chr(c) for c in range(0x21, 0x7F))            # half-width ASCII incl. digits
+    add(chr(c) for c in range(0xFF66, 0xFFA0))        # half-width katakana + ﾞ ﾟ
+    add(chr(c) for c in range(0x4E00, 0x4E00 + VOCAB))  # CJK ideographs fill the rest
+    assert len(toks) == VOCAB
+    return toks
+
+
+class Vocab:
+    """id -> token table of a character-level vocabulary (one token per id)."""
+
+    def __init__(self, tokens: Sequence[str]):
+        self.tokens = list(tokens)
+        # ids whose token is [..]-bracketed specials are dropped on decode
+        self.special_ids = frozenset(i for i, t in enumerate(self.tokens) if t in SPECIAL_TOKENS)
+
+    @classmethod
+    def synthetic(cls) -> "Vocab":
+        return cls(_synthetic_tokens())
+
+    @classmethod
+    def from_file(cls, path: str) -> "Vocab":
+        with open(path, encoding="utf-8") as f:
+            return cls([line.rstrip("\n") for line in f])
+
+    def decode(self, ids: Iterable[int]) -> str:
+        """``tokenizer.decode(ids, skip_special_tokens=True)``."""
+        n = len(self.tokens)
+        return " ".join(self.tokens[i] if 0 <= i < n else "[UNK]"
+                        for i in (int(x) for x in ids) if i not in self.special_ids)
+
+
+# --- jaconv.h2z(ascii=True, digit=True, kana=True) restated -----------------
+
+_HW_KANA = "ｦｧｨｩｪｫｬｭｮｯｰｱｲｳｴｵｶｷｸｹｺｻｼｽｾｿﾀﾁﾂﾃﾄﾅﾆﾇﾈﾉﾊﾋﾌﾍﾎﾏﾐﾑﾒﾓﾔﾕﾖﾗﾘﾙﾚﾛﾜﾝ"
+_FW_KANA = "ヲァィゥェォャュョッーアイウエオカキクケコサシスセソタチツテトナニヌネノハヒフヘホマミムメモヤユヨラリルレロワン"
+_HW_PUNCT = "｡｢｣､･ﾞﾟ"
+_FW_PUNCT = "。「」、・゛゜"
+_VOICED_SRC = "ｶｷｸｹｺｻｼｽｾｿﾀﾁﾂﾃﾄﾊﾋﾌﾍﾎｳ"
+_VOICED_DST = "ガギグゲゴザジズゼゾダヂヅデドバビブベボヴ"
+_SEMI_SRC = "ﾊﾋﾌﾍﾎ"
+_SEMI_DST = "パピプペポ"
+
+_H2Z_SINGLE = {ord(a): b for a, b in zip(_HW_KANA + _HW_PUNCT, _FW_KANA + _FW_PUNCT)}
+_H2Z_SINGLE.update({c: chr(c + 0xFEE0) for c in range(0x21, 0x7F)})   # ASCII + digits
+_H2Z_SINGLE[0x20] = "　"
+_H2Z_PAIRS = {a + "ﾞ": b for a, b in zip(_VOICED_SRC, _VOICED_DST)}
+_H2Z_PAIRS.update({a + "ﾟ": b for a, b in zip(_SEMI_SRC, _SEMI_DST)})
+_PAIR_RE = re.compile("|".join(re.escape(k) for k in _H2Z_PAIRS))
+
+
+def h2z(text: str) -> str:
+    """Half-width -> full-width (ASCII, digits, katakana incl. (semi-)voiced marks)."""
+    text = _PAIR_RE.sub(lambda m: _H2Z_PAIRS[m.group(0)], text)
+    return text.translate(_H2Z_SINGLE)
+
+
+_DOTS_RE = re.compile("[・.]{2,}")
+
+
+def post_process(text: str) -> str:
+    """Upstream ``manga_ocr.ocr.post_process`` restated."""
+    text = "".join(text.split())
+    text = text.replace("…", "...")
+    text = _DOTS_RE.sub(lambda m: (m.end() - m.start()) * ".", text)
+    return h2z(text)
+
+
+def ids_to_text(vocab: Vocab, ids: Iterable[int]) -> str:
+    return post_process(vocab.decode(ids))
