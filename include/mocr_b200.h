@@ -1,0 +1,127 @@
+/* mocr_b200.h - C ABI of the B200-native Manga-OCR recognition engine.
+ *
+ * This is the drop-in boundary for ONE hot path of irazawa/Manga-OCR: the call
+ *     raw_text = self.manga_ocr_reader(pil_img)         reference/src/ui/main_window.py:9801
+ * where manga_ocr_reader = MangaOcr()                    reference/src/ui/main_window.py:3394
+ * and MangaOcr comes from `from manga_ocr import MangaOcr`   reference/src/core/config.py:433.
+ * The reference has no FFI of its own (it is pure Python); the entry points below are what a
+ * ctypes binding for that call needs (INTEGRATION.md shows the binding).  Plain pointers and
+ * sizes only; no C++ or torch types; every function returns 0 or a negative mocr_status and
+ * never throws or aborts; mocr_last_error() gives the message of the last failure.
+ *
+ * Threading: one handle may be used from many host threads (the app calls the engine from up
+ * to 50 worker threads, reference/src/ui/main_window.py:608-611,4317-4327); calls on the same
+ * handle are serialised internally.
+ */
+#ifndef MOCR_B200_H_
+#define MOCR_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MOCR_ABI_VERSION 1
+
+typedef struct mocr_handle mocr_handle_t;
+
+enum mocr_status {
+  MOCR_OK = 0,
+  MOCR_ERR_INVALID = -1,   /* bad argument / bad state                       */
+  MOCR_ERR_CUDA = -2,      /* a CUDA call or kernel failed                   */
+  MOCR_ERR_WEIGHTS = -3,   /* missing / mis-shaped tensor                    */
+  MOCR_ERR_CAPACITY = -4,  /* batch, length or crop size beyond the handle's */
+  MOCR_ERR_NO_DEVICE = -5  /* no usable sm_100 device                        */
+};
+
+/* One text-bubble crop as the app hands it over: interleaved uint8 pixels in HOST memory.
+ * Replaces the PIL.Image argument of MangaOcr.__call__ (reference/src/ui/main_window.py:9800:
+ * Image.fromarray(cv2.cvtColor(img, cv2.COLOR_BGR2RGB)) - a contiguous uint8 [H,W,3] array). */
+typedef struct {
+  const uint8_t* data; /* pixel (0,0)                                      */
+  int32_t height;      /* >= 1                                             */
+  int32_t width;       /* >= 1                                             */
+  int32_t stride;      /* bytes between rows (>= width * channels)         */
+  int32_t channels;    /* 1 = luma, 3 = RGB/BGR, 4 = RGBA/BGRA (alpha ignored) */
+} mocr_crop_t;
+
+enum mocr_channel_order { MOCR_RGB = 0, MOCR_BGR = 1 };
+
+/* ---- life cycle -------------------------------------------------------------------- */
+
+int mocr_abi_version(void);
+
+/* Replaces MangaOcr.__init__ (model construction + .cuda()).  max_batch = crops decoded
+ * together; max_length = decode cap (the reference hard-codes 300, <= 512). */
+int mocr_create(int device, int max_batch, int max_length, mocr_handle_t** out);
+int mocr_destroy(mocr_handle_t* h);
+
+/* Weights by their reference state_dict name, fp32, host memory,
+ * row-major.  Replaces VisionEncoderDecoderModel.from_pretrained.  After the last tensor call
+ * mocr_finalize_weights once: it folds / converts / uploads (bf16 matrices, fp32 vectors). */
+int mocr_set_weight(mocr_handle_t* h, const char* name, const float* data, const int64_t* shape, int ndim);
+int mocr_finalize_weights(mocr_handle_t* h);
+
+/* ---- the path, all in one ------------------------------------------------------------- */
+
+/* n crops (any n; processed in chunks of max_batch) -> greedy token ids.
+ * Replaces processor(...) + model.generate(x[None], max_length=300)[0] of MangaOcr.__call__.
+ * out_ids: [n, max_length] int32, row i = [CLS] t1 t2 ... (EOS included when produced), padded
+ * with PAD(0); out_lens[i] = number of valid ids in row i. */
+int mocr_recognize(mocr_handle_t* h, const mocr_crop_t* crops, int n, int channel_order, int max_length,
+                   int32_t* out_ids, int32_t* out_lens);
+
+/* ---- the path, stage by stage (n <= max_batch) ------------------------------------------ */
+
+/* Host crops -> pinned staging -> device arena (async on the handle's stream). */
+int mocr_stage_crops(mocr_handle_t* h, const mocr_crop_t* crops, int n, int channel_order);
+/* Fused luma + Pillow-exact bilinear 224x224 + patch rows, on the staged crops.
+ * Replaces img.convert("L").convert("RGB") and ViTImageProcessor (resize, rescale, normalize). */
+int mocr_preprocess(mocr_handle_t* h);
+/* ViT-base encoder on the patch rows + the once-per-crop cross-attention K/V projection.
+ * Replaces ViTModel.forward and BertCrossAttention's K/V Linear of decode step 0. */
+int mocr_encode(mocr_handle_t* h);
+/* Batched greedy decode of the encoded crops; ids stay on the device until mocr_fetch_ids.
+ * forced_ids (host, [n, max_length], may be NULL): teacher forcing for parity tests - the
+ * input token of step t is forced_ids[i][t] while the arg-max of every step is still recorded.
+ * Replaces GenerationMixin._sample (greedy) over BertLMHeadModel. */
+int mocr_decode_greedy(mocr_handle_t* h, int max_length, const int32_t* forced_ids);
+int mocr_fetch_ids(mocr_handle_t* h, int32_t* out_ids /*[n,max_length]*/, int32_t* out_lens /*[n]*/);
+/* stage_crops must have been called; runs preprocess + encode + decode with no host copies. */
+int mocr_run_resident(mocr_handle_t* h, int max_length);
+
+/* ---- parity taps (tests only; enable before the stage they tap) ------------------------ */
+
+enum mocr_tap { MOCR_TAP_PIXELS = 1, MOCR_TAP_ENCODER = 2, MOCR_TAP_LOGITS = 4 };
+int mocr_set_taps(mocr_handle_t* h, int taps);
+int mocr_get_pixels_u8(mocr_handle_t* h, uint8_t* out /*[n,224,224]*/);
+int mocr_get_pixel_values(mocr_handle_t* h, float* out /*[n,224,224] (the 3 planes are equal)*/);
+int mocr_get_encoder_hidden(mocr_handle_t* h, float* out /*[n,197,768]*/);
+int mocr_get_step_logits(mocr_handle_t* h, float* out /*[n,max_length-1,6144]*/);
+
+/* Kernel-level unit hooks (tests only): run ONE product kernel on caller-supplied host data.
+ * epi: 0 bf16, 1 bf16+GELU, 2 f32+residual, 4 arg-max (out = logits), 5 f32+GELU.
+ * out = epilogue(A[M,K] * Wt[N,K]^T + bias), inputs rounded to bf16 exactly as the engine stores them.
+ * Note the attention hook expects the 1/sqrt(64) scale already folded into q. */
+int mocr_test_gemm(mocr_handle_t* h, int epi, int bn, int M, int N, int K, const float* A, const float* Wt, const float* bias,
+                   const float* resid, float* out, int32_t* out_argmax);
+int mocr_test_encoder_attention(mocr_handle_t* h, int n, const float* qkv /*[n*197,2304]*/, float* out /*[n*197,768]*/);
+
+/* ---- plumbing --------------------------------------------------------------------------- */
+
+void* mocr_stream(mocr_handle_t* h);            /* the cudaStream_t all work is launched on   */
+int mocr_sync(mocr_handle_t* h);
+int64_t mocr_launch_count(mocr_handle_t* h);    /* kernels launched by this handle so far     */
+int mocr_last_steps(mocr_handle_t* h);          /* decode steps executed by the last decode   */
+int mocr_set_option(mocr_handle_t* h, const char* key, int value);
+/* Times `iters` back-to-back launches of one named kernel of the path on the handle's stream
+ * with CUDA events, on the current batch state (used by bench.py for the roofline line). */
+int mocr_time_kernel(mocr_handle_t* h, const char* kernel, int iters, float* ms_per_launch, double* algo_bytes,
+                     double* algo_flops);
+const char* mocr_last_error(mocr_handle_t* h);  /* h may be NULL: error of the last failed create */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOCR_B200_H_ */

@@ -1,0 +1,1278 @@
+// Engine behind the C ABI of include/mocr_b200.h: weights, device workspace, launch
+// sequences for preprocess -> ViT encoder -> cross-K/V projection -> batched greedy decode.
+//
+// The path it replaces:
+//   upstream MangaOcr.__call__  -> ViTImageProcessor  -> VisionEncoderDecoderModel.generate
+//   (transformers/models/vit/modeling_vit.py:428-458, models/bert/modeling_bert.py:856-910,
+//    generation/utils.py:2743-2805), called from reference/src/ui/main_window.py:9801.
+//
+// Everything on the device is a hand-written sm_100a kernel from this directory; there is
+// no library GEMM and no CPU fallback: without a B200 every compute entry point fails.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <mutex>
+#include <new>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/mocr_b200.h"
+#include "common.cuh"
+#include "decode_attn.cuh"
+#include "encoder_attn.cuh"
+#include "gemm_tcgen05.cuh"
+#include "preprocess.cuh"
+#include "rowops.cuh"
+
+using namespace mocr;
+
+namespace {
+
+constexpr int kPadId = 0, kClsId = 2, kSepId = 3;
+constexpr float kQScale = 0.125f;   // 1/sqrt(64), folded into every query projection (exact in bf16)
+
+thread_local std::string g_create_error;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+uint16_t f32_to_bf16(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return static_cast<uint16_t>((u >> 16) | 0x40);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return static_cast<uint16_t>(u >> 16);
+}
+
+struct HostTensor {
+  std::vector<int64_t> shape;
+  std::vector<float> data;
+};
+
+// A Linear layer on the device: W [N, K] bf16 (K-major = the UMMA B operand as stored by
+// nn.Linear), bias [N] fp32, and one TMA descriptor per N-tile width in use.
+struct Linear {
+  __nv_bfloat16* w = nullptr;
+  float* bias = nullptr;
+  int N = 0, K = 0;
+  std::map<int, CUtensorMap> maps;
+};
+
+// A bf16 activation buffer [rows_cap, K] used as the UMMA A operand.
+struct ActBuf {
+  __nv_bfloat16* p = nullptr;
+  int rows_cap = 0, K = 0;
+  CUtensorMap map;
+};
+
+struct LnParams {
+  float* g = nullptr;
+  float* b = nullptr;
+};
+
+struct EncLayer {
+  LnParams ln1, ln2;
+  Linear qkv, out, fc1, fc2;
+};
+struct DecLayer {
+  Linear self_qkv, self_out, cross_q, cross_out, fc1, fc2;
+  LnParams ln_self, ln_cross, ln_ffn;
+};
+
+}  // namespace
+
+struct mocr_handle {
+  int device = 0;
+  int max_batch = 0;
+  int max_length = 0;
+  int sms = 148;
+  cudaStream_t stream = nullptr;
+  std::mutex mu;
+  std::string error;
+  int64_t launches = 0;
+  int taps = 0;
+  bool finalized = false;
+  std::vector<void*> allocs;
+  std::map<std::string, HostTensor> staged;
+
+  // tile widths (mocr_set_option)
+  int enc_bn = 256;
+  int dec_bn = 32;
+  int head_bn = 64;
+  int check_every = 16;
+  int use_graph = 1;
+
+  // ---- weights
+  Linear patch;
+  float* pos = nullptr;   // [197,768]
+  float* cls = nullptr;   // [768]
+  EncLayer enc[kEncLayers];
+  LnParams enc_ln;
+  Linear cross_kv;        // [3072,768]: K0 V0 K1 V1
+  EmbedWeights emb{};
+  DecLayer dec[kDecLayers];
+  Linear head_t, head_dec;
+  LnParams head_ln;
+  float* lut = nullptr;   // [256] reference rescale+normalize values
+
+  // ---- workspace
+  int rows_cap = 0;       // encoder token rows (multiple of 128)
+  int brow_cap = 0;       // decoder rows (multiple of 128)
+  ActBuf patches, xn, ctx, mlp, enc_out;
+  __nv_bfloat16* qkv = nullptr;       // [rows_cap, 2304]
+  float* hres = nullptr;              // [rows_cap, 768] fp32 residual stream
+  float* enc_f32 = nullptr;           // tap
+  __nv_bfloat16* crosskv = nullptr;   // [rows_cap, 3072]
+  ActBuf d_xb, d_ctx, d_ffn, d_tb;
+  float* d_x = nullptr;               // [brow_cap, 768]
+  float* d_tmp = nullptr;             // [brow_cap, 768]
+  __nv_bfloat16* d_qkv = nullptr;     // [brow_cap, 2304]
+  __nv_bfloat16* d_q = nullptr;       // [brow_cap, 768]
+  __nv_bfloat16* self_k[kDecLayers] = {nullptr, nullptr};   // [max_batch, max_length, 768]
+  __nv_bfloat16* self_v[kDecLayers] = {nullptr, nullptr};
+  float* part_max = nullptr;
+  int* part_idx = nullptr;
+  int* d_ids = nullptr;               // [max_batch, max_length]
+  int* d_pos = nullptr;
+  int* d_finished = nullptr;
+  int* d_forced = nullptr;
+  int* d_zero = nullptr;              // [max_batch] zeros
+  int* h_flags = nullptr;             // pinned [max_batch]
+  float* logits_tap = nullptr;        // [n, max_length-1, 6144]
+  size_t logits_tap_bytes = 0;
+  uint8_t* px_u8 = nullptr;           // taps [max_batch,224,224]
+  float* px_f32 = nullptr;
+
+  // ---- crop staging
+  uint8_t* h_arena = nullptr;
+  uint8_t* d_arena = nullptr;
+  size_t arena_cap = 0;
+  CropDesc* h_descs = nullptr;        // pinned [max_batch]
+  CropDesc* d_descs = nullptr;
+  std::vector<int> h_coefs;
+  int* d_coefs = nullptr;
+  size_t d_coefs_cap = 0, d_coefs_used = 0;
+  struct TableRef { int offset, ksize, strip_rows; };
+  std::unordered_map<int, TableRef> tables;
+  int pre_pitch = 0, pre_tmp_rows = 0, pre_bgr = 0;
+
+  // ---- batch state
+  int n = 0;              // crops of the current batch
+  int cur_len = 0;        // max_length of the last decode
+  int last_steps = 0;
+  bool staged_ok = false, pre_ok = false, enc_ok = false, dec_ok = false;
+
+  // ---- decode-step graphs keyed by (n, max_length, forced?, tap?)
+  struct StepGraph { cudaGraphExec_t exec; int launches; };
+  std::map<uint64_t, StepGraph> graphs;
+};
+
+namespace {
+
+int fail(mocr_handle* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (h != nullptr) h->error = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CK(call)                                                                                        \
+  do {                                                                                                  \
+    cudaError_t e_ = (call);                                                                            \
+    if (e_ != cudaSuccess)                                                                              \
+      return fail(h, MOCR_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+#define TRY(call)             \
+  do {                        \
+    int r_ = (call);          \
+    if (r_ != MOCR_OK) return r_; \
+  } while (0)
+
+template <typename T>
+int dmalloc(mocr_handle* h, T** out, size_t count, bool zero = true) {
+  void* p = nullptr;
+  CK(cudaMalloc(&p, std::max<size_t>(count * sizeof(T), 256)));
+  h->allocs.push_back(p);
+  if (zero) CK(cudaMemsetAsync(p, 0, std::max<size_t>(count * sizeof(T), 256), h->stream));
+  *out = static_cast<T*>(p);
+  return MOCR_OK;
+}
+
+int make_map(mocr_handle* h, CUtensorMap* m, const void* base, int rows, int cols, int box_rows) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (enc == nullptr) return fail(h, MOCR_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kGemmBK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(h, MOCR_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d box=%d", (int)r, rows, cols, box_rows);
+  return MOCR_OK;
+}
+
+int make_act(mocr_handle* h, ActBuf* a, int rows_cap, int K) {
+  a->rows_cap = rows_cap;
+  a->K = K;
+  TRY(dmalloc(h, &a->p, static_cast<size_t>(rows_cap) * K));
+  return make_map(h, &a->map, a->p, rows_cap, K, kGemmBM);
+}
+
+// ------------------------------------------------------------------ weights ---
+
+const HostTensor* find(mocr_handle* h, const std::string& name) {
+  auto it = h->staged.find(name);
+  return it == h->staged.end() ? nullptr : &it->second;
+}
+
+int need(mocr_handle* h, const std::string& name, size_t numel, const HostTensor** out) {
+  const HostTensor* t = find(h, name);
+  if (t == nullptr) return fail(h, MOCR_ERR_WEIGHTS, "missing tensor %s", name.c_str());
+  if (t->data.size() != numel) return fail(h, MOCR_ERR_WEIGHTS, "tensor %s has %zu elements, expected %zu", name.c_str(), t->data.size(), numel);
+  *out = t;
+  return MOCR_OK;
+}
+
+int upload_f32(mocr_handle* h, float** dst, const float* src, size_t n) {
+  TRY(dmalloc(h, dst, n, false));
+  CK(cudaMemcpy(*dst, src, n * sizeof(float), cudaMemcpyHostToDevice));
+  return MOCR_OK;
+}
+int upload_vec(mocr_handle* h, float** dst, const std::string& name, size_t n) {
+  const HostTensor* t;
+  TRY(need(h, name, n, &t));
+  return upload_f32(h, dst, t->data.data(), n);
+}
+int upload_ln(mocr_handle* h, LnParams* ln, const std::string& prefix) {
+  TRY(upload_vec(h, &ln->g, prefix + ".weight", kD));
+  return upload_vec(h, &ln->b, prefix + ".bias", kD);
+}
+
+// rows of `parts` are concatenated along N; row_scale[i] multiplies part i (weights and bias).
+int upload_linear(mocr_handle* h, Linear* L, int K, const std::vector<std::string>& parts, const std::vector<int>& part_n,
+                  const std::vector<float>& part_scale) {
+  int N = 0;
+  for (int v : part_n) N += v;
+  std::vector<uint16_t> wb(static_cast<size_t>(N) * K);
+  std::vector<float> bias(static_cast<size_t>(N));
+  size_t row = 0;
+  for (size_t i = 0; i < parts.size(); ++i) {
+    const HostTensor *w, *b;
+    TRY(need(h, parts[i] + ".weight", static_cast<size_t>(part_n[i]) * K, &w));
+    TRY(need(h, parts[i] + ".bias", static_cast<size_t>(part_n[i]), &b));
+    const float sc = part_scale[i];
+    for (size_t j = 0; j < static_cast<size_t>(part_n[i]) * K; ++j) wb[row * K + j] = f32_to_bf16(w->data[j] * sc);
+    for (int j = 0; j < part_n[i]; ++j) bias[row + j] = b->data[j] * sc;
+    row += part_n[i];
+  }
+  L->N = N;
+  L->K = K;
+  TRY(dmalloc(h, &L->w, wb.size(), false));
+  CK(cudaMemcpy(L->w, wb.data(), wb.size() * 2, cudaMemcpyHostToDevice));
+  return upload_f32(h, &L->bias, bias.data(), bias.size());
+}
+int upload_linear1(mocr_handle* h, Linear* L, int N, int K, const std::string& name, float scale = 1.0f) {
+  return upload_linear(h, L, K, {name}, {N}, {scale});
+}
+
+int linear_map(mocr_handle* h, Linear* L, int bn, const CUtensorMap** out) {
+  auto it = L->maps.find(bn);
+  if (it == L->maps.end()) {
+    CUtensorMap m;
+    TRY(make_map(h, &m, L->w, L->N, L->K, bn));
+    it = L->maps.emplace(bn, m).first;
+  }
+  *out = &it->second;
+  return MOCR_OK;
+}
+
+int finalize_weights(mocr_handle* h) {
+  const std::string e = "encoder.", el = "encoder.encoder.layer.";
+  // ---- ViT patch embedding: fold the 3 equal input planes (K 768 -> 256) and the
+  // rescale/normalize affine map x = (u8-128)*2/255 + 1/255 into weight and bias.
+  {
+    const HostTensor *w, *b;
+    TRY(need(h, e + "embeddings.patch_embeddings.projection.weight", static_cast<size_t>(kD) * 3 * 256, &w));
+    TRY(need(h, e + "embeddings.patch_embeddings.projection.bias", kD, &b));
+    std::vector<uint16_t> wb(static_cast<size_t>(kD) * kPatchK);
+    std::vector<float> bias(kD);
+    for (int n = 0; n < kD; ++n) {
+      double tot = 0.0;
+      for (int k = 0; k < kPatchK; ++k) {
+        const double s = static_cast<double>(w->data[(static_cast<size_t>(n) * 3 + 0) * 256 + k]) +
+                         w->data[(static_cast<size_t>(n) * 3 + 1) * 256 + k] + w->data[(static_cast<size_t>(n) * 3 + 2) * 256 + k];
+        tot += s;
+        wb[static_cast<size_t>(n) * kPatchK + k] = f32_to_bf16(static_cast<float>(s * (2.0 / 255.0)));
+      }
+      bias[n] = static_cast<float>(b->data[n] + tot * (1.0 / 255.0));
+    }
+    h->patch.N = kD;
+    h->patch.K = kPatchK;
+    TRY(dmalloc(h, &h->patch.w, wb.size(), false));
+    CK(cudaMemcpy(h->patch.w, wb.data(), wb.size() * 2, cudaMemcpyHostToDevice));
+    TRY(upload_f32(h, &h->patch.bias, bias.data(), bias.size()));
+  }
+  TRY(upload_vec(h, &h->pos, e + "embeddings.position_embeddings", static_cast<size_t>(kEncTokens) * kD));
+  TRY(upload_vec(h, &h->cls, e + "embeddings.cls_token", kD));
+  for (int i = 0; i < kEncLayers; ++i) {
+    const std::string p = el + std::to_string(i) + ".";
+    EncLayer& L = h->enc[i];
+    TRY(upload_ln(h, &L.ln1, p + "layernorm_before"));
+    TRY(upload_ln(h, &L.ln2, p + "layernorm_after"));
+    TRY(upload_linear(h, &L.qkv, kD, {p + "attention.attention.query", p + "attention.attention.key", p + "attention.attention.value"},
+                      {kD, kD, kD}, {kQScale, 1.f, 1.f}));
+    TRY(upload_linear1(h, &L.out, kD, kD, p + "attention.output.dense"));
+    TRY(upload_linear1(h, &L.fc1, kFFN, kD, p + "intermediate.dense"));
+    TRY(upload_linear1(h, &L.fc2, kD, kFFN, p + "output.dense"));
+  }
+  TRY(upload_ln(h, &h->enc_ln, e + "layernorm"));
+
+  const std::string d = "decoder.bert.", dl = "decoder.bert.encoder.layer.";
+  {
+    float* t;
+    TRY(upload_vec(h, &t, d + "embeddings.word_embeddings.weight", static_cast<size_t>(kVocab) * kD));
+    h->emb.word = t;
+    TRY(upload_vec(h, &t, d + "embeddings.position_embeddings.weight", static_cast<size_t>(kMaxPos) * kD));
+    h->emb.posemb = t;
+    const HostTensor* tt;
+    TRY(need(h, d + "embeddings.token_type_embeddings.weight", 2 * kD, &tt));
+    TRY(upload_f32(h, &t, tt->data.data(), kD));   // row 0 only: token_type_ids are all zero
+    h->emb.type0 = t;
+    LnParams ln;
+    TRY(upload_ln(h, &ln, d + "embeddings.LayerNorm"));
+    h->emb.gamma = ln.g;
+    h->emb.beta = ln.b;
+  }
+  std::vector<std::string> ckv;
+  for (int i = 0; i < kDecLayers; ++i) {
+    const std::string p = dl + std::to_string(i) + ".";
+    DecLayer& L = h->dec[i];
+    TRY(upload_linear(h, &L.self_qkv, kD, {p + "attention.self.query", p + "attention.self.key", p + "attention.self.value"},
+                      {kD, kD, kD}, {kQScale, 1.f, 1.f}));
+    TRY(upload_linear1(h, &L.self_out, kD, kD, p + "attention.output.dense"));
+    TRY(upload_ln(h, &L.ln_self, p + "attention.output.LayerNorm"));
+    TRY(upload_linear1(h, &L.cross_q, kD, kD, p + "crossattention.self.query", kQScale));
+    TRY(upload_linear1(h, &L.cross_out, kD, kD, p + "crossattention.output.dense"));
+    TRY(upload_ln(h, &L.ln_cross, p + "crossattention.output.LayerNorm"));
+    TRY(upload_linear1(h, &L.fc1, kFFN, kD, p + "intermediate.dense"));
+    TRY(upload_linear1(h, &L.fc2, kD, kFFN, p + "output.dense"));
+    TRY(upload_ln(h, &L.ln_ffn, p + "output.LayerNorm"));
+    ckv.push_back(p + "crossattention.self.key");
+    ckv.push_back(p + "crossattention.self.value");
+  }
+  TRY(upload_linear(h, &h->cross_kv, kD, ckv, {kD, kD, kD, kD}, {1.f, 1.f, 1.f, 1.f}));
+  const std::string c = "decoder.cls.predictions.";
+  TRY(upload_linear1(h, &h->head_t, kD, kD, c + "transform.dense"));
+  TRY(upload_ln(h, &h->head_ln, c + "transform.LayerNorm"));
+  {
+    // LM head: weight may be tied to the word embeddings; bias is predictions.bias.
+    const HostTensor* w = find(h, c + "decoder.weight");
+    if (w == nullptr) w = find(h, d + "embeddings.word_embeddings.weight");
+    const HostTensor* b = find(h, c + "bias");
+    if (b == nullptr) b = find(h, c + "decoder.bias");
+    if (w == nullptr || b == nullptr || w->data.size() != static_cast<size_t>(kVocab) * kD || b->data.size() != static_cast<size_t>(kVocab))
+      return fail(h, MOCR_ERR_WEIGHTS, "missing or mis-shaped LM head (decoder.cls.predictions.decoder.weight / .bias)");
+    std::vector<uint16_t> wb(w->data.size());
+    for (size_t j = 0; j < wb.size(); ++j) wb[j] = f32_to_bf16(w->data[j]);
+    h->head_dec.N = kVocab;
+    h->head_dec.K = kD;
+    TRY(dmalloc(h, &h->head_dec.w, wb.size(), false));
+    CK(cudaMemcpy(h->head_dec.w, wb.data(), wb.size() * 2, cudaMemcpyHostToDevice));
+    TRY(upload_f32(h, &h->head_dec.bias, b->data.data(), kVocab));
+  }
+  {
+    // rescale + normalize as the reference computes them (transformers/image_transforms.py:
+    // 89-124 then 384-442): float32(float64(v) * (1/255)), then (x - 0.5f) / 0.5f in float32.
+    float lut[256];
+    for (int v = 0; v < 256; ++v) {
+      const float x = static_cast<float>(static_cast<double>(v) * (1.0 / 255.0));
+      lut[v] = (x - 0.5f) / 0.5f;
+    }
+    TRY(upload_f32(h, &h->lut, lut, 256));
+  }
+  h->staged.clear();
+  h->finalized = true;
+  return MOCR_OK;
+}
+
+// ------------------------------------------------------------------ launches ---
+
+template <int BN, int EPI>
+int launch_gemm_t(mocr_handle* h, const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& a) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_done[16] = {};
+  if (!attr_done[h->device & 15]) {
+    CK(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_done[h->device & 15] = true;
+  }
+  const int tiles = ((a.M + kGemmBM - 1) / kGemmBM) * (a.N / BN);
+  const int grid = std::min(tiles, h->sms);
+  gemm_tcgen05_kernel<BN, EPI><<<grid, kGemmThreads, Cfg::kSmemBytes, h->stream>>>(ma, mb, a);
+  CK(cudaGetLastError());
+  ++h->launches;
+  return MOCR_OK;
+}
+
+template <int EPI>
+int launch_gemm_bn(mocr_handle* h, int bn, const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& a) {
+  switch (bn) {
+    case 32: return launch_gemm_t<32, EPI>(h, ma, mb, a);
+    case 64: return launch_gemm_t<64, EPI>(h, ma, mb, a);
+    case 128: return launch_gemm_t<128, EPI>(h, ma, mb, a);
+    case 192: return launch_gemm_t<192, EPI>(h, ma, mb, a);
+    case 256: return launch_gemm_t<256, EPI>(h, ma, mb, a);
+    default: return fail(h, MOCR_ERR_INVALID, "unsupported GEMM tile width %d", bn);
+  }
+}
+
+// out = epilogue(A[M,K] * W^T + bias)
+int gemm(mocr_handle* h, int epi, int bn, const ActBuf& A, Linear& L, int M, GemmArgs a) {
+  if (A.K != L.K || M > A.rows_cap || L.N % bn != 0 || L.K % kGemmBK != 0)
+    return fail(h, MOCR_ERR_INVALID, "gemm shape mismatch: M=%d A.K=%d W=[%d,%d] bn=%d", M, A.K, L.N, L.K, bn);
+  const CUtensorMap* mb;
+  TRY(linear_map(h, &L, bn, &mb));
+  a.M = M;
+  a.N = L.N;
+  a.K = L.K;
+  a.bias = L.bias;
+  switch (epi) {
+    case EPI_BF16: return launch_gemm_bn<EPI_BF16>(h, bn, A.map, *mb, a);
+    case EPI_BF16_GELU: return launch_gemm_bn<EPI_BF16_GELU>(h, bn, A.map, *mb, a);
+    case EPI_F32_RESID: return launch_gemm_bn<EPI_F32_RESID>(h, bn, A.map, *mb, a);
+    case EPI_PATCH: return launch_gemm_bn<EPI_PATCH>(h, bn, A.map, *mb, a);
+    case EPI_ARGMAX: return launch_gemm_bn<EPI_ARGMAX>(h, bn, A.map, *mb, a);
+    case EPI_F32_GELU: return launch_gemm_bn<EPI_F32_GELU>(h, bn, A.map, *mb, a);
+    default: return fail(h, MOCR_ERR_INVALID, "bad epilogue %d", epi);
+  }
+}
+
+GemmArgs out_bf16(__nv_bfloat16* out, int ldo) {
+  GemmArgs a{};
+  a.out = out;
+  a.ldo = ldo;
+  return a;
+}
+GemmArgs out_f32(float* out, int ldo, const float* resid = nullptr, int ldr = 0) {
+  GemmArgs a{};
+  a.out = out;
+  a.ldo = ldo;
+  a.resid = resid;
+  a.ldr = ldr;
+  return a;
+}
+
+int layernorm(mocr_handle* h, const float* x, int rows, const LnParams& ln, __nv_bfloat16* ob, float* of) {
+  layernorm_rows_kernel<<<(rows + 7) / 8, 256, 0, h->stream>>>(x, rows, ln.g, ln.b, ob, of);
+  CK(cudaGetLastError());
+  ++h->launches;
+  return MOCR_OK;
+}
+
+// ------------------------------------------------------------------ preprocess ---
+
+int table_for(mocr_handle* h, int in_size, mocr_handle::TableRef* out) {
+  auto it = h->tables.find(in_size);
+  if (it == h->tables.end()) {
+    ResampleTable t = make_resample_table(in_size);
+    mocr_handle::TableRef r{static_cast<int>(h->h_coefs.size()), t.ksize, t.max_strip_rows};
+    h->h_coefs.insert(h->h_coefs.end(), t.data.begin(), t.data.end());
+    it = h->tables.emplace(in_size, r).first;
+  }
+  *out = it->second;
+  return MOCR_OK;
+}
+
+int stage_crops(mocr_handle* h, const mocr_crop_t* crops, int n, int order) {
+  if (!h->finalized) return fail(h, MOCR_ERR_INVALID, "weights are not finalized");
+  if (n < 1 || n > h->max_batch) return fail(h, MOCR_ERR_CAPACITY, "batch of %d crops, handle capacity is %d", n, h->max_batch);
+  if (crops == nullptr) return fail(h, MOCR_ERR_INVALID, "crops is NULL");
+  h->staged_ok = h->pre_ok = h->enc_ok = h->dec_ok = false;
+  size_t total = 0;
+  int max_w = 0, tmp_rows = kPreStripRows;
+  for (int i = 0; i < n; ++i) {
+    const mocr_crop_t& c = crops[i];
+    if (c.data == nullptr || c.height < 1 || c.width < 1 || (c.channels != 1 && c.channels != 3 && c.channels != 4) ||
+        c.stride < c.width * c.channels)
+      return fail(h, MOCR_ERR_INVALID, "crop %d is malformed (h=%d w=%d stride=%d channels=%d)", i, c.height, c.width, c.stride, c.channels);
+    if (c.height > 32768 || c.width > 32768) return fail(h, MOCR_ERR_CAPACITY, "crop %d is larger than 32768 px", i);
+    total += (static_cast<size_t>(c.height) * c.width * c.channels + 15) & ~static_cast<size_t>(15);
+    max_w = std::max(max_w, c.width);
+  }
+  // the previous batch may still be reading the arena / tables
+  CK(cudaStreamSynchronize(h->stream));
+  if (total > h->arena_cap) {
+    if (h->h_arena) cudaFreeHost(h->h_arena);
+    if (h->d_arena) cudaFree(h->d_arena);
+    h->h_arena = nullptr;
+    h->d_arena = nullptr;
+    h->arena_cap = 0;
+    const size_t cap = std::max<size_t>(total + total / 4, 8u << 20);
+    CK(cudaMallocHost(reinterpret_cast<void**>(&h->h_arena), cap));
+    CK(cudaMalloc(reinterpret_cast<void**>(&h->d_arena), cap));
+    h->arena_cap = cap;
+  }
+  size_t off = 0;
+  for (int i = 0; i < n; ++i) {
+    const mocr_crop_t& c = crops[i];
+    const size_t rowb = static_cast<size_t>(c.width) * c.channels;
+    if (static_cast<size_t>(c.stride) == rowb) {
+      memcpy(h->h_arena + off, c.data, rowb * c.height);
+    } else {
+      for (int y = 0; y < c.height; ++y) memcpy(h->h_arena + off + y * rowb, c.data + static_cast<size_t>(y) * c.stride, rowb);
+    }
+    CropDesc& d = h->h_descs[i];
+    d.offset = static_cast<long long>(off);
+    d.h = c.height;
+    d.w = c.width;
+    d.stride = static_cast<int>(rowb);
+    d.channels = c.channels;
+    d.hcoef = d.vcoef = -1;
+    d.hks = d.vks = 0;
+    mocr_handle::TableRef t;
+    if (c.width != kImage) {
+      TRY(table_for(h, c.width, &t));
+      d.hcoef = t.offset;
+      d.hks = t.ksize;
+    }
+    if (c.height != kImage) {
+      TRY(table_for(h, c.height, &t));
+      d.vcoef = t.offset;
+      d.vks = t.ksize;
+      tmp_rows = std::max(tmp_rows, t.strip_rows);
+    }
+    off += (rowb * c.height + 15) & ~static_cast<size_t>(15);
+  }
+  h->pre_pitch = round_up(max_w, 16);
+  h->pre_tmp_rows = tmp_rows;
+  h->pre_bgr = order == MOCR_BGR ? 1 : 0;
+  const size_t smem = static_cast<size_t>(kPreThreads / 32) * h->pre_pitch + static_cast<size_t>(tmp_rows) * kImage;
+  if (smem > 200 * 1024) return fail(h, MOCR_ERR_CAPACITY, "crop extents need %zu B of shared memory (limit 204800)", smem);
+  if (h->h_coefs.size() > h->d_coefs_cap) {
+    if (h->d_coefs) cudaFree(h->d_coefs);
+    h->d_coefs = nullptr;
+    h->d_coefs_cap = h->d_coefs_used = 0;
+    const size_t cap = std::max<size_t>(h->h_coefs.size() * 2, 1u << 20);
+    CK(cudaMalloc(reinterpret_cast<void**>(&h->d_coefs), cap * sizeof(int)));
+    h->d_coefs_cap = cap;
+  }
+  if (h->h_coefs.size() > h->d_coefs_used) {
+    CK(cudaMemcpyAsync(h->d_coefs + h->d_coefs_used, h->h_coefs.data() + h->d_coefs_used,
+                       (h->h_coefs.size() - h->d_coefs_used) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    // h_coefs is pageable: the copy above is staged synchronously by the runtime, safe to reuse
+    h->d_coefs_used = h->h_coefs.size();
+  }
+  CK(cudaMemcpyAsync(h->d_arena, h->h_arena, off, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->d_descs, h->h_descs, sizeof(CropDesc) * n, cudaMemcpyHostToDevice, h->stream));
+  h->n = n;
+  h->staged_ok = true;
+  return MOCR_OK;
+}
+
+int preprocess(mocr_handle* h) {
+  if (!h->staged_ok) return fail(h, MOCR_ERR_INVALID, "no crops staged");
+  const size_t smem = static_cast<size_t>(kPreThreads / 32) * h->pre_pitch + static_cast<size_t>(h->pre_tmp_rows) * kImage;
+  static size_t smem_set[16] = {};
+  if (smem > 48 * 1024 && smem > smem_set[h->device & 15]) {
+    CK(cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    smem_set[h->device & 15] = 200 * 1024;
+  }
+  const bool tap = (h->taps & MOCR_TAP_PIXELS) != 0;
+  dim3 grid(kImage / kPreStripRows, h->n);
+  preprocess_kernel<<<grid, kPreThreads, smem, h->stream>>>(h->d_arena, h->d_descs, h->d_coefs, h->pre_bgr, h->pre_pitch, h->patches.p,
+                                                           tap ? h->px_u8 : nullptr, tap ? h->px_f32 : nullptr, h->lut);
+  CK(cudaGetLastError());
+  ++h->launches;
+  h->pre_ok = true;
+  h->enc_ok = h->dec_ok = false;
+  return MOCR_OK;
+}
+
+// ------------------------------------------------------------------ encoder ---
+
+int attention197(mocr_handle* h, int n) {
+  static bool done[16] = {};
+  if (!done[h->device & 15]) {
+    CK(cudaFuncSetAttribute(encoder_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
+    done[h->device & 15] = true;
+  }
+  encoder_attention_kernel<<<dim3(2, kHeads, n), kAttnThreads, kAttnSmemBytes, h->stream>>>(h->qkv, h->ctx.p);
+  CK(cudaGetLastError());
+  ++h->launches;
+  return MOCR_OK;
+}
+
+int encode(mocr_handle* h) {
+  if (!h->pre_ok) return fail(h, MOCR_ERR_INVALID, "preprocess has not run on the staged crops");
+  const int n = h->n, M = n * kEncTokens, bn = h->enc_bn;
+  // embeddings: patch rows -> h[b*197+1+p] = conv + pos ; h[b*197] = cls + pos[0]   (modeling_vit.py:100-128)
+  {
+    GemmArgs a = out_f32(h->hres, kD);
+    a.pos = h->pos;
+    TRY(gemm(h, EPI_PATCH, bn, h->patches, h->patch, n * kPatches, a));
+    cls_rows_kernel<<<n, 192, 0, h->stream>>>(h->hres, h->cls, h->pos);
+    CK(cudaGetLastError());
+    ++h->launches;
+  }
+  for (int l = 0; l < kEncLayers; ++l) {
+    EncLayer& L = h->enc[l];
+    TRY(layernorm(h, h->hres, M, L.ln1, h->xn.p, nullptr));                                   // modeling_vit.py:333
+    TRY(gemm(h, EPI_BF16, bn, h->xn, L.qkv, M, out_bf16(h->qkv, 3 * kD)));                   // :228-230
+    TRY(attention197(h, n));                                                                  // :236-246
+    TRY(gemm(h, EPI_F32_RESID, bn, h->ctx, L.out, M, out_f32(h->hres, kD, h->hres, kD)));    // :266, :337
+    TRY(layernorm(h, h->hres, M, L.ln2, h->xn.p, nullptr));                                   // :340
+    TRY(gemm(h, EPI_BF16_GELU, bn, h->xn, L.fc1, M, out_bf16(h->mlp.p, kFFN)));              // :297-298
+    TRY(gemm(h, EPI_F32_RESID, bn, h->mlp, L.fc2, M, out_f32(h->hres, kD, h->hres, kD)));    // :309-311
+  }
+  TRY(layernorm(h, h->hres, M, h->enc_ln, h->enc_out.p, (h->taps & MOCR_TAP_ENCODER) ? h->enc_f32 : nullptr));   // :455
+  // cross-attention K/V of both decoder layers, once per crop (modeling_bert.py:252-267)
+  TRY(gemm(h, EPI_BF16, bn, h->enc_out, h->cross_kv, M, out_bf16(h->crosskv, 4 * kD)));
+  h->enc_ok = true;
+  h->dec_ok = false;
+  return MOCR_OK;
+}
+
+// ------------------------------------------------------------------ decoder ---
+
+DecodeState decode_state(mocr_handle* h, bool forced, int max_length) {
+  DecodeState st{};
+  st.ids = h->d_ids;
+  st.pos = h->d_pos;
+  st.finished = h->d_finished;
+  st.forced = forced ? h->d_forced : nullptr;
+  st.max_len = max_length;
+  st.x = h->d_x;
+  st.xb = h->d_xb.p;
+  return st;
+}
+
+int decode_attn(mocr_handle* h, int n, const DecodeAttnArgs& a) {
+  decode_attention_kernel<<<dim3(kHeads, n), kDecAttnThreads, 0, h->stream>>>(a);
+  CK(cudaGetLastError());
+  ++h->launches;
+  return MOCR_OK;
+}
+
+// One greedy step for all n rows (BertLayer x2 + LM head + arg-max / EOS / append / embed).
+int decode_step(mocr_handle* h, int n, int max_length, bool forced, bool tap) {
+  const int bn = h->dec_bn;
+  for (int l = 0; l < kDecLayers; ++l) {
+    DecLayer& L = h->dec[l];
+    // self-attention (modeling_bert.py:143-207) + BertSelfOutput (:287-298)
+    TRY(gemm(h, EPI_BF16, bn, h->d_xb, L.self_qkv, n, out_bf16(h->d_qkv, 3 * kD)));
+    DecodeAttnArgs sa{};
+    sa.q = h->d_qkv;
+    sa.ldq = 3 * kD;
+    sa.kcache = h->self_k[l];
+    sa.vcache = h->self_v[l];
+    sa.b_stride = static_cast<long long>(h->max_length) * kD;
+    sa.key_stride = kD;
+    sa.new_k = h->d_qkv + kD;
+    sa.new_v = h->d_qkv + 2 * kD;
+    sa.ld_new = 3 * kD;
+    sa.pos = h->d_pos;
+    sa.finished = h->d_finished;
+    sa.ctx = h->d_ctx.p;
+    TRY(decode_attn(h, n, sa));
+    TRY(gemm(h, EPI_F32_RESID, bn, h->d_ctx, L.self_out, n, out_f32(h->d_tmp, kD, h->d_x, kD)));
+    TRY(layernorm(h, h->d_tmp, n, L.ln_self, h->d_xb.p, h->d_x));
+    // cross-attention over the cached encoder K/V (:210-284)
+    TRY(gemm(h, EPI_BF16, bn, h->d_xb, L.cross_q, n, out_bf16(h->d_q, kD)));
+    DecodeAttnArgs ca{};
+    ca.q = h->d_q;
+    ca.ldq = kD;
+    ca.kcache = h->crosskv + l * 2 * kD;
+    ca.vcache = h->crosskv + l * 2 * kD + kD;
+    ca.b_stride = static_cast<long long>(kEncTokens) * 4 * kD;
+    ca.key_stride = 4 * kD;
+    ca.fixed_keys = kEncTokens;
+    ca.finished = h->d_finished;
+    ca.ctx = h->d_ctx.p;
+    TRY(decode_attn(h, n, ca));
+    TRY(gemm(h, EPI_F32_RESID, bn, h->d_ctx, L.cross_out, n, out_f32(h->d_tmp, kD, h->d_x, kD)));
+    TRY(layernorm(h, h->d_tmp, n, L.ln_cross, h->d_xb.p, h->d_x));
+    // feed-forward (:330-356)
+    TRY(gemm(h, EPI_BF16_GELU, bn, h->d_xb, L.fc1, n, out_bf16(h->d_ffn.p, kFFN)));
+    TRY(gemm(h, EPI_F32_RESID, bn, h->d_ffn, L.fc2, n, out_f32(h->d_tmp, kD, h->d_x, kD)));
+    TRY(layernorm(h, h->d_tmp, n, L.ln_ffn, h->d_xb.p, h->d_x));
+  }
+  // LM head (:471-501): dense + GELU + LayerNorm, then the vocabulary projection fused with
+  // the per-tile arg-max; logits only leave the SM when the parity tap is on.
+  TRY(gemm(h, EPI_F32_GELU, bn, h->d_xb, h->head_t, n, out_f32(h->d_tmp, kD)));
+  TRY(layernorm(h, h->d_tmp, n, h->head_ln, h->d_tb.p, nullptr));
+  GemmArgs a{};
+  a.part_max = h->part_max;
+  a.part_idx = h->part_idx;
+  a.logits = tap ? h->logits_tap : nullptr;
+  a.step = h->d_pos;
+  a.tap_steps = max_length - 1;
+  TRY(gemm(h, EPI_ARGMAX, h->head_bn, h->d_tb, h->head_dec, n, a));
+  next_token_kernel<<<n, 256, 0, h->stream>>>(decode_state(h, forced, max_length), h->emb, h->part_max, h->part_idx,
+                                              kVocab / h->head_bn, kSepId);
+  CK(cudaGetLastError());
+  ++h->launches;
+  return MOCR_OK;
+}
+
+int decode(mocr_handle* h, int max_length, const int32_t* forced_ids) {
+  if (!h->enc_ok) return fail(h, MOCR_ERR_INVALID, "encode has not run on the staged crops");
+  if (max_length < 2 || max_length > h->max_length)
+    return fail(h, MOCR_ERR_CAPACITY, "max_length %d outside [2, %d]", max_length, h->max_length);
+  const int n = h->n;
+  const bool forced = forced_ids != nullptr;
+  const bool tap = (h->taps & MOCR_TAP_LOGITS) != 0;
+  if (forced) CK(cudaMemcpyAsync(h->d_forced, forced_ids, sizeof(int) * n * max_length, cudaMemcpyHostToDevice, h->stream));
+  if (tap) {
+    const size_t need_b = static_cast<size_t>(n) * (max_length - 1) * kVocab * sizeof(float);
+    if (need_b > h->logits_tap_bytes) {
+      CK(cudaStreamSynchronize(h->stream));
+      if (h->logits_tap) cudaFree(h->logits_tap);
+      h->logits_tap = nullptr;
+      h->logits_tap_bytes = 0;
+      CK(cudaMalloc(reinterpret_cast<void**>(&h->logits_tap), need_b));
+      h->logits_tap_bytes = need_b;
+      for (auto& g : h->graphs) cudaGraphExecDestroy(g.second.exec);   // they captured the old tap pointer
+      h->graphs.clear();
+    }
+    CK(cudaMemsetAsync(h->logits_tap, 0, need_b, h->stream));
+  }
+  decode_begin_kernel<<<n, 256, 0, h->stream>>>(decode_state(h, forced, max_length), h->emb, kClsId, kPadId);
+  CK(cudaGetLastError());
+  ++h->launches;
+
+  const int steps = max_length - 1;
+  cudaGraphExec_t exec = nullptr;
+  int64_t per_step = 0;
+  if (h->use_graph) {
+    const uint64_t key = (static_cast<uint64_t>(n) << 32) | (static_cast<uint64_t>(max_length) << 8) | (forced ? 2u : 0u) | (tap ? 1u : 0u);
+    auto it = h->graphs.find(key);
+    if (it == h->graphs.end()) {
+      // warm every kernel variant once outside capture (function attributes, tensor maps),
+      // on throw-away state: re-run decode_begin afterwards.
+      const int64_t l0 = h->launches;
+      TRY(decode_step(h, n, max_length, forced, tap));
+      per_step = h->launches - l0;
+      decode_begin_kernel<<<n, 256, 0, h->stream>>>(decode_state(h, forced, max_length), h->emb, kClsId, kPadId);
+      CK(cudaGetLastError());
+      ++h->launches;
+      if (tap) CK(cudaMemsetAsync(h->logits_tap, 0, static_cast<size_t>(n) * (max_length - 1) * kVocab * sizeof(float), h->stream));
+      cudaGraph_t graph;
+      CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+      const int64_t l1 = h->launches;
+      int r = decode_step(h, n, max_length, forced, tap);
+      h->launches = l1;
+      cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+      if (r != MOCR_OK) return r;
+      if (ce != cudaSuccess) return fail(h, MOCR_ERR_CUDA, "stream capture failed: %s", cudaGetErrorString(ce));
+      CK(cudaGraphInstantiate(&exec, graph, 0));
+      cudaGraphDestroy(graph);
+      if (h->graphs.size() >= 64) {
+        for (auto& g : h->graphs) cudaGraphExecDestroy(g.second.exec);
+        h->graphs.clear();
+      }
+      h->graphs[key] = mocr_handle::StepGraph{exec, static_cast<int>(per_step)};
+    } else {
+      exec = it->second.exec;
+      per_step = it->second.launches;
+    }
+  }
+  int done_steps = 0;
+  while (done_steps < steps) {
+    const int chunk = std::min(forced ? steps : h->check_every, steps - done_steps);
+    for (int s = 0; s < chunk; ++s) {
+      if (exec != nullptr) {
+        CK(cudaGraphLaunch(exec, h->stream));
+        h->launches += per_step;
+      } else {
+        TRY(decode_step(h, n, max_length, forced, tap));
+      }
+    }
+    done_steps += chunk;
+    if (!forced && done_steps < steps) {
+      // every row finished? (generation/utils.py:2805 does this check, with a host sync, every step)
+      CK(cudaMemcpyAsync(h->h_flags, h->d_finished, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      bool all = true;
+      for (int i = 0; i < n; ++i) all = all && h->h_flags[i] != 0;
+      if (all) break;
+    }
+  }
+  h->last_steps = done_steps;
+  h->cur_len = max_length;
+  h->dec_ok = true;
+  return MOCR_OK;
+}
+
+int fetch_ids(mocr_handle* h, int32_t* out_ids, int32_t* out_lens) {
+  if (!h->dec_ok) return fail(h, MOCR_ERR_INVALID, "no decode result to fetch");
+  const int n = h->n, T = h->cur_len;
+  CK(cudaMemcpyAsync(out_ids, h->d_ids, sizeof(int) * n * T, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(h->h_flags, h->d_pos, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (out_lens != nullptr)
+    for (int i = 0; i < n; ++i) out_lens[i] = std::min(h->h_flags[i] + 1, T);
+  return MOCR_OK;
+}
+
+int check_handle(mocr_handle* h) {
+  if (h == nullptr) return fail(nullptr, MOCR_ERR_INVALID, "handle is NULL");
+  cudaError_t e = cudaSetDevice(h->device);
+  if (e != cudaSuccess) return fail(h, MOCR_ERR_CUDA, "cudaSetDevice(%d): %s", h->device, cudaGetErrorString(e));
+  return MOCR_OK;
+}
+
+int create_impl(mocr_handle* h) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(h, MOCR_ERR_NO_DEVICE, "no CUDA device (%s); this engine has no CPU path", e == cudaSuccess ? "count is 0" : cudaGetErrorString(e));
+  if (h->device < 0 || h->device >= count) return fail(h, MOCR_ERR_NO_DEVICE, "device %d out of range (%d devices)", h->device, count);
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, h->device));
+  if (prop.major != 10)
+    return fail(h, MOCR_ERR_NO_DEVICE, "device %d is sm_%d%d; the kernels are built for sm_100a (B200) only", h->device, prop.major, prop.minor);
+  CK(cudaSetDevice(h->device));
+  h->sms = prop.multiProcessorCount;
+  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  const int B = h->max_batch, T = h->max_length;
+  h->rows_cap = round_up(B * kEncTokens, kGemmBM);
+  h->brow_cap = round_up(B, kGemmBM);
+  TRY(make_act(h, &h->patches, round_up(B * kPatches, kGemmBM), kPatchK));
+  TRY(make_act(h, &h->xn, h->rows_cap, kD));
+  TRY(make_act(h, &h->ctx, h->rows_cap, kD));
+  TRY(make_act(h, &h->mlp, h->rows_cap, kFFN));
+  TRY(make_act(h, &h->enc_out, h->rows_cap, kD));
+  TRY(dmalloc(h, &h->qkv, static_cast<size_t>(h->rows_cap) * 3 * kD));
+  TRY(dmalloc(h, &h->hres, static_cast<size_t>(h->rows_cap) * kD));
+  TRY(dmalloc(h, &h->crosskv, static_cast<size_t>(h->rows_cap) * 4 * kD));
+  TRY(make_act(h, &h->d_xb, h->brow_cap, kD));
+  TRY(make_act(h, &h->d_ctx, h->brow_cap, kD));
+  TRY(make_act(h, &h->d_ffn, h->brow_cap, kFFN));
+  TRY(make_act(h, &h->d_tb, h->brow_cap, kD));
+  TRY(dmalloc(h, &h->d_x, static_cast<size_t>(h->brow_cap) * kD));
+  TRY(dmalloc(h, &h->d_tmp, static_cast<size_t>(h->brow_cap) * kD));
+  TRY(dmalloc(h, &h->d_qkv, static_cast<size_t>(h->brow_cap) * 3 * kD));
+  TRY(dmalloc(h, &h->d_q, static_cast<size_t>(h->brow_cap) * kD));
+  for (int l = 0; l < kDecLayers; ++l) {
+    TRY(dmalloc(h, &h->self_k[l], static_cast<size_t>(B) * T * kD));
+    TRY(dmalloc(h, &h->self_v[l], static_cast<size_t>(B) * T * kD));
+  }
+  TRY(dmalloc(h, &h->part_max, static_cast<size_t>(h->brow_cap) * (kVocab / 32)));
+  TRY(dmalloc(h, &h->part_idx, static_cast<size_t>(h->brow_cap) * (kVocab / 32)));
+  TRY(dmalloc(h, &h->d_ids, static_cast<size_t>(B) * T));
+  TRY(dmalloc(h, &h->d_forced, static_cast<size_t>(B) * T));
+  TRY(dmalloc(h, &h->d_pos, static_cast<size_t>(B)));
+  TRY(dmalloc(h, &h->d_finished, static_cast<size_t>(B)));
+  TRY(dmalloc(h, &h->d_zero, static_cast<size_t>(B)));
+  TRY(dmalloc(h, &h->d_descs, static_cast<size_t>(B)));
+  CK(cudaMallocHost(reinterpret_cast<void**>(&h->h_flags), sizeof(int) * B));
+  CK(cudaMallocHost(reinterpret_cast<void**>(&h->h_descs), sizeof(CropDesc) * B));
+  CK(cudaStreamSynchronize(h->stream));
+  return MOCR_OK;
+}
+
+int ensure_taps(mocr_handle* h) {
+  const size_t B = h->max_batch;
+  if ((h->taps & MOCR_TAP_PIXELS) && h->px_u8 == nullptr) {
+    TRY(dmalloc(h, &h->px_u8, B * kImage * kImage));
+    TRY(dmalloc(h, &h->px_f32, B * kImage * kImage));
+  }
+  if ((h->taps & MOCR_TAP_ENCODER) && h->enc_f32 == nullptr) TRY(dmalloc(h, &h->enc_f32, static_cast<size_t>(h->rows_cap) * kD));
+  return MOCR_OK;
+}
+
+int d2h(mocr_handle* h, void* dst, const void* src, size_t bytes) {
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return MOCR_OK;
+}
+
+}  // namespace
+
+// ===================================================================== C ABI ===
+
+extern "C" {
+
+int mocr_abi_version(void) { return MOCR_ABI_VERSION; }
+
+int mocr_create(int device, int max_batch, int max_length, mocr_handle_t** out) {
+  if (out == nullptr) return fail(nullptr, MOCR_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  if (max_batch < 1 || max_batch > 4096) return fail(nullptr, MOCR_ERR_INVALID, "max_batch %d outside [1, 4096]", max_batch);
+  if (max_length < 2 || max_length > kMaxPos) return fail(nullptr, MOCR_ERR_INVALID, "max_length %d outside [2, %d]", max_length, kMaxPos);
+  mocr_handle* h = new (std::nothrow) mocr_handle();
+  if (h == nullptr) return fail(nullptr, MOCR_ERR_INVALID, "out of host memory");
+  h->device = device;
+  h->max_batch = max_batch;
+  h->max_length = max_length;
+  int r = create_impl(h);
+  if (r != MOCR_OK) {
+    g_create_error = h->error;
+    mocr_destroy(h);
+    return r;
+  }
+  *out = h;
+  return MOCR_OK;
+}
+
+int mocr_destroy(mocr_handle_t* h) {
+  if (h == nullptr) return MOCR_OK;
+  if (cudaSetDevice(h->device) == cudaSuccess) {
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (auto& g : h->graphs) cudaGraphExecDestroy(g.second.exec);
+    for (void* p : h->allocs) cudaFree(p);
+    if (h->logits_tap) cudaFree(h->logits_tap);
+    if (h->d_arena) cudaFree(h->d_arena);
+    if (h->h_arena) cudaFreeHost(h->h_arena);
+    if (h->d_coefs) cudaFree(h->d_coefs);
+    if (h->h_flags) cudaFreeHost(h->h_flags);
+    if (h->h_descs) cudaFreeHost(h->h_descs);
+    if (h->stream) cudaStreamDestroy(h->stream);
+  }
+  delete h;
+  return MOCR_OK;
+}
+
+int mocr_set_weight(mocr_handle_t* h, const char* name, const float* data, const int64_t* shape, int ndim) {
+  TRY(check_handle(h));
+  std::lock_guard<std::mutex> lock(h->mu);
+  if (name == nullptr || data == nullptr || shape == nullptr || ndim < 1 || ndim > 8) return fail(h, MOCR_ERR_INVALID, "bad tensor argument");
+  if (h->finalized) return fail(h, MOCR_ERR_INVALID, "weights are already finalized");
+  HostTensor t;
+  size_t numel = 1;
+  for (int i = 0; i < ndim; ++i) {
+    if (shape[i] < 1) return fail(h, MOCR_ERR_INVALID, "tensor %s has a non-positive extent", name);
+    t.shape.push_back(shape[i]);
+    numel *= static_cast<size_t>(shape[i]);
+  }
+  if (numel > (1u << 28)) return fail(h, MOCR_ERR_INVALID, "tensor %s is implausibly large", name);
+  t.data.assign(data, data + numel);
+  h->staged[name] = std::move(t);
+  return MOCR_OK;
+}
+
+int mocr_finalize_weights(mocr_handle_t* h) {
+  TRY(check_handle(h));
+  std::lock_guard<std::mutex> lock(h->mu);
+  if (h->finalized) return fail(h, MOCR_ERR_INVALID, "weights are already finalized");
+  return finalize_weights(h);
+}
+
+int mocr_stage_crops(mocr_handle_t* h, const mocr_crop_t* crops, int n, int channel_order) {
+  TRY(check_handle(h));
+  std::lock_guard<std::mutex> lock(h->mu);
+  return stage_crops(h, crops, n, channel_order);
+}
+
+int mocr_preprocess(mocr_handle_t* h) {
+  TRY(check_handle(h));
+  std::lock_guard<std::mutex> lock(h->mu);
+  return preprocess(h);
+}
+
+int mocr_encode(mocr_handle_t* h) {
+  TRY(check_handle(h));
+  std::lock_guard<std::mutex> lock(h->mu);
+  return encode(h);
+}
+
+int mocr_decode_greedy(mocr_handle_t* h, int max_length, const int32_t* forced_ids) {
+  TRY(check_handle(h));
+  std::lock_guard<std::mutex> lock(h->mu);
+  return decode(h, max_length, forced_ids);
+}
+
+int mocr_fetch_ids(mocr_handle_t* h, int32_t* out_ids, int32_t* out_lens) {
+  TRY(check_handle(h));
+  std::lock_guard<std::mutex> lock(h->mu);
+  if (out_ids == nullptr) return fail(h, MOCR_ERR_INVALID, "out_ids is NULL");
+  return fetch_ids(h, out_ids, out_lens);
+}
+
+int mocr_run_resident(mocr_handle_t* h, int max_length) {
+  TRY(check_handle(h));
+  std::lock_guard<std::mutex> lock(h->mu);
+  TRY(preprocess(h));
+  TRY(encode(h));
+  return decode(h, max_length, nullptr);
+}
+
+int mocr_recognize(mocr_handle_t* h, const mocr_crop_t* crops, int n, int channel_order, int max_length, int32_t* out_ids,
+                   int32_t* out_lens) {
+  TRY(check_handle(h));
+  std::lock_guard<std::mutex> lock(h->mu);
+  if (n < 0 || (n > 0 && (crops == nullptr || out_ids == nullptr))) return fail(h, MOCR_ERR_INVALID, "bad argument");
+  for (int i0 = 0; i0 < n; i0 += h->max_batch) {
+    const int m = std::min(h->max_batch, n - i0);
+    TRY(stage_crops(h, crops + i0, m, channel_order));
+    TRY(preprocess(h));
+    TRY(encode(h));
+    TRY(decode(h, max_length, nullptr));
+    TRY(fetch_ids(h, out_ids + static_cast<size_t>(i0) * max_length, out_lens ? out_lens + i0 : nullptr));
+  }
+  return MOCR_OK;
+}
+
+int mocr_set_taps(mocr_handle_t* h, int taps) {
+  TRY(check_handle(h));
+  std::lock_guard<std::mutex> lock(h->mu);
+  h->taps = taps;
+  return ensure_taps(h);
+}
+
+int mocr_get_pixels_u8(mocr_handle_t* h, uint8_t* out) {
+  TRY(check_handle(h));
+  std::lock_guard<std::mutex> lock(h->mu);
+  if (!h->pre_ok || h->px_u8 == nullptr || out == nullptr) return fail(h, MOCR_ERR_INVALID, "pixel tap not available");
+  return d2h(h, out, h->px_u8, static_cast<size_t>(h->n) * kImage * kImage);
+}
+
+int mocr_get_pixel_values(mocr_handle_t* h, float* out) {
+  TRY(check_handle(h));
+  std::lock_guard<std::mutex> lock(h->mu);
+  if (!h->pre_ok || h->px_f32 == nullptr || out == nullptr) return fail(h, MOCR_ERR_INVALID, "pixel tap not available");
+  return d2h(h, out, h->px_f32, static_cast<size_t>(h->n) * kImage * kImage * sizeof(float));
+}
+
+int mocr_get_encoder_hidden(mocr_handle_t* h, float* out) {
+  TRY(check_handle(h));
+  std::lock_guard<std::mutex> lock(h->mu);
+  if (!h->enc_ok || h->enc_f32 == nullptr || out == nullptr) return fail(h, MOCR_ERR_INVALID, "encoder tap not available");
+  return d2h(h, out, h->enc_f32, static_cast<size_t>(h->n) * kEncTokens * kD * sizeof(float));
+}
+
+int mocr_get_step_logits(mocr_handle_t* h, float* out) {
+  TRY(check_handle(h));
+  std::lock_guard<std::mutex> lock(h->mu);
+  if (!h->dec_ok || h->logits_tap == nullptr || out == nullptr) return fail(h, MOCR_ERR_INVALID, "logits tap not available");
+  return d2h(h, out, h->logits_tap, static_cast<size_t>(h->n) * (h->cur_len - 1) * kVocab * sizeof(float));
+}
+
+void* mocr_stream(mocr_handle_t* h) { return h ? static_cast<void*>(h->stream) : nullptr; }
+
+int mocr_sync(mocr_handle_t* h) {
+  TRY(check_handle(h));
+  CK(cudaStreamSynchronize(h->stream));
+  return MOCR_OK;
+}
+
+int64_t mocr_launch_count(mocr_handle_t* h) { return h ? h->launches : 0; }
+int mocr_last_steps(mocr_handle_t* h) { return h ? h->last_steps : 0; }
+
+int mocr_set_option(mocr_handle_t* h, const char* key, int value) {
+  TRY(check_handle(h));
+  std::lock_guard<std::mutex> lock(h->mu);
+  if (key == nullptr) return fail(h, MOCR_ERR_INVALID, "key is NULL");
+  const std::string k = key;
+  auto bn_ok = [](int v) { return v == 32 || v == 64 || v == 128 || v == 192 || v == 256; };
+  if (k == "enc_bn" && bn_ok(value) && kD % value == 0) h->enc_bn = value;
+  else if (k == "dec_bn" && bn_ok(value) && kD % value == 0) h->dec_bn = value;
+  else if (k == "head_bn" && bn_ok(value) && kVocab % value == 0) h->head_bn = value;
+  else if (k == "check_every" && value >= 1) h->check_every = value;
+  else if (k == "use_graph") h->use_graph = value != 0;
+  else return fail(h, MOCR_ERR_INVALID, "unknown option or bad value: %s=%d", key, value);
+  for (auto& g : h->graphs) cudaGraphExecDestroy(g.second.exec);
+  h->graphs.clear();
+  return MOCR_OK;
+}
+
+int mocr_time_kernel(mocr_handle_t* h, const char* kernel, int iters, float* ms_per_launch, double* algo_bytes, double* algo_flops) {
+  TRY(check_handle(h));
+  std::lock_guard<std::mutex> lock(h->mu);
+  if (kernel == nullptr || iters < 1 || ms_per_launch == nullptr) return fail(h, MOCR_ERR_INVALID, "bad argument");
+  if (!h->enc_ok) return fail(h, MOCR_ERR_INVALID, "run a batch through mocr_encode first");
+  const std::string k = kernel;
+  const int n = h->n, M = n * kEncTokens;
+  double bytes = 0, flops = 0;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  int r = MOCR_OK;
+  for (int i = -2; i < iters && r == MOCR_OK; ++i) {
+    if (i == 0) CK(cudaEventRecord(e0, h->stream));
+    if (k == "enc_fc1") {
+      r = gemm(h, EPI_BF16_GELU, h->enc_bn, h->xn, h->enc[0].fc1, M, out_bf16(h->mlp.p, kFFN));
+      flops = 2.0 * M * kFFN * kD;
+      bytes = 2.0 * (static_cast<double>(M) * kD + static_cast<double>(kFFN) * kD + static_cast<double>(M) * kFFN);
+    } else if (k == "enc_fc2") {
+      r = gemm(h, EPI_BF16, h->enc_bn, h->mlp, h->enc[0].fc2, M, out_bf16(h->ctx.p, kD));
+      flops = 2.0 * M * kFFN * kD;
+      bytes = 2.0 * (static_cast<double>(M) * kFFN + static_cast<double>(kFFN) * kD + static_cast<double>(M) * kD);
+    } else if (k == "enc_qkv") {
+      r = gemm(h, EPI_BF16, h->enc_bn, h->xn, h->enc[0].qkv, M, out_bf16(h->qkv, 3 * kD));
+      flops = 2.0 * M * 3 * kD * kD;
+      bytes = 2.0 * (static_cast<double>(M) * kD + 3.0 * kD * kD + static_cast<double>(M) * 3 * kD);
+    } else if (k == "enc_attn") {
+      r = attention197(h, n);
+      flops = 4.0 * n * kHeads * kEncTokens * kEncTokens * kHeadDim;
+      bytes = 2.0 * (static_cast<double>(M) * 3 * kD + static_cast<double>(M) * kD);
+    } else if (k == "dec_cross_attn") {
+      if (!h->dec_ok) { r = fail(h, MOCR_ERR_INVALID, "run a decode first"); break; }
+      DecodeAttnArgs ca{};
+      ca.q = h->d_q;
+      ca.ldq = kD;
+      ca.kcache = h->crosskv;
+      ca.vcache = h->crosskv + kD;
+      ca.b_stride = static_cast<long long>(kEncTokens) * 4 * kD;
+      ca.key_stride = 4 * kD;
+      ca.fixed_keys = kEncTokens;
+      ca.finished = h->d_zero;      // time every row, finished or not
+      ca.ctx = h->d_ctx.p;
+      r = decode_attn(h, n, ca);
+      bytes = static_cast<double>(n) * (2.0 * kEncTokens * kD * 2 + 2.0 * kD * 2);
+      flops = 4.0 * n * kEncTokens * kD;
+    } else {
+      r = fail(h, MOCR_ERR_INVALID, "unknown kernel name %s", kernel);
+    }
+  }
+  if (r == MOCR_OK) {
+    CK(cudaEventRecord(e1, h->stream));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    *ms_per_launch = ms / iters;
+    if (algo_bytes) *algo_bytes = bytes;
+    if (algo_flops) *algo_flops = flops;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return r;
+}
+
+// ---- kernel-level unit hooks (tests only): run ONE product kernel on caller-supplied data ----
+
+int mocr_test_gemm(mocr_handle_t* h, int epi, int bn, int M, int N, int K, const float* A, const float* Wt, const float* bias,
+                   const float* resid, float* out, int32_t* out_argmax) {
+  TRY(check_handle(h));
+  std::lock_guard<std::mutex> lock(h->mu);
+  if (M < 1 || N < 1 || K < 1 || A == nullptr || Wt == nullptr || bias == nullptr || out == nullptr || N % bn != 0 || K % kGemmBK != 0)
+    return fail(h, MOCR_ERR_INVALID, "bad test_gemm argument");
+  if (epi == EPI_PATCH) return fail(h, MOCR_ERR_INVALID, "EPI_PATCH is covered by the encoder test");
+  const int Mp = round_up(M, kGemmBM);
+  std::vector<uint16_t> ab(static_cast<size_t>(Mp) * K, 0), wb(static_cast<size_t>(N) * K);
+  for (size_t i = 0; i < static_cast<size_t>(M) * K; ++i) ab[i] = f32_to_bf16(A[i]);
+  for (size_t i = 0; i < wb.size(); ++i) wb[i] = f32_to_bf16(Wt[i]);
+  ActBuf a;
+  Linear L;
+  void *d_out = nullptr, *d_res = nullptr, *d_pm = nullptr, *d_pi = nullptr, *d_step = nullptr;
+  const size_t mn = static_cast<size_t>(M) * N;
+  int r = MOCR_OK;
+  auto body = [&]() -> int {
+    CK(cudaMalloc(reinterpret_cast<void**>(&a.p), ab.size() * 2));
+    CK(cudaMalloc(reinterpret_cast<void**>(&L.w), wb.size() * 2));
+    CK(cudaMalloc(reinterpret_cast<void**>(&L.bias), N * sizeof(float)));
+    CK(cudaMalloc(&d_out, mn * sizeof(float)));
+    CK(cudaMemcpy(a.p, ab.data(), ab.size() * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(L.w, wb.data(), wb.size() * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(L.bias, bias, N * sizeof(float), cudaMemcpyHostToDevice));
+    CK(cudaMemset(d_out, 0, mn * sizeof(float)));
+    a.rows_cap = Mp;
+    a.K = K;
+    L.N = N;
+    L.K = K;
+    TRY(make_map(h, &a.map, a.p, Mp, K, kGemmBM));
+    GemmArgs g{};
+    g.out = d_out;
+    g.ldo = N;
+    if (epi == EPI_F32_RESID) {
+      if (resid == nullptr) return fail(h, MOCR_ERR_INVALID, "resid is NULL");
+      CK(cudaMalloc(&d_res, mn * sizeof(float)));
+      CK(cudaMemcpy(d_res, resid, mn * sizeof(float), cudaMemcpyHostToDevice));
+      g.resid = static_cast<const float*>(d_res);
+      g.ldr = N;
+    }
+    const int parts = N / bn;
+    if (epi == EPI_ARGMAX) {
+      CK(cudaMalloc(&d_pm, static_cast<size_t>(M) * parts * sizeof(float)));
+      CK(cudaMalloc(&d_pi, static_cast<size_t>(M) * parts * sizeof(int)));
+      CK(cudaMalloc(&d_step, static_cast<size_t>(M) * sizeof(int)));
+      CK(cudaMemset(d_step, 0, static_cast<size_t>(M) * sizeof(int)));
+      g.part_max = static_cast<float*>(d_pm);
+      g.part_idx = static_cast<int*>(d_pi);
+      g.logits = static_cast<float*>(d_out);
+      g.step = static_cast<const int*>(d_step);
+      g.tap_steps = 1;
+    }
+    TRY(gemm(h, epi, bn, a, L, M, g));
+    CK(cudaStreamSynchronize(h->stream));
+    if (epi == EPI_BF16 || epi == EPI_BF16_GELU) {
+      std::vector<uint16_t> ob(mn);
+      CK(cudaMemcpy(ob.data(), d_out, mn * 2, cudaMemcpyDeviceToHost));
+      for (size_t i = 0; i < mn; ++i) {
+        const uint32_t u = static_cast<uint32_t>(ob[i]) << 16;
+        memcpy(&out[i], &u, 4);
+      }
+    } else {
+      CK(cudaMemcpy(out, d_out, mn * sizeof(float), cudaMemcpyDeviceToHost));
+    }
+    if (epi == EPI_ARGMAX && out_argmax != nullptr) {
+      std::vector<float> pm(static_cast<size_t>(M) * parts);
+      std::vector<int> pi(static_cast<size_t>(M) * parts);
+      CK(cudaMemcpy(pm.data(), d_pm, pm.size() * sizeof(float), cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(pi.data(), d_pi, pi.size() * sizeof(int), cudaMemcpyDeviceToHost));
+      for (int m = 0; m < M; ++m) {
+        float bv = -INFINITY;
+        int bi = 0x7fffffff;
+        for (int p = 0; p < parts; ++p) {
+          const float v = pm[static_cast<size_t>(m) * parts + p];
+          const int ix = pi[static_cast<size_t>(m) * parts + p];
+          if (v > bv || (v == bv && ix < bi)) { bv = v; bi = ix; }
+        }
+        out_argmax[m] = bi;
+      }
+    }
+    return MOCR_OK;
+  };
+  r = body();
+  cudaStreamSynchronize(h->stream);
+  cudaFree(a.p); cudaFree(L.w); cudaFree(L.bias); cudaFree(d_out); cudaFree(d_res); cudaFree(d_pm); cudaFree(d_pi); cudaFree(d_step);
+  return r;
+}
+
+int mocr_test_encoder_attention(mocr_handle_t* h, int n, const float* qkv, float* out) {
+  TRY(check_handle(h));
+  std::lock_guard<std::mutex> lock(h->mu);
+  if (n < 1 || n > h->max_batch || qkv == nullptr || out == nullptr) return fail(h, MOCR_ERR_INVALID, "bad test_encoder_attention argument");
+  const size_t rows = static_cast<size_t>(n) * kEncTokens;
+  std::vector<uint16_t> qb(rows * 3 * kD);
+  for (size_t i = 0; i < qb.size(); ++i) qb[i] = f32_to_bf16(qkv[i]);
+  CK(cudaMemcpyAsync(h->qkv, qb.data(), qb.size() * 2, cudaMemcpyHostToDevice, h->stream));
+  TRY(attention197(h, n));
+  std::vector<uint16_t> ob(rows * kD);
+  CK(cudaMemcpyAsync(ob.data(), h->ctx.p, ob.size() * 2, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  for (size_t i = 0; i < ob.size(); ++i) {
+    const uint32_t u = static_cast<uint32_t>(ob[i]) << 16;
+    memcpy(&out[i], &u, 4);
+  }
+  h->pre_ok = h->enc_ok = h->dec_ok = false;   // scratch buffers were overwritten
+  return MOCR_OK;
+}
+
+const char* mocr_last_error(mocr_handle_t* h) { return h ? h->error.c_str() : g_create_error.c_str(); }
+
+}  // extern "C"

@@ -27,6 +27,7 @@ enum GemmEpilogue : int {
   EPI_F32_RESID = 2,   // out(f32)  = acc + bias + resid(f32)      (resid may alias out)
   EPI_PATCH = 3,       // ViT embeddings: out(f32)[b*197+1+p] = acc + bias + pos[1+p]
   EPI_ARGMAX = 4,      // LM head: per-row (max, argmax) over this tile's columns; logits optional
+  EPI_F32_GELU = 5,    // out(f32)  = gelu_erf(acc + bias)         (LM-head transform, feeds a LayerNorm)
 };
 
 struct GemmArgs {
@@ -39,7 +40,9 @@ struct GemmArgs {
   const float* pos;      // EPI_PATCH: position table [197, 768] f32
   float* part_max;       // EPI_ARGMAX: [M, N/BN]
   int* part_idx;         // EPI_ARGMAX: [M, N/BN]
-  float* logits;         // EPI_ARGMAX: optional [M, N] f32 tap for parity tests (may be null)
+  float* logits;         // EPI_ARGMAX: optional f32 tap for parity tests (may be null):
+  const int* step;       //   row r writes logits[(r * tap_steps + step[r]) * N ...]
+  int tap_steps;
 };
 
 constexpr int kGemmBM = 128;
@@ -51,8 +54,9 @@ struct GemmCfg {
   static constexpr int kStageBytesA = kGemmBM * kGemmBK * 2;
   static constexpr int kStageBytesB = BN * kGemmBK * 2;
   static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
-  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
-  static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;     // power of two for BN in {16..256}
+  static constexpr int kStagesFit = (200 * 1024) / kStageBytes;
+  static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
+  static constexpr int kTmemCols = 2 * BN <= 32 ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -209,6 +213,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               dst[j] = q;
             }
           }
+        } else if (EPI == EPI_F32_GELU) {
+          if (row_ok) {
+            float4* dst = reinterpret_cast<float4*>(static_cast<float*>(args.out) + static_cast<size_t>(row) * args.ldo + col0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              dst[j] = make_float4(gelu_erf(f[4 * j]), gelu_erf(f[4 * j + 1]), gelu_erf(f[4 * j + 2]), gelu_erf(f[4 * j + 3]));
+          }
         } else if (EPI == EPI_F32_RESID || EPI == EPI_PATCH) {
           if (row_ok) {
             const float4* ex = reinterpret_cast<const float4*>(extra + col0);
@@ -224,8 +235,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           for (int j = 0; j < 32; ++j) {
             if (f[j] > best) { best = f[j]; best_i = col0 + j; }   // strict > keeps the lowest index on ties
           }
-          if (args.logits != nullptr && row_ok) {
-            float4* dst = reinterpret_cast<float4*>(args.logits + static_cast<size_t>(row) * args.N + col0);
+          if (args.logits != nullptr && row_ok && args.step[row] < args.tap_steps) {
+            float4* dst = reinterpret_cast<float4*>(
+                args.logits + (static_cast<size_t>(row) * args.tap_steps + args.step[row]) * args.N + col0);
 #pragma unroll
             for (int j = 0; j < 8; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
           }

@@ -8,9 +8,9 @@
 //     (PIL.Image.resize, BILINEAR)  [Pillow src/libImaging/Resample.c]
 //   transformers/image_transforms.py:89-124 (rescale) and :384-442 (normalize)
 //
-// The rescale+normalize affine map is folded into the patch-embed weights
-// (x = u8*2/255 - 1), so the A operand holds the uint8 values themselves, which
-// are exact in bf16.  The fp32 pixel_values plane (256-entry LUT built by the
+// The rescale+normalize affine map is folded into the patch-embed weights and bias
+// (x = u8*2/255 - 1 = (u8-128)*2/255 + 1/255), so the A operand holds the centred
+// integers u8-128, which are exact in bf16.  The fp32 pixel_values plane (256-entry LUT built by the
 // host with the reference's numpy expression) is only written when a debug tap
 // is requested by the parity tests.
 #pragma once
@@ -33,6 +33,7 @@ struct CropDesc {
   int hcoef;          // int32 offset of the horizontal table in the coefficient arena (-1: w == 224)
   int vcoef;          // same for the vertical table (-1: h == 224)
   int hks, vks;       // taps per output (table row width)
+  int channels;       // bytes per pixel: 1 (luma), 3 (RGB/BGR) or 4 (RGBA/BGRA, alpha ignored)
 };
 
 // One table = xmin[224] | count[224] | k[224 * ksize]  (all int32)
@@ -120,9 +121,14 @@ preprocess_kernel(const uint8_t* __restrict__ arena, const CropDesc* __restrict_
     const uint8_t* src = arena + cd.offset + static_cast<long long>(r) * cd.stride;
     uint8_t* trow = tmp + (r - r_lo) * kImage;
     uint8_t* lrow = (cd.hcoef >= 0) ? rowbuf : trow;
-    for (int x = lane; x < cd.w; x += 32) {
-      const unsigned c0 = src[3 * x], c1 = src[3 * x + 1], c2 = src[3 * x + 2];
-      lrow[x] = static_cast<uint8_t>((cr * c0 + 38470u * c1 + cb * c2 + 0x8000u) >> 16);
+    if (cd.channels == 1) {
+      for (int x = lane; x < cd.w; x += 32) lrow[x] = src[x];
+    } else {
+      const int pc = cd.channels;
+      for (int x = lane; x < cd.w; x += 32) {
+        const unsigned c0 = src[pc * x], c1 = src[pc * x + 1], c2 = src[pc * x + 2];
+        lrow[x] = static_cast<uint8_t>((cr * c0 + 38470u * c1 + cb * c2 + 0x8000u) >> 16);
+      }
     }
     if (cd.hcoef >= 0) {
       __syncwarp();
@@ -156,7 +162,7 @@ preprocess_kernel(const uint8_t* __restrict__ arena, const CropDesc* __restrict_
     }
     const int patch = (y >> 4) * 14 + (x >> 4);
     patches[(static_cast<size_t>(blockIdx.y) * kPatches + patch) * kPatchK + (y & 15) * 16 + (x & 15)] =
-        __float2bfloat16(static_cast<float>(val));
+        __float2bfloat16(static_cast<float>(val - 128));
     const size_t o = (static_cast<size_t>(blockIdx.y) * kImage + y) * kImage + x;
     if (dbg_u8) dbg_u8[o] = static_cast<uint8_t>(val);
     if (dbg_f32) dbg_f32[o] = lut[val];

@@ -1,0 +1,211 @@
+"""Python face of the C ABI (include/mocr_b200.h): one ``Engine`` = one handle on one GPU.
+
+Crops are ``uint8`` numpy arrays ``[H, W]``, ``[H, W, 3]`` or ``[H, W, 4]`` exactly as the app
+builds them before calling the reference engine (reference/src/ui/main_window.py:9800).
+All arithmetic happens in the CUDA library; this file only marshals pointers.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import POINTER, byref, c_double, c_float, c_int32, c_int64, c_uint8, c_void_p
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from .weights import D, ENC_TOKENS, IMAGE, VOCAB
+
+RGB, BGR = 0, 1
+TAP_PIXELS, TAP_ENCODER, TAP_LOGITS = 1, 2, 4
+MAX_LENGTH = 300   # hard-coded by upstream MangaOcr.__call__
+
+
+class MocrError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"mocr_b200 error {code}: {message}")
+        self.code = code
+
+
+def _as_crop_array(crops: Sequence[np.ndarray]) -> Tuple[ctypes.Array, List[np.ndarray]]:
+    """Build the mocr_crop_t[] view of the arrays (kept alive by the returned list)."""
+    keep: List[np.ndarray] = []
+    arr = (_lib.mocr_crop_t * len(crops))()
+    for i, c in enumerate(crops):
+        if not isinstance(c, np.ndarray) or c.dtype != np.uint8 or c.ndim not in (2, 3):
+            raise ValueError(f"crop {i}: expected a uint8 array [H,W], [H,W,3] or [H,W,4]")
+        ch = 1 if c.ndim == 2 else c.shape[2]
+        if ch not in (1, 3, 4) or c.shape[0] < 1 or c.shape[1] < 1:
+            raise ValueError(f"crop {i}: unsupported shape {c.shape}")
+        if c.strides[-1] != 1 or (c.ndim == 3 and c.strides[1] != ch) or c.strides[0] < c.shape[1] * ch:
+            c = np.ascontiguousarray(c)
+        keep.append(c)
+        arr[i].data = c.ctypes.data
+        arr[i].height = c.shape[0]
+        arr[i].width = c.shape[1]
+        arr[i].stride = c.strides[0]
+        arr[i].channels = ch
+    return arr, keep
+
+
+class Engine:
+    """B200 recognition engine: preprocess -> ViT encoder -> greedy BERT decoder."""
+
+    def __init__(self, weights: Dict[str, np.ndarray], device: int = 0, max_batch: int = 64, max_length: int = MAX_LENGTH):
+        self._lib = _lib.load()
+        self._h = c_void_p()
+        self.device = device
+        self.max_batch = max_batch
+        self.max_length = max_length
+        self.n = 0
+        self._cur_len = 0
+        rc = self._lib.mocr_create(device, max_batch, max_length, byref(self._h))
+        if rc != 0:
+            msg = self._lib.mocr_last_error(None)
+            self._h = c_void_p()
+            raise MocrError(rc, msg.decode() if msg else "mocr_create failed")
+        try:
+            for name, arr in weights.items():
+                a = np.ascontiguousarray(arr, dtype=np.float32)
+                shape = (c_int64 * max(a.ndim, 1))(*(a.shape if a.ndim else (1,)))
+                self._ck(self._lib.mocr_set_weight(self._h, name.encode(), a.ctypes.data_as(POINTER(c_float)), shape, max(a.ndim, 1)))
+            self._ck(self._lib.mocr_finalize_weights(self._h))
+        except Exception:
+            self.close()
+            raise
+
+    # ---- plumbing
+    def _ck(self, rc: int) -> None:
+        if rc != 0:
+            msg = self._lib.mocr_last_error(self._h)
+            raise MocrError(rc, msg.decode() if msg else "unknown error")
+
+    def close(self) -> None:
+        h, self._h = self._h, c_void_p()
+        if h:
+            self._lib.mocr_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def stream(self) -> int:
+        return int(self._lib.mocr_stream(self._h) or 0)
+
+    def sync(self) -> None:
+        self._ck(self._lib.mocr_sync(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.mocr_launch_count(self._h))
+
+    @property
+    def last_steps(self) -> int:
+        return int(self._lib.mocr_last_steps(self._h))
+
+    def set_option(self, key: str, value: int) -> None:
+        self._ck(self._lib.mocr_set_option(self._h, key.encode(), int(value)))
+
+    def set_taps(self, taps: int) -> None:
+        self._ck(self._lib.mocr_set_taps(self._h, int(taps)))
+
+    # ---- the path
+    def recognize(self, crops: Sequence[np.ndarray], order: int = RGB, max_length: Optional[int] = None):
+        """crops -> (ids [n, max_length] int32 PAD-filled, lens [n]); any n (chunked by max_batch)."""
+        T = max_length or self.max_length
+        n = len(crops)
+        ids = np.zeros((n, T), np.int32)
+        lens = np.zeros((n,), np.int32)
+        if n == 0:
+            return ids, lens
+        arr, keep = _as_crop_array(crops)
+        self._ck(self._lib.mocr_recognize(self._h, arr, n, order, T, ids.ctypes.data_as(POINTER(c_int32)),
+                                          lens.ctypes.data_as(POINTER(c_int32))))
+        del keep
+        return ids, lens
+
+    def stage(self, crops: Sequence[np.ndarray], order: int = RGB) -> None:
+        arr, keep = _as_crop_array(crops)
+        self._ck(self._lib.mocr_stage_crops(self._h, arr, len(crops), order))
+        self.n = len(crops)
+        del keep
+
+    def preprocess(self) -> None:
+        self._ck(self._lib.mocr_preprocess(self._h))
+
+    def encode(self) -> None:
+        self._ck(self._lib.mocr_encode(self._h))
+
+    def decode(self, max_length: Optional[int] = None, forced_ids: Optional[np.ndarray] = None) -> None:
+        T = max_length or self.max_length
+        p = None
+        if forced_ids is not None:
+            forced_ids = np.ascontiguousarray(forced_ids, dtype=np.int32)
+            if forced_ids.shape != (self.n, T):
+                raise ValueError(f"forced_ids must be [{self.n}, {T}]")
+            p = forced_ids.ctypes.data_as(POINTER(c_int32))
+        self._ck(self._lib.mocr_decode_greedy(self._h, T, p))
+        self._cur_len = T
+
+    def run_resident(self, max_length: Optional[int] = None) -> None:
+        T = max_length or self.max_length
+        self._ck(self._lib.mocr_run_resident(self._h, T))
+        self._cur_len = T
+
+    def fetch_ids(self):
+        ids = np.zeros((self.n, self._cur_len), np.int32)
+        lens = np.zeros((self.n,), np.int32)
+        self._ck(self._lib.mocr_fetch_ids(self._h, ids.ctypes.data_as(POINTER(c_int32)), lens.ctypes.data_as(POINTER(c_int32))))
+        return ids, lens
+
+    # ---- parity taps
+    def pixels_u8(self) -> np.ndarray:
+        out = np.empty((self.n, IMAGE, IMAGE), np.uint8)
+        self._ck(self._lib.mocr_get_pixels_u8(self._h, out.ctypes.data_as(POINTER(c_uint8))))
+        return out
+
+    def pixel_values(self) -> np.ndarray:
+        out = np.empty((self.n, IMAGE, IMAGE), np.float32)
+        self._ck(self._lib.mocr_get_pixel_values(self._h, out.ctypes.data_as(POINTER(c_float))))
+        return out
+
+    def encoder_hidden(self) -> np.ndarray:
+        out = np.empty((self.n, ENC_TOKENS, D), np.float32)
+        self._ck(self._lib.mocr_get_encoder_hidden(self._h, out.ctypes.data_as(POINTER(c_float))))
+        return out
+
+    def step_logits(self) -> np.ndarray:
+        out = np.empty((self.n, self._cur_len - 1, VOCAB), np.float32)
+        self._ck(self._lib.mocr_get_step_logits(self._h, out.ctypes.data_as(POINTER(c_float))))
+        return out
+
+    def time_kernel(self, name: str, iters: int = 20):
+        """(ms per launch, algorithmic bytes, algorithmic flops) of one named kernel, CUDA-event timed."""
+        ms, by, fl = c_float(), c_double(), c_double()
+        self._ck(self._lib.mocr_time_kernel(self._h, name.encode(), iters, byref(ms), byref(by), byref(fl)))
+        return ms.value, by.value, fl.value
+
+    # ---- kernel-level unit hooks (tests)
+    def test_gemm(self, epi: int, bn: int, A: np.ndarray, Wt: np.ndarray, bias: np.ndarray, resid: Optional[np.ndarray] = None):
+        """out = epilogue(A @ Wt.T + bias) through the tcgen05 kernel; returns (out f32 [M,N], argmax [M])."""
+        A = np.ascontiguousarray(A, np.float32)
+        Wt = np.ascontiguousarray(Wt, np.float32)
+        bias = np.ascontiguousarray(bias, np.float32)
+        M, K = A.shape
+        N = Wt.shape[0]
+        out = np.zeros((M, N), np.float32)
+        am = np.zeros((M,), np.int32)
+        fp = lambda a: a.ctypes.data_as(POINTER(c_float))
+        r = None if resid is None else np.ascontiguousarray(resid, np.float32)
+        self._ck(self._lib.mocr_test_gemm(self._h, epi, bn, M, N, K, fp(A), fp(Wt), fp(bias), None if r is None else fp(r), fp(out),
+                                          am.ctypes.data_as(POINTER(c_int32))))
+        return out, am
+
+    def test_encoder_attention(self, qkv: np.ndarray) -> np.ndarray:
+        qkv = np.ascontiguousarray(qkv, np.float32)
+        n = qkv.shape[0] // ENC_TOKENS
+        out = np.zeros((n * ENC_TOKENS, D), np.float32)
+        self._ck(self._lib.mocr_test_encoder_attention(self._h, n, qkv.ctypes.data_as(POINTER(c_float)), out.ctypes.data_as(POINTER(c_float))))
+        return out

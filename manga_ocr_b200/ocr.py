@@ -1,0 +1,207 @@
+"""``MangaOcr`` - drop-in for the class the app imports from the ``manga-ocr`` package
+(reference/src/core/config.py:433), constructs once with no arguments
+(reference/src/ui/main_window.py:3394) and calls per crop from up to 50 worker threads with no
+lock (reference/src/ui/main_window.py:9800-9801, 608-611, 4317-4327).
+
+Same constructor signature, same ``__call__(img_or_path) -> str``, same ``ValueError`` for a
+bad argument; exceptions propagate (the workers catch them, reference/src/core/workers.py:
+241-244).  Underneath, concurrent single-crop callers are gathered into one GPU batch (the
+reference never batches: upstream runs ``x[None]``), one dispatcher thread per GPU.
+"""
+from __future__ import annotations
+
+import glob
+import os
+import threading
+from collections import deque
+from pathlib import Path
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import weights as W
+from .engine import BGR, MAX_LENGTH, RGB, Engine
+from .text import Vocab, ids_to_text
+
+DEFAULT_MODEL = "kha-white/manga-ocr-base"
+
+
+def _find_checkpoint(name_or_path: str):
+    """Resolve a local checkpoint directory/file; returns (weights_path, vocab_path | None) or None."""
+    cands: List[str] = []
+    if name_or_path and os.path.exists(name_or_path):
+        cands.append(name_or_path)
+    env = os.environ.get("MOCR_WEIGHTS", "")
+    if env and os.path.exists(env):
+        cands.append(env)
+    hub = os.path.join(os.environ.get("HF_HOME", os.path.expanduser("~/.cache/huggingface")), "hub",
+                       "models--" + name_or_path.replace("/", "--"), "snapshots", "*")
+    cands.extend(sorted(glob.glob(hub)))
+    for c in cands:
+        if os.path.isdir(c):
+            for fn in ("model.safetensors", "weights.npz"):
+                p = os.path.join(c, fn)
+                if os.path.exists(p):
+                    v = os.path.join(c, "vocab.txt")
+                    return p, (v if os.path.exists(v) else None)
+        elif c.endswith((".safetensors", ".npz")):
+            v = os.path.join(os.path.dirname(c), "vocab.txt")
+            return c, (v if os.path.exists(v) else None)
+    return None
+
+
+def image_to_array(img) -> np.ndarray:
+    """PIL image -> the uint8 array the engine reads.  The luma conversion itself
+    (``img.convert("L")``) happens on the GPU; modes whose ``convert("L")`` is not the plain
+    ITU-R 601 map of their RGB bytes are first expanded to RGB by Pillow."""
+    if img.mode not in ("RGB", "L", "RGBA"):
+        img = img.convert("RGB")
+    a = np.asarray(img)
+    if a.dtype != np.uint8:
+        a = a.astype(np.uint8)
+    return a
+
+
+class _Request:
+    __slots__ = ("crop", "event", "text", "error")
+
+    def __init__(self, crop: np.ndarray):
+        self.crop = crop
+        self.event = threading.Event()
+        self.text: Optional[str] = None
+        self.error: Optional[BaseException] = None
+
+
+class MangaOcr:
+    def __init__(self, pretrained_model_name_or_path: str = DEFAULT_MODEL, force_cpu: bool = False, *,
+                 weights: Optional[Dict[str, np.ndarray]] = None, vocab: Optional[Vocab] = None,
+                 devices: Optional[Sequence[int]] = None, max_batch: int = 64, max_length: int = MAX_LENGTH,
+                 warmup: bool = True):
+        if force_cpu:
+            raise RuntimeError("manga_ocr_b200 has no CPU path (force_cpu=True is not supported); it needs a B200 GPU")
+        if weights is None:
+            name = pretrained_model_name_or_path
+            env = os.environ.get("MOCR_WEIGHTS", "")
+            if name.startswith("random") or env.startswith("random"):
+                spec = (name if name.startswith("random") else env).split(":")
+                seed = int(spec[1]) if len(spec) > 1 else 0
+                eos_bias = float(spec[2]) if len(spec) > 2 else 0.0
+                weights = W.random_init(seed, eos_bias=eos_bias)
+            else:
+                found = _find_checkpoint(name)
+                if found is None:
+                    raise FileNotFoundError(
+                        f"no local checkpoint for {name!r}: pass a directory holding model.safetensors (+ vocab.txt), "
+                        "set MOCR_WEIGHTS to one, or use 'random[:seed[:eos_bias]]' for random-init weights")
+                weights = W.load_weights(found[0])
+                if vocab is None and found[1]:
+                    vocab = Vocab.from_file(found[1])
+        else:
+            weights = W.complete(weights)
+        self.vocab = vocab or Vocab.synthetic()
+        self.max_length = max_length
+        self.max_batch = max_batch
+        devs = list(devices) if devices is not None else [int(os.environ.get("MOCR_DEVICE", os.environ.get("LOCAL_RANK", "0")))]
+        self.engines = [Engine(weights, device=d, max_batch=max_batch, max_length=max_length) for d in devs]
+        self._queue: deque = deque()
+        self._cv = threading.Condition()
+        self._closed = False
+        self._threads = [threading.Thread(target=self._dispatch, args=(e,), name=f"mocr-gpu{e.device}", daemon=True)
+                         for e in self.engines]
+        for t in self._threads:
+            t.start()
+        if warmup:   # upstream runs one example image through the model inside __init__
+            self(_example_image())
+
+    # ---- reference API ------------------------------------------------------------
+    def __call__(self, img_or_path) -> str:
+        from PIL import Image
+        if isinstance(img_or_path, (str, Path)):
+            img = Image.open(img_or_path)
+        elif isinstance(img_or_path, Image.Image):
+            img = img_or_path
+        else:
+            raise ValueError(f"img_or_path must be a path or PIL.Image, instead got: {img_or_path}")
+        req = _Request(image_to_array(img))
+        with self._cv:
+            if self._closed:
+                raise RuntimeError("MangaOcr instance is closed")
+            self._queue.append(req)
+            self._cv.notify()
+        req.event.wait()
+        if req.error is not None:
+            raise req.error
+        return req.text  # type: ignore[return-value]
+
+    # ---- batch API (for callers that hold a whole page of crops) ----
+    def recognize_batch(self, crops: Sequence, order: int = RGB) -> List[str]:
+        """crops: PIL images or uint8 arrays ([H,W], [H,W,3], [H,W,4]) -> list of strings."""
+        arrays = [c if isinstance(c, np.ndarray) else image_to_array(c) for c in crops]
+        ids = self.recognize_ids(arrays, order)
+        return [ids_to_text(self.vocab, row) for row in ids]
+
+    def recognize_ids(self, arrays: Sequence[np.ndarray], order: int = RGB) -> np.ndarray:
+        if len(self.engines) == 1 or len(arrays) <= 1:
+            return self.engines[0].recognize(arrays, order, self.max_length)[0]
+        # host-side job splitter: contiguous blocks, one worker thread per GPU, no collective
+        from .splitter import shard_bounds
+        out = np.zeros((len(arrays), self.max_length), np.int32)
+        errs: List[BaseException] = []
+
+        def work(k: int) -> None:
+            lo, hi = shard_bounds(len(arrays), len(self.engines), k)
+            try:
+                if hi > lo:
+                    out[lo:hi] = self.engines[k].recognize(arrays[lo:hi], order, self.max_length)[0]
+            except BaseException as e:   # noqa: BLE001 - re-raised on the caller's thread
+                errs.append(e)
+
+        ts = [threading.Thread(target=work, args=(k,)) for k in range(len(self.engines))]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        if errs:
+            raise errs[0]
+        return out
+
+    # ---- cross-thread micro-batcher ------------------------------------------------
+    def _dispatch(self, engine: Engine) -> None:
+        while True:
+            with self._cv:
+                while not self._queue and not self._closed:
+                    self._cv.wait()
+                if self._closed and not self._queue:
+                    return
+                batch = [self._queue.popleft() for _ in range(min(len(self._queue), self.max_batch))]
+            try:
+                ids, _ = engine.recognize([r.crop for r in batch], RGB, self.max_length)
+                for r, row in zip(batch, ids):
+                    r.text = ids_to_text(self.vocab, row)
+            except BaseException as e:   # noqa: BLE001 - delivered to every waiting caller
+                for r in batch:
+                    r.error = e
+            for r in batch:
+                r.event.set()
+
+    def close(self) -> None:
+        with self._cv:
+            self._closed = True
+            self._cv.notify_all()
+        for t in self._threads:
+            if t is not threading.current_thread():
+                t.join(timeout=5)
+        for e in self.engines:
+            e.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _example_image():
+    from PIL import Image
+    from .crops import single_224
+    return Image.fromarray(single_224()[0])
