@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""Benchmark of the Manga-OCR recognition hot path (BASELINE.json metric: crops/sec, 224^2 crop,
+greedy decode).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+         --master-port P bench.py --gpus N --steps K --warmup W
+
+A step = one pass of the whole path (fused preprocess -> ViT encoder -> cross-K/V projection ->
+batched greedy decode to max_length 300) over one batch of 64 synthetic bubble crops per GPU
+(BASELINE.json configs[1]; weak scaling: every rank takes its own 64 crops, no collective on the
+math path, one final NCCL gather of the id rows in the e2e leg).  One JSON line on rank 0:
+  value        crops/s, inputs already resident in HBM, CUDA-event timed, L2 flushed between steps
+  e2e          crops/s through MangaOcr.recognize_batch with HOST crops (H2D + D2H + strings inside)
+  roofline     dominant kernel: algorithmic bytes / CUDA-event time vs MEASURED_PEAKS.json
+  cpu_baseline the oracle (reference path on transformers, CPU fp32, batch 1) on a bounded sample
+--impl reference times that CPU path as the reference arm.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "crops/sec (224^2 crop, greedy decode)"
+UNIT = "crops/s"
+BATCH = 64
+MAX_LENGTH = 300
+WORKLOAD = "configs[1]: manga-ocr-base arch, batch=64 synthetic bubble crops per GPU, bf16, greedy decode to max_length=300"
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": float(d["bf16_tflops"]),
+                "bf16_tflops_sustained": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ CPU reference arm ---
+
+def cpu_reference(crops, n_calls, max_length=MAX_LENGTH):
+    """Reference path on the host CPU: PIL convert/resize + transformers generate, fp32, batch 1
+    per call exactly like the app.  Returns (crops/s, tokens/s, threads)."""
+    import torch
+    from PIL import Image
+    from manga_ocr_b200 import weights as W
+    from manga_ocr_b200.text import Vocab
+    from oracle.reference_ocr import ReferenceMangaOcr
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    ocr = cpu_reference.cache.get("ocr")
+    if ocr is None:
+        ocr = cpu_reference.cache["ocr"] = ReferenceMangaOcr(W.random_init(0), Vocab.synthetic().tokens, max_length=max_length)
+    t0 = time.perf_counter()
+    toks = 0
+    for i in range(n_calls):
+        img = Image.fromarray(crops[i % len(crops)])
+        ids = ocr.generate_ids(img)
+        toks += len(ids) - 1
+    dt = time.perf_counter() - t0
+    return n_calls / dt, toks / dt, torch.get_num_threads()
+
+
+cpu_reference.cache = {}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    from manga_ocr_b200 import crops as C
+    crops = C.bubble_batch(BATCH, seed=1002)
+    per_step = 2
+    for _ in range(args.warmup):
+        cpu_reference(crops, 1)
+    t0 = time.perf_counter()
+    done = 0
+    toks_s = []
+    for s in range(args.steps):
+        cps, tps, cores = cpu_reference(crops[(s * per_step) % BATCH:] + crops, per_step)
+        toks_s.append(tps)
+        done += per_step
+    dt = time.perf_counter() - t0
+    value = done / dt
+    sample = f"{per_step} crops per step (of the 64-crop batch), batch 1 per call, max_length {MAX_LENGTH}, fp32, torch CPU threads={cores}"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
+        "decode_tokens_per_s": float(np.mean(toks_s)) if toks_s else None,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------ B200 arm ---
+
+def run_b200(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from manga_ocr_b200 import crops as C, weights as W
+    from manga_ocr_b200.engine import RGB
+    from manga_ocr_b200.ocr import MangaOcr
+    from manga_ocr_b200.splitter import gather_ids
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the B200 arm has no CPU fallback (use --impl reference for the CPU path)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    weights = W.random_init(0)
+    ocr = MangaOcr(weights=weights, devices=[local_rank], max_batch=BATCH, max_length=MAX_LENGTH, warmup=False)
+    eng = ocr.engines[0]
+    crops = C.bubble_batch(BATCH, seed=1002 + 7919 * rank)
+    in_bytes = int(sum(c.nbytes for c in crops))
+    stream = torch.cuda.ExternalStream(eng.stream, device=local_rank)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")   # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def flush_l2():
+        with torch.cuda.stream(stream):
+            flush.add_(1)
+
+    # ---- resident leg: crops staged once, the device path timed with CUDA events
+    eng.stage(crops, RGB)
+    for _ in range(args.warmup):
+        eng.run_resident(MAX_LENGTH)
+    eng.sync()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    launches0 = eng.launch_count
+    evs = []
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush_l2()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        eng.run_resident(MAX_LENGTH)
+        e1.record(stream)
+        evs.append((e0, e1))
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    launches = eng.launch_count - launches0
+    ms = sum(a.elapsed_time(b) for a, b in evs)
+    steps_decoded = eng.last_steps
+    ids_res, lens = eng.fetch_ids()
+
+    # ---- e2e leg: host crops in, strings out, through the public batch API
+    for _ in range(max(1, min(args.warmup, 2))):
+        ocr.recognize_batch(crops)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ids = ocr.recognize_ids(crops)
+        texts = [None] * len(ids)
+        from manga_ocr_b200.text import ids_to_text
+        texts = [ids_to_text(ocr.vocab, r) for r in ids]
+        if world > 1:
+            gather_ids(ids, BATCH * world)       # final result gather: NCCL all_gather of [64, 300] int32 per rank
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max, e2e_ms_max = float(t[0]), float(t[1])
+
+    # ---- roofline of the dominant kernel, timed live with CUDA events on the engine's stream
+    peaks = measured_peaks()
+    roof = None
+    if rank == 0:
+        name = args.roofline_kernel
+        k_ms, k_bytes, k_flops = eng.time_kernel(name, 50)
+        if k_flops > 0 and name.startswith("enc_") and name != "enc_attn":
+            ach = k_flops / (k_ms * 1e-3) / 1e12
+            roof = {"bound": "tensor", "kernel": name, "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                    "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None, "peak_source": peaks["source"] + " (sustained)",
+                    "ms_per_launch": k_ms}
+        else:
+            ach = k_bytes / (k_ms * 1e-3) / 1e9
+            roof = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+                    "traffic": None, "peak_source": peaks["source"], "ms_per_launch": k_ms, "algorithmic_bytes": k_bytes}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        n_calls = 8
+        cpu_reference(crops, 1)
+        cps, tps, cores = cpu_reference(crops, n_calls)
+        cpu = {"value": cps, "unit": UNIT, "cores": cores, "kind": "port", "decode_tokens_per_s": tps,
+               "sample": f"first {n_calls} crops of the batch, batch 1 per call, max_length {MAX_LENGTH}, fp32"}
+
+    if rank == 0:
+        total_crops = BATCH * world * args.steps
+        value = total_crops / (ms_max * 1e-3)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "crops_per_gpu": BATCH, "max_length": MAX_LENGTH, "decode_steps_run": steps_decoded,
+                       "weights": "random-init manga-ocr-base (numpy PCG64 seed 0)", "l2": "flushed between timed steps (256 MiB write)",
+                       "parallelism": f"dp{world} (crops sharded, no collective on the math path)"},
+            "decode_tokens_per_s": BATCH * world * steps_decoded * args.steps / (ms_max * 1e-3),
+            "e2e": {"value": total_crops / (e2e_ms_max * 1e-3), "unit": UNIT, "h2d_bytes_per_step": in_bytes + 40 * BATCH,
+                    "d2h_bytes_per_step": BATCH * MAX_LENGTH * 4 + BATCH * 4, "api": "MangaOcr.recognize_batch (host uint8 crops -> strings)"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "wall_s_timed_region": t_wall,
+        }
+        print(json.dumps(line), flush=True)
+    ocr.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--roofline-kernel", default="dec_cross_attn")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--max-length", type=int, default=MAX_LENGTH, help="profiling only; the metric is defined at 300")
+    args = ap.parse_args()
+    rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
+    global MAX_LENGTH
+    MAX_LENGTH = args.max_length
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if args.gpus != world and world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under torch.distributed.run
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", str(29400 + os.getpid() % 500), os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    run_b200(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

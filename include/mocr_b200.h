@@ -108,6 +108,11 @@ int mocr_test_gemm(mocr_handle_t* h, int epi, int bn, int M, int N, int K, const
                    const float* resid, float* out, int32_t* out_argmax);
 int mocr_test_encoder_attention(mocr_handle_t* h, int n, const float* qkv /*[n*197,2304]*/, float* out /*[n*197,768]*/);
 
+/* Host-only (no CUDA call): the Pillow-exact resampling table for one input extent, as the
+ * preprocess kernel reads it: xmin[224] | count[224] | k[224*ksize] (int32).  Returns the number
+ * of int32 written (or needed when out is NULL), negative on error. */
+int mocr_resample_table(int in_size, int32_t* ksize, int32_t* out, int capacity);
+
 /* ---- plumbing --------------------------------------------------------------------------- */
 
 void* mocr_stream(mocr_handle_t* h);            /* the cudaStream_t all work is launched on   */

@@ -1273,6 +1273,19 @@ int mocr_test_encoder_attention(mocr_handle_t* h, int n, const float* qkv, float
   return MOCR_OK;
 }
 
+// Host-only: the Pillow-exact coefficient table the preprocess kernel reads for one input
+// extent (xmin[224] | count[224] | k[224*ksize], int32).  No CUDA call; usable without a GPU.
+int mocr_resample_table(int in_size, int32_t* ksize, int32_t* out, int capacity) {
+  if (in_size < 1 || in_size > 32768 || ksize == nullptr) return MOCR_ERR_INVALID;
+  ResampleTable t = make_resample_table(in_size);
+  *ksize = t.ksize;
+  if (out != nullptr) {
+    if (capacity < static_cast<int>(t.data.size())) return MOCR_ERR_CAPACITY;
+    memcpy(out, t.data.data(), t.data.size() * sizeof(int));
+  }
+  return static_cast<int>(t.data.size());
+}
+
 const char* mocr_last_error(mocr_handle_t* h) { return h ? h->error.c_str() : g_create_error.c_str(); }
 
 }  // extern "C"

@@ -97,7 +97,7 @@ def manifest() -> Iterator[Tuple[str, Tuple[int, ...], str]]:
 
 
 def random_init(seed: int = 0, *, plain_hf_init: bool = False, untie_lm_head: bool = False,
-                eos_bias: float = 0.0) -> Dict[str, np.ndarray]:
+                eos_bias: float = 0.0, gain: float = 1.0) -> Dict[str, np.ndarray]:
     """Random weights of the manga-ocr-base architecture as {name: float32 array}.
 
     Matrices follow the reference's initialiser (trunc-normal, sigma 0.02, cut
@@ -105,6 +105,10 @@ def random_init(seed: int = 0, *, plain_hf_init: bool = False, untie_lm_head: bo
     and LayerNorm is identity exactly as a fresh reference model; the default
     instead draws small non-zero biases and LayerNorm affine terms so that every
     bias / gamma / beta path of the kernels is exercised by the parity tests.
+
+    gain scales sigma of every matrix: at the reference's sigma = 0.02 the decoder's output is
+    almost independent of the image (the cross-attention contribution is tiny next to the
+    residual stream), so tests that must tell crops apart use gain > 1.
 
     eos_bias is added to ``cls.predictions.bias[SEP_ID]`` so that greedy decode
     terminates at varied lengths (with a plain init EOS essentially never wins
@@ -114,8 +118,8 @@ def random_init(seed: int = 0, *, plain_hf_init: bool = False, untie_lm_head: bo
     out: Dict[str, np.ndarray] = {}
     for name, shape, kind in manifest():
         if kind == "w":
-            a = rng.standard_normal(shape, dtype=np.float32) * np.float32(0.02)
-            np.clip(a, -0.04, 0.04, out=a)
+            a = rng.standard_normal(shape, dtype=np.float32) * np.float32(0.02 * gain)
+            np.clip(a, -0.04 * gain, 0.04 * gain, out=a)
         elif kind == "b":
             a = (np.zeros(shape, np.float32) if plain_hf_init
                  else rng.standard_normal(shape, dtype=np.float32) * np.float32(0.02))
