@@ -124,6 +124,9 @@ int mocr_set_option(mocr_handle_t* h, const char* key, int value);
  * with CUDA events, on the current batch state (used by bench.py for the roofline line). */
 int mocr_time_kernel(mocr_handle_t* h, const char* kernel, int iters, float* ms_per_launch, double* algo_bytes,
                      double* algo_flops);
+/* Debug / tuning: SM-clock timeline (wait-exit / arrive of every stage, CTA 0) of the last
+ * persistent decode, recorded when option "decode_prof" is 1. */
+int mocr_get_decode_profile(mocr_handle_t* h, int64_t* out, int n);
 const char* mocr_last_error(mocr_handle_t* h);  /* h may be NULL: error of the last failed create */
 
 #ifdef __cplusplus

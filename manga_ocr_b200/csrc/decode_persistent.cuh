@@ -1,0 +1,896 @@
+// Persistent greedy decoder: ONE cooperative launch runs every decode step of a batch.
+//
+// Replaces the per-step host loop of GenerationMixin._sample (transformers/generation/utils.py:
+// 2743-2805: ~120 library launches and a host sync per token).  One CTA per SM stays resident and
+// interprets a small stage table (26 entries per token):
+//   BertLayer x2 [QKV -> self-attn -> out -> LN -> cross-q -> cross-attn -> out -> LN -> FFN1 -> FFN2 -> LN]
+//   (modeling_bert.py:143-421), LM head (:471-501), arg-max / EOS / append / embed (utils.py:2793-2805).
+// Stages are separated by a grid-wide barrier (one release-atomic + a poll, 1.1 us measured) and the
+// loop ends on the device when every row has produced [SEP] or reached max_length - no host round
+// trip per token.
+//
+// Design rules that came out of measurements on the B200 (tools/microbench.cu, tools/decode_prof.py):
+//  * a token is latency/bandwidth-bound (M = batch rows, 46 MFLOP per row), so the small-M GEMMs use
+//    warp-level mma.sync fed straight from L2 with 16-byte loads in a k-permuted fragment order
+//    that needs no shared-memory staging;
+//  * what costs is the broadcast of the activation to all CTAs (98 KB per CTA = 1.3 us at the L2's
+//    ~11 TB/s aggregate): the N = 768 projections are therefore split over K as well as N
+//    (48 x 3 tiles), each CTA reads a third of the activation, and the raw fp32 partials are summed
+//    in a fixed order (no atomics: results are deterministic) by the LayerNorm / attention stage
+//    that consumes them, together with bias, GELU and residual;
+//  * weights and the encoder K/V do not depend on the previous stage, so they are requested BEFORE
+//    waiting on the barrier; attention K/V travel through cp.async into per-thread shared-memory
+//    staging slots (no registers held, double-buffered across units);
+//  * the code is kept small (one instance per stage TYPE, rolled loops): the stage sequence does not
+//    fit in the instruction caches, and an earlier fully inlined version (247 KB of SASS) lost more
+//    to instruction fetch than it gained.
+#pragma once
+#include "common.cuh"
+#include "rowops.cuh"
+
+namespace mocr {
+
+constexpr int kPdThreads = 256;              // 8 warps, one CTA per SM
+constexpr int kPdWarps = kPdThreads / 32;
+constexpr int kPdRowsPerBlock = 64;          // activation rows per pass (4 m-tiles of 16)
+constexpr int kPdKSlices = 2;                // warps per m-tile: K is split in two inside a CTA
+constexpr int kPdGroups = kPdThreads / 128;  // attention groups of 4 warps
+constexpr int kPdKeySlots = 7;               // 7 * 16 = 112 keys per staged block (a 197-key unit = 2 blocks)
+constexpr int kPdStageBytes = 2 * kPdKeySlots * 128 * 16;          // K and V of one block, one group
+constexpr int kPdMaxNT = 48;
+constexpr int kPdRedFloats = kPdKSlices * kPdRowsPerBlock * (kPdMaxNT + 1);
+constexpr int kPdMaxStages = 32;
+constexpr int kPdVocabTiles = kVocab / kPdMaxNT;
+constexpr int kPdSplit = 3;                  // CTA-level K split of the N = 768 projections
+
+struct PdLinear {
+  const __nv_bfloat16* w;   // [N, K]
+  const float* bias;        // [N]
+};
+struct PdLn {
+  const float* g;
+  const float* b;
+};
+struct PdLayer {
+  PdLinear qkv, self_out, cross_q, cross_out, fc1, fc2;
+  PdLn ln_self, ln_cross, ln_ffn;
+  __nv_bfloat16* self_k;    // [B, cache_len, 768]
+  __nv_bfloat16* self_v;
+};
+
+struct PdParams {
+  int B;                    // rows
+  int max_len;              // this decode's max_length
+  int cache_len;            // self-KV cache capacity per row (tokens)
+  int eos_id;
+  PdLayer layer[kDecLayers];
+  PdLinear head_t, head_dec;
+  PdLn head_ln;
+  EmbedWeights emb;
+  const __nv_bfloat16* crosskv;   // [B*197, 3072]: K0 V0 K1 V1
+  // state
+  int* ids;                 // [B, max_len]
+  int* pos;                 // [B]
+  int* finished;            // [B]
+  const int* forced;        // teacher forcing or null
+  float* x;                 // [B, 768] post-LN hidden (fp32 residual)
+  __nv_bfloat16* xb;        // [B, 768] bf16 copy (GEMM A operand)
+  float* y;                 // [3, B, 768] split-K partials of the projections that feed a LayerNorm
+  float* yq;                // [3, B, 768] split-K partials of the cross-attention query
+  __nv_bfloat16* qkv;       // [B, 2304]
+  __nv_bfloat16* ctx;       // [B, 768]
+  __nv_bfloat16* ffn;       // [B, 3072]
+  float* part_max;          // [B, kPdVocabTiles]
+  int* part_idx;
+  float* logits;            // tap or null: [B, max_len-1, 6144]
+  unsigned int* barrier;    // grid barrier counter (zeroed by the host before launch)
+  int* steps_done;          // out
+  long long* prof;          // optional [4096] stage timeline of CTA 0 (debug / tuning), or null
+};
+
+enum PdStageType { PD_GEMM16 = 0, PD_GEMM32 = 1, PD_GEMM48 = 2, PD_ATTN_SELF = 3, PD_ATTN_CROSS = 4, PD_LN = 5, PD_NEXT = 6 };
+enum PdEpi { PD_BF16 = 0, PD_BF16_GELU = 1, PD_F32_PARTIAL = 2, PD_ARGMAX = 3 };
+
+// One entry of the per-token program, built once in shared memory.
+struct PdStage {
+  int type;
+  int epi;                  // GEMM: PdEpi.  LN: bit 0 = GELU before the norm (LM-head transform)
+  int N, K, ksplit, ldo;
+  int parts;                // LN: number of split-K partials to add
+  int layer;                // attention: decoder layer
+  const __nv_bfloat16* A;   // GEMM A operand [B, K]
+  const __nv_bfloat16* W;   // GEMM weights [N, K]
+  const float* bias;        // GEMM bias (unsplit) / LN: bias of the producing projection / cross: query bias
+  __nv_bfloat16* ob;        // GEMM bf16 out / LN bf16 out
+  float* of;                // GEMM fp32 partial out / LN fp32 out (nullable)
+  const float* src;         // LN: partials [parts][B][768]
+  const float* resid;       // LN: residual rows (nullable)
+  const float* g;           // LN gamma / beta
+  const float* b;
+};
+
+// ------------------------------------------------------------------ primitives ---
+
+__device__ __forceinline__ uint4 ldg_nc16(const void* p) {   // read-only data (weights, cross K/V)
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint4 ldg_cg16(const void* p) {   // data written by other CTAs during this launch: L2 only
+  uint4 r;
+  asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ float ldg_cg_f32(const float* p) {
+  float r;
+  asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(r) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ int ldg_cg_s32(const int* p) {
+  int r;
+  asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ float4 ldg_cg_f4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p) : "memory");
+  return r;
+}
+// Barrier poll.  Deliberately relaxed: an acquire load at gpu scope makes ptxas invalidate the
+// SM's whole L1 (CCTL.IVALL) at every barrier, evicting the cached LayerNorm / bias vectors.
+// Every datum that another CTA writes during the launch is read with ld.global.cg (L2, the
+// coherence point) and the writer publishes with red.release.gpu, so no L1 line can be stale; the
+// consuming loads are issued after the poll loop exits (control dependence + bar.sync).
+__device__ __forceinline__ unsigned int ld_poll_u32(const unsigned int* p) {
+  unsigned int r;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ void group_sync(int group) {      // 128-thread named barrier (ids 1..)
+  asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cp_async16_cg(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+
+// Grid barrier, split so that independent loads can be issued between arrive and wait.
+struct GridBarrier {
+  unsigned int* ctr;
+  unsigned int target;
+  long long* prof;        // optional stage timeline of CTA 0 (clock64 at every wait-exit and arrive), or null
+  int prof_n;
+  __device__ __forceinline__ void stamp() {
+    if (prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && prof_n < 4096) prof[prof_n] = clock64();
+    ++prof_n;
+  }
+  __device__ __forceinline__ void arrive() {
+    __syncthreads();                       // every thread's writes of this stage are done
+    stamp();
+    if (threadIdx.x == 0) {
+      // release at gpu scope: the CTA's writes (ordered before this by the barrier above) become
+      // visible to whoever observes the counter
+      asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(ctr), "r"(1u) : "memory");
+    }
+    target += gridDim.x;
+  }
+  __device__ __forceinline__ void wait() {
+    if (threadIdx.x == 0) {
+      const long long t0 = clock64();
+      while (ld_poll_u32(ctr) < target) {
+        if (clock64() - t0 > 8000000000LL) __trap();   // a lost arrival must not hang the GPU box
+      }
+    }
+    __syncthreads();
+    stamp();
+  }
+};
+
+// Stage kernels launched one by one (CUDA graph) use the same stage code with this no-op barrier:
+// stream order provides the dependency.
+struct NullBarrier {
+  __device__ __forceinline__ void arrive() {}
+  __device__ __forceinline__ void wait() {}
+};
+
+// ------------------------------------------------------------------ small-M GEMM stage ---
+//
+// out[r, n] = epilogue( sum_k A[r,k] * W[n,k] (+ bias[n]) ),  r < B; tile = (N-slice of NT columns,
+// K-split kq of ksplit).
+//
+// mma.m16n8k16 fragments want, per thread (g = lane/4, t = lane%4), logical k slots {2t,2t+1,2t+8,2t+9}
+// of a 16-wide k-step.  The sum over k is order-free, so a 32-wide chunk of physical k is mapped
+// onto two k-steps such that thread t owns the 8 CONSECUTIVE physical elements [8t, 8t+8): one
+// 16-byte load per row gives a0/a2 (or b0/b1) of both k-steps.  A and W use the same mapping, so
+// the product is exact, every 32-byte sector fetched is fully used, and nothing is staged in smem.
+// Inside the CTA the 8 warps are 4 m-tiles x 2 K halves, reduced through smem in a fixed order.
+template <int NT, int CH, class Bar>
+__device__ __forceinline__ void pd_gemm_stage(Bar& bar, float* red, const PdParams& p, const PdStage& st) {
+  constexpr int NTL = NT / 8;
+  constexpr int kIters = (kPdRowsPerBlock * NT + kPdThreads - 1) / kPdThreads;
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int mt = warp & 3, ks = warp >> 2;
+  const int B = p.B, K = st.K, N = st.N, ksplit = st.ksplit, epi = st.epi;
+  const int kslice = K / (kPdKSlices * ksplit);
+  const int n_chunks = kslice / 32;
+  const int n_tiles = (N / NT) * ksplit;
+  bool waited = false;
+
+  for (int tile = blockIdx.x; tile < n_tiles || !waited; tile += gridDim.x) {
+    const bool has_tile = tile < n_tiles;
+    const int n0 = (tile / ksplit) * NT;
+    const int kq = tile % ksplit;
+    const int k0 = (kq * kPdKSlices + ks) * kslice;
+    // Two K batches are in flight: the fragments of batch n+1 (A and W) are requested before the
+    // MMAs of batch n are issued.  Batch 0's weights do not depend on the previous stage and are
+    // requested before the grid barrier.
+    uint4 wf[2][CH][NTL], af[2][CH][2];
+    const __nv_bfloat16* wbase = st.W + static_cast<size_t>(n0 + g) * K + k0 + 8 * t;
+    if (has_tile) {
+#pragma unroll
+      for (int c = 0; c < CH; ++c)
+#pragma unroll
+        for (int j = 0; j < NTL; ++j) wf[0][c][j] = ldg_nc16(wbase + static_cast<size_t>(8 * j) * K + c * 32);
+    }
+    if (!waited) {
+      bar.wait();
+      waited = true;
+    }
+    if (!has_tile) break;
+    const int n_batches = n_chunks / CH;       // even by construction (K / 32 / (2 ksplit) / CH)
+#pragma unroll 1
+    for (int rb = 0; rb < B; rb += kPdRowsPerBlock) {
+      const int r_lo = rb + mt * 16 + g, r_hi = r_lo + 8;
+      const bool lo_ok = r_lo < B, hi_ok = r_hi < B;
+      const __nv_bfloat16* a_lo = st.A + static_cast<size_t>(lo_ok ? r_lo : 0) * K + k0 + 8 * t;
+      const __nv_bfloat16* a_hi = st.A + static_cast<size_t>(hi_ok ? r_hi : 0) * K + k0 + 8 * t;
+      float acc[NTL][4];
+#pragma unroll
+      for (int j = 0; j < NTL; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+      if (rb > 0) {
+#pragma unroll
+        for (int c = 0; c < CH; ++c)
+#pragma unroll
+          for (int j = 0; j < NTL; ++j) wf[0][c][j] = ldg_nc16(wbase + static_cast<size_t>(8 * j) * K + c * 32);
+      }
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        af[0][c][0] = ldg_cg16(a_lo + c * 32);
+        af[0][c][1] = ldg_cg16(a_hi + c * 32);
+      }
+#pragma unroll 1
+      for (int bt = 0; bt < n_batches; bt += 2) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int nb = bt + half + 1;          // batch to request now (into the other buffer)
+          if (nb < n_batches) {
+#pragma unroll
+            for (int c = 0; c < CH; ++c) {
+              af[half ^ 1][c][0] = ldg_cg16(a_lo + (nb * CH + c) * 32);
+              af[half ^ 1][c][1] = ldg_cg16(a_hi + (nb * CH + c) * 32);
+#pragma unroll
+              for (int j = 0; j < NTL; ++j)
+                wf[half ^ 1][c][j] = ldg_nc16(wbase + static_cast<size_t>(8 * j) * K + (nb * CH + c) * 32);
+            }
+          }
+          if (bt + half < n_batches) {
+#pragma unroll
+            for (int c = 0; c < CH; ++c) {
+              uint4 a0 = af[half][c][0], a1 = af[half][c][1];
+              if (!lo_ok) a0 = make_uint4(0, 0, 0, 0);
+              if (!hi_ok) a1 = make_uint4(0, 0, 0, 0);
+#pragma unroll
+              for (int j = 0; j < NTL; ++j) {
+                mma16816(acc[j], a0.x, a1.x, a0.y, a1.y, wf[half][c][j].x, wf[half][c][j].y);
+                mma16816(acc[j], a0.z, a1.z, a0.w, a1.w, wf[half][c][j].z, wf[half][c][j].w);
+              }
+            }
+          }
+        }
+      }
+      // fixed-order K reduction through shared memory
+      if (rb > 0) __syncthreads();       // previous row block's readers are done with `red`
+      {
+        float* rr = red + (ks * kPdRowsPerBlock + mt * 16) * (NT + 1);
+#pragma unroll
+        for (int j = 0; j < NTL; ++j) {
+          rr[g * (NT + 1) + 8 * j + 2 * t] = acc[j][0];
+          rr[g * (NT + 1) + 8 * j + 2 * t + 1] = acc[j][1];
+          rr[(g + 8) * (NT + 1) + 8 * j + 2 * t] = acc[j][2];
+          rr[(g + 8) * (NT + 1) + 8 * j + 2 * t + 1] = acc[j][3];
+        }
+      }
+      __syncthreads();
+      float vals[kIters];
+#pragma unroll
+      for (int it = 0; it < kIters; ++it) {
+        const int i = tid + it * kPdThreads;
+        const int rl = i / NT, c = i - rl * NT;
+        float v = 0.f;
+        if (i < kPdRowsPerBlock * NT) {
+          if (epi != PD_F32_PARTIAL) v = __ldg(st.bias + n0 + c);      // L1-resident after the first token
+          v += red[rl * (NT + 1) + c] + red[(kPdRowsPerBlock + rl) * (NT + 1) + c];
+        }
+        vals[it] = v;
+      }
+      if (epi == PD_ARGMAX) {
+        __syncthreads();                  // all partial sums are read: reuse slice 0 of `red` for the logits
+#pragma unroll
+        for (int it = 0; it < kIters; ++it) {
+          const int i = tid + it * kPdThreads;
+          if (i < kPdRowsPerBlock * NT) red[(i / NT) * (NT + 1) + i % NT] = vals[it];
+        }
+        __syncthreads();
+        if (tid < kPdRowsPerBlock && rb + tid < B) {
+          const int r = rb + tid;
+          float best = -INFINITY;
+          int best_i = 0;
+          float* lg = nullptr;
+          if (p.logits != nullptr) {
+            const int stp = ldg_cg_s32(p.pos + r);
+            if (stp < p.max_len - 1) lg = p.logits + (static_cast<size_t>(r) * (p.max_len - 1) + stp) * N + n0;
+          }
+#pragma unroll 4
+          for (int cc = 0; cc < NT; ++cc) {
+            const float v = red[tid * (NT + 1) + cc];
+            if (v > best) { best = v; best_i = n0 + cc; }     // strict >: lowest index wins ties
+            if (lg != nullptr) lg[cc] = v;
+          }
+          p.part_max[static_cast<size_t>(r) * kPdVocabTiles + tile] = best;
+          p.part_idx[static_cast<size_t>(r) * kPdVocabTiles + tile] = best_i;
+        }
+      } else {
+#pragma unroll
+        for (int it = 0; it < kIters; ++it) {
+          const int i = tid + it * kPdThreads;
+          const int r = rb + i / NT, c = i % NT;
+          if (i < kPdRowsPerBlock * NT && r < B) {
+            float v = vals[it];
+            if (epi == PD_BF16_GELU) v = gelu_erf(v);
+            if (epi == PD_F32_PARTIAL) st.of[(static_cast<size_t>(kq) * B + r) * st.ldo + n0 + c] = v;
+            else st.ob[static_cast<size_t>(r) * st.ldo + n0 + c] = __float2bfloat16(v);
+          }
+        }
+      }
+    }
+    __syncthreads();                      // `red` is free for the next tile
+  }
+  bar.arrive();
+}
+
+// ------------------------------------------------------------------ row stages (one warp per row) ---
+
+__device__ __forceinline__ void pd_ln_row_warp(const float (&v)[24], const float* g, const float* b, float* x, __nv_bfloat16* xb, int lane) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 24; ++i) s += v[i];
+  const float mean = warp_sum(s) * (1.0f / kD);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 24; ++i) q += (v[i] - mean) * (v[i] - mean);
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / kD) + kLnEps);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const int c = (lane + 32 * i) * 4;
+    const float4 gm = __ldg(reinterpret_cast<const float4*>(g + c));
+    const float4 bt = __ldg(reinterpret_cast<const float4*>(b + c));
+    float4 yv;
+    yv.x = (v[4 * i] - mean) * rstd * gm.x + bt.x;
+    yv.y = (v[4 * i + 1] - mean) * rstd * gm.y + bt.y;
+    yv.z = (v[4 * i + 2] - mean) * rstd * gm.z + bt.z;
+    yv.w = (v[4 * i + 3] - mean) * rstd * gm.w + bt.w;
+    if (x != nullptr) *reinterpret_cast<float4*>(x + c) = yv;
+    uint2 pk;
+    pk.x = pack_bf16(yv.x, yv.y);
+    pk.y = pack_bf16(yv.z, yv.w);
+    *reinterpret_cast<uint2*>(xb + c) = pk;
+  }
+}
+
+// x, xb = LayerNorm( [gelu]( sum_parts src[part] + bias ) + resid )   (BERT post-LN, modeling_bert.py:
+// 297, 355, 484).  The split-K partials of the producing projection are added here in a fixed order.
+template <class Bar>
+__device__ __forceinline__ void pd_ln_stage(Bar& bar, const PdParams& p, const PdStage& st) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int B = p.B;
+  bar.wait();
+  for (int r = blockIdx.x * kPdWarps + warp; r < B; r += gridDim.x * kPdWarps) {
+    // every load is requested before the first add (the .cg loads are ordered volatile asm: a load
+    // placed after a dependent add would cost a full L2 round trip each)
+    float4 part[kPdSplit][6], rs[6];
+#pragma unroll
+    for (int pt = 0; pt < kPdSplit; ++pt)
+#pragma unroll
+      for (int i = 0; i < 6; ++i) part[pt][i] = ldg_cg_f4(st.src + (static_cast<size_t>(pt) * B + r) * kD + (lane + 32 * i) * 4);
+    if (st.resid != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) rs[i] = ldg_cg_f4(st.resid + static_cast<size_t>(r) * kD + (lane + 32 * i) * 4);
+    }
+    float v[24];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const int c = (lane + 32 * i) * 4;
+      float4 f = __ldg(reinterpret_cast<const float4*>(st.bias + c));
+#pragma unroll
+      for (int pt = 0; pt < kPdSplit; ++pt) { f.x += part[pt][i].x; f.y += part[pt][i].y; f.z += part[pt][i].z; f.w += part[pt][i].w; }
+      if (st.epi & 1) { f.x = gelu_erf(f.x); f.y = gelu_erf(f.y); f.z = gelu_erf(f.z); f.w = gelu_erf(f.w); }
+      if (st.resid != nullptr) { f.x += rs[i].x; f.y += rs[i].y; f.z += rs[i].z; f.w += rs[i].w; }
+      v[4 * i] = f.x; v[4 * i + 1] = f.y; v[4 * i + 2] = f.z; v[4 * i + 3] = f.w;
+    }
+    pd_ln_row_warp(v, st.g, st.b, st.of != nullptr ? st.of + static_cast<size_t>(r) * kD : nullptr, st.ob + static_cast<size_t>(r) * kD, lane);
+  }
+  bar.arrive();
+}
+
+__device__ __forceinline__ void pd_embed_row_warp(const PdParams& p, int r, int tok, int position, int lane) {
+  float v[24];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const int c = (lane + 32 * i) * 4;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p.emb.word + static_cast<size_t>(tok) * kD + c));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p.emb.type0 + c));
+    const float4 d = __ldg(reinterpret_cast<const float4*>(p.emb.posemb + static_cast<size_t>(position) * kD + c));
+    v[4 * i] = a.x + b.x + d.x; v[4 * i + 1] = a.y + b.y + d.y; v[4 * i + 2] = a.z + b.z + d.z; v[4 * i + 3] = a.w + b.w + d.w;
+  }
+  pd_ln_row_warp(v, p.emb.gamma, p.emb.beta, p.x + static_cast<size_t>(r) * kD, p.xb + static_cast<size_t>(r) * kD, lane);
+}
+
+// Greedy step tail (generation/utils.py:2793-2805, stopping_criteria.py:76,470): final arg-max over
+// the vocabulary tiles, EOS / max_length rules, append, embed the next input token.
+template <class Bar>
+__device__ __forceinline__ void pd_next_token_stage(Bar& bar, const PdParams& p) {
+  bar.wait();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = blockIdx.x * kPdWarps + warp; r < p.B; r += gridDim.x * kPdWarps) {
+    const int ps = ldg_cg_s32(p.pos + r);
+    const bool was_finished = ldg_cg_s32(p.finished + r) != 0;
+    if (was_finished && (p.forced == nullptr || ps >= p.max_len - 1)) continue;
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = lane; i < kPdVocabTiles; i += 32) {
+      const float v = ldg_cg_f32(p.part_max + static_cast<size_t>(r) * kPdVocabTiles + i);
+      const int ix = ldg_cg_s32(p.part_idx + static_cast<size_t>(r) * kPdVocabTiles + i);
+      if (v > bv || (v == bv && ix < bi)) { bv = v; bi = ix; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (bi < 0 || bi >= kVocab) bi = 1;    // all-NaN logits: [UNK] rather than an out-of-range index
+    int tok = bi;
+    const int np = ps + 1;
+    int fin = was_finished ? 1 : 0;
+    if (tok == p.eos_id && p.forced == nullptr) fin = 1;
+    if (np >= p.max_len - 1) fin = 1;
+    if (lane == 0) {
+      if (np < p.max_len) p.ids[static_cast<size_t>(r) * p.max_len + np] = tok;
+      p.finished[r] = fin;
+      p.pos[r] = np;
+    }
+    if (p.forced != nullptr && np < p.max_len) tok = p.forced[static_cast<size_t>(r) * p.max_len + np];
+    if (np >= p.max_len - 1 || np >= kMaxPos) continue;
+    pd_embed_row_warp(p, r, tok, np, lane);
+  }
+  bar.arrive();
+}
+
+// ------------------------------------------------------------------ attention stage ---
+// Single-query attention for (row, head) units, 4 warps per unit.  Key j of a 208-key block is
+// owned by (warp gw, lane quarter sub, slot i): j = 16 i + 4 gw + sub; the 8 lanes of a quarter
+// hold 8 channels each.  Every thread requests ALL its K and V rows of a block with cp.async into
+// 16-byte staging slots that only it reads back (no barrier, no registers held while the loads
+// fly), keeps a private online-softmax state (m, l, acc[8]); the 16 partial states of a unit are
+// merged at the end in a fixed order.  The staging area is double-buffered: the next unit's rows
+// are requested before the current unit is reduced, and for cross-attention the first unit is
+// requested BEFORE the grid barrier - the encoder K/V never change during a decode, so the
+// dominant HBM stream of the token overlaps the barrier.
+// self: the key at index pos[b] is this token's K/V row, taken straight from the QKV buffer and
+// appended to the cache here (modeling_bert.py:190 re-concatenates the whole cache instead).
+
+__device__ __forceinline__ void pd_bf16x8(const uint4& u, float (&f)[8]) {
+  const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(p[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+
+struct PdAttnUnit {
+  const __nv_bfloat16* kc;     // this thread's 16-byte column of the unit's key rows
+  const __nv_bfloat16* vc;
+  const __nv_bfloat16* nk;     // self: this token's K / V row in the QKV buffer
+  const __nv_bfloat16* nv;
+  int b, h, n_keys, ps;
+  bool skip;
+};
+
+__device__ __forceinline__ void pd_attn_request(uint4* stage, const PdAttnUnit& a, int key_stride, int j0, int gt) {
+  const int gw = gt >> 5, sub = (gt & 31) >> 3;
+#pragma unroll 1
+  for (int i = 0; i < kPdKeySlots; ++i) {
+    const int j = j0 + 16 * i + 4 * gw + sub;
+    if (j < a.n_keys) {
+      const bool fresh = j == a.ps;
+      cp_async16_cg(stage + i * 128 + gt, fresh ? a.nk : a.kc + static_cast<size_t>(j) * key_stride);
+      cp_async16_cg(stage + (kPdKeySlots + i) * 128 + gt, fresh ? a.nv : a.vc + static_cast<size_t>(j) * key_stride);
+    }
+  }
+}
+
+template <bool SELF, class Bar>
+__device__ __forceinline__ void pd_attention_stage(Bar& bar, uint8_t* smem, const PdParams& p, const PdStage& st) {
+  constexpr int kBlockKeys = 16 * kPdKeySlots;
+  const int tid = threadIdx.x;
+  const int n_groups = blockDim.x >> 7;       // 2 in the persistent kernel, 1 in the stage kernel
+  const int group = tid >> 7, gt = tid & 127;
+  const int gw = gt >> 5, lane = gt & 31;
+  const int sub = lane >> 3, ch = lane & 7;
+  uint4* stage0 = reinterpret_cast<uint4*>(smem + (group * 2) * kPdStageBytes);
+  uint4* stage1 = reinterpret_cast<uint4*>(smem + (group * 2 + 1) * kPdStageBytes);
+  float* s_part = reinterpret_cast<float*>(smem + n_groups * 2 * kPdStageBytes) + group * 4 * (2 + kHeadDim);
+  const PdLayer& L = p.layer[st.layer];
+  const __nv_bfloat16* kbase = SELF ? L.self_k : p.crosskv + st.layer * 2 * kD;
+  const __nv_bfloat16* vbase = SELF ? L.self_v : p.crosskv + st.layer * 2 * kD + kD;
+  const long long b_stride = SELF ? static_cast<long long>(p.cache_len) * kD : static_cast<long long>(kEncTokens) * 4 * kD;
+  const int key_stride = SELF ? kD : 4 * kD;
+  const int units = p.B * kHeads;
+  const int ustride = gridDim.x * n_groups;
+  const int u0 = blockIdx.x * n_groups + group;
+
+  auto make_unit = [&](int u, bool state_visible) {
+    PdAttnUnit a;
+    a.b = u / kHeads;
+    a.h = u - a.b * kHeads;
+    a.kc = kbase + static_cast<size_t>(a.b) * b_stride + a.h * kHeadDim + ch * 8;
+    a.vc = vbase + static_cast<size_t>(a.b) * b_stride + a.h * kHeadDim + ch * 8;
+    a.nk = a.nv = nullptr;
+    a.n_keys = kEncTokens;
+    a.ps = -1;
+    a.skip = false;
+    if (state_visible) {
+      const int fin = ldg_cg_s32(p.finished + a.b);
+      const int pos = SELF ? ldg_cg_s32(p.pos + a.b) : 0;
+      a.skip = fin != 0 && p.forced == nullptr;     // group-uniform
+      if (SELF) {
+        a.ps = pos;
+        a.n_keys = a.ps + 1;
+        a.nk = p.qkv + static_cast<size_t>(a.b) * 3 * kD + kD + a.h * kHeadDim + ch * 8;
+        a.nv = a.nk + kD;
+      }
+      if (a.skip) a.n_keys = 0;                     // a finished row contributes no blocks
+    }
+    return a;
+  };
+
+  // The group's work is one stream of 112-key blocks (unit after unit) flowing through a two-deep
+  // ring of staging buffers: block n+1 is requested before block n is reduced.
+  PdAttnUnit cur = make_unit(u0 < units ? u0 : 0, false);
+  if (!SELF) {   // encoder K/V never change during a decode: request the first block before the barrier
+    if (u0 < units) pd_attn_request(stage0, cur, key_stride, 0, gt);
+    cp_async_commit();
+  }
+  bar.wait();
+  int u = u0;
+  if (u < units) {
+    cur = make_unit(u, true);
+    while (cur.n_keys == 0 && u + ustride < units) { u += ustride; cur = make_unit(u, true); }   // skip finished rows
+    if (SELF || u != u0) {
+      if (!SELF) cp_async_wait_group<0>();          // (a prefetched block of a finished row is dropped)
+      if (cur.n_keys > 0) pd_attn_request(stage0, cur, key_stride, 0, gt);
+      cp_async_commit();
+    }
+  }
+  int par = 0, j0 = 0;
+  float q[8], m = -INFINITY, l = 0.f, acc[8];
+#pragma unroll 1
+  while (u < units && cur.n_keys > 0) {
+    uint4* stage = par ? stage1 : stage0;
+    // ---- locate and request the next block of the stream
+    PdAttnUnit nxt = cur;
+    int nu = u, nj0 = j0 + kBlockKeys;
+    if (nj0 >= cur.n_keys) {
+      nj0 = 0;
+      nu = u + ustride;
+      bool found = false;
+      while (nu < units) {
+        nxt = make_unit(nu, true);
+        if (nxt.n_keys > 0) { found = true; break; }
+        nu += ustride;
+      }
+      if (!found) nu = units;
+    }
+    if (nu < units) pd_attn_request(par ? stage0 : stage1, nxt, key_stride, nj0, gt);
+    cp_async_commit();
+    // ---- first block of a unit: the query and a fresh online-softmax state
+    if (j0 == 0) {
+      if (SELF) {
+        pd_bf16x8(ldg_cg16(p.qkv + static_cast<size_t>(cur.b) * 3 * kD + cur.h * kHeadDim + ch * 8), q);
+      } else {   // query = bias + split-K partials of the cross-q projection, added in a fixed order
+        const int c = cur.h * kHeadDim + ch * 8;
+        float4 lo = __ldg(reinterpret_cast<const float4*>(st.bias + c)), hi = __ldg(reinterpret_cast<const float4*>(st.bias + c + 4));
+        float4 e0[kPdSplit], e1[kPdSplit];
+#pragma unroll
+        for (int pt = 0; pt < kPdSplit; ++pt) {
+          const float* src = p.yq + (static_cast<size_t>(pt) * p.B + cur.b) * kD + c;
+          e0[pt] = ldg_cg_f4(src);
+          e1[pt] = ldg_cg_f4(src + 4);
+        }
+#pragma unroll
+        for (int pt = 0; pt < kPdSplit; ++pt) {
+          lo.x += e0[pt].x; lo.y += e0[pt].y; lo.z += e0[pt].z; lo.w += e0[pt].w;
+          hi.x += e1[pt].x; hi.y += e1[pt].y; hi.z += e1[pt].z; hi.w += e1[pt].w;
+        }
+        q[0] = lo.x; q[1] = lo.y; q[2] = lo.z; q[3] = lo.w;
+        q[4] = hi.x; q[5] = hi.y; q[6] = hi.z; q[7] = hi.w;
+      }
+      m = -INFINITY;
+      l = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    }
+    cp_async_wait_group<1>();             // everything but the newest group (the next block) has landed
+    // ---- pass 1: the block's scores (independent dot products: the shuffles overlap)
+    float sc[kPdKeySlots];
+    float bm = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < kPdKeySlots; ++i) {
+      const int j = j0 + 16 * i + 4 * gw + sub;
+      sc[i] = -INFINITY;
+      if (j0 + 16 * i < cur.n_keys) {         // warp-uniform: this slot holds at least one live key
+        const bool ok = j < cur.n_keys;       // uniform over the 8 lanes that share a key
+        const uint4 kq = ok ? stage[i * 128 + gt] : make_uint4(0, 0, 0, 0);
+        if (SELF && ok && j == cur.ps)        // append this token's K row to the cache
+          *reinterpret_cast<uint4*>(const_cast<__nv_bfloat16*>(cur.kc) + static_cast<size_t>(j) * key_stride) = kq;
+        float f[8];
+        pd_bf16x8(kq, f);
+        float d = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) d = fmaf(q[e], f[e], d);
+        d += __shfl_xor_sync(0xffffffffu, d, 1);
+        d += __shfl_xor_sync(0xffffffffu, d, 2);
+        d += __shfl_xor_sync(0xffffffffu, d, 4);
+        if (ok) {
+          sc[i] = d;
+          bm = fmaxf(bm, d);
+        }
+      }
+    }
+    // ---- pass 2: one rescale of the running state per block, then independent exp / FMA per key
+    {
+      const float mn = fmaxf(m, bm);
+      const float cs = mn == -INFINITY ? 0.f : __expf(m - mn);
+      l *= cs;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] *= cs;
+      m = mn;
+#pragma unroll
+      for (int i = 0; i < kPdKeySlots; ++i) {
+        const int j = j0 + 16 * i + 4 * gw + sub;
+        if (j < cur.n_keys) {
+          const uint4 vq = stage[(kPdKeySlots + i) * 128 + gt];
+          if (SELF && j == cur.ps)              // append this token's V row to the cache
+            *reinterpret_cast<uint4*>(const_cast<__nv_bfloat16*>(cur.vc) + static_cast<size_t>(j) * key_stride) = vq;
+          const float e0 = __expf(sc[i] - mn);
+          float f[8];
+          pd_bf16x8(vq, f);
+          l += e0;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[e] = fmaf(e0, f[e], acc[e]);
+        }
+      }
+    }
+    // ---- last block of a unit: merge the 16 partial states in a fixed order and write the context
+    if (j0 + kBlockKeys >= cur.n_keys) {
+      float mm = m, ll = l;
+#pragma unroll
+      for (int o = 8; o <= 16; o <<= 1) {
+        const float m2 = __shfl_xor_sync(0xffffffffu, mm, o);
+        const float l2 = __shfl_xor_sync(0xffffffffu, ll, o);
+        const float mn = fmaxf(mm, m2);
+        const float c1 = mn == -INFINITY ? 0.f : __expf(mm - mn);
+        const float c2 = mn == -INFINITY ? 0.f : __expf(m2 - mn);
+        ll = ll * c1 + l2 * c2;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float a2 = __shfl_xor_sync(0xffffffffu, acc[e], o);
+          acc[e] = acc[e] * c1 + a2 * c2;
+        }
+        mm = mn;
+      }
+      if (sub == 0) {
+        float* dst = s_part + gw * (2 + kHeadDim);
+        if (ch == 0) { dst[0] = mm; dst[1] = ll; }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) dst[2 + ch * 8 + e] = acc[e];
+      }
+      group_sync(group);
+      if (gt < kHeadDim) {
+        float mx = -INFINITY;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) mx = fmaxf(mx, s_part[w * (2 + kHeadDim)]);
+        float lt = 0.f, ot = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          const float mw = s_part[w * (2 + kHeadDim)];
+          const float cw = mw == -INFINITY ? 0.f : __expf(mw - mx);
+          lt += s_part[w * (2 + kHeadDim) + 1] * cw;
+          ot += s_part[w * (2 + kHeadDim) + 2 + gt] * cw;
+        }
+        p.ctx[static_cast<size_t>(cur.b) * kD + cur.h * kHeadDim + gt] = __float2bfloat16(__fdividef(ot, lt));   // lt >= 1
+      }
+      group_sync(group);     // s_part is reused by the next unit
+    }
+    cur = nxt;
+    u = nu;
+    j0 = nj0;
+    par ^= 1;
+  }
+  cp_async_wait_group<0>();   // nothing may still be landing in the staging area: the next stage reuses it
+  bar.arrive();
+}
+
+// ------------------------------------------------------------------ the kernel ---
+
+constexpr int kPdSmemBytes = kPdGroups * 2 * kPdStageBytes + kPdGroups * 4 * (2 + kHeadDim) * 4 + kPdMaxStages * static_cast<int>(sizeof(PdStage)) + 128;
+static_assert(kPdRedFloats * 4 <= kPdGroups * 2 * kPdStageBytes, "reduction scratch must fit in the staging area it aliases");
+
+__host__ __device__ inline PdStage pd_gemm_desc(int type, int epi, const __nv_bfloat16* A, int K, const PdLinear& lin, int N, int ksplit,
+                                                __nv_bfloat16* ob, float* of, int ldo) {
+  PdStage s{};
+  s.type = type; s.epi = epi; s.A = A; s.K = K; s.W = lin.w; s.bias = lin.bias; s.N = N; s.ksplit = ksplit; s.ob = ob; s.of = of; s.ldo = ldo;
+  return s;
+}
+__host__ __device__ inline PdStage pd_ln_desc(const float* src, int parts, const float* bias, int gelu, const float* resid, const PdLn& ln,
+                                              float* x, __nv_bfloat16* xb) {
+  PdStage s{};
+  s.type = PD_LN; s.epi = gelu; s.src = src; s.parts = parts; s.bias = bias; s.resid = resid; s.g = ln.g; s.b = ln.b; s.of = x; s.ob = xb;
+  return s;
+}
+
+// The per-token program (shared by the persistent kernel, which builds it in shared memory, and
+// by the host, which launches it stage by stage in the CUDA-graph mode).
+__host__ __device__ inline int pd_build_program(const PdParams& p, PdStage* prog) {
+  int n = 0;
+  for (int l = 0; l < kDecLayers; ++l) {
+    const PdLayer& L = p.layer[l];
+    PdStage a{};
+    // self-attention block (modeling_bert.py:143-207, 287-298)
+    prog[n++] = pd_gemm_desc(PD_GEMM16, PD_BF16, p.xb, kD, L.qkv, 3 * kD, 1, p.qkv, nullptr, 3 * kD);
+    a = PdStage{}; a.type = PD_ATTN_SELF; a.layer = l; prog[n++] = a;
+    prog[n++] = pd_gemm_desc(PD_GEMM16, PD_F32_PARTIAL, p.ctx, kD, L.self_out, kD, kPdSplit, nullptr, p.y, kD);
+    prog[n++] = pd_ln_desc(p.y, kPdSplit, L.self_out.bias, 0, p.x, L.ln_self, p.x, p.xb);
+    // cross-attention block (:210-284)
+    prog[n++] = pd_gemm_desc(PD_GEMM16, PD_F32_PARTIAL, p.xb, kD, L.cross_q, kD, kPdSplit, nullptr, p.yq, kD);
+    a = PdStage{}; a.type = PD_ATTN_CROSS; a.layer = l; a.bias = L.cross_q.bias; prog[n++] = a;
+    prog[n++] = pd_gemm_desc(PD_GEMM16, PD_F32_PARTIAL, p.ctx, kD, L.cross_out, kD, kPdSplit, nullptr, p.y, kD);
+    prog[n++] = pd_ln_desc(p.y, kPdSplit, L.cross_out.bias, 0, p.x, L.ln_cross, p.x, p.xb);
+    // feed-forward (:330-356)
+    prog[n++] = pd_gemm_desc(PD_GEMM32, PD_BF16_GELU, p.xb, kD, L.fc1, kFFN, 1, p.ffn, nullptr, kFFN);
+    prog[n++] = pd_gemm_desc(PD_GEMM16, PD_F32_PARTIAL, p.ffn, kFFN, L.fc2, kD, kPdSplit, nullptr, p.y, kD);
+    prog[n++] = pd_ln_desc(p.y, kPdSplit, L.fc2.bias, 0, p.x, L.ln_ffn, p.x, p.xb);
+  }
+  // LM head (:471-501): dense -> GELU -> LayerNorm, then the vocabulary projection fused with the
+  // per-tile arg-max: logits never leave the SM unless the parity tap is on
+  prog[n++] = pd_gemm_desc(PD_GEMM16, PD_F32_PARTIAL, p.xb, kD, p.head_t, kD, kPdSplit, nullptr, p.y, kD);
+  prog[n++] = pd_ln_desc(p.y, kPdSplit, p.head_t.bias, 1, nullptr, p.head_ln, nullptr, p.xb);
+  prog[n++] = pd_gemm_desc(PD_GEMM48, PD_ARGMAX, p.xb, kD, p.head_dec, kVocab, 1, nullptr, nullptr, 0);
+  PdStage nx{};
+  nx.type = PD_NEXT;
+  prog[n++] = nx;
+  return n;
+}
+
+// One out-of-line instance per stage type keeps the persistent kernel's code small.
+template <int NT, int CH>
+__device__ __noinline__ void pd_gemm_call(GridBarrier& bar, float* red, const PdParams& p, const PdStage& st) { pd_gemm_stage<NT, CH>(bar, red, p, st); }
+template <bool SELF>
+__device__ __noinline__ void pd_attention_call(GridBarrier& bar, uint8_t* smem, const PdParams& p, const PdStage& st) { pd_attention_stage<SELF>(bar, smem, p, st); }
+__device__ __noinline__ void pd_ln_call(GridBarrier& bar, const PdParams& p, const PdStage& st) { pd_ln_stage(bar, p, st); }
+__device__ __noinline__ void pd_next_call(GridBarrier& bar, const PdParams& p) { pd_next_token_stage(bar, p); }
+
+__global__ void __launch_bounds__(kPdThreads, 1) decode_persistent_kernel(const __grid_constant__ PdParams p) {
+  extern __shared__ __align__(128) uint8_t pd_smem[];
+  float* red = reinterpret_cast<float*>(pd_smem);     // aliases the attention staging area (stages never overlap)
+  PdStage* prog = reinterpret_cast<PdStage*>(pd_smem + kPdGroups * 2 * kPdStageBytes + kPdGroups * 4 * (2 + kHeadDim) * 4);
+  __shared__ int s_nstages;
+  GridBarrier bar{p.barrier, 0u, p.prof, 0};
+  const int B = p.B;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) s_nstages = pd_build_program(p, prog);   // the per-token program
+
+  // step 0 input: ids[b][0] = [CLS] (generation/utils.py:806-863), PAD elsewhere; x = embed([CLS], 0)
+  for (int r = blockIdx.x * kPdWarps + warp; r < B; r += gridDim.x * kPdWarps) {
+    for (int i = lane; i < p.max_len; i += 32) p.ids[static_cast<size_t>(r) * p.max_len + i] = i == 0 ? 2 : 0;
+    if (lane == 0) {
+      p.pos[r] = 0;
+      p.finished[r] = p.max_len <= 1 ? 1 : 0;
+    }
+    pd_embed_row_warp(p, r, 2, 0, lane);
+  }
+  bar.arrive();       // (also orders the program table: arrive() starts with __syncthreads)
+  const int n_stages = s_nstages;
+
+  const int max_steps = p.max_len - 1;
+  int step = 0;
+#pragma unroll 1
+  for (; step < max_steps; ++step) {
+#pragma unroll 1
+    for (int si = 0; si < n_stages; ++si) {
+      const PdStage& st = prog[si];
+      switch (st.type) {
+        case PD_GEMM16: pd_gemm_call<16, 4>(bar, red, p, st); break;
+        case PD_GEMM32: pd_gemm_call<32, 2>(bar, red, p, st); break;
+        case PD_GEMM48: pd_gemm_call<48, 2>(bar, red, p, st); break;
+        case PD_ATTN_SELF: pd_attention_call<true>(bar, pd_smem, p, st); break;
+        case PD_ATTN_CROSS: pd_attention_call<false>(bar, pd_smem, p, st); break;
+        case PD_LN: pd_ln_call(bar, p, st); break;
+        default: pd_next_call(bar, p); break;
+      }
+    }
+    // device-side termination (generation/utils.py:2805 does this with a host sync per token)
+    bar.wait();
+    int live = 0;
+    for (int r = threadIdx.x; r < B; r += kPdThreads) live |= (ldg_cg_s32(p.finished + r) == 0) ? 1 : 0;
+    live = __syncthreads_or(live);      // no arrive: the next stage's wait() passes at once (same target)
+    if (!live && p.forced == nullptr) { ++step; break; }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *p.steps_done = step;
+}
+
+
+// ------------------------------------------------------------------ stage kernels (CUDA-graph mode) ---
+// The same stage code, one launch per stage; grid = number of tiles / units so that every CTA has
+// exactly one piece of work and several CTAs share an SM (latency hiding the persistent kernel,
+// with 8 warps per SM, does not have).
+
+template <int NT, int CH>
+__global__ void __launch_bounds__(kPdThreads) pd_gemm_kernel(const __grid_constant__ PdParams p, const __grid_constant__ PdStage st) {
+  __shared__ float red[kPdKSlices * kPdRowsPerBlock * (NT + 1)];
+  NullBarrier bar;
+  pd_gemm_stage<NT, CH>(bar, red, p, st);
+}
+template <bool SELF>
+__global__ void __launch_bounds__(128) pd_attention_kernel(const __grid_constant__ PdParams p, const __grid_constant__ PdStage st) {
+  extern __shared__ __align__(128) uint8_t pd_smem[];
+  NullBarrier bar;
+  pd_attention_stage<SELF>(bar, pd_smem, p, st);
+}
+__global__ void __launch_bounds__(kPdThreads) pd_ln_kernel(const __grid_constant__ PdParams p, const __grid_constant__ PdStage st) {
+  NullBarrier bar;
+  pd_ln_stage(bar, p, st);
+}
+__global__ void __launch_bounds__(kPdThreads) pd_next_kernel(const __grid_constant__ PdParams p) {
+  NullBarrier bar;
+  pd_next_token_stage(bar, p);
+}
+// ids[b][0] = [CLS], pos = 0, finished = 0, x = embed([CLS], 0)
+__global__ void __launch_bounds__(kPdThreads) pd_begin_kernel(const __grid_constant__ PdParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = blockIdx.x * kPdWarps + warp; r < p.B; r += gridDim.x * kPdWarps) {
+    for (int i = lane; i < p.max_len; i += 32) p.ids[static_cast<size_t>(r) * p.max_len + i] = i == 0 ? 2 : 0;
+    if (lane == 0) {
+      p.pos[r] = 0;
+      p.finished[r] = p.max_len <= 1 ? 1 : 0;
+    }
+    pd_embed_row_warp(p, r, 2, 0, lane);
+  }
+}
+
+constexpr int kPdAttnSmemBytes = 2 * kPdStageBytes + 4 * (2 + kHeadDim) * 4;     // one 128-thread group per CTA
+
+}  // namespace mocr

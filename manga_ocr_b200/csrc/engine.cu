@@ -25,6 +25,7 @@
 #include "../../include/mocr_b200.h"
 #include "common.cuh"
 #include "decode_attn.cuh"
+#include "decode_persistent.cuh"
 #include "encoder_attn.cuh"
 #include "gemm_tcgen05.cuh"
 #include "preprocess.cuh"
@@ -122,6 +123,7 @@ struct mocr_handle {
   int head_bn = 64;
   int check_every = 16;
   int use_graph = 1;
+  int decode_mode = 2;   // 2 = stage kernels in a CUDA graph (default), 1 = persistent cooperative kernel, 0 = first version (tcgen05 GEMMs)
 
   // ---- weights
   Linear patch;
@@ -159,6 +161,13 @@ struct mocr_handle {
   int* d_forced = nullptr;
   int* d_zero = nullptr;              // [max_batch] zeros
   int* h_flags = nullptr;             // pinned [max_batch]
+  int* h_steps = nullptr;             // pinned [1]
+  unsigned int* d_barrier = nullptr;  // grid barrier counter of the persistent decoder
+  int* d_steps = nullptr;
+  float* d_y = nullptr;               // [3, brow_cap, 768] split-K partials of the persistent decoder (projections feeding a LN)
+  float* d_yq = nullptr;              // [3, brow_cap, 768] split-K partials of the cross-attention query
+  long long* d_prof = nullptr;        // [4096] stage timeline of the persistent decoder (option decode_prof)
+  int decode_prof = 0;
   float* logits_tap = nullptr;        // [n, max_length-1, 6144]
   size_t logits_tap_bytes = 0;
   uint8_t* px_u8 = nullptr;           // taps [max_batch,224,224]
@@ -738,6 +747,100 @@ int decode_step(mocr_handle* h, int n, int max_length, bool forced, bool tap) {
   return MOCR_OK;
 }
 
+PdLinear pd_lin(const Linear& L) { return PdLinear{L.w, L.bias}; }
+PdLn pd_ln(const LnParams& l) { return PdLn{l.g, l.b}; }
+
+PdParams make_pd_params(mocr_handle* h, int n, int max_length, bool forced, bool tap) {
+  PdParams p{};
+  p.B = n;
+  p.max_len = max_length;
+  p.cache_len = h->max_length;
+  p.eos_id = kSepId;
+  for (int l = 0; l < kDecLayers; ++l) {
+    DecLayer& L = h->dec[l];
+    PdLayer& P = p.layer[l];
+    P.qkv = pd_lin(L.self_qkv);
+    P.self_out = pd_lin(L.self_out);
+    P.cross_q = pd_lin(L.cross_q);
+    P.cross_out = pd_lin(L.cross_out);
+    P.fc1 = pd_lin(L.fc1);
+    P.fc2 = pd_lin(L.fc2);
+    P.ln_self = pd_ln(L.ln_self);
+    P.ln_cross = pd_ln(L.ln_cross);
+    P.ln_ffn = pd_ln(L.ln_ffn);
+    P.self_k = h->self_k[l];
+    P.self_v = h->self_v[l];
+  }
+  p.head_t = pd_lin(h->head_t);
+  p.head_dec = pd_lin(h->head_dec);
+  p.head_ln = pd_ln(h->head_ln);
+  p.emb = h->emb;
+  p.crosskv = h->crosskv;
+  p.ids = h->d_ids;
+  p.pos = h->d_pos;
+  p.finished = h->d_finished;
+  p.forced = forced ? h->d_forced : nullptr;
+  p.x = h->d_x;
+  p.xb = h->d_xb.p;
+  p.y = h->d_y;
+  p.yq = h->d_yq;
+  p.qkv = h->d_qkv;
+  p.ctx = h->d_ctx.p;
+  p.ffn = h->d_ffn.p;
+  p.part_max = h->part_max;
+  p.part_idx = h->part_idx;
+  p.logits = tap ? h->logits_tap : nullptr;
+  p.barrier = h->d_barrier;
+  p.steps_done = h->d_steps;
+  p.prof = h->decode_prof ? h->d_prof : nullptr;
+  return p;
+}
+
+// The whole greedy decode in one cooperative launch (decode_persistent.cuh).
+int decode_persistent(mocr_handle* h, int n, int max_length, bool forced, bool tap) {
+  static bool done[16] = {};
+  if (!done[h->device & 15]) {
+    CK(cudaFuncSetAttribute(decode_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPdSmemBytes));
+    done[h->device & 15] = true;
+  }
+  PdParams p = make_pd_params(h, n, max_length, forced, tap);
+  CK(cudaMemsetAsync(h->d_barrier, 0, sizeof(unsigned int), h->stream));
+  void* args[] = {&p};
+  CK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(decode_persistent_kernel), dim3(h->sms), dim3(kPdThreads), args,
+                                 static_cast<size_t>(kPdSmemBytes), h->stream));
+  ++h->launches;
+  CK(cudaMemcpyAsync(h->h_steps, h->d_steps, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  return MOCR_OK;
+}
+
+// One greedy step as a sequence of stage kernels (decode_persistent.cuh), one launch per stage.
+int decode_stage_step(mocr_handle* h, const PdParams& p) {
+  static bool done[16] = {};
+  if (!done[h->device & 15]) {
+    CK(cudaFuncSetAttribute(pd_attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPdAttnSmemBytes));
+    CK(cudaFuncSetAttribute(pd_attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPdAttnSmemBytes));
+    done[h->device & 15] = true;
+  }
+  PdStage prog[kPdMaxStages];
+  const int n_stages = pd_build_program(p, prog);
+  const int row_ctas = (p.B + kPdWarps - 1) / kPdWarps;
+  for (int i = 0; i < n_stages; ++i) {
+    const PdStage& st = prog[i];
+    switch (st.type) {
+      case PD_GEMM16: pd_gemm_kernel<16, 4><<<(st.N / 16) * st.ksplit, kPdThreads, 0, h->stream>>>(p, st); break;
+      case PD_GEMM32: pd_gemm_kernel<32, 2><<<(st.N / 32) * st.ksplit, kPdThreads, 0, h->stream>>>(p, st); break;
+      case PD_GEMM48: pd_gemm_kernel<48, 2><<<(st.N / 48) * st.ksplit, kPdThreads, 0, h->stream>>>(p, st); break;
+      case PD_ATTN_SELF: pd_attention_kernel<true><<<p.B * kHeads, 128, kPdAttnSmemBytes, h->stream>>>(p, st); break;
+      case PD_ATTN_CROSS: pd_attention_kernel<false><<<p.B * kHeads, 128, kPdAttnSmemBytes, h->stream>>>(p, st); break;
+      case PD_LN: pd_ln_kernel<<<row_ctas, kPdThreads, 0, h->stream>>>(p, st); break;
+      default: pd_next_kernel<<<row_ctas, kPdThreads, 0, h->stream>>>(p); break;
+    }
+    CK(cudaGetLastError());
+    ++h->launches;
+  }
+  return MOCR_OK;
+}
+
 int decode(mocr_handle* h, int max_length, const int32_t* forced_ids) {
   if (!h->enc_ok) return fail(h, MOCR_ERR_INVALID, "encode has not run on the staged crops");
   if (max_length < 2 || max_length > h->max_length)
@@ -760,30 +863,43 @@ int decode(mocr_handle* h, int max_length, const int32_t* forced_ids) {
     }
     CK(cudaMemsetAsync(h->logits_tap, 0, need_b, h->stream));
   }
-  decode_begin_kernel<<<n, 256, 0, h->stream>>>(decode_state(h, forced, max_length), h->emb, kClsId, kPadId);
-  CK(cudaGetLastError());
-  ++h->launches;
+  if (h->decode_mode == 1) {
+    TRY(decode_persistent(h, n, max_length, forced, tap));
+    h->last_steps = -1;       // read back lazily from the pinned counter
+    h->cur_len = max_length;
+    h->dec_ok = true;
+    return MOCR_OK;
+  }
+  const bool stage_mode = h->decode_mode == 2;
+  const PdParams pdp = make_pd_params(h, n, max_length, forced, tap);
+  auto begin = [&]() -> int {
+    if (stage_mode) pd_begin_kernel<<<(n + kPdWarps - 1) / kPdWarps, kPdThreads, 0, h->stream>>>(pdp);
+    else decode_begin_kernel<<<n, 256, 0, h->stream>>>(decode_state(h, forced, max_length), h->emb, kClsId, kPadId);
+    CK(cudaGetLastError());
+    ++h->launches;
+    return MOCR_OK;
+  };
+  auto one_step = [&]() -> int { return stage_mode ? decode_stage_step(h, pdp) : decode_step(h, n, max_length, forced, tap); };
+  TRY(begin());
 
   const int steps = max_length - 1;
   cudaGraphExec_t exec = nullptr;
   int64_t per_step = 0;
   if (h->use_graph) {
-    const uint64_t key = (static_cast<uint64_t>(n) << 32) | (static_cast<uint64_t>(max_length) << 8) | (forced ? 2u : 0u) | (tap ? 1u : 0u);
+    const uint64_t key = (static_cast<uint64_t>(n) << 32) | (static_cast<uint64_t>(max_length) << 8) | (stage_mode ? 4u : 0u) | (forced ? 2u : 0u) | (tap ? 1u : 0u);
     auto it = h->graphs.find(key);
     if (it == h->graphs.end()) {
       // warm every kernel variant once outside capture (function attributes, tensor maps),
       // on throw-away state: re-run decode_begin afterwards.
       const int64_t l0 = h->launches;
-      TRY(decode_step(h, n, max_length, forced, tap));
+      TRY(one_step());
       per_step = h->launches - l0;
-      decode_begin_kernel<<<n, 256, 0, h->stream>>>(decode_state(h, forced, max_length), h->emb, kClsId, kPadId);
-      CK(cudaGetLastError());
-      ++h->launches;
+      TRY(begin());
       if (tap) CK(cudaMemsetAsync(h->logits_tap, 0, static_cast<size_t>(n) * (max_length - 1) * kVocab * sizeof(float), h->stream));
       cudaGraph_t graph;
       CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
       const int64_t l1 = h->launches;
-      int r = decode_step(h, n, max_length, forced, tap);
+      int r = one_step();
       h->launches = l1;
       cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
       if (r != MOCR_OK) return r;
@@ -808,7 +924,7 @@ int decode(mocr_handle* h, int max_length, const int32_t* forced_ids) {
         CK(cudaGraphLaunch(exec, h->stream));
         h->launches += per_step;
       } else {
-        TRY(decode_step(h, n, max_length, forced, tap));
+        TRY(one_step());
       }
     }
     done_steps += chunk;
@@ -875,6 +991,8 @@ int create_impl(mocr_handle* h) {
   TRY(make_act(h, &h->d_tb, h->brow_cap, kD));
   TRY(dmalloc(h, &h->d_x, static_cast<size_t>(h->brow_cap) * kD));
   TRY(dmalloc(h, &h->d_tmp, static_cast<size_t>(h->brow_cap) * kD));
+  TRY(dmalloc(h, &h->d_y, static_cast<size_t>(h->brow_cap) * kD * kPdSplit));
+  TRY(dmalloc(h, &h->d_yq, static_cast<size_t>(h->brow_cap) * kD * kPdSplit));
   TRY(dmalloc(h, &h->d_qkv, static_cast<size_t>(h->brow_cap) * 3 * kD));
   TRY(dmalloc(h, &h->d_q, static_cast<size_t>(h->brow_cap) * kD));
   for (int l = 0; l < kDecLayers; ++l) {
@@ -888,6 +1006,11 @@ int create_impl(mocr_handle* h) {
   TRY(dmalloc(h, &h->d_pos, static_cast<size_t>(B)));
   TRY(dmalloc(h, &h->d_finished, static_cast<size_t>(B)));
   TRY(dmalloc(h, &h->d_zero, static_cast<size_t>(B)));
+  TRY(dmalloc(h, &h->d_barrier, 4));
+  TRY(dmalloc(h, &h->d_steps, 4));
+  TRY(dmalloc(h, &h->d_prof, 4096));
+  CK(cudaMallocHost(reinterpret_cast<void**>(&h->h_steps), sizeof(int)));
+  *h->h_steps = 0;
   TRY(dmalloc(h, &h->d_descs, static_cast<size_t>(B)));
   CK(cudaMallocHost(reinterpret_cast<void**>(&h->h_flags), sizeof(int) * B));
   CK(cudaMallocHost(reinterpret_cast<void**>(&h->h_descs), sizeof(CropDesc) * B));
@@ -950,6 +1073,7 @@ int mocr_destroy(mocr_handle_t* h) {
     if (h->h_arena) cudaFreeHost(h->h_arena);
     if (h->d_coefs) cudaFree(h->d_coefs);
     if (h->h_flags) cudaFreeHost(h->h_flags);
+    if (h->h_steps) cudaFreeHost(h->h_steps);
     if (h->h_descs) cudaFreeHost(h->h_descs);
     if (h->stream) cudaStreamDestroy(h->stream);
   }
@@ -1081,7 +1205,14 @@ int mocr_sync(mocr_handle_t* h) {
 }
 
 int64_t mocr_launch_count(mocr_handle_t* h) { return h ? h->launches : 0; }
-int mocr_last_steps(mocr_handle_t* h) { return h ? h->last_steps : 0; }
+int mocr_last_steps(mocr_handle_t* h) {
+  if (h == nullptr) return 0;
+  if (h->last_steps < 0) {
+    if (cudaSetDevice(h->device) != cudaSuccess || cudaStreamSynchronize(h->stream) != cudaSuccess) return -1;
+    h->last_steps = *h->h_steps;
+  }
+  return h->last_steps;
+}
 
 int mocr_set_option(mocr_handle_t* h, const char* key, int value) {
   TRY(check_handle(h));
@@ -1094,6 +1225,8 @@ int mocr_set_option(mocr_handle_t* h, const char* key, int value) {
   else if (k == "head_bn" && bn_ok(value) && kVocab % value == 0) h->head_bn = value;
   else if (k == "check_every" && value >= 1) h->check_every = value;
   else if (k == "use_graph") h->use_graph = value != 0;
+  else if (k == "decode_mode" && value >= 0 && value <= 2) h->decode_mode = value;
+  else if (k == "decode_prof") h->decode_prof = value != 0;
   else return fail(h, MOCR_ERR_INVALID, "unknown option or bad value: %s=%d", key, value);
   for (auto& g : h->graphs) cudaGraphExecDestroy(g.second.exec);
   h->graphs.clear();
@@ -1284,6 +1417,14 @@ int mocr_resample_table(int in_size, int32_t* ksize, int32_t* out, int capacity)
     memcpy(out, t.data.data(), t.data.size() * sizeof(int));
   }
   return static_cast<int>(t.data.size());
+}
+
+// Debug / tuning: clock64 timeline of CTA 0 of the last persistent decode (option decode_prof=1).
+int mocr_get_decode_profile(mocr_handle_t* h, int64_t* out, int n) {
+  TRY(check_handle(h));
+  std::lock_guard<std::mutex> lock(h->mu);
+  if (out == nullptr || n < 1 || n > 4096) return fail(h, MOCR_ERR_INVALID, "bad argument");
+  return d2h(h, out, h->d_prof, static_cast<size_t>(n) * sizeof(long long));
 }
 
 const char* mocr_last_error(mocr_handle_t* h) { return h ? h->error.c_str() : g_create_error.c_str(); }

@@ -209,3 +209,8 @@ class Engine:
         out = np.zeros((n * ENC_TOKENS, D), np.float32)
         self._ck(self._lib.mocr_test_encoder_attention(self._h, n, qkv.ctypes.data_as(POINTER(c_float)), out.ctypes.data_as(POINTER(c_float))))
         return out
+
+    def decode_profile(self, n: int = 4096) -> np.ndarray:
+        out = np.zeros((n,), np.int64)
+        self._ck(self._lib.mocr_get_decode_profile(self._h, out.ctypes.data_as(POINTER(c_int64)), n))
+        return out
