@@ -196,10 +196,14 @@ struct GridBarrier {
 
 // Stage kernels launched one by one (CUDA graph) use the same stage code with this no-op barrier:
 // stream order provides the dependency.
+// With programmatic dependent launch the next stage kernel is already resident while this one
+// runs: everything before wait() (weight / encoder-K/V prefetch, index arithmetic) overlaps the
+// previous stage, and wait() returns once the previous grid has completed and flushed.
 struct NullBarrier {
   __device__ __forceinline__ void arrive() {}
-  __device__ __forceinline__ void wait() {}
+  __device__ __forceinline__ void wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 };
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ------------------------------------------------------------------ small-M GEMM stage ---
 //
@@ -211,17 +215,19 @@ struct NullBarrier {
 // onto two k-steps such that thread t owns the 8 CONSECUTIVE physical elements [8t, 8t+8): one
 // 16-byte load per row gives a0/a2 (or b0/b1) of both k-steps.  A and W use the same mapping, so
 // the product is exact, every 32-byte sector fetched is fully used, and nothing is staged in smem.
-// Inside the CTA the 8 warps are 4 m-tiles x 2 K halves, reduced through smem in a fixed order.
-template <int NT, int CH, class Bar>
+// Inside the CTA the warps are 4 m-tiles x KS K-slices, reduced through smem in a fixed order
+// (KS = 2 in the persistent kernel, 4 in the stage kernels: 512 threads keep ~130 KB in flight).
+template <int NT, int CH, int KS, class Bar>
 __device__ __forceinline__ void pd_gemm_stage(Bar& bar, float* red, const PdParams& p, const PdStage& st) {
   constexpr int NTL = NT / 8;
-  constexpr int kIters = (kPdRowsPerBlock * NT + kPdThreads - 1) / kPdThreads;
+  constexpr int kThreads = 128 * KS;           // 4 m-tiles x KS K-slices of one warp each
+  constexpr int kIters = (kPdRowsPerBlock * NT + kThreads - 1) / kThreads;
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   const int mt = warp & 3, ks = warp >> 2;
   const int B = p.B, K = st.K, N = st.N, ksplit = st.ksplit, epi = st.epi;
-  const int kslice = K / (kPdKSlices * ksplit);
+  const int kslice = K / (KS * ksplit);
   const int n_chunks = kslice / 32;
   const int n_tiles = (N / NT) * ksplit;
   bool waited = false;
@@ -230,7 +236,7 @@ __device__ __forceinline__ void pd_gemm_stage(Bar& bar, float* red, const PdPara
     const bool has_tile = tile < n_tiles;
     const int n0 = (tile / ksplit) * NT;
     const int kq = tile % ksplit;
-    const int k0 = (kq * kPdKSlices + ks) * kslice;
+    const int k0 = (kq * KS + ks) * kslice;
     // Two K batches are in flight: the fragments of batch n+1 (A and W) are requested before the
     // MMAs of batch n are issued.  Batch 0's weights do not depend on the previous stage and are
     // requested before the grid barrier.
@@ -314,12 +320,13 @@ __device__ __forceinline__ void pd_gemm_stage(Bar& bar, float* red, const PdPara
       float vals[kIters];
 #pragma unroll
       for (int it = 0; it < kIters; ++it) {
-        const int i = tid + it * kPdThreads;
+        const int i = tid + it * kThreads;
         const int rl = i / NT, c = i - rl * NT;
         float v = 0.f;
         if (i < kPdRowsPerBlock * NT) {
           if (epi != PD_F32_PARTIAL) v = __ldg(st.bias + n0 + c);      // L1-resident after the first token
-          v += red[rl * (NT + 1) + c] + red[(kPdRowsPerBlock + rl) * (NT + 1) + c];
+#pragma unroll
+          for (int sl = 0; sl < KS; ++sl) v += red[(sl * kPdRowsPerBlock + rl) * (NT + 1) + c];
         }
         vals[it] = v;
       }
@@ -327,7 +334,7 @@ __device__ __forceinline__ void pd_gemm_stage(Bar& bar, float* red, const PdPara
         __syncthreads();                  // all partial sums are read: reuse slice 0 of `red` for the logits
 #pragma unroll
         for (int it = 0; it < kIters; ++it) {
-          const int i = tid + it * kPdThreads;
+          const int i = tid + it * kThreads;
           if (i < kPdRowsPerBlock * NT) red[(i / NT) * (NT + 1) + i % NT] = vals[it];
         }
         __syncthreads();
@@ -352,7 +359,7 @@ __device__ __forceinline__ void pd_gemm_stage(Bar& bar, float* red, const PdPara
       } else {
 #pragma unroll
         for (int it = 0; it < kIters; ++it) {
-          const int i = tid + it * kPdThreads;
+          const int i = tid + it * kThreads;
           const int r = rb + i / NT, c = i % NT;
           if (i < kPdRowsPerBlock * NT && r < B) {
             float v = vals[it];
@@ -796,7 +803,7 @@ __host__ __device__ inline int pd_build_program(const PdParams& p, PdStage* prog
 
 // One out-of-line instance per stage type keeps the persistent kernel's code small.
 template <int NT, int CH>
-__device__ __noinline__ void pd_gemm_call(GridBarrier& bar, float* red, const PdParams& p, const PdStage& st) { pd_gemm_stage<NT, CH>(bar, red, p, st); }
+__device__ __noinline__ void pd_gemm_call(GridBarrier& bar, float* red, const PdParams& p, const PdStage& st) { pd_gemm_stage<NT, CH, kPdKSlices>(bar, red, p, st); }
 template <bool SELF>
 __device__ __noinline__ void pd_attention_call(GridBarrier& bar, uint8_t* smem, const PdParams& p, const PdStage& st) { pd_attention_stage<SELF>(bar, smem, p, st); }
 __device__ __noinline__ void pd_ln_call(GridBarrier& bar, const PdParams& p, const PdStage& st) { pd_ln_stage(bar, p, st); }
@@ -858,28 +865,36 @@ __global__ void __launch_bounds__(kPdThreads, 1) decode_persistent_kernel(const 
 // exactly one piece of work and several CTAs share an SM (latency hiding the persistent kernel,
 // with 8 warps per SM, does not have).
 
+constexpr int kPdStageKS = 4;                  // K-slices (warps per m-tile) of the stage-kernel GEMMs: 512 threads
+constexpr int pd_gemm_smem_bytes(int nt) { return kPdStageKS * kPdRowsPerBlock * (nt + 1) * 4; }
 template <int NT, int CH>
-__global__ void __launch_bounds__(kPdThreads) pd_gemm_kernel(const __grid_constant__ PdParams p, const __grid_constant__ PdStage st) {
-  __shared__ float red[kPdKSlices * kPdRowsPerBlock * (NT + 1)];
+__global__ void __launch_bounds__(128 * kPdStageKS, 1) pd_gemm_kernel(const __grid_constant__ PdParams p, const __grid_constant__ PdStage st) {
+  extern __shared__ __align__(16) float red[];      // kPdStageKS * 64 * (NT + 1) floats (pd_gemm_smem_bytes)
   NullBarrier bar;
-  pd_gemm_stage<NT, CH>(bar, red, p, st);
+  pdl_launch_dependents();
+  pd_gemm_stage<NT, CH, kPdStageKS>(bar, red, p, st);
 }
 template <bool SELF>
 __global__ void __launch_bounds__(128) pd_attention_kernel(const __grid_constant__ PdParams p, const __grid_constant__ PdStage st) {
   extern __shared__ __align__(128) uint8_t pd_smem[];
   NullBarrier bar;
+  pdl_launch_dependents();
   pd_attention_stage<SELF>(bar, pd_smem, p, st);
 }
 __global__ void __launch_bounds__(kPdThreads) pd_ln_kernel(const __grid_constant__ PdParams p, const __grid_constant__ PdStage st) {
   NullBarrier bar;
+  pdl_launch_dependents();
   pd_ln_stage(bar, p, st);
 }
 __global__ void __launch_bounds__(kPdThreads) pd_next_kernel(const __grid_constant__ PdParams p) {
   NullBarrier bar;
+  pdl_launch_dependents();
   pd_next_token_stage(bar, p);
 }
 // ids[b][0] = [CLS], pos = 0, finished = 0, x = embed([CLS], 0)
 __global__ void __launch_bounds__(kPdThreads) pd_begin_kernel(const __grid_constant__ PdParams p) {
+  pdl_launch_dependents();
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int r = blockIdx.x * kPdWarps + warp; r < p.B; r += gridDim.x * kPdWarps) {
     for (int i = lane; i < p.max_len; i += 32) p.ids[static_cast<size_t>(r) * p.max_len + i] = i == 0 ? 2 : 0;

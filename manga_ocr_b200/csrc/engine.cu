@@ -121,8 +121,10 @@ struct mocr_handle {
   int enc_bn = 256;
   int dec_bn = 32;
   int head_bn = 64;
-  int check_every = 16;
+  int check_every = 26;
   int use_graph = 1;
+  int use_pdl = 1;          // programmatic dependent launch between the decoder's stage kernels
+  int steps_per_graph = 13; // decode steps captured in one CUDA graph (299 = 23 x 13)
   int decode_mode = 2;   // 2 = stage kernels in a CUDA graph (default), 1 = persistent cooperative kernel, 0 = first version (tcgen05 GEMMs)
 
   // ---- weights
@@ -813,12 +815,30 @@ int decode_persistent(mocr_handle* h, int n, int max_length, bool forced, bool t
   return MOCR_OK;
 }
 
+// Launch with programmatic stream serialization: the kernel may start while its predecessor is
+// still running; it synchronises with griddepcontrol.wait before touching dependent data.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(mocr_handle* h, void (*kernel)(KArgs...), int grid, int block, size_t smem, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = h->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = h->use_pdl ? 1 : 0;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 // One greedy step as a sequence of stage kernels (decode_persistent.cuh), one launch per stage.
 int decode_stage_step(mocr_handle* h, const PdParams& p) {
   static bool done[16] = {};
   if (!done[h->device & 15]) {
     CK(cudaFuncSetAttribute(pd_attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPdAttnSmemBytes));
     CK(cudaFuncSetAttribute(pd_attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPdAttnSmemBytes));
+    CK(cudaFuncSetAttribute(pd_gemm_kernel<48, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pd_gemm_smem_bytes(48)));
     done[h->device & 15] = true;
   }
   PdStage prog[kPdMaxStages];
@@ -827,15 +847,14 @@ int decode_stage_step(mocr_handle* h, const PdParams& p) {
   for (int i = 0; i < n_stages; ++i) {
     const PdStage& st = prog[i];
     switch (st.type) {
-      case PD_GEMM16: pd_gemm_kernel<16, 4><<<(st.N / 16) * st.ksplit, kPdThreads, 0, h->stream>>>(p, st); break;
-      case PD_GEMM32: pd_gemm_kernel<32, 2><<<(st.N / 32) * st.ksplit, kPdThreads, 0, h->stream>>>(p, st); break;
-      case PD_GEMM48: pd_gemm_kernel<48, 2><<<(st.N / 48) * st.ksplit, kPdThreads, 0, h->stream>>>(p, st); break;
-      case PD_ATTN_SELF: pd_attention_kernel<true><<<p.B * kHeads, 128, kPdAttnSmemBytes, h->stream>>>(p, st); break;
-      case PD_ATTN_CROSS: pd_attention_kernel<false><<<p.B * kHeads, 128, kPdAttnSmemBytes, h->stream>>>(p, st); break;
-      case PD_LN: pd_ln_kernel<<<row_ctas, kPdThreads, 0, h->stream>>>(p, st); break;
-      default: pd_next_kernel<<<row_ctas, kPdThreads, 0, h->stream>>>(p); break;
+      case PD_GEMM16: CK(launch_pdl(h, pd_gemm_kernel<16, 2>, (st.N / 16) * st.ksplit, 128 * kPdStageKS, pd_gemm_smem_bytes(16), p, st)); break;
+      case PD_GEMM32: CK(launch_pdl(h, pd_gemm_kernel<32, 2>, (st.N / 32) * st.ksplit, 128 * kPdStageKS, pd_gemm_smem_bytes(32), p, st)); break;
+      case PD_GEMM48: CK(launch_pdl(h, pd_gemm_kernel<48, 1>, (st.N / 48) * st.ksplit, 128 * kPdStageKS, pd_gemm_smem_bytes(48), p, st)); break;
+      case PD_ATTN_SELF: CK(launch_pdl(h, pd_attention_kernel<true>, p.B * kHeads, 128, kPdAttnSmemBytes, p, st)); break;
+      case PD_ATTN_CROSS: CK(launch_pdl(h, pd_attention_kernel<false>, p.B * kHeads, 128, kPdAttnSmemBytes, p, st)); break;
+      case PD_LN: CK(launch_pdl(h, pd_ln_kernel, row_ctas, kPdThreads, 0, p, st)); break;
+      default: CK(launch_pdl(h, pd_next_kernel, row_ctas, kPdThreads, 0, p)); break;
     }
-    CK(cudaGetLastError());
     ++h->launches;
   }
   return MOCR_OK;
@@ -873,7 +892,7 @@ int decode(mocr_handle* h, int max_length, const int32_t* forced_ids) {
   const bool stage_mode = h->decode_mode == 2;
   const PdParams pdp = make_pd_params(h, n, max_length, forced, tap);
   auto begin = [&]() -> int {
-    if (stage_mode) pd_begin_kernel<<<(n + kPdWarps - 1) / kPdWarps, kPdThreads, 0, h->stream>>>(pdp);
+    if (stage_mode) CK(launch_pdl(h, pd_begin_kernel, (n + kPdWarps - 1) / kPdWarps, kPdThreads, 0, pdp));
     else decode_begin_kernel<<<n, 256, 0, h->stream>>>(decode_state(h, forced, max_length), h->emb, kClsId, kPadId);
     CK(cudaGetLastError());
     ++h->launches;
@@ -887,6 +906,7 @@ int decode(mocr_handle* h, int max_length, const int32_t* forced_ids) {
   int64_t per_step = 0;
   if (h->use_graph) {
     const uint64_t key = (static_cast<uint64_t>(n) << 32) | (static_cast<uint64_t>(max_length) << 8) | (stage_mode ? 4u : 0u) | (forced ? 2u : 0u) | (tap ? 1u : 0u);
+    const int spg = std::max(1, std::min(h->steps_per_graph, max_length - 1));
     auto it = h->graphs.find(key);
     if (it == h->graphs.end()) {
       // warm every kernel variant once outside capture (function attributes, tensor maps),
@@ -899,8 +919,10 @@ int decode(mocr_handle* h, int max_length, const int32_t* forced_ids) {
       cudaGraph_t graph;
       CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
       const int64_t l1 = h->launches;
-      int r = one_step();
+      int r = MOCR_OK;
+      for (int s = 0; s < spg && r == MOCR_OK; ++s) r = one_step();
       h->launches = l1;
+      per_step *= spg;
       cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
       if (r != MOCR_OK) return r;
       if (ce != cudaSuccess) return fail(h, MOCR_ERR_CUDA, "stream capture failed: %s", cudaGetErrorString(ce));
@@ -916,18 +938,23 @@ int decode(mocr_handle* h, int max_length, const int32_t* forced_ids) {
       per_step = it->second.launches;
     }
   }
+  // A graph replays steps_per_graph steps; steps past max_length - 1 are no-ops for the result
+  // (every row is finished by then: no id, position or cache row is written).
+  const int spg = exec != nullptr ? std::max(1, std::min(h->steps_per_graph, max_length - 1)) : 1;
   int done_steps = 0;
   while (done_steps < steps) {
-    const int chunk = std::min(forced ? steps : h->check_every, steps - done_steps);
-    for (int s = 0; s < chunk; ++s) {
+    const int chunk = forced ? steps - done_steps : std::min(std::max(h->check_every, spg), steps - done_steps);
+    int ran = 0;
+    while (ran < chunk) {
       if (exec != nullptr) {
         CK(cudaGraphLaunch(exec, h->stream));
         h->launches += per_step;
       } else {
         TRY(one_step());
       }
+      ran += spg;
     }
-    done_steps += chunk;
+    done_steps += ran;
     if (!forced && done_steps < steps) {
       // every row finished? (generation/utils.py:2805 does this check, with a host sync, every step)
       CK(cudaMemcpyAsync(h->h_flags, h->d_finished, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
@@ -937,7 +964,7 @@ int decode(mocr_handle* h, int max_length, const int32_t* forced_ids) {
       if (all) break;
     }
   }
-  h->last_steps = done_steps;
+  h->last_steps = std::min(done_steps, steps);
   h->cur_len = max_length;
   h->dec_ok = true;
   return MOCR_OK;
@@ -1225,6 +1252,8 @@ int mocr_set_option(mocr_handle_t* h, const char* key, int value) {
   else if (k == "head_bn" && bn_ok(value) && kVocab % value == 0) h->head_bn = value;
   else if (k == "check_every" && value >= 1) h->check_every = value;
   else if (k == "use_graph") h->use_graph = value != 0;
+  else if (k == "use_pdl") h->use_pdl = value != 0;
+  else if (k == "steps_per_graph" && value >= 1 && value <= 64) h->steps_per_graph = value;
   else if (k == "decode_mode" && value >= 0 && value <= 2) h->decode_mode = value;
   else if (k == "decode_prof") h->decode_prof = value != 0;
   else return fail(h, MOCR_ERR_INVALID, "unknown option or bad value: %s=%d", key, value);
@@ -1263,21 +1292,37 @@ int mocr_time_kernel(mocr_handle_t* h, const char* kernel, int iters, float* ms_
       r = attention197(h, n);
       flops = 4.0 * n * kHeads * kEncTokens * kEncTokens * kHeadDim;
       bytes = 2.0 * (static_cast<double>(M) * 3 * kD + static_cast<double>(M) * kD);
-    } else if (k == "dec_cross_attn") {
+    } else if (k.rfind("dec_", 0) == 0) {
+      // one stage kernel of the decoder's per-token program, on the state the last decode left
+      // (finished flags cleared through a forced-decoding view so that every row is processed)
       if (!h->dec_ok) { r = fail(h, MOCR_ERR_INVALID, "run a decode first"); break; }
-      DecodeAttnArgs ca{};
-      ca.q = h->d_q;
-      ca.ldq = kD;
-      ca.kcache = h->crosskv;
-      ca.vcache = h->crosskv + kD;
-      ca.b_stride = static_cast<long long>(kEncTokens) * 4 * kD;
-      ca.key_stride = 4 * kD;
-      ca.fixed_keys = kEncTokens;
-      ca.finished = h->d_zero;      // time every row, finished or not
-      ca.ctx = h->d_ctx.p;
-      r = decode_attn(h, n, ca);
-      bytes = static_cast<double>(n) * (2.0 * kEncTokens * kD * 2 + 2.0 * kD * 2);
-      flops = 4.0 * n * kEncTokens * kD;
+      PdParams p = make_pd_params(h, n, h->cur_len, true, false);
+      PdStage prog[kPdMaxStages];
+      pd_build_program(p, prog);
+      // program order per layer: qkv, self_attn, self_out, ln, cross_q, cross_attn, cross_out, ln, fc1, fc2, ln; head: t, ln, vocab, next
+      int idx = -1;
+      const double w768 = 2.0 * kD * kD, act = 2.0 * n * kD;
+      if (k == "dec_qkv") { idx = 0; bytes = 3 * w768 + act + 3 * act; }
+      else if (k == "dec_self_attn") { idx = 1; bytes = 0; }     // depends on the positions; reported by bench.py
+      else if (k == "dec_self_out") { idx = 2; bytes = w768 + act + kPdSplit * 2 * act; }
+      else if (k == "dec_ln") { idx = 3; bytes = (kPdSplit + 1) * 2 * act + 2 * act + act; }
+      else if (k == "dec_cross_attn") { idx = 5; bytes = static_cast<double>(n) * (2.0 * kEncTokens * kD * 2 + 2.0 * kD * 2); }
+      else if (k == "dec_fc1") { idx = 8; bytes = 4 * w768 + act + 4 * act; }
+      else if (k == "dec_fc2") { idx = 9; bytes = 4 * w768 + 4 * act + kPdSplit * 2 * act; }
+      else if (k == "dec_vocab") { idx = 24; bytes = 2.0 * kVocab * kD + act; }
+      if (idx < 0) { r = fail(h, MOCR_ERR_INVALID, "unknown kernel name %s", kernel); break; }
+      const PdStage& st = prog[idx];
+      switch (st.type) {
+        case PD_GEMM16: pd_gemm_kernel<16, 2><<<(st.N / 16) * st.ksplit, 128 * kPdStageKS, pd_gemm_smem_bytes(16), h->stream>>>(p, st); break;
+        case PD_GEMM32: pd_gemm_kernel<32, 2><<<(st.N / 32) * st.ksplit, 128 * kPdStageKS, pd_gemm_smem_bytes(32), h->stream>>>(p, st); break;
+        case PD_GEMM48: pd_gemm_kernel<48, 1><<<(st.N / 48) * st.ksplit, 128 * kPdStageKS, pd_gemm_smem_bytes(48), h->stream>>>(p, st); break;
+        case PD_ATTN_SELF: pd_attention_kernel<true><<<p.B * kHeads, 128, kPdAttnSmemBytes, h->stream>>>(p, st); break;
+        case PD_ATTN_CROSS: pd_attention_kernel<false><<<p.B * kHeads, 128, kPdAttnSmemBytes, h->stream>>>(p, st); break;
+        default: pd_ln_kernel<<<(p.B + kPdWarps - 1) / kPdWarps, kPdThreads, 0, h->stream>>>(p, st); break;
+      }
+      if (cudaGetLastError() != cudaSuccess) r = fail(h, MOCR_ERR_CUDA, "stage kernel launch failed");
+      ++h->launches;
+      flops = 0;
     } else {
       r = fail(h, MOCR_ERR_INVALID, "unknown kernel name %s", kernel);
     }
