@@ -143,6 +143,21 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
 // ------------------------------------------------------------------- math ---
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
+// erf-GELU with erf from Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, far below the bf16 output
+// it feeds): one MUFU.RCP, one MUFU.EX2 and a 5-term Horner instead of erff's ~30 instructions.
+// Used by the encoder MLP epilogue, where 38.7 M activations per layer made the epilogue, not the
+// tensor pipe, the bottleneck.
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = 1.0f - p * t * __expf(-z * z);     // erf(|x|/sqrt2)
+  return 0.5f * x * (1.0f + copysignf(e, x));
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -125,6 +125,7 @@ struct mocr_handle {
   int use_graph = 1;
   int use_pdl = 1;          // programmatic dependent launch between the decoder's stage kernels
   int steps_per_graph = 13; // decode steps captured in one CUDA graph (299 = 23 x 13)
+  int attn_grid = 384;      // CTAs of the decoder attention stage kernels (0 = one per (row, head) unit); 384 measured best at B = 64
   int decode_mode = 2;   // 2 = stage kernels in a CUDA graph (default), 1 = persistent cooperative kernel, 0 = first version (tcgen05 GEMMs)
 
   // ---- weights
@@ -743,7 +744,7 @@ int decode_step(mocr_handle* h, int n, int max_length, bool forced, bool tap) {
   a.tap_steps = max_length - 1;
   TRY(gemm(h, EPI_ARGMAX, h->head_bn, h->d_tb, h->head_dec, n, a));
   next_token_kernel<<<n, 256, 0, h->stream>>>(decode_state(h, forced, max_length), h->emb, h->part_max, h->part_idx,
-                                              kVocab / h->head_bn, kSepId);
+                                              2 * (kVocab / h->head_bn), kSepId);
   CK(cudaGetLastError());
   ++h->launches;
   return MOCR_OK;
@@ -844,14 +845,15 @@ int decode_stage_step(mocr_handle* h, const PdParams& p) {
   PdStage prog[kPdMaxStages];
   const int n_stages = pd_build_program(p, prog);
   const int row_ctas = (p.B + kPdWarps - 1) / kPdWarps;
+  const int attn_grid = h->attn_grid > 0 ? std::min(h->attn_grid, p.B * kHeads) : p.B * kHeads;
   for (int i = 0; i < n_stages; ++i) {
     const PdStage& st = prog[i];
     switch (st.type) {
       case PD_GEMM16: CK(launch_pdl(h, pd_gemm_kernel<16, 2>, (st.N / 16) * st.ksplit, 128 * kPdStageKS, pd_gemm_smem_bytes(16), p, st)); break;
       case PD_GEMM32: CK(launch_pdl(h, pd_gemm_kernel<32, 2>, (st.N / 32) * st.ksplit, 128 * kPdStageKS, pd_gemm_smem_bytes(32), p, st)); break;
       case PD_GEMM48: CK(launch_pdl(h, pd_gemm_kernel<48, 1>, (st.N / 48) * st.ksplit, 128 * kPdStageKS, pd_gemm_smem_bytes(48), p, st)); break;
-      case PD_ATTN_SELF: CK(launch_pdl(h, pd_attention_kernel<true>, p.B * kHeads, 128, kPdAttnSmemBytes, p, st)); break;
-      case PD_ATTN_CROSS: CK(launch_pdl(h, pd_attention_kernel<false>, p.B * kHeads, 128, kPdAttnSmemBytes, p, st)); break;
+      case PD_ATTN_SELF: CK(launch_pdl(h, pd_attention_kernel<true>, attn_grid, 128, kPdAttnSmemBytes, p, st)); break;
+      case PD_ATTN_CROSS: CK(launch_pdl(h, pd_attention_kernel<false>, attn_grid, 128, kPdAttnSmemBytes, p, st)); break;
       case PD_LN: CK(launch_pdl(h, pd_ln_kernel, row_ctas, kPdThreads, 0, p, st)); break;
       default: CK(launch_pdl(h, pd_next_kernel, row_ctas, kPdThreads, 0, p)); break;
     }
@@ -1026,8 +1028,8 @@ int create_impl(mocr_handle* h) {
     TRY(dmalloc(h, &h->self_k[l], static_cast<size_t>(B) * T * kD));
     TRY(dmalloc(h, &h->self_v[l], static_cast<size_t>(B) * T * kD));
   }
-  TRY(dmalloc(h, &h->part_max, static_cast<size_t>(h->brow_cap) * (kVocab / 32)));
-  TRY(dmalloc(h, &h->part_idx, static_cast<size_t>(h->brow_cap) * (kVocab / 32)));
+  TRY(dmalloc(h, &h->part_max, static_cast<size_t>(h->brow_cap) * 2 * (kVocab / 32)));
+  TRY(dmalloc(h, &h->part_idx, static_cast<size_t>(h->brow_cap) * 2 * (kVocab / 32)));
   TRY(dmalloc(h, &h->d_ids, static_cast<size_t>(B) * T));
   TRY(dmalloc(h, &h->d_forced, static_cast<size_t>(B) * T));
   TRY(dmalloc(h, &h->d_pos, static_cast<size_t>(B)));
@@ -1253,6 +1255,7 @@ int mocr_set_option(mocr_handle_t* h, const char* key, int value) {
   else if (k == "check_every" && value >= 1) h->check_every = value;
   else if (k == "use_graph") h->use_graph = value != 0;
   else if (k == "use_pdl") h->use_pdl = value != 0;
+  else if (k == "attn_grid" && value >= 0) h->attn_grid = value;
   else if (k == "steps_per_graph" && value >= 1 && value <= 64) h->steps_per_graph = value;
   else if (k == "decode_mode" && value >= 0 && value <= 2) h->decode_mode = value;
   else if (k == "decode_prof") h->decode_prof = value != 0;
@@ -1383,7 +1386,7 @@ int mocr_test_gemm(mocr_handle_t* h, int epi, int bn, int M, int N, int K, const
       g.resid = static_cast<const float*>(d_res);
       g.ldr = N;
     }
-    const int parts = N / bn;
+    const int parts = 2 * (N / bn);
     if (epi == EPI_ARGMAX) {
       CK(cudaMalloc(&d_pm, static_cast<size_t>(M) * parts * sizeof(float)));
       CK(cudaMalloc(&d_pi, static_cast<size_t>(M) * parts * sizeof(int)));

@@ -13,7 +13,8 @@
 //   * warp 1: single-thread tcgen05.mma issuer, UMMA 128 x BN x 16, fp32
 //     accumulators in TMEM, double-buffered (2 x BN columns) so the epilogue of
 //     tile i overlaps the main loop of tile i+1;
-//   * warps 2-5: epilogue - tcgen05.ld (32 lanes x 32 columns per warp), fused
+//   * warps 2-9: epilogue - two warps per TMEM lane quadrant, each owning half of the tile's
+//     columns; tcgen05.ld (32 lanes x 32 columns per instruction), fused
 //     bias / erf-GELU / fp32 residual / position-embedding / arg-max, direct
 //     vectorised global stores.
 #pragma once
@@ -38,8 +39,8 @@ struct GemmArgs {
   const float* resid;    // EPI_F32_RESID: [M, ldr] f32
   int ldr;
   const float* pos;      // EPI_PATCH: position table [197, 768] f32
-  float* part_max;       // EPI_ARGMAX: [M, N/BN]
-  int* part_idx;         // EPI_ARGMAX: [M, N/BN]
+  float* part_max;       // EPI_ARGMAX: [M, 2 * N/BN] (one entry per epilogue warp half)
+  int* part_idx;         // EPI_ARGMAX: [M, 2 * N/BN]
   float* logits;         // EPI_ARGMAX: optional f32 tap for parity tests (may be null):
   const int* step;       //   row r writes logits[(r * tap_steps + step[r]) * N ...]
   int tap_steps;
@@ -47,7 +48,8 @@ struct GemmArgs {
 
 constexpr int kGemmBM = 128;
 constexpr int kGemmBK = 64;
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (2 per TMEM lane quadrant)
+constexpr int kGemmEpiThreads = 256;
 
 template <int BN>
 struct GemmCfg {
@@ -93,7 +95,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 128);
+      mbar_init(&acc_empty[s], kGemmEpiThreads);
     }
     fence_barrier_init();
   }
@@ -158,6 +160,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   } else {
     // ------------------------------------------------ epilogue --------------
     const int quad = warp & 3;                    // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;             // which half of the tile's 32-column chunks it owns
+    constexpr int kChunks = BN / 32;
+    const int c_lo = half == 0 ? 0 : (kChunks + 1) / 2, c_hi = half == 0 ? (kChunks + 1) / 2 : kChunks;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
@@ -172,7 +177,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * BN);
 
       float best = -INFINITY;
-      int best_i = 0;
+      int best_i = 0x7fffffff;
       int out_row = row;
       const float* extra = nullptr;               // per-row fp32 addend (residual or position row)
       if (EPI == EPI_F32_RESID) extra = args.resid + static_cast<size_t>(row) * args.ldr;
@@ -182,7 +187,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         extra = args.pos + static_cast<size_t>(1 + p) * kD;
       }
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = c_lo; c < c_hi; ++c) {
         uint32_t v[32];
         tmem_ld32(taddr + static_cast<uint32_t>(c * 32), v);
         tmem_ld_wait();
@@ -199,7 +204,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (EPI == EPI_BF16 || EPI == EPI_BF16_GELU) {
           if (EPI == EPI_BF16_GELU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+            for (int j = 0; j < 32; ++j) f[j] = gelu_erf_fast(f[j]);
           }
           if (row_ok) {
             uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(args.out) + static_cast<size_t>(row) * args.ldo + col0);
@@ -244,8 +249,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
       }
       if (EPI == EPI_ARGMAX && row_ok) {
-        args.part_max[static_cast<size_t>(row) * n_tiles + nt] = best;
-        args.part_idx[static_cast<size_t>(row) * n_tiles + nt] = best_i;
+        args.part_max[(static_cast<size_t>(row) * n_tiles + nt) * 2 + half] = best;
+        args.part_idx[(static_cast<size_t>(row) * n_tiles + nt) * 2 + half] = best_i;
       }
       tc_fence_before();
       mbar_arrive(&acc_empty[as]);
