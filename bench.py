@@ -282,7 +282,7 @@ def run_b200(args, rank, local_rank, world):
             ach = k_bytes / (k_ms * 1e-3) / 1e9
             roof = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
                     "traffic": None, "peak_source": peaks["source"], "ms_per_launch": k_ms, "algorithmic_bytes": k_bytes,
-                    "note": "back-to-back launches on warm L2 (the 77 MB encoder K/V of 64 crops fit the 126 MB L2)"}
+                    "note": "50 back-to-back launches with programmatic dependent launch, exactly as in the decode loop; L2 warm"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

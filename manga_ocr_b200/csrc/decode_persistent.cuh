@@ -199,9 +199,38 @@ struct GridBarrier {
 // With programmatic dependent launch the next stage kernel is already resident while this one
 // runs: everything before wait() (weight / encoder-K/V prefetch, index arithmetic) overlaps the
 // previous stage, and wait() returns once the previous grid has completed and flushed.
+__device__ __forceinline__ long long global_timer_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 struct NullBarrier {
-  __device__ __forceinline__ void arrive() {}
-  __device__ __forceinline__ void wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+  long long* prof;      // optional timeline (option decode_prof): prof[0] = entry count, then (tag, t_entry, t_ready, t_done) records
+  int tag;
+  long long t_entry, t_ready;
+  __device__ __forceinline__ void begin(long long* prof_, int tag_) {
+    prof = prof_;
+    tag = tag_;
+    if (prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0) t_entry = global_timer_ns();
+  }
+  __device__ __forceinline__ void arrive() {
+    if (prof != nullptr && blockIdx.x == 0) {
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const int i = static_cast<int>(atomicAdd(reinterpret_cast<unsigned long long*>(prof), 1ull));
+        if (i < 1000) {
+          prof[1 + 4 * i] = tag;
+          prof[2 + 4 * i] = t_entry;
+          prof[3 + 4 * i] = t_ready;
+          prof[4 + 4 * i] = global_timer_ns();
+        }
+      }
+    }
+  }
+  __device__ __forceinline__ void wait() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0) t_ready = global_timer_ns();
+  }
 };
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
@@ -242,11 +271,21 @@ __device__ __forceinline__ void pd_gemm_stage(Bar& bar, float* red, const PdPara
     // requested before the grid barrier.
     uint4 wf[2][CH][NTL], af[2][CH][2];
     const __nv_bfloat16* wbase = st.W + static_cast<size_t>(n0 + g) * K + k0 + 8 * t;
+    float bias_v[kIters];
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) bias_v[it] = 0.f;
     if (has_tile) {
 #pragma unroll
       for (int c = 0; c < CH; ++c)
 #pragma unroll
         for (int j = 0; j < NTL; ++j) wf[0][c][j] = ldg_nc16(wbase + static_cast<size_t>(8 * j) * K + c * 32);
+      if (epi != PD_F32_PARTIAL) {       // the bias vector is a constant too (a fresh kernel starts with a cold L1)
+#pragma unroll
+        for (int it = 0; it < kIters; ++it) {
+          const int i = tid + it * kThreads;
+          if (i < kPdRowsPerBlock * NT) bias_v[it] = __ldg(st.bias + n0 + i % NT);
+        }
+      }
     }
     if (!waited) {
       bar.wait();
@@ -322,9 +361,8 @@ __device__ __forceinline__ void pd_gemm_stage(Bar& bar, float* red, const PdPara
       for (int it = 0; it < kIters; ++it) {
         const int i = tid + it * kThreads;
         const int rl = i / NT, c = i - rl * NT;
-        float v = 0.f;
+        float v = bias_v[it];
         if (i < kPdRowsPerBlock * NT) {
-          if (epi != PD_F32_PARTIAL) v = __ldg(st.bias + n0 + c);      // L1-resident after the first token
 #pragma unroll
           for (int sl = 0; sl < KS; ++sl) v += red[(sl * kPdRowsPerBlock + rl) * (NT + 1) + c];
         }
@@ -407,11 +445,25 @@ __device__ __forceinline__ void pd_ln_row_warp(const float (&v)[24], const float
 // x, xb = LayerNorm( [gelu]( sum_parts src[part] + bias ) + resid )   (BERT post-LN, modeling_bert.py:
 // 297, 355, 484).  The split-K partials of the producing projection are added here in a fixed order.
 template <class Bar>
-__device__ __forceinline__ void pd_ln_stage(Bar& bar, const PdParams& p, const PdStage& st) {
+__device__ __forceinline__ void pd_ln_stage(Bar& bar, const PdParams& p, const PdStage& st, int n_ctas) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int B = p.B;
+  const int wpc = blockDim.x >> 5;
+  const int r0 = blockIdx.x * wpc + warp;
+  // gamma, beta and the producing projection's bias are constants: request them before the
+  // dependency wait (a fresh kernel starts with a cold L1, each would cost an L2 round trip after it)
+  float4 gm[6], bt[6], bs[6];
+  if (r0 < B) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const int c = (lane + 32 * i) * 4;
+      gm[i] = __ldg(reinterpret_cast<const float4*>(st.g + c));
+      bt[i] = __ldg(reinterpret_cast<const float4*>(st.b + c));
+      bs[i] = __ldg(reinterpret_cast<const float4*>(st.bias + c));
+    }
+  }
   bar.wait();
-  for (int r = blockIdx.x * kPdWarps + warp; r < B; r += gridDim.x * kPdWarps) {
+  for (int r = r0; r < B; r += n_ctas * wpc) {
     // every load is requested before the first add (the .cg loads are ordered volatile asm: a load
     // placed after a dependent add would cost a full L2 round trip each)
     float4 part[kPdSplit][6], rs[6];
@@ -424,51 +476,128 @@ __device__ __forceinline__ void pd_ln_stage(Bar& bar, const PdParams& p, const P
       for (int i = 0; i < 6; ++i) rs[i] = ldg_cg_f4(st.resid + static_cast<size_t>(r) * kD + (lane + 32 * i) * 4);
     }
     float v[24];
+    float s = 0.f;
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
-      const int c = (lane + 32 * i) * 4;
-      float4 f = __ldg(reinterpret_cast<const float4*>(st.bias + c));
+      float4 f = bs[i];
 #pragma unroll
       for (int pt = 0; pt < kPdSplit; ++pt) { f.x += part[pt][i].x; f.y += part[pt][i].y; f.z += part[pt][i].z; f.w += part[pt][i].w; }
       if (st.epi & 1) { f.x = gelu_erf(f.x); f.y = gelu_erf(f.y); f.z = gelu_erf(f.z); f.w = gelu_erf(f.w); }
       if (st.resid != nullptr) { f.x += rs[i].x; f.y += rs[i].y; f.z += rs[i].z; f.w += rs[i].w; }
       v[4 * i] = f.x; v[4 * i + 1] = f.y; v[4 * i + 2] = f.z; v[4 * i + 3] = f.w;
+      s += (f.x + f.y) + (f.z + f.w);
     }
-    pd_ln_row_warp(v, st.g, st.b, st.of != nullptr ? st.of + static_cast<size_t>(r) * kD : nullptr, st.ob + static_cast<size_t>(r) * kD, lane);
+    const float mean = warp_sum(s) * (1.0f / kD);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 24; ++i) q += (v[i] - mean) * (v[i] - mean);
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / kD) + kLnEps);
+    float* x = st.of != nullptr ? st.of + static_cast<size_t>(r) * kD : nullptr;
+    __nv_bfloat16* xb = st.ob + static_cast<size_t>(r) * kD;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const int c = (lane + 32 * i) * 4;
+      float4 yv;
+      yv.x = (v[4 * i] - mean) * rstd * gm[i].x + bt[i].x;
+      yv.y = (v[4 * i + 1] - mean) * rstd * gm[i].y + bt[i].y;
+      yv.z = (v[4 * i + 2] - mean) * rstd * gm[i].z + bt[i].z;
+      yv.w = (v[4 * i + 3] - mean) * rstd * gm[i].w + bt[i].w;
+      if (x != nullptr) *reinterpret_cast<float4*>(x + c) = yv;
+      uint2 pk;
+      pk.x = pack_bf16(yv.x, yv.y);
+      pk.y = pack_bf16(yv.z, yv.w);
+      *reinterpret_cast<uint2*>(xb + c) = pk;
+    }
   }
   bar.arrive();
 }
 
-__device__ __forceinline__ void pd_embed_row_warp(const PdParams& p, int r, int tok, int position, int lane) {
-  float v[24];
+struct PdEmbedConsts {
+  float4 gm[6], bt[6], ty[6];
+};
+__device__ __forceinline__ void pd_embed_consts(const PdParams& p, int lane, PdEmbedConsts& k) {
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
     const int c = (lane + 32 * i) * 4;
-    const float4 a = __ldg(reinterpret_cast<const float4*>(p.emb.word + static_cast<size_t>(tok) * kD + c));
-    const float4 b = __ldg(reinterpret_cast<const float4*>(p.emb.type0 + c));
-    const float4 d = __ldg(reinterpret_cast<const float4*>(p.emb.posemb + static_cast<size_t>(position) * kD + c));
-    v[4 * i] = a.x + b.x + d.x; v[4 * i + 1] = a.y + b.y + d.y; v[4 * i + 2] = a.z + b.z + d.z; v[4 * i + 3] = a.w + b.w + d.w;
+    k.gm[i] = __ldg(reinterpret_cast<const float4*>(p.emb.gamma + c));
+    k.bt[i] = __ldg(reinterpret_cast<const float4*>(p.emb.beta + c));
+    k.ty[i] = __ldg(reinterpret_cast<const float4*>(p.emb.type0 + c));
   }
-  pd_ln_row_warp(v, p.emb.gamma, p.emb.beta, p.x + static_cast<size_t>(r) * kD, p.xb + static_cast<size_t>(r) * kD, lane);
+}
+
+// x = LayerNorm(word[tok] + type[0] + pos[position])   (modeling_bert.py:102-111), one warp per row
+__device__ __forceinline__ void pd_embed_row_warp(const PdParams& p, const PdEmbedConsts& k, int r, int tok, int position, int lane) {
+  float4 a[6], d[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const int c = (lane + 32 * i) * 4;
+    a[i] = __ldg(reinterpret_cast<const float4*>(p.emb.word + static_cast<size_t>(tok) * kD + c));
+    d[i] = __ldg(reinterpret_cast<const float4*>(p.emb.posemb + static_cast<size_t>(position) * kD + c));
+  }
+  float v[24];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    v[4 * i] = a[i].x + k.ty[i].x + d[i].x; v[4 * i + 1] = a[i].y + k.ty[i].y + d[i].y;
+    v[4 * i + 2] = a[i].z + k.ty[i].z + d[i].z; v[4 * i + 3] = a[i].w + k.ty[i].w + d[i].w;
+    s += (v[4 * i] + v[4 * i + 1]) + (v[4 * i + 2] + v[4 * i + 3]);
+  }
+  const float mean = warp_sum(s) * (1.0f / kD);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 24; ++i) q += (v[i] - mean) * (v[i] - mean);
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / kD) + kLnEps);
+  float* x = p.x + static_cast<size_t>(r) * kD;
+  __nv_bfloat16* xb = p.xb + static_cast<size_t>(r) * kD;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const int c = (lane + 32 * i) * 4;
+    float4 yv;
+    yv.x = (v[4 * i] - mean) * rstd * k.gm[i].x + k.bt[i].x;
+    yv.y = (v[4 * i + 1] - mean) * rstd * k.gm[i].y + k.bt[i].y;
+    yv.z = (v[4 * i + 2] - mean) * rstd * k.gm[i].z + k.bt[i].z;
+    yv.w = (v[4 * i + 3] - mean) * rstd * k.gm[i].w + k.bt[i].w;
+    *reinterpret_cast<float4*>(x + c) = yv;
+    uint2 pk;
+    pk.x = pack_bf16(yv.x, yv.y);
+    pk.y = pack_bf16(yv.z, yv.w);
+    *reinterpret_cast<uint2*>(xb + c) = pk;
+  }
 }
 
 // Greedy step tail (generation/utils.py:2793-2805, stopping_criteria.py:76,470): final arg-max over
 // the vocabulary tiles, EOS / max_length rules, append, embed the next input token.
 template <class Bar>
-__device__ __forceinline__ void pd_next_token_stage(Bar& bar, const PdParams& p) {
-  bar.wait();
+__device__ __forceinline__ void pd_next_token_stage(Bar& bar, const PdParams& p, int n_ctas) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int r = blockIdx.x * kPdWarps + warp; r < p.B; r += gridDim.x * kPdWarps) {
+  const int wpc = blockDim.x >> 5;
+  const int r0 = blockIdx.x * wpc + warp;
+  PdEmbedConsts k;
+  if (r0 < p.B) pd_embed_consts(p, lane, k);         // constants: before the dependency wait
+  bar.wait();
+  for (int r = r0; r < p.B; r += n_ctas * wpc) {
+    // one round trip: state and the 128 per-tile (max, arg-max) partials together
     const int ps = ldg_cg_s32(p.pos + r);
-    const bool was_finished = ldg_cg_s32(p.finished + r) != 0;
+    const int fin0 = ldg_cg_s32(p.finished + r);
+    float pv[(kPdVocabTiles + 31) / 32];
+    int pi[(kPdVocabTiles + 31) / 32];
+#pragma unroll
+    for (int j = 0; j < (kPdVocabTiles + 31) / 32; ++j) {
+      const int i = lane + 32 * j;
+      pv[j] = -INFINITY;
+      pi[j] = 0x7fffffff;
+      if (i < kPdVocabTiles) {
+        pv[j] = ldg_cg_f32(p.part_max + static_cast<size_t>(r) * kPdVocabTiles + i);
+        pi[j] = ldg_cg_s32(p.part_idx + static_cast<size_t>(r) * kPdVocabTiles + i);
+      }
+    }
+    const bool was_finished = fin0 != 0;
     if (was_finished && (p.forced == nullptr || ps >= p.max_len - 1)) continue;
     float bv = -INFINITY;
     int bi = 0x7fffffff;
-    for (int i = lane; i < kPdVocabTiles; i += 32) {
-      const float v = ldg_cg_f32(p.part_max + static_cast<size_t>(r) * kPdVocabTiles + i);
-      const int ix = ldg_cg_s32(p.part_idx + static_cast<size_t>(r) * kPdVocabTiles + i);
-      if (v > bv || (v == bv && ix < bi)) { bv = v; bi = ix; }
-    }
+#pragma unroll
+    for (int j = 0; j < (kPdVocabTiles + 31) / 32; ++j)
+      if (pv[j] > bv || (pv[j] == bv && pi[j] < bi)) { bv = pv[j]; bi = pi[j]; }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
@@ -488,7 +617,7 @@ __device__ __forceinline__ void pd_next_token_stage(Bar& bar, const PdParams& p)
     }
     if (p.forced != nullptr && np < p.max_len) tok = p.forced[static_cast<size_t>(r) * p.max_len + np];
     if (np >= p.max_len - 1 || np >= kMaxPos) continue;
-    pd_embed_row_warp(p, r, tok, np, lane);
+    pd_embed_row_warp(p, k, r, tok, np, lane);
   }
   bar.arrive();
 }
@@ -586,8 +715,14 @@ __device__ __forceinline__ void pd_attention_stage(Bar& bar, uint8_t* smem, cons
   // The group's work is one stream of 112-key blocks (unit after unit) flowing through a two-deep
   // ring of staging buffers: block n+1 is requested before block n is reduced.
   PdAttnUnit cur = make_unit(u0 < units ? u0 : 0, false);
-  if (!SELF) {   // encoder K/V never change during a decode: request the first block before the barrier
-    if (u0 < units) pd_attn_request(stage0, cur, key_stride, 0, gt);
+  bool pre2 = false;       // both blocks of the first unit were requested before the dependency wait
+  if (!SELF) {   // encoder K/V never change during a decode: request the first unit (2 blocks) before the wait
+    if (u0 < units) {
+      pd_attn_request(stage0, cur, key_stride, 0, gt);
+      cp_async_commit();
+      pd_attn_request(stage1, cur, key_stride, kBlockKeys, gt);
+      pre2 = true;
+    }
     cp_async_commit();
   }
   bar.wait();
@@ -596,7 +731,8 @@ __device__ __forceinline__ void pd_attention_stage(Bar& bar, uint8_t* smem, cons
     cur = make_unit(u, true);
     while (cur.n_keys == 0 && u + ustride < units) { u += ustride; cur = make_unit(u, true); }   // skip finished rows
     if (SELF || u != u0) {
-      if (!SELF) cp_async_wait_group<0>();          // (a prefetched block of a finished row is dropped)
+      if (!SELF) cp_async_wait_group<0>();          // (the prefetched blocks of a finished row are dropped)
+      pre2 = false;
       if (cur.n_keys > 0) pd_attn_request(stage0, cur, key_stride, 0, gt);
       cp_async_commit();
     }
@@ -620,7 +756,8 @@ __device__ __forceinline__ void pd_attention_stage(Bar& bar, uint8_t* smem, cons
       }
       if (!found) nu = units;
     }
-    if (nu < units) pd_attn_request(par ? stage0 : stage1, nxt, key_stride, nj0, gt);
+    if (pre2) pre2 = false;                       // (u0, block 1) is already on its way
+    else if (nu < units) pd_attn_request(par ? stage0 : stage1, nxt, key_stride, nj0, gt);
     cp_async_commit();
     // ---- first block of a unit: the query and a fresh online-softmax state
     if (j0 == 0) {
@@ -806,8 +943,8 @@ template <int NT, int CH>
 __device__ __noinline__ void pd_gemm_call(GridBarrier& bar, float* red, const PdParams& p, const PdStage& st) { pd_gemm_stage<NT, CH, kPdKSlices>(bar, red, p, st); }
 template <bool SELF>
 __device__ __noinline__ void pd_attention_call(GridBarrier& bar, uint8_t* smem, const PdParams& p, const PdStage& st) { pd_attention_stage<SELF>(bar, smem, p, st); }
-__device__ __noinline__ void pd_ln_call(GridBarrier& bar, const PdParams& p, const PdStage& st) { pd_ln_stage(bar, p, st); }
-__device__ __noinline__ void pd_next_call(GridBarrier& bar, const PdParams& p) { pd_next_token_stage(bar, p); }
+__device__ __noinline__ void pd_ln_call(GridBarrier& bar, const PdParams& p, const PdStage& st) { pd_ln_stage(bar, p, st, gridDim.x); }
+__device__ __noinline__ void pd_next_call(GridBarrier& bar, const PdParams& p) { pd_next_token_stage(bar, p, gridDim.x); }
 
 __global__ void __launch_bounds__(kPdThreads, 1) decode_persistent_kernel(const __grid_constant__ PdParams p) {
   extern __shared__ __align__(128) uint8_t pd_smem[];
@@ -827,7 +964,9 @@ __global__ void __launch_bounds__(kPdThreads, 1) decode_persistent_kernel(const 
       p.pos[r] = 0;
       p.finished[r] = p.max_len <= 1 ? 1 : 0;
     }
-    pd_embed_row_warp(p, r, 2, 0, lane);
+    PdEmbedConsts ek;
+    pd_embed_consts(p, lane, ek);
+    pd_embed_row_warp(p, ek, r, 2, 0, lane);
   }
   bar.arrive();       // (also orders the program table: arrive() starts with __syncthreads)
   const int n_stages = s_nstages;
@@ -867,29 +1006,61 @@ __global__ void __launch_bounds__(kPdThreads, 1) decode_persistent_kernel(const 
 
 constexpr int kPdStageKS = 4;                  // K-slices (warps per m-tile) of the stage-kernel GEMMs: 512 threads
 constexpr int pd_gemm_smem_bytes(int nt) { return kPdStageKS * kPdRowsPerBlock * (nt + 1) * 4; }
+// `tail` (PD_LN or PD_NEXT, or type < 0 for none) is the row stage that consumes this GEMM: it is
+// fused into the same launch.  Every CTA publishes its tile with a release-add on `counter`; the
+// first `tail_ctas` CTAs then wait until all tiles have arrived and run the row stage.  All CTAs
+// of the grid are co-resident (grid <= SM count, one 512-thread CTA per SM), so the wait cannot
+// deadlock; it replaces a 3.5 us dependent launch by a ~1 us counter poll.  The counters are
+// zeroed by the first kernel of every token step (flag kPdZeroCounters).
+constexpr int kPdCounters = 16;
+constexpr int kPdZeroCounters = 0x100;          // PdStage::epi flag of the step's first GEMM
+
 template <int NT, int CH>
-__global__ void __launch_bounds__(128 * kPdStageKS, 1) pd_gemm_kernel(const __grid_constant__ PdParams p, const __grid_constant__ PdStage st) {
+__global__ void __launch_bounds__(128 * kPdStageKS, 1) pd_gemm_kernel(const __grid_constant__ PdParams p, const __grid_constant__ PdStage st,
+                                                                       const __grid_constant__ PdStage tail, unsigned int* counters, int slot,
+                                                                       int tail_ctas) {
   extern __shared__ __align__(16) float red[];      // kPdStageKS * 64 * (NT + 1) floats (pd_gemm_smem_bytes)
   NullBarrier bar;
+  bar.begin(p.prof, st.type * 100 + st.ksplit * 10 + (st.K > 1000 ? 1 : 0));
   pdl_launch_dependents();
-  pd_gemm_stage<NT, CH, kPdStageKS>(bar, red, p, st);
+  PdStage mine = st;
+  mine.epi = st.epi & 0xff;
+  pd_gemm_stage<NT, CH, kPdStageKS>(bar, red, p, mine);
+  if ((st.epi & kPdZeroCounters) && blockIdx.x == 0 && threadIdx.x < kPdCounters && threadIdx.x != slot) counters[threadIdx.x] = 0u;
+  if (tail.type < 0) return;
+  __syncthreads();                                   // the whole tile is written
+  if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(counters + slot), "r"(1u) : "memory");
+  if (blockIdx.x >= tail_ctas) return;
+  if (threadIdx.x == 0) {
+    const long long t0 = clock64();
+    while (ld_poll_u32(counters + slot) < gridDim.x) {
+      if (clock64() - t0 > 8000000000LL) __trap();
+    }
+  }
+  __syncthreads();
+  struct Passed { __device__ __forceinline__ void arrive() {} __device__ __forceinline__ void wait() {} } done;
+  if (tail.type == PD_LN) pd_ln_stage(done, p, tail, tail_ctas);
+  else pd_next_token_stage(done, p, tail_ctas);
 }
 template <bool SELF>
 __global__ void __launch_bounds__(128) pd_attention_kernel(const __grid_constant__ PdParams p, const __grid_constant__ PdStage st) {
   extern __shared__ __align__(128) uint8_t pd_smem[];
   NullBarrier bar;
+  bar.begin(p.prof, st.type * 100);
   pdl_launch_dependents();
   pd_attention_stage<SELF>(bar, pd_smem, p, st);
 }
 __global__ void __launch_bounds__(kPdThreads) pd_ln_kernel(const __grid_constant__ PdParams p, const __grid_constant__ PdStage st) {
   NullBarrier bar;
+  bar.begin(p.prof, st.type * 100);
   pdl_launch_dependents();
-  pd_ln_stage(bar, p, st);
+  pd_ln_stage(bar, p, st, gridDim.x);
 }
 __global__ void __launch_bounds__(kPdThreads) pd_next_kernel(const __grid_constant__ PdParams p) {
   NullBarrier bar;
+  bar.begin(p.prof, PD_NEXT * 100);
   pdl_launch_dependents();
-  pd_next_token_stage(bar, p);
+  pd_next_token_stage(bar, p, gridDim.x);
 }
 // ids[b][0] = [CLS], pos = 0, finished = 0, x = embed([CLS], 0)
 __global__ void __launch_bounds__(kPdThreads) pd_begin_kernel(const __grid_constant__ PdParams p) {
@@ -902,7 +1073,9 @@ __global__ void __launch_bounds__(kPdThreads) pd_begin_kernel(const __grid_const
       p.pos[r] = 0;
       p.finished[r] = p.max_len <= 1 ? 1 : 0;
     }
-    pd_embed_row_warp(p, r, 2, 0, lane);
+    PdEmbedConsts ek;
+    pd_embed_consts(p, lane, ek);
+    pd_embed_row_warp(p, ek, r, 2, 0, lane);
   }
 }
 

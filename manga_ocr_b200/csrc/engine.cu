@@ -125,6 +125,7 @@ struct mocr_handle {
   int use_graph = 1;
   int use_pdl = 1;          // programmatic dependent launch between the decoder's stage kernels
   int steps_per_graph = 13; // decode steps captured in one CUDA graph (299 = 23 x 13)
+  int fuse_rows = 0;        // fuse LayerNorm / next-token row stages into the GEMM launch that feeds them
   int attn_grid = 384;      // CTAs of the decoder attention stage kernels (0 = one per (row, head) unit); 384 measured best at B = 64
   int decode_mode = 2;   // 2 = stage kernels in a CUDA graph (default), 1 = persistent cooperative kernel, 0 = first version (tcgen05 GEMMs)
 
@@ -166,6 +167,7 @@ struct mocr_handle {
   int* h_flags = nullptr;             // pinned [max_batch]
   int* h_steps = nullptr;             // pinned [1]
   unsigned int* d_barrier = nullptr;  // grid barrier counter of the persistent decoder
+  unsigned int* d_counters = nullptr; // arrival counters of the fused GEMM + row-stage kernels
   int* d_steps = nullptr;
   float* d_y = nullptr;               // [3, brow_cap, 768] split-K partials of the persistent decoder (projections feeding a LN)
   float* d_yq = nullptr;              // [3, brow_cap, 768] split-K partials of the cross-attention query
@@ -845,17 +847,34 @@ int decode_stage_step(mocr_handle* h, const PdParams& p) {
   PdStage prog[kPdMaxStages];
   const int n_stages = pd_build_program(p, prog);
   const int row_ctas = (p.B + kPdWarps - 1) / kPdWarps;
+  const int tail_ctas = (p.B + 4 * kPdStageKS - 1) / (4 * kPdStageKS);      // 16 warps per GEMM CTA, one row each
   const int attn_grid = h->attn_grid > 0 ? std::min(h->attn_grid, p.B * kHeads) : p.B * kHeads;
+  PdStage none{};
+  none.type = -1;
+  int slot = 0;
   for (int i = 0; i < n_stages; ++i) {
-    const PdStage& st = prog[i];
-    switch (st.type) {
-      case PD_GEMM16: CK(launch_pdl(h, pd_gemm_kernel<16, 2>, (st.N / 16) * st.ksplit, 128 * kPdStageKS, pd_gemm_smem_bytes(16), p, st)); break;
-      case PD_GEMM32: CK(launch_pdl(h, pd_gemm_kernel<32, 2>, (st.N / 32) * st.ksplit, 128 * kPdStageKS, pd_gemm_smem_bytes(32), p, st)); break;
-      case PD_GEMM48: CK(launch_pdl(h, pd_gemm_kernel<48, 1>, (st.N / 48) * st.ksplit, 128 * kPdStageKS, pd_gemm_smem_bytes(48), p, st)); break;
-      case PD_ATTN_SELF: CK(launch_pdl(h, pd_attention_kernel<true>, attn_grid, 128, kPdAttnSmemBytes, p, st)); break;
-      case PD_ATTN_CROSS: CK(launch_pdl(h, pd_attention_kernel<false>, attn_grid, 128, kPdAttnSmemBytes, p, st)); break;
-      case PD_LN: CK(launch_pdl(h, pd_ln_kernel, row_ctas, kPdThreads, 0, p, st)); break;
-      default: CK(launch_pdl(h, pd_next_kernel, row_ctas, kPdThreads, 0, p)); break;
+    PdStage st = prog[i];
+    if (st.type == PD_GEMM16 || st.type == PD_GEMM32 || st.type == PD_GEMM48) {
+      // fuse the row stage that consumes this GEMM (LayerNorm or next-token) into the same launch
+      const PdStage* tail = &none;
+      if (h->fuse_rows && i + 1 < n_stages && (prog[i + 1].type == PD_LN || prog[i + 1].type == PD_NEXT)) tail = &prog[i + 1];
+      if (i == 0) st.epi |= kPdZeroCounters;
+      const int nt = st.type == PD_GEMM16 ? 16 : (st.type == PD_GEMM32 ? 32 : 48);
+      const int grid = (st.N / nt) * st.ksplit;
+      const int tc = std::min(tail_ctas, grid);
+      const int my_slot = tail->type >= 0 ? slot++ : kPdCounters - 1;
+      if (st.type == PD_GEMM16) CK(launch_pdl(h, pd_gemm_kernel<16, 2>, grid, 128 * kPdStageKS, pd_gemm_smem_bytes(16), p, st, *tail, h->d_counters, my_slot, tc));
+      else if (st.type == PD_GEMM32) CK(launch_pdl(h, pd_gemm_kernel<32, 2>, grid, 128 * kPdStageKS, pd_gemm_smem_bytes(32), p, st, *tail, h->d_counters, my_slot, tc));
+      else CK(launch_pdl(h, pd_gemm_kernel<48, 1>, grid, 128 * kPdStageKS, pd_gemm_smem_bytes(48), p, st, *tail, h->d_counters, my_slot, tc));
+      if (tail->type >= 0) ++i;
+    } else if (st.type == PD_ATTN_SELF) {
+      CK(launch_pdl(h, pd_attention_kernel<true>, attn_grid, 128, kPdAttnSmemBytes, p, st));
+    } else if (st.type == PD_ATTN_CROSS) {
+      CK(launch_pdl(h, pd_attention_kernel<false>, attn_grid, 128, kPdAttnSmemBytes, p, st));
+    } else if (st.type == PD_LN) {
+      CK(launch_pdl(h, pd_ln_kernel, row_ctas, kPdThreads, 0, p, st));
+    } else {
+      CK(launch_pdl(h, pd_next_kernel, row_ctas, kPdThreads, 0, p));
     }
     ++h->launches;
   }
@@ -892,6 +911,7 @@ int decode(mocr_handle* h, int max_length, const int32_t* forced_ids) {
     return MOCR_OK;
   }
   const bool stage_mode = h->decode_mode == 2;
+  if (stage_mode && h->decode_prof) CK(cudaMemsetAsync(h->d_prof, 0, 8, h->stream));
   const PdParams pdp = make_pd_params(h, n, max_length, forced, tap);
   auto begin = [&]() -> int {
     if (stage_mode) CK(launch_pdl(h, pd_begin_kernel, (n + kPdWarps - 1) / kPdWarps, kPdThreads, 0, pdp));
@@ -1036,6 +1056,7 @@ int create_impl(mocr_handle* h) {
   TRY(dmalloc(h, &h->d_finished, static_cast<size_t>(B)));
   TRY(dmalloc(h, &h->d_zero, static_cast<size_t>(B)));
   TRY(dmalloc(h, &h->d_barrier, 4));
+  TRY(dmalloc(h, &h->d_counters, kPdCounters));
   TRY(dmalloc(h, &h->d_steps, 4));
   TRY(dmalloc(h, &h->d_prof, 4096));
   CK(cudaMallocHost(reinterpret_cast<void**>(&h->h_steps), sizeof(int)));
@@ -1256,6 +1277,7 @@ int mocr_set_option(mocr_handle_t* h, const char* key, int value) {
   else if (k == "use_graph") h->use_graph = value != 0;
   else if (k == "use_pdl") h->use_pdl = value != 0;
   else if (k == "attn_grid" && value >= 0) h->attn_grid = value;
+  else if (k == "fuse_rows") h->fuse_rows = value != 0;
   else if (k == "steps_per_graph" && value >= 1 && value <= 64) h->steps_per_graph = value;
   else if (k == "decode_mode" && value >= 0 && value <= 2) h->decode_mode = value;
   else if (k == "decode_prof") h->decode_prof = value != 0;
@@ -1315,15 +1337,20 @@ int mocr_time_kernel(mocr_handle_t* h, const char* kernel, int iters, float* ms_
       else if (k == "dec_vocab") { idx = 24; bytes = 2.0 * kVocab * kD + act; }
       if (idx < 0) { r = fail(h, MOCR_ERR_INVALID, "unknown kernel name %s", kernel); break; }
       const PdStage& st = prog[idx];
+      PdStage none{};
+      none.type = -1;
+      cudaError_t le = cudaSuccess;
+      // launched exactly as in the decode loop (programmatic dependent launch: the next launch's
+      // constant / K-V prefetch overlaps the tail of the previous one)
       switch (st.type) {
-        case PD_GEMM16: pd_gemm_kernel<16, 2><<<(st.N / 16) * st.ksplit, 128 * kPdStageKS, pd_gemm_smem_bytes(16), h->stream>>>(p, st); break;
-        case PD_GEMM32: pd_gemm_kernel<32, 2><<<(st.N / 32) * st.ksplit, 128 * kPdStageKS, pd_gemm_smem_bytes(32), h->stream>>>(p, st); break;
-        case PD_GEMM48: pd_gemm_kernel<48, 1><<<(st.N / 48) * st.ksplit, 128 * kPdStageKS, pd_gemm_smem_bytes(48), h->stream>>>(p, st); break;
-        case PD_ATTN_SELF: pd_attention_kernel<true><<<p.B * kHeads, 128, kPdAttnSmemBytes, h->stream>>>(p, st); break;
-        case PD_ATTN_CROSS: pd_attention_kernel<false><<<p.B * kHeads, 128, kPdAttnSmemBytes, h->stream>>>(p, st); break;
-        default: pd_ln_kernel<<<(p.B + kPdWarps - 1) / kPdWarps, kPdThreads, 0, h->stream>>>(p, st); break;
+        case PD_GEMM16: le = launch_pdl(h, pd_gemm_kernel<16, 2>, (st.N / 16) * st.ksplit, 128 * kPdStageKS, pd_gemm_smem_bytes(16), p, st, none, h->d_counters, kPdCounters - 1, 0); break;
+        case PD_GEMM32: le = launch_pdl(h, pd_gemm_kernel<32, 2>, (st.N / 32) * st.ksplit, 128 * kPdStageKS, pd_gemm_smem_bytes(32), p, st, none, h->d_counters, kPdCounters - 1, 0); break;
+        case PD_GEMM48: le = launch_pdl(h, pd_gemm_kernel<48, 1>, (st.N / 48) * st.ksplit, 128 * kPdStageKS, pd_gemm_smem_bytes(48), p, st, none, h->d_counters, kPdCounters - 1, 0); break;
+        case PD_ATTN_SELF: le = launch_pdl(h, pd_attention_kernel<true>, h->attn_grid > 0 ? std::min(h->attn_grid, p.B * kHeads) : p.B * kHeads, 128, kPdAttnSmemBytes, p, st); break;
+        case PD_ATTN_CROSS: le = launch_pdl(h, pd_attention_kernel<false>, h->attn_grid > 0 ? std::min(h->attn_grid, p.B * kHeads) : p.B * kHeads, 128, kPdAttnSmemBytes, p, st); break;
+        default: le = launch_pdl(h, pd_ln_kernel, (p.B + kPdWarps - 1) / kPdWarps, kPdThreads, 0, p, st); break;
       }
-      if (cudaGetLastError() != cudaSuccess) r = fail(h, MOCR_ERR_CUDA, "stage kernel launch failed");
+      if (le != cudaSuccess) r = fail(h, MOCR_ERR_CUDA, "stage kernel launch failed: %s", cudaGetErrorString(le));
       ++h->launches;
       flops = 0;
     } else {
