@@ -19,6 +19,8 @@ from __future__ import annotations
 import re
 from typing import Iterable, List, Sequence
 
+import numpy as np
+
 from .weights import VOCAB
 
 SPECIAL_TOKENS = ["[PAD]", "[UNK]", "[CLS]", "[SEP]", "[MASK]"]
@@ -52,6 +54,8 @@ class Vocab:
         self.tokens = list(tokens)
         # ids whose token is [..]-bracketed specials are dropped on decode
         self.special_ids = frozenset(i for i, t in enumerate(self.tokens) if t in SPECIAL_TOKENS)
+        self._special_mask = np.zeros(len(self.tokens), bool)
+        self._special_mask[list(self.special_ids)] = True
 
     @classmethod
     def synthetic(cls) -> "Vocab":
@@ -62,11 +66,29 @@ class Vocab:
         with open(path, encoding="utf-8") as f:
             return cls([line.rstrip("\n") for line in f])
 
+    def _kept_tokens(self, ids: Iterable[int]) -> List[str]:
+        n = len(self.tokens)
+        if isinstance(ids, np.ndarray):
+            row = ids.astype(np.int64, copy=False).ravel()
+            mask = self._special_mask
+            ok = (row >= 0) & (row < n)
+            keep = np.ones(row.shape, bool)
+            keep[ok] = ~mask[row[ok]]
+            toks = self.tokens
+            return [toks[i] if 0 <= i < n else "[UNK]" for i in row[keep].tolist()]
+        sp = self.special_ids
+        return [self.tokens[i] if 0 <= i < n else "[UNK]" for i in (int(x) for x in ids) if i not in sp]
+
+    def _fast_tables(self):
+        """(per-token post-processed strings, mask of tokens that need the context-aware slow path)."""
+        if getattr(self, "_fast", None) is None:
+            slow = np.array([any(ch in _TRIGGERS or ch.isspace() for ch in t) for t in self.tokens], bool)
+            self._fast = ([t if s else h2z(t) for t, s in zip(self.tokens, slow)], slow)
+        return self._fast
+
     def decode(self, ids: Iterable[int]) -> str:
         """``tokenizer.decode(ids, skip_special_tokens=True)``."""
-        n = len(self.tokens)
-        return " ".join(self.tokens[i] if 0 <= i < n else "[UNK]"
-                        for i in (int(x) for x in ids) if i not in self.special_ids)
+        return " ".join(self._kept_tokens(ids))
 
 
 # --- jaconv.h2z(ascii=True, digit=True, kana=True) restated -----------------
@@ -105,5 +127,22 @@ def post_process(text: str) -> str:
     return h2z(text)
 
 
+_TRIGGERS = set("ﾞﾟ…・.")      # characters whose post-processing depends on their neighbours
+
+
 def ids_to_text(vocab: Vocab, ids: Iterable[int]) -> str:
-    return post_process(vocab.decode(ids))
+    """``post_process(tokenizer.decode(ids, skip_special_tokens=True))``.  The reference joins the
+    tokens with spaces and then strips ALL whitespace; concatenating directly is the same string.
+    Fast path: when no token of the row contains a context-dependent character (dots, ellipsis,
+    half-width voiced marks) or whitespace, post_process acts on every character independently and
+    the per-token results are precomputed."""
+    if isinstance(ids, np.ndarray):
+        fast = vocab._fast_tables()
+        row = ids.astype(np.int64, copy=False).ravel()
+        n = len(vocab.tokens)
+        if row.size and row.min() >= 0 and row.max() < n:
+            kept = row[~vocab._special_mask[row]]
+            if not fast[1][kept].any():
+                tz = fast[0]
+                return "".join([tz[i] for i in kept.tolist()])
+    return post_process("".join(vocab._kept_tokens(ids)))
