@@ -2,8 +2,8 @@
 //   ctx = softmax(Q K^T) V          (1/sqrt(64) is folded into W_q at load time)
 // Reference: transformers/models/vit/modeling_vit.py:199-251 (non-causal, no mask).
 //
-// One CTA = (128-query tile, head, crop).  K and V of the head (197 x 64 bf16 each)
-// are staged once in shared memory; each of the 8 warps owns 16 query rows, keeps the
+// One CTA = (64-query tile, head, crop).  K and V of the head (197 x 64 bf16 each)
+// are staged once in shared memory; each of the 4 warps owns 16 query rows, keeps the
 // whole 16 x 208 score tile in registers (no online rescaling needed at S = 197),
 // does the softmax in fp32 and feeds P straight back as the A operand of P V.
 // Tensor-core path: warp-level mma.sync m16n8k16 (bf16 in, fp32 accumulate).
@@ -15,7 +15,9 @@ namespace mocr {
 
 constexpr int kAttnKeysPad = 208;     // 197 keys padded to 13 x 16
 constexpr int kAttnPitch = 72;        // bf16 elements per smem row (64 + 8 pad: conflict-free fragments)
-constexpr int kAttnThreads = 256;
+constexpr int kAttnThreads = 128;     // 4 warps x 16 query rows; 3 CTAs per SM overlap K/V staging with the MMAs
+constexpr int kAttnQTile = kAttnThreads / 32 * 16;
+constexpr int kAttnQTiles = (kEncTokens + kAttnQTile - 1) / kAttnQTile;
 constexpr int kAttnSmemBytes = 2 * kAttnKeysPad * kAttnPitch * 2;
 
 __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -25,8 +27,8 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// grid = (2, 12, n_crops), block = 256
-__global__ void __launch_bounds__(kAttnThreads, 1)
+// grid = (kAttnQTiles, 12, n_crops), block = 128
+__global__ void __launch_bounds__(kAttnThreads, 3)
 encoder_attention_kernel(const __nv_bfloat16* __restrict__ qkv /*[n*197, 2304]*/, __nv_bfloat16* __restrict__ ctx /*[n*197, 768]*/) {
   extern __shared__ __align__(16) uint8_t attn_smem[];
   __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(attn_smem);
@@ -37,21 +39,26 @@ encoder_attention_kernel(const __nv_bfloat16* __restrict__ qkv /*[n*197, 2304]*/
   const size_t row0 = static_cast<size_t>(crop) * kEncTokens;
   const int ld = 3 * kD;
 
-  // Stage K and V (rows >= 197 zero-filled): 8 threads x 16 B per 128-B row.
+  // Stage K and V (rows >= 197 zero-filled): 8 threads x 16 B per 128-B row, through cp.async so
+  // that all 26 requests of a thread are in flight at once (a load->store loop costs one L2 round
+  // trip per iteration).
   for (int i = threadIdx.x; i < kAttnKeysPad * 8; i += kAttnThreads) {
     const int r = i >> 3, ch = i & 7;
-    uint4 kq = make_uint4(0, 0, 0, 0), vq = make_uint4(0, 0, 0, 0);
+    __nv_bfloat16* kd = Ks + r * kAttnPitch + ch * 8;
+    __nv_bfloat16* vd = Vs + r * kAttnPitch + ch * 8;
     if (r < kEncTokens) {
       const __nv_bfloat16* src = qkv + (row0 + r) * ld + head * kHeadDim + ch * 8;
-      kq = *reinterpret_cast<const uint4*>(src + kD);
-      vq = *reinterpret_cast<const uint4*>(src + 2 * kD);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(kd)), "l"(src + kD) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(vd)), "l"(src + 2 * kD) : "memory");
+    } else {
+      *reinterpret_cast<uint4*>(kd) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(vd) = make_uint4(0, 0, 0, 0);
     }
-    *reinterpret_cast<uint4*>(Ks + r * kAttnPitch + ch * 8) = kq;
-    *reinterpret_cast<uint4*>(Vs + r * kAttnPitch + ch * 8) = vq;
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
 
   // Q fragments of this warp's 16 rows straight from global memory.
-  const int qrow = qt * 128 + warp * 16;
+  const int qrow = qt * kAttnQTile + warp * 16;
   uint32_t qa[4][4];
   {
     const int r_lo = qrow + g, r_hi = qrow + g + 8;
@@ -66,6 +73,7 @@ encoder_attention_kernel(const __nv_bfloat16* __restrict__ qkv /*[n*197, 2304]*/
       qa[ks][3] = r_hi < kEncTokens ? *reinterpret_cast<const uint32_t*>(q_hi + c + 8) : 0u;
     }
   }
+  asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
   if (qrow >= kEncTokens) return;      // warp-uniform: this warp's rows are all padding
 

@@ -634,7 +634,7 @@ int attention197(mocr_handle* h, int n) {
     CK(cudaFuncSetAttribute(encoder_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
     done[h->device & 15] = true;
   }
-  encoder_attention_kernel<<<dim3(2, kHeads, n), kAttnThreads, kAttnSmemBytes, h->stream>>>(h->qkv, h->ctx.p);
+  encoder_attention_kernel<<<dim3(kAttnQTiles, kHeads, n), kAttnThreads, kAttnSmemBytes, h->stream>>>(h->qkv, h->ctx.p);
   CK(cudaGetLastError());
   ++h->launches;
   return MOCR_OK;
