@@ -119,6 +119,7 @@ struct mocr_handle {
 
   // tile widths (mocr_set_option)
   int enc_bn = 256;
+  int gemm_pair = 0;        // 1: cta_group::2 GEMM (CTA pairs, 256-row tiles) for the large-M encoder GEMMs; parity-tested, measured no faster (K = 768 tiles are not smem-bound enough)
   int enc_bn768 = 256;      // tile width of the N = 768 encoder GEMMs (192 gives 2.68 waves instead of 2.007 but measured 3 % slower: the tiles are smem-bandwidth-bound)
   int dec_bn = 32;
   int head_bn = 64;
@@ -319,7 +320,7 @@ int linear_map(mocr_handle* h, Linear* L, int bn, const CUtensorMap** out) {
   auto it = L->maps.find(bn);
   if (it == L->maps.end()) {
     CUtensorMap m;
-    TRY(make_map(h, &m, L->w, L->N, L->K, bn));
+    TRY(make_map(h, &m, L->w, L->N, L->K, bn < 0 ? -bn / 2 : bn));
     it = L->maps.emplace(bn, m).first;
   }
   *out = &it->second;
@@ -453,6 +454,22 @@ int launch_gemm_t(mocr_handle* h, const CUtensorMap& ma, const CUtensorMap& mb, 
   return MOCR_OK;
 }
 
+template <int BN, int EPI>
+int launch_gemm_pair_t(mocr_handle* h, const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& a) {
+  using Cfg = GemmPairCfg<BN>;
+  static bool attr_done[16] = {};
+  if (!attr_done[h->device & 15]) {
+    CK(cudaFuncSetAttribute(gemm_tcgen05_pair_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_done[h->device & 15] = true;
+  }
+  const int tiles = ((a.M + 2 * kGemmBM - 1) / (2 * kGemmBM)) * (a.N / BN);
+  const int pairs = std::min(tiles, h->sms / 2);
+  gemm_tcgen05_pair_kernel<BN, EPI><<<2 * pairs, kGemmThreads, Cfg::kSmemBytes, h->stream>>>(ma, mb, a);
+  CK(cudaGetLastError());
+  ++h->launches;
+  return MOCR_OK;
+}
+
 template <int EPI>
 int launch_gemm_bn(mocr_handle* h, int bn, const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& a) {
   switch (bn) {
@@ -469,12 +486,24 @@ int launch_gemm_bn(mocr_handle* h, int bn, const CUtensorMap& ma, const CUtensor
 int gemm(mocr_handle* h, int epi, int bn, const ActBuf& A, Linear& L, int M, GemmArgs a) {
   if (A.K != L.K || M > A.rows_cap || L.N % bn != 0 || L.K % kGemmBK != 0)
     return fail(h, MOCR_ERR_INVALID, "gemm shape mismatch: M=%d A.K=%d W=[%d,%d] bn=%d", M, A.K, L.N, L.K, bn);
-  const CUtensorMap* mb;
-  TRY(linear_map(h, &L, bn, &mb));
   a.M = M;
   a.N = L.N;
   a.K = L.K;
   a.bias = L.bias;
+  if (h->gemm_pair && bn == 256 && M >= 2 * kGemmBM && epi != EPI_ARGMAX && epi != EPI_F32_GELU) {
+    // CTA-pair kernel: each CTA loads half of the B tile -> the B descriptor's box is bn/2 rows (cached under key -bn)
+    const CUtensorMap* mbh;
+    TRY(linear_map(h, &L, -bn, &mbh));
+    switch (epi) {
+      case EPI_BF16: return launch_gemm_pair_t<256, EPI_BF16>(h, A.map, *mbh, a);
+      case EPI_BF16_GELU: return launch_gemm_pair_t<256, EPI_BF16_GELU>(h, A.map, *mbh, a);
+      case EPI_F32_RESID: return launch_gemm_pair_t<256, EPI_F32_RESID>(h, A.map, *mbh, a);
+      case EPI_PATCH: return launch_gemm_pair_t<256, EPI_PATCH>(h, A.map, *mbh, a);
+      default: break;
+    }
+  }
+  const CUtensorMap* mb;
+  TRY(linear_map(h, &L, bn, &mb));
   switch (epi) {
     case EPI_BF16: return launch_gemm_bn<EPI_BF16>(h, bn, A.map, *mb, a);
     case EPI_BF16_GELU: return launch_gemm_bn<EPI_BF16_GELU>(h, bn, A.map, *mb, a);
@@ -1273,6 +1302,7 @@ int mocr_set_option(mocr_handle_t* h, const char* key, int value) {
   auto bn_ok = [](int v) { return v == 32 || v == 64 || v == 128 || v == 192 || v == 256; };
   if (k == "enc_bn" && bn_ok(value) && kD % value == 0) h->enc_bn = value;
   else if (k == "enc_bn768" && bn_ok(value) && kD % value == 0) h->enc_bn768 = value;
+  else if (k == "gemm_pair") h->gemm_pair = value != 0;
   else if (k == "dec_bn" && bn_ok(value) && kD % value == 0) h->dec_bn = value;
   else if (k == "head_bn" && bn_ok(value) && kVocab % value == 0) h->head_bn = value;
   else if (k == "check_every" && value >= 1) h->check_every = value;

@@ -62,6 +62,109 @@ struct GemmCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
+// Epilogue of one accumulator tile for one epilogue warp: TMEM -> registers -> fused bias /
+// activation / residual / arg-max -> global.  `taddr` addresses the warp's 32 TMEM lanes at the
+// tile's first column; `half` selects which half of the tile's 32-column chunks this warp owns.
+// The tile's bias values, one column per lane and chunk, requested BEFORE the wait on the
+// accumulator: this only warms L1 for the epilogue's float4 loads (a shuffle-broadcast variant and a
+// software-pipelined tcgen05.ld were measured slower: +32 SHFL per chunk made the GELU epilogue
+// instruction-bound).
+template <int BN>
+struct GemmBiasLanes {
+  float v[(BN / 32 + 1) / 2];
+};
+template <int BN>
+__device__ __forceinline__ void gemm_load_bias(const GemmArgs& args, int n0, int half, int lane, GemmBiasLanes<BN>& b) {
+  constexpr int kChunks = BN / 32;
+  const int c_lo = half == 0 ? 0 : (kChunks + 1) / 2, c_hi = half == 0 ? (kChunks + 1) / 2 : kChunks;
+#pragma unroll
+  for (int i = 0; i < (kChunks + 1) / 2; ++i) b.v[i] = c_lo + i < c_hi ? __ldg(args.bias + n0 + (c_lo + i) * 32 + lane) : 0.f;
+}
+
+template <int BN, int EPI>
+__device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, uint32_t taddr, int row, bool row_ok, int n0, int nt, int n_tiles,
+                                                   int half, const GemmBiasLanes<BN>& bias) {
+  constexpr int kChunks = BN / 32;
+  const int c_lo = half == 0 ? 0 : (kChunks + 1) / 2, c_hi = half == 0 ? (kChunks + 1) / 2 : kChunks;
+  float best = -INFINITY;
+  int best_i = 0x7fffffff;
+  int out_row = row;
+  const float* extra = nullptr;               // per-row fp32 addend (residual or position row)
+  if (EPI == EPI_F32_RESID) extra = args.resid + static_cast<size_t>(row) * args.ldr;
+  if (EPI == EPI_PATCH) {
+    const int b = row / kPatches, p = row % kPatches;
+    out_row = b * kEncTokens + 1 + p;
+    extra = args.pos + static_cast<size_t>(1 + p) * kD;
+  }
+  (void)bias;
+#pragma unroll 1
+  for (int c = c_lo; c < c_hi; ++c) {
+    uint32_t v[32];
+    tmem_ld32(taddr + static_cast<uint32_t>(c * 32), v);
+    tmem_ld_wait();
+    const int col0 = n0 + c * 32;
+    float f[32];
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(args.bias + col0 + j));
+      f[j] = __uint_as_float(v[j]) + bb.x;
+      f[j + 1] = __uint_as_float(v[j + 1]) + bb.y;
+      f[j + 2] = __uint_as_float(v[j + 2]) + bb.z;
+      f[j + 3] = __uint_as_float(v[j + 3]) + bb.w;
+    }
+    if (EPI == EPI_BF16 || EPI == EPI_BF16_GELU) {
+      if (EPI == EPI_BF16_GELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = gelu_erf_fast(f[j]);
+      }
+      if (row_ok) {
+        uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(args.out) + static_cast<size_t>(row) * args.ldo + col0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 q;
+          q.x = pack_bf16(f[8 * j + 0], f[8 * j + 1]);
+          q.y = pack_bf16(f[8 * j + 2], f[8 * j + 3]);
+          q.z = pack_bf16(f[8 * j + 4], f[8 * j + 5]);
+          q.w = pack_bf16(f[8 * j + 6], f[8 * j + 7]);
+          dst[j] = q;
+        }
+      }
+    } else if (EPI == EPI_F32_GELU) {
+      if (row_ok) {
+        float4* dst = reinterpret_cast<float4*>(static_cast<float*>(args.out) + static_cast<size_t>(row) * args.ldo + col0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          dst[j] = make_float4(gelu_erf(f[4 * j]), gelu_erf(f[4 * j + 1]), gelu_erf(f[4 * j + 2]), gelu_erf(f[4 * j + 3]));
+      }
+    } else if (EPI == EPI_F32_RESID || EPI == EPI_PATCH) {
+      if (row_ok) {
+        const float4* ex = reinterpret_cast<const float4*>(extra + col0);
+        float4* dst = reinterpret_cast<float4*>(static_cast<float*>(args.out) + static_cast<size_t>(out_row) * args.ldo + col0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 e = ex[j];
+          dst[j] = make_float4(f[4 * j] + e.x, f[4 * j + 1] + e.y, f[4 * j + 2] + e.z, f[4 * j + 3] + e.w);
+        }
+      }
+    } else {  // EPI_ARGMAX
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (f[j] > best) { best = f[j]; best_i = col0 + j; }   // strict > keeps the lowest index on ties
+      }
+      if (args.logits != nullptr && row_ok && args.step[row] < args.tap_steps) {
+        float4* dst = reinterpret_cast<float4*>(
+            args.logits + (static_cast<size_t>(row) * args.tap_steps + args.step[row]) * args.N + col0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+      }
+    }
+  }
+  if (EPI == EPI_ARGMAX && row_ok) {
+    args.part_max[(static_cast<size_t>(row) * n_tiles + nt) * 2 + half] = best;
+    args.part_idx[(static_cast<size_t>(row) * n_tiles + nt) * 2 + half] = best_i;
+  }
+}
+
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmArgs args) {
@@ -161,8 +264,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     // ------------------------------------------------ epilogue --------------
     const int quad = warp & 3;                    // TMEM lane quadrant this warp may access
     const int half = (warp - 2) >> 2;             // which half of the tile's 32-column chunks it owns
-    constexpr int kChunks = BN / 32;
-    const int c_lo = half == 0 ? 0 : (kChunks + 1) / 2, c_hi = half == 0 ? (kChunks + 1) / 2 : kChunks;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
@@ -172,86 +273,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int n0 = nt * BN;
       const int row = m0 + quad * 32 + lane;
       const bool row_ok = row < args.M;
+      GemmBiasLanes<BN> bias;
+      gemm_load_bias<BN>(args, n0, half, lane, bias);
       mbar_wait(&acc_full[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * BN);
-
-      float best = -INFINITY;
-      int best_i = 0x7fffffff;
-      int out_row = row;
-      const float* extra = nullptr;               // per-row fp32 addend (residual or position row)
-      if (EPI == EPI_F32_RESID) extra = args.resid + static_cast<size_t>(row) * args.ldr;
-      if (EPI == EPI_PATCH) {
-        const int b = row / kPatches, p = row % kPatches;
-        out_row = b * kEncTokens + 1 + p;
-        extra = args.pos + static_cast<size_t>(1 + p) * kD;
-      }
-#pragma unroll 1
-      for (int c = c_lo; c < c_hi; ++c) {
-        uint32_t v[32];
-        tmem_ld32(taddr + static_cast<uint32_t>(c * 32), v);
-        tmem_ld_wait();
-        const int col0 = n0 + c * 32;
-        float f[32];
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 bb = __ldg(reinterpret_cast<const float4*>(args.bias + col0 + j));
-          f[j] = __uint_as_float(v[j]) + bb.x;
-          f[j + 1] = __uint_as_float(v[j + 1]) + bb.y;
-          f[j + 2] = __uint_as_float(v[j + 2]) + bb.z;
-          f[j + 3] = __uint_as_float(v[j + 3]) + bb.w;
-        }
-        if (EPI == EPI_BF16 || EPI == EPI_BF16_GELU) {
-          if (EPI == EPI_BF16_GELU) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = gelu_erf_fast(f[j]);
-          }
-          if (row_ok) {
-            uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(args.out) + static_cast<size_t>(row) * args.ldo + col0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 q;
-              q.x = pack_bf16(f[8 * j + 0], f[8 * j + 1]);
-              q.y = pack_bf16(f[8 * j + 2], f[8 * j + 3]);
-              q.z = pack_bf16(f[8 * j + 4], f[8 * j + 5]);
-              q.w = pack_bf16(f[8 * j + 6], f[8 * j + 7]);
-              dst[j] = q;
-            }
-          }
-        } else if (EPI == EPI_F32_GELU) {
-          if (row_ok) {
-            float4* dst = reinterpret_cast<float4*>(static_cast<float*>(args.out) + static_cast<size_t>(row) * args.ldo + col0);
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              dst[j] = make_float4(gelu_erf(f[4 * j]), gelu_erf(f[4 * j + 1]), gelu_erf(f[4 * j + 2]), gelu_erf(f[4 * j + 3]));
-          }
-        } else if (EPI == EPI_F32_RESID || EPI == EPI_PATCH) {
-          if (row_ok) {
-            const float4* ex = reinterpret_cast<const float4*>(extra + col0);
-            float4* dst = reinterpret_cast<float4*>(static_cast<float*>(args.out) + static_cast<size_t>(out_row) * args.ldo + col0);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 e = ex[j];
-              dst[j] = make_float4(f[4 * j] + e.x, f[4 * j + 1] + e.y, f[4 * j + 2] + e.z, f[4 * j + 3] + e.w);
-            }
-          }
-        } else {  // EPI_ARGMAX
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (f[j] > best) { best = f[j]; best_i = col0 + j; }   // strict > keeps the lowest index on ties
-          }
-          if (args.logits != nullptr && row_ok && args.step[row] < args.tap_steps) {
-            float4* dst = reinterpret_cast<float4*>(
-                args.logits + (static_cast<size_t>(row) * args.tap_steps + args.step[row]) * args.N + col0);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-          }
-        }
-      }
-      if (EPI == EPI_ARGMAX && row_ok) {
-        args.part_max[(static_cast<size_t>(row) * n_tiles + nt) * 2 + half] = best;
-        args.part_idx[(static_cast<size_t>(row) * n_tiles + nt) * 2 + half] = best_i;
-      }
+      gemm_epilogue_tile<BN, EPI>(args, taddr, row, row_ok, n0, nt, n_tiles, half, bias);
       tc_fence_before();
       mbar_arrive(&acc_empty[as]);
     }
@@ -262,6 +289,158 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------ CTA-pair variant ---
+// Same GEMM on `tcgen05.mma.cta_group::2`: two CTAs of a cluster (the two SMs of a TPC) compute one
+// 256 x BN tile.  Each CTA stages its own 128 rows of A and HALF of the B tile (BN/2 rows), the
+// leader CTA issues UMMA 256 x BN x 16 for the pair, and the tensor cores of both SMs read the
+// two B halves from both shared memories.  Per SM and k-block that is 32 KB of TMA writes instead
+// of 48 KB and half the B reads: the single-CTA 128 x 256 tile needs ~187 B/clk of shared-memory
+// bandwidth against the 128 B/clk an SM has (measured: tensor pipe active 42-47 %), the pair
+// needs ~125 B/clk.
+template <int BN>
+struct GemmPairCfg {
+  static constexpr int kStageBytesA = kGemmBM * kGemmBK * 2;
+  static constexpr int kStageBytesB = (BN / 2) * kGemmBK * 2;
+  static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
+  static constexpr int kStagesFit = (200 * 1024) / kStageBytes;
+  static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
+  static constexpr int kTmemCols = 2 * BN <= 32 ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+template <int BN, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmArgs args) {
+  using Cfg = GemmPairCfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * Cfg::kStageBytesA;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;                    // [kStages]  used in the leader: TMA of both CTAs -> MMA
+  uint64_t* empty_bar = bars + kStages;         // [kStages]  in each CTA: MMA (multicast commit) -> its TMA producer
+  uint64_t* acc_full = bars + 2 * kStages;      // [2]        in each CTA: MMA (multicast commit) -> its epilogue
+  uint64_t* acc_empty = bars + 2 * kStages + 2; // [2]        used in the leader: epilogues of both CTAs -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();      // 0 = leader
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int m_tiles = (args.M + 2 * kGemmBM - 1) / (2 * kGemmBM);
+  const int n_tiles = args.N / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int k_blocks = args.K / kGemmBK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 2 * kGemmEpiThreads);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc2(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                           // barrier inits and TMEM of both CTAs are in place
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------ TMA producer (both CTAs) ----------
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = pair; tile < num_tiles; tile += n_pairs) {
+      const int m0 = (tile / n_tiles) * 2 * kGemmBM + static_cast<int>(rank) * kGemmBM;
+      const int n0 = (tile % n_tiles) * BN + static_cast<int>(rank) * (BN / 2);
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        if (lane == 0) {
+          const uint32_t leader_full = mapa_u32(&full_bar[stage], 0);
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);   // bytes of both CTAs
+          tma_load_2d_pair(smem_a + stage * Cfg::kStageBytesA, &tmap_a, leader_full, kb * kGemmBK, m0);
+          tma_load_2d_pair(smem_b + stage * Cfg::kStageBytesB, &tmap_b, leader_full, kb * kGemmBK, n0);
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer (leader CTA only) ------
+    if (rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * kGemmBM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = pair; tile < num_tiles; tile += n_pairs, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1u;
+        mbar_wait(&acc_empty[as], aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * BN);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint64_t da = umma_desc_k_sw128(smem_u32(smem_a + stage * Cfg::kStageBytesA));
+            const uint64_t db = umma_desc_k_sw128(smem_u32(smem_b + stage * Cfg::kStageBytesB));
+#pragma unroll
+            for (int k = 0; k < kGemmBK / 16; ++k)
+              umma_bf16_pair(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
+                             static_cast<uint32_t>((kb | k) != 0));
+            umma_commit_pair(&empty_bar[stage]);                      // frees the slot in BOTH CTAs
+            if (kb == k_blocks - 1) umma_commit_pair(&acc_full[as]);  // accumulators complete in both CTAs
+          }
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------ epilogue (each CTA drains its 128 rows) ----
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const uint32_t leader_acc_empty0 = mapa_u32(&acc_empty[0], 0), leader_acc_empty1 = mapa_u32(&acc_empty[1], 0);
+    int it = 0;
+    for (int tile = pair; tile < num_tiles; tile += n_pairs, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1u;
+      const int m0 = (tile / n_tiles) * 2 * kGemmBM + static_cast<int>(rank) * kGemmBM;
+      const int nt = tile % n_tiles;
+      const int n0 = nt * BN;
+      const int row = m0 + quad * 32 + lane;
+      const bool row_ok = row < args.M;
+      GemmBiasLanes<BN> bias;
+      gemm_load_bias<BN>(args, n0, half, lane, bias);
+      mbar_wait(&acc_full[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * BN);
+      gemm_epilogue_tile<BN, EPI>(args, taddr, row, row_ok, n0, nt, n_tiles, half, bias);
+      tc_fence_before();
+      mbar_arrive_cluster(as == 0 ? leader_acc_empty0 : leader_acc_empty1);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                           // the peer may still be reading this CTA's smem / signalling its barriers
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, Cfg::kTmemCols);
   }
 }
 
