@@ -85,3 +85,50 @@ def test_full_size_batch64_len300_properties(weights0):
         assert eng.last_steps <= 299
     finally:
         eng.close()
+
+
+def test_checkpoint_directory_and_vocab_file(tmp_path, weights0):
+    """`MangaOcr(path)` with a local checkpoint directory (weights.npz + vocab.txt) - the route a real
+    kha-white/manga-ocr-base snapshot takes (model.safetensors is read by the same loader)."""
+    from manga_ocr_b200.ocr import MangaOcr
+    from manga_ocr_b200.text import Vocab
+    d = tmp_path / "ckpt"
+    d.mkdir()
+    np.savez(d / "weights.npz", **{k: v for k, v in weights0.items() if k != "decoder.cls.predictions.decoder.weight"})   # tied head omitted
+    toks = Vocab.synthetic().tokens
+    toks[100], toks[101] = toks[101], toks[100]           # a vocabulary that differs from the built-in one
+    (d / "vocab.txt").write_text("\n".join(toks) + "\n", encoding="utf-8")
+    o = MangaOcr(str(d), max_batch=4, max_length=12)
+    ref = MangaOcr(weights=weights0, max_batch=4, max_length=12, warmup=False)
+    try:
+        crop = C.single_224()[0]
+        assert o.vocab.tokens[100] == toks[100]
+        ids_a = o.recognize_ids([crop])
+        ids_b = ref.recognize_ids([crop])
+        assert np.array_equal(ids_a, ids_b)               # same weights through the file route
+        assert isinstance(o(Image.fromarray(crop)), str)
+    finally:
+        o.close()
+        ref.close()
+
+
+def test_two_engines_share_a_gpu(weights0):
+    """Two handles on one device (the in-process multi-GPU dispatcher uses one handle per GPU; on a
+    single-GPU box both dispatchers land on cuda:0) give the same strings as one."""
+    from manga_ocr_b200.ocr import MangaOcr
+    crops = C.bubble_batch(12, seed=5)
+    one = MangaOcr(weights=weights0, devices=[0], max_batch=8, max_length=12, warmup=False)
+    two = MangaOcr(weights=weights0, devices=[0, 0], max_batch=8, max_length=12, warmup=False)
+    try:
+        want = one.recognize_batch(crops)
+        assert two.recognize_batch(crops) == want          # splitter: two contiguous blocks, two worker threads
+        got = [None] * 12
+        ts = [threading.Thread(target=lambda k=k: got.__setitem__(k, two(Image.fromarray(crops[k])))) for k in range(12)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        assert got == want
+    finally:
+        one.close()
+        two.close()
