@@ -27,6 +27,7 @@
 #include "decode_attn.cuh"
 #include "decode_persistent.cuh"
 #include "encoder_attn.cuh"
+#include "encoder_attn_tc.cuh"
 #include "gemm_tcgen05.cuh"
 #include "preprocess.cuh"
 #include "rowops.cuh"
@@ -119,6 +120,7 @@ struct mocr_handle {
 
   // tile widths (mocr_set_option)
   int enc_bn = 256;
+  int attn_tc = 1;          // encoder attention on tcgen05 (0: the warp-level mma.sync kernel)
   int gemm_pair = 0;        // 1: cta_group::2 GEMM (CTA pairs, 256-row tiles) for the large-M encoder GEMMs; parity-tested, measured no faster (K = 768 tiles are not smem-bound enough)
   int enc_bn768 = 256;      // tile width of the N = 768 encoder GEMMs (192 gives 2.68 waves instead of 2.007 but measured 3 % slower: the tiles are smem-bandwidth-bound)
   int dec_bn = 32;
@@ -149,6 +151,7 @@ struct mocr_handle {
   int brow_cap = 0;       // decoder rows (multiple of 128)
   ActBuf patches, xn, ctx, mlp, enc_out;
   __nv_bfloat16* qkv = nullptr;       // [rows_cap, 2304]
+  CUtensorMap map_qkv_q, map_qkv_kv;  // TMA views of qkv for the tcgen05 attention (boxes 64 x 128 and 64 x 208)
   float* hres = nullptr;              // [rows_cap, 768] fp32 residual stream
   float* enc_f32 = nullptr;           // tap
   __nv_bfloat16* crosskv = nullptr;   // [rows_cap, 3072]
@@ -662,9 +665,13 @@ int attention197(mocr_handle* h, int n) {
   static bool done[16] = {};
   if (!done[h->device & 15]) {
     CK(cudaFuncSetAttribute(encoder_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
+    CK(cudaFuncSetAttribute(encoder_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtcSmemBytes));
     done[h->device & 15] = true;
   }
-  encoder_attention_kernel<<<dim3(kAttnQTiles, kHeads, n), kAttnThreads, kAttnSmemBytes, h->stream>>>(h->qkv, h->ctx.p);
+  if (h->attn_tc)
+    encoder_attention_tc_kernel<<<dim3(kHeads, n), kAtcThreads, kAtcSmemBytes, h->stream>>>(h->map_qkv_q, h->map_qkv_kv, h->ctx.p);
+  else
+    encoder_attention_kernel<<<dim3(kAttnQTiles, kHeads, n), kAttnThreads, kAttnSmemBytes, h->stream>>>(h->qkv, h->ctx.p);
   CK(cudaGetLastError());
   ++h->launches;
   return MOCR_OK;
@@ -1062,6 +1069,8 @@ int create_impl(mocr_handle* h) {
   TRY(make_act(h, &h->mlp, h->rows_cap, kFFN));
   TRY(make_act(h, &h->enc_out, h->rows_cap, kD));
   TRY(dmalloc(h, &h->qkv, static_cast<size_t>(h->rows_cap) * 3 * kD));
+  TRY(make_map(h, &h->map_qkv_q, h->qkv, h->rows_cap, 3 * kD, 128));
+  TRY(make_map(h, &h->map_qkv_kv, h->qkv, h->rows_cap, 3 * kD, kAtcKeys));
   TRY(dmalloc(h, &h->hres, static_cast<size_t>(h->rows_cap) * kD));
   TRY(dmalloc(h, &h->crosskv, static_cast<size_t>(h->rows_cap) * 4 * kD));
   TRY(make_act(h, &h->d_xb, h->brow_cap, kD));
@@ -1303,6 +1312,7 @@ int mocr_set_option(mocr_handle_t* h, const char* key, int value) {
   if (k == "enc_bn" && bn_ok(value) && kD % value == 0) h->enc_bn = value;
   else if (k == "enc_bn768" && bn_ok(value) && kD % value == 0) h->enc_bn768 = value;
   else if (k == "gemm_pair") h->gemm_pair = value != 0;
+  else if (k == "attn_tc") h->attn_tc = value != 0;
   else if (k == "dec_bn" && bn_ok(value) && kD % value == 0) h->dec_bn = value;
   else if (k == "head_bn" && bn_ok(value) && kVocab % value == 0) h->head_bn = value;
   else if (k == "check_every" && value >= 1) h->check_every = value;

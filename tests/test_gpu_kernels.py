@@ -91,3 +91,20 @@ def test_pair_gemm_cta_group2_against_torch(engine8, M, N, K, epi):
         ref = ref + torch.from_numpy(R).double()
     err = np.abs(got - ref.numpy()).max()
     assert err <= (2.0 ** -8 * max(1.0, float(ref.abs().max())) if epi in (0, 1) else 1e-3), err
+
+
+def test_encoder_attention_mma_sync_variant(engine8):
+    """The warp-level mma.sync attention kernel (option attn_tc = 0) stays covered."""
+    import torch
+    rng = np.random.default_rng(9)
+    qkv = rng.standard_normal((2 * 197, 2304), dtype=np.float32)
+    qkv[:, :768] *= 0.25
+    engine8.set_option("attn_tc", 0)
+    try:
+        got = engine8.test_encoder_attention(qkv)
+    finally:
+        engine8.set_option("attn_tc", 1)
+    q = torch.from_numpy(_bf16(qkv)).double().view(2, 197, 3, 12, 64)
+    Q, K, V = (q[:, :, i].transpose(1, 2) for i in range(3))
+    ref = (torch.softmax(Q @ K.transpose(-1, -2), dim=-1) @ V).transpose(1, 2).reshape(2 * 197, 768).numpy()
+    assert np.abs(got - ref).max() < 2e-2
