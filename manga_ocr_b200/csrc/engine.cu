@@ -205,6 +205,7 @@ struct mocr_handle {
   // ---- decode-step graphs keyed by (n, max_length, forced?, tap?)
   struct StepGraph { cudaGraphExec_t exec; int launches; };
   std::map<uint64_t, StepGraph> graphs;
+  std::map<uint64_t, StepGraph> enc_graphs;   // encoder launches per (batch size, tap)
 };
 
 namespace {
@@ -677,8 +678,7 @@ int attention197(mocr_handle* h, int n) {
   return MOCR_OK;
 }
 
-int encode(mocr_handle* h) {
-  if (!h->pre_ok) return fail(h, MOCR_ERR_INVALID, "preprocess has not run on the staged crops");
+int encode_launches(mocr_handle* h) {
   const int n = h->n, M = n * kEncTokens, bn = h->enc_bn, bn7 = h->enc_bn768;
   // embeddings: patch rows -> h[b*197+1+p] = conv + pos ; h[b*197] = cls + pos[0]   (modeling_vit.py:100-128)
   {
@@ -702,6 +702,42 @@ int encode(mocr_handle* h) {
   TRY(layernorm(h, h->hres, M, h->enc_ln, h->enc_out.p, (h->taps & MOCR_TAP_ENCODER) ? h->enc_f32 : nullptr));   // :455
   // cross-attention K/V of both decoder layers, once per crop (modeling_bert.py:252-267)
   TRY(gemm(h, EPI_BF16, bn, h->enc_out, h->cross_kv, M, out_bf16(h->crosskv, 4 * kD)));
+  return MOCR_OK;
+}
+
+// The 88 encoder launches are host-bound when issued one by one (~6 us of CPU per launch with two
+// 128-byte tensor maps as parameters): they are captured once per batch size and replayed as a graph.
+int encode(mocr_handle* h) {
+  if (!h->pre_ok) return fail(h, MOCR_ERR_INVALID, "preprocess has not run on the staged crops");
+  if (!h->use_graph) {
+    TRY(encode_launches(h));
+  } else {
+    const uint64_t key = (static_cast<uint64_t>(h->n) << 8) | ((h->taps & MOCR_TAP_ENCODER) ? 1u : 0u);
+    auto it = h->enc_graphs.find(key);
+    if (it == h->enc_graphs.end()) {
+      const int64_t l0 = h->launches;
+      TRY(encode_launches(h));            // warm run: function attributes, tensor maps (result is valid, kept)
+      const int per = static_cast<int>(h->launches - l0);
+      cudaGraph_t graph;
+      cudaGraphExec_t exec = nullptr;
+      CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+      const int r = encode_launches(h);
+      h->launches = l0 + per;
+      const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+      if (r != MOCR_OK) return r;
+      if (ce != cudaSuccess) return fail(h, MOCR_ERR_CUDA, "encoder stream capture failed: %s", cudaGetErrorString(ce));
+      CK(cudaGraphInstantiate(&exec, graph, 0));
+      cudaGraphDestroy(graph);
+      if (h->enc_graphs.size() >= 64) {
+        for (auto& g : h->enc_graphs) cudaGraphExecDestroy(g.second.exec);
+        h->enc_graphs.clear();
+      }
+      h->enc_graphs[key] = mocr_handle::StepGraph{exec, per};
+    } else {
+      CK(cudaGraphLaunch(it->second.exec, h->stream));
+      h->launches += it->second.launches;
+    }
+  }
   h->enc_ok = true;
   h->dec_ok = false;
   return MOCR_OK;
@@ -1156,6 +1192,7 @@ int mocr_destroy(mocr_handle_t* h) {
   if (cudaSetDevice(h->device) == cudaSuccess) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (auto& g : h->graphs) cudaGraphExecDestroy(g.second.exec);
+    for (auto& g : h->enc_graphs) cudaGraphExecDestroy(g.second.exec);
     for (void* p : h->allocs) cudaFree(p);
     if (h->logits_tap) cudaFree(h->logits_tap);
     if (h->d_arena) cudaFree(h->d_arena);
@@ -1326,6 +1363,8 @@ int mocr_set_option(mocr_handle_t* h, const char* key, int value) {
   else return fail(h, MOCR_ERR_INVALID, "unknown option or bad value: %s=%d", key, value);
   for (auto& g : h->graphs) cudaGraphExecDestroy(g.second.exec);
   h->graphs.clear();
+  for (auto& g : h->enc_graphs) cudaGraphExecDestroy(g.second.exec);
+  h->enc_graphs.clear();
   return MOCR_OK;
 }
 
