@@ -21,6 +21,7 @@ struct DecodeAttnArgs {
   __nv_bfloat16* vcache;
   long long b_stride;         // elements
   int key_stride;             // elements
+  int head_stride;            // elements between heads (0: heads are 64-column slices of a key row)
   const __nv_bfloat16* new_k; // self-attention: this step's K/V rows [B, ld_new] to append at pos[b]; null for cross
   const __nv_bfloat16* new_v;
   int ld_new;
@@ -50,8 +51,9 @@ decode_attention_kernel(const DecodeAttnArgs a) {
   if (a.finished[b]) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int sub = lane >> 3, ch = lane & 7;
-  __nv_bfloat16* kc = a.kcache + static_cast<size_t>(b) * a.b_stride + h * kHeadDim;
-  __nv_bfloat16* vc = a.vcache + static_cast<size_t>(b) * a.b_stride + h * kHeadDim;
+  const int hs = a.head_stride > 0 ? a.head_stride : kHeadDim;
+  __nv_bfloat16* kc = a.kcache + static_cast<size_t>(b) * a.b_stride + static_cast<size_t>(h) * hs;
+  __nv_bfloat16* vc = a.vcache + static_cast<size_t>(b) * a.b_stride + static_cast<size_t>(h) * hs;
   int n_keys = a.fixed_keys;
   if (a.new_k != nullptr) {
     const int p = a.pos[b];

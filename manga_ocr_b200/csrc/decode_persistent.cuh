@@ -67,7 +67,7 @@ struct PdParams {
   PdLinear head_t, head_dec;
   PdLn head_ln;
   EmbedWeights emb;
-  const __nv_bfloat16* crosskv;   // [B*197, 3072]: K0 V0 K1 V1
+  const __nv_bfloat16* crosskv;   // [B][layer][K|V][head][197][64]
   // state
   int* ids;                 // [B, max_len]
   int* pos;                 // [B]
@@ -679,10 +679,12 @@ __device__ __forceinline__ void pd_attention_stage(Bar& bar, uint8_t* smem, cons
   uint4* stage1 = reinterpret_cast<uint4*>(smem + (group * 2 + 1) * kPdStageBytes);
   float* s_part = reinterpret_cast<float*>(smem + n_groups * 2 * kPdStageBytes) + group * 4 * (2 + kHeadDim);
   const PdLayer& L = p.layer[st.layer];
-  const __nv_bfloat16* kbase = SELF ? L.self_k : p.crosskv + st.layer * 2 * kD;
-  const __nv_bfloat16* vbase = SELF ? L.self_v : p.crosskv + st.layer * 2 * kD + kD;
+  // self: cache rows [B][t][768], a head is a 64-column slice; cross: one contiguous [197][64] block per (crop, layer, K|V, head)
+  const __nv_bfloat16* kbase = SELF ? L.self_k : p.crosskv + static_cast<size_t>(st.layer * 2) * kHeads * kEncTokens * kHeadDim;
+  const __nv_bfloat16* vbase = SELF ? L.self_v : p.crosskv + static_cast<size_t>(st.layer * 2 + 1) * kHeads * kEncTokens * kHeadDim;
   const long long b_stride = SELF ? static_cast<long long>(p.cache_len) * kD : static_cast<long long>(kEncTokens) * 4 * kD;
-  const int key_stride = SELF ? kD : 4 * kD;
+  const int key_stride = SELF ? kD : kHeadDim;
+  const int head_stride = SELF ? kHeadDim : kEncTokens * kHeadDim;
   const int units = p.B * kHeads;
   const int ustride = gridDim.x * n_groups;
   const int u0 = blockIdx.x * n_groups + group;
@@ -691,8 +693,8 @@ __device__ __forceinline__ void pd_attention_stage(Bar& bar, uint8_t* smem, cons
     PdAttnUnit a;
     a.b = u / kHeads;
     a.h = u - a.b * kHeads;
-    a.kc = kbase + static_cast<size_t>(a.b) * b_stride + a.h * kHeadDim + ch * 8;
-    a.vc = vbase + static_cast<size_t>(a.b) * b_stride + a.h * kHeadDim + ch * 8;
+    a.kc = kbase + static_cast<size_t>(a.b) * b_stride + static_cast<size_t>(a.h) * head_stride + ch * 8;
+    a.vc = vbase + static_cast<size_t>(a.b) * b_stride + static_cast<size_t>(a.h) * head_stride + ch * 8;
     a.nk = a.nv = nullptr;
     a.n_keys = kEncTokens;
     a.ps = -1;

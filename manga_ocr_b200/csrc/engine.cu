@@ -154,7 +154,7 @@ struct mocr_handle {
   CUtensorMap map_qkv_q, map_qkv_kv;  // TMA views of qkv for the tcgen05 attention (boxes 64 x 128 and 64 x 208)
   float* hres = nullptr;              // [rows_cap, 768] fp32 residual stream
   float* enc_f32 = nullptr;           // tap
-  __nv_bfloat16* crosskv = nullptr;   // [rows_cap, 3072]
+  __nv_bfloat16* crosskv = nullptr;   // [crop][layer][K|V][head][197][64]: cross-attention K/V, one contiguous block per (crop, layer, head)
   ActBuf d_xb, d_ctx, d_ffn, d_tb;
   float* d_x = nullptr;               // [brow_cap, 768]
   float* d_tmp = nullptr;             // [brow_cap, 768]
@@ -503,6 +503,7 @@ int gemm(mocr_handle* h, int epi, int bn, const ActBuf& A, Linear& L, int M, Gem
       case EPI_BF16_GELU: return launch_gemm_pair_t<256, EPI_BF16_GELU>(h, A.map, *mbh, a);
       case EPI_F32_RESID: return launch_gemm_pair_t<256, EPI_F32_RESID>(h, A.map, *mbh, a);
       case EPI_PATCH: return launch_gemm_pair_t<256, EPI_PATCH>(h, A.map, *mbh, a);
+      case EPI_CROSSKV: return launch_gemm_pair_t<256, EPI_CROSSKV>(h, A.map, *mbh, a);
       default: break;
     }
   }
@@ -515,6 +516,7 @@ int gemm(mocr_handle* h, int epi, int bn, const ActBuf& A, Linear& L, int M, Gem
     case EPI_PATCH: return launch_gemm_bn<EPI_PATCH>(h, bn, A.map, *mb, a);
     case EPI_ARGMAX: return launch_gemm_bn<EPI_ARGMAX>(h, bn, A.map, *mb, a);
     case EPI_F32_GELU: return launch_gemm_bn<EPI_F32_GELU>(h, bn, A.map, *mb, a);
+    case EPI_CROSSKV: return launch_gemm_bn<EPI_CROSSKV>(h, bn, A.map, *mb, a);
     default: return fail(h, MOCR_ERR_INVALID, "bad epilogue %d", epi);
   }
 }
@@ -701,7 +703,7 @@ int encode_launches(mocr_handle* h) {
   }
   TRY(layernorm(h, h->hres, M, h->enc_ln, h->enc_out.p, (h->taps & MOCR_TAP_ENCODER) ? h->enc_f32 : nullptr));   // :455
   // cross-attention K/V of both decoder layers, once per crop (modeling_bert.py:252-267)
-  TRY(gemm(h, EPI_BF16, bn, h->enc_out, h->cross_kv, M, out_bf16(h->crosskv, 4 * kD)));
+  TRY(gemm(h, EPI_CROSSKV, bn, h->enc_out, h->cross_kv, M, out_bf16(h->crosskv, 4 * kD)));
   return MOCR_OK;
 }
 
@@ -792,10 +794,11 @@ int decode_step(mocr_handle* h, int n, int max_length, bool forced, bool tap) {
     DecodeAttnArgs ca{};
     ca.q = h->d_q;
     ca.ldq = kD;
-    ca.kcache = h->crosskv + l * 2 * kD;
-    ca.vcache = h->crosskv + l * 2 * kD + kD;
+    ca.kcache = h->crosskv + static_cast<size_t>(l * 2) * kHeads * kEncTokens * kHeadDim;
+    ca.vcache = h->crosskv + static_cast<size_t>(l * 2 + 1) * kHeads * kEncTokens * kHeadDim;
     ca.b_stride = static_cast<long long>(kEncTokens) * 4 * kD;
-    ca.key_stride = 4 * kD;
+    ca.key_stride = kHeadDim;
+    ca.head_stride = kEncTokens * kHeadDim;
     ca.fixed_keys = kEncTokens;
     ca.finished = h->d_finished;
     ca.ctx = h->d_ctx.p;

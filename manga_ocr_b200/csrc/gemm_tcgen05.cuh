@@ -29,6 +29,7 @@ enum GemmEpilogue : int {
   EPI_PATCH = 3,       // ViT embeddings: out(f32)[b*197+1+p] = acc + bias + pos[1+p]
   EPI_ARGMAX = 4,      // LM head: per-row (max, argmax) over this tile's columns; logits optional
   EPI_F32_GELU = 5,    // out(f32)  = gelu_erf(acc + bias)         (LM-head transform, feeds a LayerNorm)
+  EPI_CROSSKV = 6,     // out(bf16) = acc + bias, scattered into the per-head cross-attention K/V cache layout
 };
 
 struct GemmArgs {
@@ -112,13 +113,22 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, uint32_
       f[j + 2] = __uint_as_float(v[j + 2]) + bb.z;
       f[j + 3] = __uint_as_float(v[j + 3]) + bb.w;
     }
-    if (EPI == EPI_BF16 || EPI == EPI_BF16_GELU) {
+    if (EPI == EPI_BF16 || EPI == EPI_BF16_GELU || EPI == EPI_CROSSKV) {
       if (EPI == EPI_BF16_GELU) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = gelu_erf_fast(f[j]);
       }
       if (row_ok) {
         uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(args.out) + static_cast<size_t>(row) * args.ldo + col0);
+        if (EPI == EPI_CROSSKV) {
+          // column = (layer * 2 + kv) * 768 + head * 64 + d  ->  cache[crop][layer][kv][head][token][64]: every
+          // (crop, layer, head) K or V block is one contiguous 25 KB stream for the decoder's attention
+          const int crop = row / kEncTokens, tok = row - crop * kEncTokens;
+          const int lkv = col0 / kD, hd = col0 - lkv * kD;
+          dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(args.out) +
+                                         ((static_cast<size_t>(crop) * 4 + lkv) * kHeads + hd / kHeadDim) * (kEncTokens * kHeadDim) +
+                                         static_cast<size_t>(tok) * kHeadDim + (hd & (kHeadDim - 1)));
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           uint4 q;
