@@ -689,7 +689,11 @@ __device__ __forceinline__ void pd_attention_stage(Bar& bar, uint8_t* smem, cons
   const int ustride = gridDim.x * n_groups;
   const int u0 = blockIdx.x * n_groups + group;
 
-  auto make_unit = [&](int u, bool state_visible) {
+  // Row state (finished flag, position) of the first kPre units of this group is requested in one go
+  // right after the dependency wait; together with the first unit's query they cost ONE L2 round trip.
+  constexpr int kPre = 4;
+  int pre_fin[kPre] = {0, 0, 0, 0}, pre_pos[kPre] = {0, 0, 0, 0};
+  auto make_unit = [&](int u, int fin, int pos, bool state_visible) {
     PdAttnUnit a;
     a.b = u / kHeads;
     a.h = u - a.b * kHeads;
@@ -700,8 +704,6 @@ __device__ __forceinline__ void pd_attention_stage(Bar& bar, uint8_t* smem, cons
     a.ps = -1;
     a.skip = false;
     if (state_visible) {
-      const int fin = ldg_cg_s32(p.finished + a.b);
-      const int pos = SELF ? ldg_cg_s32(p.pos + a.b) : 0;
       a.skip = fin != 0 && p.forced == nullptr;     // group-uniform
       if (SELF) {
         a.ps = pos;
@@ -713,10 +715,63 @@ __device__ __forceinline__ void pd_attention_stage(Bar& bar, uint8_t* smem, cons
     }
     return a;
   };
+  auto unit_state = [&](int u, int k) {             // k = index of u in this group's unit sequence
+    int fin, pos;
+    if (k < kPre) {
+      fin = pre_fin[0];
+      pos = pre_pos[0];
+#pragma unroll
+      for (int i = 1; i < kPre; ++i) {              // (select chain: the arrays stay in registers)
+        if (k == i) {
+          fin = pre_fin[i];
+          pos = pre_pos[i];
+        }
+      }
+    } else {
+      fin = ldg_cg_s32(p.finished + u / kHeads);
+      pos = SELF ? ldg_cg_s32(p.pos + u / kHeads) : 0;
+    }
+    return make_unit(u, fin, pos, true);
+  };
+  // The query of a unit, requested (raw) one unit ahead and summed when the unit starts:
+  // self: bf16 row of the QKV buffer; cross: bias + split-K partials of the cross-q projection.
+  struct QRaw {
+    uint4 qb;
+    float4 e0[kPdSplit], e1[kPdSplit];
+  };
+  auto issue_q = [&](int u, QRaw& raw) {
+    const int b = u / kHeads, h = u - b * kHeads;
+    if (SELF) {
+      raw.qb = ldg_cg16(p.qkv + static_cast<size_t>(b) * 3 * kD + h * kHeadDim + ch * 8);
+    } else {
+      const int c = h * kHeadDim + ch * 8;
+#pragma unroll
+      for (int pt = 0; pt < kPdSplit; ++pt) {
+        const float* src = p.yq + (static_cast<size_t>(pt) * p.B + b) * kD + c;
+        raw.e0[pt] = ldg_cg_f4(src);
+        raw.e1[pt] = ldg_cg_f4(src + 4);
+      }
+    }
+  };
+  auto finish_q = [&](int u, const QRaw& raw, float (&qq)[8]) {
+    if (SELF) {
+      pd_bf16x8(raw.qb, qq);
+    } else {
+      const int c = (u % kHeads) * kHeadDim + ch * 8;
+      float4 lo = __ldg(reinterpret_cast<const float4*>(st.bias + c)), hi = __ldg(reinterpret_cast<const float4*>(st.bias + c + 4));
+#pragma unroll
+      for (int pt = 0; pt < kPdSplit; ++pt) {       // fixed order
+        lo.x += raw.e0[pt].x; lo.y += raw.e0[pt].y; lo.z += raw.e0[pt].z; lo.w += raw.e0[pt].w;
+        hi.x += raw.e1[pt].x; hi.y += raw.e1[pt].y; hi.z += raw.e1[pt].z; hi.w += raw.e1[pt].w;
+      }
+      qq[0] = lo.x; qq[1] = lo.y; qq[2] = lo.z; qq[3] = lo.w;
+      qq[4] = hi.x; qq[5] = hi.y; qq[6] = hi.z; qq[7] = hi.w;
+    }
+  };
 
   // The group's work is one stream of 112-key blocks (unit after unit) flowing through a two-deep
   // ring of staging buffers: block n+1 is requested before block n is reduced.
-  PdAttnUnit cur = make_unit(u0 < units ? u0 : 0, false);
+  PdAttnUnit cur = make_unit(u0 < units ? u0 : 0, 0, 0, false);
   bool pre2 = false;       // both blocks of the first unit were requested before the dependency wait
   if (!SELF) {   // encoder K/V never change during a decode: request the first unit (2 blocks) before the wait
     if (u0 < units) {
@@ -728,10 +783,27 @@ __device__ __forceinline__ void pd_attention_stage(Bar& bar, uint8_t* smem, cons
     cp_async_commit();
   }
   bar.wait();
-  int u = u0;
+  QRaw raw_cur, raw_nxt;
+#pragma unroll
+  for (int k = 0; k < kPre; ++k) {
+    const int uk = u0 + k * ustride;
+    pre_fin[k] = 0;
+    pre_pos[k] = 0;
+    if (uk < units) {
+      pre_fin[k] = ldg_cg_s32(p.finished + uk / kHeads);
+      if (SELF) pre_pos[k] = ldg_cg_s32(p.pos + uk / kHeads);
+    }
+  }
+  if (u0 < units) issue_q(u0, raw_cur);
+  int u = u0, uk_idx = 0;
   if (u < units) {
-    cur = make_unit(u, true);
-    while (cur.n_keys == 0 && u + ustride < units) { u += ustride; cur = make_unit(u, true); }   // skip finished rows
+    cur = unit_state(u, uk_idx);
+    while (cur.n_keys == 0 && u + ustride < units) {   // skip finished rows
+      u += ustride;
+      ++uk_idx;
+      cur = unit_state(u, uk_idx);
+      issue_q(u, raw_cur);
+    }
     if (SELF || u != u0) {
       if (!SELF) cp_async_wait_group<0>();          // (the prefetched blocks of a finished row are dropped)
       pre2 = false;
@@ -746,48 +818,32 @@ __device__ __forceinline__ void pd_attention_stage(Bar& bar, uint8_t* smem, cons
     uint4* stage = par ? stage1 : stage0;
     // ---- locate and request the next block of the stream
     PdAttnUnit nxt = cur;
-    int nu = u, nj0 = j0 + kBlockKeys;
+    int nu = u, nj0 = j0 + kBlockKeys, nk_idx = uk_idx;
     if (nj0 >= cur.n_keys) {
       nj0 = 0;
       nu = u + ustride;
+      nk_idx = uk_idx + 1;
       bool found = false;
       while (nu < units) {
-        nxt = make_unit(nu, true);
+        nxt = unit_state(nu, nk_idx);
         if (nxt.n_keys > 0) { found = true; break; }
         nu += ustride;
+        ++nk_idx;
       }
       if (!found) nu = units;
     }
     if (pre2) pre2 = false;                       // (u0, block 1) is already on its way
     else if (nu < units) pd_attn_request(par ? stage0 : stage1, nxt, key_stride, nj0, gt);
     cp_async_commit();
-    // ---- first block of a unit: the query and a fresh online-softmax state
+    // ---- first block of a unit: the query (requested one unit ahead) and a fresh online-softmax state
     if (j0 == 0) {
-      if (SELF) {
-        pd_bf16x8(ldg_cg16(p.qkv + static_cast<size_t>(cur.b) * 3 * kD + cur.h * kHeadDim + ch * 8), q);
-      } else {   // query = bias + split-K partials of the cross-q projection, added in a fixed order
-        const int c = cur.h * kHeadDim + ch * 8;
-        float4 lo = __ldg(reinterpret_cast<const float4*>(st.bias + c)), hi = __ldg(reinterpret_cast<const float4*>(st.bias + c + 4));
-        float4 e0[kPdSplit], e1[kPdSplit];
-#pragma unroll
-        for (int pt = 0; pt < kPdSplit; ++pt) {
-          const float* src = p.yq + (static_cast<size_t>(pt) * p.B + cur.b) * kD + c;
-          e0[pt] = ldg_cg_f4(src);
-          e1[pt] = ldg_cg_f4(src + 4);
-        }
-#pragma unroll
-        for (int pt = 0; pt < kPdSplit; ++pt) {
-          lo.x += e0[pt].x; lo.y += e0[pt].y; lo.z += e0[pt].z; lo.w += e0[pt].w;
-          hi.x += e1[pt].x; hi.y += e1[pt].y; hi.z += e1[pt].z; hi.w += e1[pt].w;
-        }
-        q[0] = lo.x; q[1] = lo.y; q[2] = lo.z; q[3] = lo.w;
-        q[4] = hi.x; q[5] = hi.y; q[6] = hi.z; q[7] = hi.w;
-      }
+      finish_q(u, raw_cur, q);
       m = -INFINITY;
       l = 0.f;
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[i] = 0.f;
     }
+    if (nu != u && nu < units) issue_q(nu, raw_nxt);      // the next unit's query travels while this block is reduced
     cp_async_wait_group<1>();             // everything but the newest group (the next block) has landed
     // ---- pass 1: the block's scores (independent dot products: the shuffles overlap)
     float sc[kPdKeySlots];
@@ -880,8 +936,10 @@ __device__ __forceinline__ void pd_attention_stage(Bar& bar, uint8_t* smem, cons
       }
       group_sync(group);     // s_part is reused by the next unit
     }
+    if (nu != u) raw_cur = raw_nxt;
     cur = nxt;
     u = nu;
+    uk_idx = nk_idx;
     j0 = nj0;
     par ^= 1;
   }
