@@ -262,7 +262,7 @@ def run_b200(args, rank, local_rank, world):
         enc_flops = BATCH * 36.056e9        # 35.126 GFLOP encoder + 0.930 GFLOP cross-K/V projection per crop
         phases["encoder_tflops"] = enc_flops / (phases["encode_ms"] * 1e-3) / 1e12
         phases["encoder_frac_of_sustained_bf16_peak"] = phases["encoder_tflops"] / peaks["bf16_tflops_sustained"]
-        for name in ("enc_qkv", "enc_attn", "enc_fc1", "enc_fc2", "dec_qkv", "dec_self_out", "dec_ln", "dec_cross_attn", "dec_fc1", "dec_fc2",
+        for name in ("enc_ln", "enc_qkv", "enc_attn", "enc_out", "enc_fc1", "enc_fc2", "dec_qkv", "dec_self_out", "dec_ln", "dec_cross_attn", "dec_fc1", "dec_fc2",
                      "dec_vocab"):
             try:
                 k_ms, k_bytes, k_flops = eng.time_kernel(name, 50)

@@ -121,6 +121,7 @@ struct mocr_handle {
   // tile widths (mocr_set_option)
   int enc_bn = 256;
   int attn_tc = 1;          // encoder attention on tcgen05 (0: the warp-level mma.sync kernel)
+  int resid_tma = 1;        // encoder residual adds through the TMA reduce-add epilogue (0: per-thread f32 loads/stores)
   int gemm_pair = 0;        // 1: cta_group::2 GEMM (CTA pairs, 256-row tiles) for the large-M encoder GEMMs; parity-tested, measured no faster (K = 768 tiles are not smem-bound enough)
   int enc_bn768 = 256;      // tile width of the N = 768 encoder GEMMs (192 gives 2.68 waves instead of 2.007 but measured 3 % slower: the tiles are smem-bandwidth-bound)
   int dec_bn = 32;
@@ -253,6 +254,20 @@ int make_map(mocr_handle* h, CUtensorMap* m, const void* base, int rows, int col
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(h, MOCR_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d box=%d", (int)r, rows, cols, box_rows);
+  return MOCR_OK;
+}
+
+// f32 [rows, cols] view for the TMA reduce-add epilogue: 32 x 32 boxes (128-byte rows, SWIZZLE_128B)
+int make_map_f32_out(mocr_handle* h, CUtensorMap* m, const void* base, int rows, int cols) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (enc == nullptr) return fail(h, MOCR_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * 4};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(h, MOCR_ERR_CUDA, "cuTensorMapEncodeTiled (f32 out) failed (%d) rows=%d cols=%d", (int)r, rows, cols);
   return MOCR_OK;
 }
 
@@ -447,12 +462,12 @@ int launch_gemm_t(mocr_handle* h, const CUtensorMap& ma, const CUtensorMap& mb, 
   using Cfg = GemmCfg<BN>;
   static bool attr_done[16] = {};
   if (!attr_done[h->device & 15]) {
-    CK(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    CK(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(Cfg::kSmemBytes, EPI)));
     attr_done[h->device & 15] = true;
   }
   const int tiles = ((a.M + kGemmBM - 1) / kGemmBM) * (a.N / BN);
   const int grid = std::min(tiles, h->sms);
-  gemm_tcgen05_kernel<BN, EPI><<<grid, kGemmThreads, Cfg::kSmemBytes, h->stream>>>(ma, mb, a);
+  gemm_tcgen05_kernel<BN, EPI><<<grid, kGemmThreads, gemm_smem_bytes(Cfg::kSmemBytes, EPI), h->stream>>>(ma, mb, a);
   CK(cudaGetLastError());
   ++h->launches;
   return MOCR_OK;
@@ -494,7 +509,7 @@ int gemm(mocr_handle* h, int epi, int bn, const ActBuf& A, Linear& L, int M, Gem
   a.N = L.N;
   a.K = L.K;
   a.bias = L.bias;
-  if (h->gemm_pair && bn == 256 && M >= 2 * kGemmBM && epi != EPI_ARGMAX && epi != EPI_F32_GELU) {
+  if (h->gemm_pair && bn == 256 && M >= 2 * kGemmBM && epi != EPI_ARGMAX && epi != EPI_F32_GELU && epi != EPI_F32_ACCUM) {
     // CTA-pair kernel: each CTA loads half of the B tile -> the B descriptor's box is bn/2 rows (cached under key -bn)
     const CUtensorMap* mbh;
     TRY(linear_map(h, &L, -bn, &mbh));
@@ -509,6 +524,10 @@ int gemm(mocr_handle* h, int epi, int bn, const ActBuf& A, Linear& L, int M, Gem
   }
   const CUtensorMap* mb;
   TRY(linear_map(h, &L, bn, &mb));
+  if (epi == EPI_F32_ACCUM) {
+    if (a.ldo != L.N || bn > 256 || bn % 64 != 0) return fail(h, MOCR_ERR_INVALID, "accumulating epilogue needs a dense [M, N] output and a 64-column multiple tile");
+    TRY(make_map_f32_out(h, &a.tmap_out, a.out, M, L.N));
+  }
   switch (epi) {
     case EPI_BF16: return launch_gemm_bn<EPI_BF16>(h, bn, A.map, *mb, a);
     case EPI_BF16_GELU: return launch_gemm_bn<EPI_BF16_GELU>(h, bn, A.map, *mb, a);
@@ -517,6 +536,7 @@ int gemm(mocr_handle* h, int epi, int bn, const ActBuf& A, Linear& L, int M, Gem
     case EPI_ARGMAX: return launch_gemm_bn<EPI_ARGMAX>(h, bn, A.map, *mb, a);
     case EPI_F32_GELU: return launch_gemm_bn<EPI_F32_GELU>(h, bn, A.map, *mb, a);
     case EPI_CROSSKV: return launch_gemm_bn<EPI_CROSSKV>(h, bn, A.map, *mb, a);
+    case EPI_F32_ACCUM: return launch_gemm_bn<EPI_F32_ACCUM>(h, bn, A.map, *mb, a);
     default: return fail(h, MOCR_ERR_INVALID, "bad epilogue %d", epi);
   }
 }
@@ -696,10 +716,10 @@ int encode_launches(mocr_handle* h) {
     TRY(layernorm(h, h->hres, M, L.ln1, h->xn.p, nullptr));                                   // modeling_vit.py:333
     TRY(gemm(h, EPI_BF16, bn, h->xn, L.qkv, M, out_bf16(h->qkv, 3 * kD)));                   // :228-230
     TRY(attention197(h, n));                                                                  // :236-246
-    TRY(gemm(h, EPI_F32_RESID, bn7, h->ctx, L.out, M, out_f32(h->hres, kD, h->hres, kD)));    // :266, :337
+    TRY(gemm(h, h->resid_tma ? EPI_F32_ACCUM : EPI_F32_RESID, bn7, h->ctx, L.out, M, out_f32(h->hres, kD, h->hres, kD)));    // :266, :337
     TRY(layernorm(h, h->hres, M, L.ln2, h->xn.p, nullptr));                                   // :340
     TRY(gemm(h, EPI_BF16_GELU, bn, h->xn, L.fc1, M, out_bf16(h->mlp.p, kFFN)));              // :297-298
-    TRY(gemm(h, EPI_F32_RESID, bn7, h->mlp, L.fc2, M, out_f32(h->hres, kD, h->hres, kD)));    // :309-311
+    TRY(gemm(h, h->resid_tma ? EPI_F32_ACCUM : EPI_F32_RESID, bn7, h->mlp, L.fc2, M, out_f32(h->hres, kD, h->hres, kD)));    // :309-311
   }
   TRY(layernorm(h, h->hres, M, h->enc_ln, h->enc_out.p, (h->taps & MOCR_TAP_ENCODER) ? h->enc_f32 : nullptr));   // :455
   // cross-attention K/V of both decoder layers, once per crop (modeling_bert.py:252-267)
@@ -1358,6 +1378,7 @@ int mocr_set_option(mocr_handle_t* h, const char* key, int value) {
   else if (k == "check_every" && value >= 1) h->check_every = value;
   else if (k == "use_graph") h->use_graph = value != 0;
   else if (k == "use_pdl") h->use_pdl = value != 0;
+  else if (k == "resid_tma") h->resid_tma = value != 0;
   else if (k == "attn_grid" && value >= 0) h->attn_grid = value;
   else if (k == "fuse_rows") h->fuse_rows = value != 0;
   else if (k == "steps_per_graph" && value >= 1 && value <= 64) h->steps_per_graph = value;
@@ -1390,9 +1411,17 @@ int mocr_time_kernel(mocr_handle_t* h, const char* kernel, int iters, float* ms_
       flops = 2.0 * M * kFFN * kD;
       bytes = 2.0 * (static_cast<double>(M) * kD + static_cast<double>(kFFN) * kD + static_cast<double>(M) * kFFN);
     } else if (k == "enc_fc2") {
-      r = gemm(h, EPI_BF16, h->enc_bn768, h->mlp, h->enc[0].fc2, M, out_bf16(h->ctx.p, kD));
+      // (as in the encoder: accumulates into the f32 residual stream, which nothing reads after the encode)
+      r = gemm(h, h->resid_tma ? EPI_F32_ACCUM : EPI_F32_RESID, h->enc_bn768, h->mlp, h->enc[0].fc2, M, out_f32(h->hres, kD, h->hres, kD));
       flops = 2.0 * M * kFFN * kD;
-      bytes = 2.0 * (static_cast<double>(M) * kFFN + static_cast<double>(kFFN) * kD + static_cast<double>(M) * kD);
+      bytes = 2.0 * (static_cast<double>(M) * kFFN + static_cast<double>(kFFN) * kD) + 8.0 * M * kD;
+    } else if (k == "enc_out") {
+      r = gemm(h, h->resid_tma ? EPI_F32_ACCUM : EPI_F32_RESID, h->enc_bn768, h->ctx, h->enc[0].out, M, out_f32(h->hres, kD, h->hres, kD));
+      flops = 2.0 * M * kD * kD;
+      bytes = 2.0 * (static_cast<double>(M) * kD + static_cast<double>(kD) * kD) + 8.0 * M * kD;
+    } else if (k == "enc_ln") {
+      r = layernorm(h, h->hres, M, h->enc[0].ln1, h->xn.p, nullptr);
+      bytes = 6.0 * M * kD;
     } else if (k == "enc_qkv") {
       r = gemm(h, EPI_BF16, h->enc_bn, h->xn, h->enc[0].qkv, M, out_bf16(h->qkv, 3 * kD));
       flops = 2.0 * M * 3 * kD * kD;
@@ -1496,6 +1525,10 @@ int mocr_test_gemm(mocr_handle_t* h, int epi, int bn, int M, int N, int K, const
       CK(cudaMemcpy(d_res, resid, mn * sizeof(float), cudaMemcpyHostToDevice));
       g.resid = static_cast<const float*>(d_res);
       g.ldr = N;
+    }
+    if (epi == EPI_F32_ACCUM) {     // out starts as the residual and is accumulated in place
+      if (resid == nullptr) return fail(h, MOCR_ERR_INVALID, "resid is NULL");
+      CK(cudaMemcpy(d_out, resid, mn * sizeof(float), cudaMemcpyHostToDevice));
     }
     const int parts = 2 * (N / bn);
     if (epi == EPI_ARGMAX) {

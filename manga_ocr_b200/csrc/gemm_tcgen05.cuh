@@ -30,6 +30,7 @@ enum GemmEpilogue : int {
   EPI_ARGMAX = 4,      // LM head: per-row (max, argmax) over this tile's columns; logits optional
   EPI_F32_GELU = 5,    // out(f32)  = gelu_erf(acc + bias)         (LM-head transform, feeds a LayerNorm)
   EPI_CROSSKV = 6,     // out(bf16) = acc + bias, scattered into the per-head cross-attention K/V cache layout
+  EPI_F32_ACCUM = 7,   // out(f32) += acc + bias, in place, by TMA reduce-add from a swizzled smem tile (encoder residual stream)
 };
 
 struct GemmArgs {
@@ -45,12 +46,16 @@ struct GemmArgs {
   float* logits;         // EPI_ARGMAX: optional f32 tap for parity tests (may be null):
   const int* step;       //   row r writes logits[(r * tap_steps + step[r]) * N ...]
   int tap_steps;
+  alignas(64) CUtensorMap tmap_out;   // EPI_F32_ACCUM: f32 [M, N] view of `out`, box 32 x 32, SWIZZLE_128B
 };
 
 constexpr int kGemmBM = 128;
 constexpr int kGemmBK = 64;
 constexpr int kGemmThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (2 per TMEM lane quadrant)
 constexpr int kGemmEpiThreads = 256;
+constexpr int kGemmAccumStage = 32 * 128;                      // EPI_F32_ACCUM: one 32-row x 128-byte staging tile per epilogue warp
+constexpr int kGemmAccumSmem = 1024 + 8 * kGemmAccumStage;     // (+ padding that keeps the tiles 1024-byte aligned)
+constexpr int gemm_smem_bytes(int base, int epi) { return base + (epi == 7 ? kGemmAccumSmem : 0); }
 
 template <int BN>
 struct GemmCfg {
@@ -84,7 +89,7 @@ __device__ __forceinline__ void gemm_load_bias(const GemmArgs& args, int n0, int
 
 template <int BN, int EPI>
 __device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, uint32_t taddr, int row, bool row_ok, int n0, int nt, int n_tiles,
-                                                   int half, const GemmBiasLanes<BN>& bias) {
+                                                   int half, const GemmBiasLanes<BN>& bias, uint8_t* stage_w = nullptr) {
   constexpr int kChunks = BN / 32;
   const int c_lo = half == 0 ? 0 : (kChunks + 1) / 2, c_hi = half == 0 ? (kChunks + 1) / 2 : kChunks;
   float best = -INFINITY;
@@ -146,6 +151,26 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, uint32_
         for (int j = 0; j < 8; ++j)
           dst[j] = make_float4(gelu_erf(f[4 * j]), gelu_erf(f[4 * j + 1]), gelu_erf(f[4 * j + 2]), gelu_erf(f[4 * j + 3]));
       }
+    } else if (EPI == EPI_F32_ACCUM) {
+      // row `lane` of the warp's 32 x 32 f32 tile -> one 128-byte row of the staging tile, 16-byte chunks
+      // XOR-swizzled with the row (conflict-free stores; the map un-swizzles), then ONE reduce-add per warp:
+      // the residual is never read by the SM and every global access is a full 128-byte line.
+      const int lane = static_cast<int>(threadIdx.x & 31u);
+      const int row0 = row - lane;
+      if (lane == 0) bulk_wait_group_read0();          // the previous chunk's tile has been read out
+      __syncwarp();
+      const uint32_t dst = smem_u32(stage_w) + static_cast<uint32_t>(lane * 128);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + static_cast<uint32_t>((j ^ (lane & 7)) << 4)), "f"(f[4 * j]),
+                     "f"(f[4 * j + 1]), "f"(f[4 * j + 2]), "f"(f[4 * j + 3])
+                     : "memory");
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0 && row0 < args.M) {                // rows >= M are clipped by the map
+        tma_reduce_add_2d(&args.tmap_out, stage_w, col0, row0);
+        bulk_commit_group();
+      }
     } else if (EPI == EPI_F32_RESID || EPI == EPI_PATCH) {
       if (row_ok) {
         const float4* ex = reinterpret_cast<const float4*>(extra + col0);
@@ -177,7 +202,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, uint32_
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmArgs args) {
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ GemmArgs args) {
   using Cfg = GemmCfg<BN>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -288,10 +313,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       mbar_wait(&acc_full[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * BN);
-      gemm_epilogue_tile<BN, EPI>(args, taddr, row, row_ok, n0, nt, n_tiles, half, bias);
+      gemm_epilogue_tile<BN, EPI>(args, taddr, row, row_ok, n0, nt, n_tiles, half, bias,
+                                  smem + kStages * Cfg::kStageBytes + 1024 + (warp - 2) * kGemmAccumStage);
       tc_fence_before();
       mbar_arrive(&acc_empty[as]);
     }
+    if (EPI == EPI_F32_ACCUM && lane == 0) bulk_wait_group0();   // every reduce-add of this warp has landed
   }
 
   tc_fence_before();

@@ -17,6 +17,8 @@ GEMM_CASES = [
     (200, 768, 768, 128, 0), (333, 768, 256, 256, 0), (788, 768, 256, 192, 0), (1576, 2304, 768, 256, 0), (1576, 3072, 768, 192, 1),
     (64, 3072, 768, 32, 1), (64, 768, 3072, 32, 2), (1000, 768, 3072, 192, 2), (1000, 768, 3072, 256, 2), (8, 768, 768, 32, 5),
     (8, 6144, 768, 64, 4), (64, 6144, 768, 128, 4), (3, 6144, 768, 32, 4),
+    # 7 = in-place f32 accumulate through the TMA reduce-add epilogue (ragged last tile: rows >= M are clipped by the map)
+    (1000, 768, 3072, 256, 7), (1576, 768, 768, 256, 7), (333, 768, 768, 128, 7), (65, 768, 256, 64, 7), (12608, 768, 768, 256, 7),
 ]
 
 
@@ -27,12 +29,12 @@ def test_gemm_against_torch(engine8, M, N, K, bn, epi):
     A = rng.standard_normal((M, K), dtype=np.float32)
     Wt = rng.standard_normal((N, K), dtype=np.float32) * 0.05
     b = rng.standard_normal((N,), dtype=np.float32)
-    R = rng.standard_normal((M, N), dtype=np.float32) if epi == 2 else None
+    R = rng.standard_normal((M, N), dtype=np.float32) if epi in (2, 7) else None
     got, am = engine8.test_gemm(epi, bn, A, Wt, b, R)
     ref = torch.from_numpy(_bf16(A)).double() @ torch.from_numpy(_bf16(Wt)).double().T + torch.from_numpy(b).double()
     if epi in (1, 5):
         ref = torch.nn.functional.gelu(ref)       # erf GELU, as the reference (ViT / BERT hidden_act="gelu")
-    if epi == 2:
+    if epi in (2, 7):
         ref = ref + torch.from_numpy(R).double()
     ref = ref.numpy()
     err = np.abs(got - ref).max()
