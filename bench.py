@@ -230,8 +230,8 @@ def run_b200(args, rank, local_rank, world):
     for _ in range(args.steps):
         ids = ocr.recognize_ids(crops)
         texts = [None] * len(ids)
-        from manga_ocr_b200.text import ids_to_text
-        texts = [ids_to_text(ocr.vocab, r) for r in ids]
+        from manga_ocr_b200.text import ids_to_texts
+        texts = ids_to_texts(ocr.vocab, ids)
         if world > 1:
             gather_ids(ids, BATCH * world)       # final result gather: NCCL all_gather of [64, 300] int32 per rank
     barrier()

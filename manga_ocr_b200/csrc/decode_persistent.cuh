@@ -62,6 +62,7 @@ struct PdParams {
   int B;                    // rows
   int max_len;              // this decode's max_length
   int cache_len;            // self-KV cache capacity per row (tokens)
+  int kv_evict_first;       // 1: encoder K/V are streamed through L2 with an evict-first policy (the per-step weights stay resident)
   int eos_id;
   PdLayer layer[kDecLayers];
   PdLinear head_t, head_dec;
@@ -654,6 +655,26 @@ struct PdAttnUnit {
   bool skip;
 };
 
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void cp_async16_cg_hint(void* smem_dst, const void* gsrc, uint64_t pol) {
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void pd_attn_request_stream(uint4* stage, const PdAttnUnit& a, int key_stride, int j0, int gt, uint64_t pol) {
+  const int gw = gt >> 5, sub = (gt & 31) >> 3;
+#pragma unroll 1
+  for (int i = 0; i < kPdKeySlots; ++i) {
+    const int j = j0 + 16 * i + 4 * gw + sub;
+    if (j < a.n_keys) {
+      const bool fresh = j == a.ps;
+      cp_async16_cg_hint(stage + i * 128 + gt, fresh ? a.nk : a.kc + static_cast<size_t>(j) * key_stride, pol);
+      cp_async16_cg_hint(stage + (kPdKeySlots + i) * 128 + gt, fresh ? a.nv : a.vc + static_cast<size_t>(j) * key_stride, pol);
+    }
+  }
+}
 __device__ __forceinline__ void pd_attn_request(uint4* stage, const PdAttnUnit& a, int key_stride, int j0, int gt) {
   const int gw = gt >> 5, sub = (gt & 31) >> 3;
 #pragma unroll 1
@@ -771,13 +792,19 @@ __device__ __forceinline__ void pd_attention_stage(Bar& bar, uint8_t* smem, cons
 
   // The group's work is one stream of 112-key blocks (unit after unit) flowing through a two-deep
   // ring of staging buffers: block n+1 is requested before block n is reduced.
+  const bool stream_kv = SELF ? (p.kv_evict_first & 2) != 0 : (p.kv_evict_first & 1) != 0;
+  const uint64_t pol = stream_kv ? l2_policy_evict_first() : 0ull;
+  auto request = [&](uint4* stage, const PdAttnUnit& a, int j0) {
+    if (stream_kv) pd_attn_request_stream(stage, a, key_stride, j0, gt, pol);
+    else pd_attn_request(stage, a, key_stride, j0, gt);
+  };
   PdAttnUnit cur = make_unit(u0 < units ? u0 : 0, 0, 0, false);
   bool pre2 = false;       // both blocks of the first unit were requested before the dependency wait
   if (!SELF) {   // encoder K/V never change during a decode: request the first unit (2 blocks) before the wait
     if (u0 < units) {
-      pd_attn_request(stage0, cur, key_stride, 0, gt);
+      request(stage0, cur, 0);
       cp_async_commit();
-      pd_attn_request(stage1, cur, key_stride, kBlockKeys, gt);
+      request(stage1, cur, kBlockKeys);
       pre2 = true;
     }
     cp_async_commit();
@@ -807,7 +834,7 @@ __device__ __forceinline__ void pd_attention_stage(Bar& bar, uint8_t* smem, cons
     if (SELF || u != u0) {
       if (!SELF) cp_async_wait_group<0>();          // (the prefetched blocks of a finished row are dropped)
       pre2 = false;
-      if (cur.n_keys > 0) pd_attn_request(stage0, cur, key_stride, 0, gt);
+      if (cur.n_keys > 0) request(stage0, cur, 0);
       cp_async_commit();
     }
   }
@@ -833,7 +860,7 @@ __device__ __forceinline__ void pd_attention_stage(Bar& bar, uint8_t* smem, cons
       if (!found) nu = units;
     }
     if (pre2) pre2 = false;                       // (u0, block 1) is already on its way
-    else if (nu < units) pd_attn_request(par ? stage0 : stage1, nxt, key_stride, nj0, gt);
+    else if (nu < units) request(par ? stage0 : stage1, nxt, nj0);
     cp_async_commit();
     // ---- first block of a unit: the query (requested one unit ahead) and a fresh online-softmax state
     if (j0 == 0) {

@@ -121,6 +121,7 @@ struct mocr_handle {
   // tile widths (mocr_set_option)
   int enc_bn = 256;
   int attn_tc = 1;          // encoder attention on tcgen05 (0: the warp-level mma.sync kernel)
+  int kv_evict_first = 1;   // decoder cross-attention streams the encoder K/V through L2 with an evict-first policy
   int resid_tma = 1;        // encoder residual adds through the TMA reduce-add epilogue (0: per-thread f32 loads/stores)
   int gemm_pair = 0;        // 1: cta_group::2 GEMM (CTA pairs, 256-row tiles) for the large-M encoder GEMMs; parity-tested, measured no faster (K = 768 tiles are not smem-bound enough)
   int enc_bn768 = 256;      // tile width of the N = 768 encoder GEMMs (192 gives 2.68 waves instead of 2.007 but measured 3 % slower: the tiles are smem-bandwidth-bound)
@@ -606,7 +607,7 @@ int stage_crops(mocr_handle* h, const mocr_crop_t* crops, int n, int order) {
     CK(cudaMalloc(reinterpret_cast<void**>(&h->d_arena), cap));
     h->arena_cap = cap;
   }
-  size_t off = 0;
+  size_t off = 0, sent = 0;
   for (int i = 0; i < n; ++i) {
     const mocr_crop_t& c = crops[i];
     const size_t rowb = static_cast<size_t>(c.width) * c.channels;
@@ -636,6 +637,10 @@ int stage_crops(mocr_handle* h, const mocr_crop_t* crops, int n, int order) {
       tmp_rows = std::max(tmp_rows, t.strip_rows);
     }
     off += (rowb * c.height + 15) & ~static_cast<size_t>(15);
+    if (off - sent >= (1u << 20)) {   // the upload of the crops staged so far overlaps the host copy of the next ones
+      CK(cudaMemcpyAsync(h->d_arena + sent, h->h_arena + sent, off - sent, cudaMemcpyHostToDevice, h->stream));
+      sent = off;
+    }
   }
   h->pre_pitch = round_up(max_w, 16);
   h->pre_tmp_rows = tmp_rows;
@@ -656,7 +661,7 @@ int stage_crops(mocr_handle* h, const mocr_crop_t* crops, int n, int order) {
     // h_coefs is pageable: the copy above is staged synchronously by the runtime, safe to reuse
     h->d_coefs_used = h->h_coefs.size();
   }
-  CK(cudaMemcpyAsync(h->d_arena, h->h_arena, off, cudaMemcpyHostToDevice, h->stream));
+  if (off > sent) CK(cudaMemcpyAsync(h->d_arena + sent, h->h_arena + sent, off - sent, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->d_descs, h->h_descs, sizeof(CropDesc) * n, cudaMemcpyHostToDevice, h->stream));
   h->n = n;
   h->staged_ok = true;
@@ -856,6 +861,7 @@ PdParams make_pd_params(mocr_handle* h, int n, int max_length, bool forced, bool
   p.B = n;
   p.max_len = max_length;
   p.cache_len = h->max_length;
+  p.kv_evict_first = h->kv_evict_first;
   p.eos_id = kSepId;
   for (int l = 0; l < kDecLayers; ++l) {
     DecLayer& L = h->dec[l];
@@ -1379,6 +1385,7 @@ int mocr_set_option(mocr_handle_t* h, const char* key, int value) {
   else if (k == "use_graph") h->use_graph = value != 0;
   else if (k == "use_pdl") h->use_pdl = value != 0;
   else if (k == "resid_tma") h->resid_tma = value != 0;
+  else if (k == "kv_evict_first" && value >= 0 && value <= 3) h->kv_evict_first = value;
   else if (k == "attn_grid" && value >= 0) h->attn_grid = value;
   else if (k == "fuse_rows") h->fuse_rows = value != 0;
   else if (k == "steps_per_graph" && value >= 1 && value <= 64) h->steps_per_graph = value;

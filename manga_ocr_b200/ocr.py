@@ -21,7 +21,7 @@ import numpy as np
 
 from . import weights as W
 from .engine import BGR, MAX_LENGTH, RGB, Engine
-from .text import Vocab, ids_to_text
+from .text import Vocab, ids_to_text, ids_to_texts
 
 DEFAULT_MODEL = "kha-white/manga-ocr-base"
 
@@ -138,7 +138,7 @@ class MangaOcr:
         """crops: PIL images or uint8 arrays ([H,W], [H,W,3], [H,W,4]) -> list of strings."""
         arrays = [c if isinstance(c, np.ndarray) else image_to_array(c) for c in crops]
         ids = self.recognize_ids(arrays, order)
-        return [ids_to_text(self.vocab, row) for row in ids]
+        return ids_to_texts(self.vocab, ids)
 
     def recognize_ids(self, arrays: Sequence[np.ndarray], order: int = RGB) -> np.ndarray:
         if len(self.engines) == 1 or len(arrays) <= 1:
@@ -176,8 +176,8 @@ class MangaOcr:
                 batch = [self._queue.popleft() for _ in range(min(len(self._queue), self.max_batch))]
             try:
                 ids, _ = engine.recognize([r.crop for r in batch], RGB, self.max_length)
-                for r, row in zip(batch, ids):
-                    r.text = ids_to_text(self.vocab, row)
+                for r, t in zip(batch, ids_to_texts(self.vocab, ids)):
+                    r.text = t
             except BaseException as e:   # noqa: BLE001 - delivered to every waiting caller
                 for r in batch:
                     r.error = e

@@ -80,10 +80,15 @@ class Vocab:
         return [self.tokens[i] if 0 <= i < n else "[UNK]" for i in (int(x) for x in ids) if i not in sp]
 
     def _fast_tables(self):
-        """(per-token post-processed strings, mask of tokens that need the context-aware slow path)."""
+        """(per-token post-processed strings, mask of tokens that need the context-aware path, UTF-32 code unit
+        per single-character token (0: none), mask of tokens whose only context dependence is the dot rules)."""
         if getattr(self, "_fast", None) is None:
             slow = np.array([any(ch in _TRIGGERS or ch.isspace() for ch in t) for t in self.tokens], bool)
-            self._fast = ([t if s else h2z(t) for t, s in zip(self.tokens, slow)], slow)
+            tz = [t if s else h2z(t) for t, s in zip(self.tokens, slow)]
+            dots = np.array([s and len(t) == 1 and t in _DOT_TRIGGERS for t, s in zip(self.tokens, slow)], bool)
+            # code unit of every token whose (post-processed, or raw for the dot characters) form is ONE character
+            cp = np.array([ord(z) if (len(z) == 1 and (not s or d)) else 0 for z, s, d in zip(tz, slow, dots)], np.uint32)
+            self._fast = (tz, slow, cp, dots)
         return self._fast
 
     def decode(self, ids: Iterable[int]) -> str:
@@ -127,7 +132,8 @@ def post_process(text: str) -> str:
     return h2z(text)
 
 
-_TRIGGERS = set("ﾞﾟ…・.")      # characters whose post-processing depends on their neighbours
+_TRIGGERS = set("ﾞﾟ…・.･")     # characters whose post-processing depends on their neighbours (･ becomes ・ AFTER the dot rule)
+_DOT_TRIGGERS = set("…・.")      # ... of which these only take part in the ellipsis / dot-run rules
 
 
 def ids_to_text(vocab: Vocab, ids: Iterable[int]) -> str:
@@ -146,3 +152,31 @@ def ids_to_text(vocab: Vocab, ids: Iterable[int]) -> str:
                 tz = fast[0]
                 return "".join([tz[i] for i in kept.tolist()])
     return post_process("".join(vocab._kept_tokens(ids)))
+
+
+def ids_to_texts(vocab: Vocab, ids: np.ndarray) -> List[str]:
+    """``ids_to_text`` for a whole batch ``[n, T]``: one vectorised pass drops the special ids and maps
+    every single-character token to its post-processed UTF-32 code unit; only rows that contain a
+    context-dependent or multi-character token take the per-row path."""
+    ids = np.asarray(ids)
+    if ids.ndim != 2:
+        raise ValueError("ids must be [n, T]")
+    n_tok = len(vocab.tokens)
+    if ids.size == 0 or int(ids.min()) < 0 or int(ids.max()) >= n_tok:
+        return [ids_to_text(vocab, row) for row in ids]
+    _, slow, cp, dots = vocab._fast_tables()
+    keep = ~vocab._special_mask[ids]
+    cps = cp[ids]
+    per_row = (((slow[ids] & ~dots[ids]) | (cps == 0)) & keep).any(axis=1)
+    has_dots = (dots[ids] & keep).any(axis=1)
+    out = []
+    for r in range(ids.shape[0]):
+        if per_row[r]:
+            out.append(ids_to_text(vocab, ids[r]))
+            continue
+        text = cps[r][keep[r]].tobytes().decode("utf-32-le")
+        if has_dots[r]:
+            # every other character is already in its final form and is not touched by these rules
+            text = _DOTS_RE.sub(lambda m: (m.end() - m.start()) * ".", text.replace("…", "...")).replace(".", "．")
+        out.append(text)
+    return out

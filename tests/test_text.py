@@ -1,5 +1,7 @@
 """Host-side tail of MangaOcr.__call__ (manga_ocr_b200/text.py): tokenizer.decode + post_process."""
-from manga_ocr_b200.text import Vocab, h2z, ids_to_text, post_process
+import numpy as np
+
+from manga_ocr_b200.text import Vocab, h2z, ids_to_text, ids_to_texts, post_process
 
 
 def test_vocab_shape_and_specials():
@@ -37,3 +39,25 @@ def test_vocab_file_roundtrip(tmp_path):
     p = tmp_path / "vocab.txt"
     p.write_text("\n".join(v.tokens) + "\n", encoding="utf-8")
     assert Vocab.from_file(str(p)).tokens == v.tokens
+
+
+def test_batch_conversion_equals_per_row_conversion():
+    """ids_to_texts (vectorised) == ids_to_text row by row, on rows that hit every path: plain characters,
+    specials in the middle, dots / ellipsis / half-width voiced marks (context-dependent), ASCII (widened)."""
+    base = Vocab.synthetic()
+    v = Vocab(base.tokens[:-2] + ["･", "ab"])      # + a half-width middle dot and a multi-character token
+    rng = np.random.default_rng(7)
+    ids = rng.integers(0, len(v.tokens), size=(40, 300)).astype(np.int32)
+    ids[:, 0] = 2
+    ids[5, 10:] = 0
+    ids[6, 1:] = 3
+    tok = {t: i for i, t in enumerate(v.tokens)}
+    ids[7, 1:6] = [tok["."], tok["."], tok["…"], tok["・"], tok["A"]]
+    ids[8, 1:4] = [tok["ｶ"], tok["ﾞ"], tok["1"]]
+    dotty = np.array([tok["."], tok["…"], tok["・"], tok["A"], tok["あ"], tok["･"]], np.int32)
+    ids[20:30, 1:] = rng.choice(dotty[:5], size=(10, 299))      # dot rules only: the vectorised path with the dot fix-up
+    ids[30:34, 1:] = rng.choice(dotty, size=(4, 299))           # half-width middle dot: must not join a dot run
+    plain = np.array([i for i, t in enumerate(v.tokens) if i > 4 and 0x4E00 <= ord(t[0])], np.int32)
+    ids[9:20, 1:] = rng.choice(plain, size=(11, 299))          # rows that stay on the vectorised path
+    assert ids_to_texts(v, ids) == [ids_to_text(v, r) for r in ids]
+    assert ids_to_texts(v, ids[:0]) == []

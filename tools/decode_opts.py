@@ -6,9 +6,8 @@ B, T = 64, 300
 eng = Engine(W.random_init(0), device=0, max_batch=B, max_length=T)
 eng.stage(C.bubble_batch(B)); eng.preprocess(); eng.encode()
 eng.set_option("decode_mode", 2)
-opts = [dict(), dict(attn_grid=444), dict(attn_grid=296), dict(attn_grid=592), dict(attn_grid=384)]
+opts = [dict(kv_evict_first=0), dict(kv_evict_first=1), dict(kv_evict_first=3), dict(kv_evict_first=2), dict(kv_evict_first=1), dict(kv_evict_first=3)]
 for o in opts:
-    eng.set_option("attn_grid", 0)
     for k, v in o.items(): eng.set_option(k, v)
     for _ in range(2):
         eng.decode(T); eng.sync()
