@@ -48,6 +48,24 @@ typedef struct {
 
 enum mocr_channel_order { MOCR_RGB = 0, MOCR_BGR = 1 };
 
+/* One selection on a page, as the reference stages it before the engine (SURVEY.md section 8f N2;
+ * reference/src/ui/main_window.py:6497-6506 polygon selection, :6429-6430 rectangle selection,
+ * :9789-9795 rotation by text orientation):
+ *   crop    = page.crop((left, top, right, bottom))          PIL semantics: right/bottom exclusive,
+ *                                                            pixels outside the page are 0
+ *   polygon : mask = cv2.fillPoly(zeros, [polygon - (left, top)], 255); crop = mask ? crop : 255
+ *             (points in PAGE coordinates; NULL / 0 points = no mask)
+ *   rotate  : cv2.rotate(crop, ROTATE_90_CLOCKWISE | ROTATE_90_COUNTERCLOCKWISE)
+ * NB the reference passes QRect.right()/bottom() (= x + w - 1) as the exclusive end, so its crops are
+ * one pixel short of the polygon's bounding box; pass the same numbers to reproduce it. */
+enum mocr_rotation { MOCR_ROT_NONE = 0, MOCR_ROT_CW = 1, MOCR_ROT_CCW = 2 };
+typedef struct {
+  int32_t left, top, right, bottom;
+  const int32_t* polygon; /* n_points (x, y) pairs, page coordinates */
+  int32_t n_points;       /* 0 .. 1024 */
+  int32_t rotate;         /* enum mocr_rotation */
+} mocr_region_t;
+
 /* ---- life cycle -------------------------------------------------------------------- */
 
 int mocr_abi_version(void);
@@ -72,10 +90,20 @@ int mocr_finalize_weights(mocr_handle_t* h);
 int mocr_recognize(mocr_handle_t* h, const mocr_crop_t* crops, int n, int channel_order, int max_length,
                    int32_t* out_ids, int32_t* out_lens);
 
+/* The same for n selections of ONE page: the page is uploaded once and every selection's crop,
+ * polygon composite on white and rotation happen on the device, inside the preprocess reads.
+ * Replaces the per-selection PIL crop / cv2 composite / rotate / colour round trips in front of
+ * MangaOcr.__call__ (reference/src/ui/main_window.py:6497-6506, 9789-9800). */
+int mocr_recognize_regions(mocr_handle_t* h, const mocr_crop_t* page, const mocr_region_t* regions, int n, int channel_order,
+                           int max_length, int32_t* out_ids, int32_t* out_lens);
+
 /* ---- the path, stage by stage (n <= max_batch) ------------------------------------------ */
 
 /* Host crops -> pinned staging -> device arena (async on the handle's stream). */
 int mocr_stage_crops(mocr_handle_t* h, const mocr_crop_t* crops, int n, int channel_order);
+/* Page + selections -> device arena, polygon masks rasterised on the device (n <= max_batch);
+ * the alternative to mocr_stage_crops in front of mocr_preprocess. */
+int mocr_stage_regions(mocr_handle_t* h, const mocr_crop_t* page, const mocr_region_t* regions, int n, int channel_order);
 /* Fused luma + Pillow-exact bilinear 224x224 + patch rows, on the staged crops.
  * Replaces img.convert("L").convert("RGB") and ViTImageProcessor (resize, rescale, normalize). */
 int mocr_preprocess(mocr_handle_t* h);
@@ -98,6 +126,8 @@ int mocr_set_taps(mocr_handle_t* h, int taps);
 int mocr_get_pixels_u8(mocr_handle_t* h, uint8_t* out /*[n,224,224]*/);
 int mocr_get_pixel_values(mocr_handle_t* h, float* out /*[n,224,224] (the 3 planes are equal)*/);
 int mocr_get_encoder_hidden(mocr_handle_t* h, float* out /*[n,197,768]*/);
+/* Polygon mask of staged region `index` as rasterised on the device: [bottom-top, right-left] uint8 (0 / 255). */
+int mocr_get_region_mask(mocr_handle_t* h, int index, uint8_t* out);
 int mocr_get_step_logits(mocr_handle_t* h, float* out /*[n,max_length-1,6144]*/);
 
 /* Kernel-level unit hooks (tests only): run ONE product kernel on caller-supplied host data.

@@ -25,6 +25,11 @@ class mocr_crop_t(ctypes.Structure):
     _fields_ = [("data", c_void_p), ("height", c_int32), ("width", c_int32), ("stride", c_int32), ("channels", c_int32)]
 
 
+class mocr_region_t(ctypes.Structure):
+    _fields_ = [("left", c_int32), ("top", c_int32), ("right", c_int32), ("bottom", c_int32), ("polygon", POINTER(c_int32)),
+                ("n_points", c_int32), ("rotate", c_int32)]
+
+
 def sources():
     return [os.path.join(CSRC, "engine.cu")]
 
@@ -56,7 +61,11 @@ _SIGNATURES = {
     "mocr_set_weight": (c_int, [c_void_p, c_char_p, POINTER(c_float), POINTER(c_int64), c_int]),
     "mocr_finalize_weights": (c_int, [c_void_p]),
     "mocr_recognize": (c_int, [c_void_p, POINTER(mocr_crop_t), c_int, c_int, c_int, POINTER(c_int32), POINTER(c_int32)]),
+    "mocr_recognize_regions": (c_int, [c_void_p, POINTER(mocr_crop_t), POINTER(mocr_region_t), c_int, c_int, c_int, POINTER(c_int32),
+                                       POINTER(c_int32)]),
     "mocr_stage_crops": (c_int, [c_void_p, POINTER(mocr_crop_t), c_int, c_int]),
+    "mocr_stage_regions": (c_int, [c_void_p, POINTER(mocr_crop_t), POINTER(mocr_region_t), c_int, c_int]),
+    "mocr_get_region_mask": (c_int, [c_void_p, c_int, POINTER(c_uint8)]),
     "mocr_preprocess": (c_int, [c_void_p]),
     "mocr_encode": (c_int, [c_void_p]),
     "mocr_decode_greedy": (c_int, [c_void_p, c_int, POINTER(c_int32)]),

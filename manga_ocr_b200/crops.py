@@ -86,3 +86,37 @@ def tall_batch(n: int = 64, seed: int = 1004) -> List[np.ndarray]:
     """Config 4: long vertical-text crops, W in [40,120], H in [600,1600]."""
     rng = np.random.default_rng(seed)
     return [make_crop(rng, int(rng.integers(600, 1601)), int(rng.integers(40, 121))) for _ in range(n)]
+
+
+def page_with_selections(n: int = 24, seed: int = 1006, height: int = 1400, width: int = 1000):
+    """A synthetic page and ``n`` selections on it, for the region-staging path:
+    speech-bubble-like polygons (12-40 points, the way the app's lasso / bubble detector produce them) around
+    glyph-like blobs; every fourth selection is a plain rectangle, every fifth has its text orientation set
+    against its aspect (so it is rotated), a few reach over the page border.
+    Returns (page uint8 [H, W, 3], list of (rect_xywh, polygon-or-None [k, 2] int32, orientation-or-None))."""
+    rng = np.random.default_rng(seed)
+    page = np.full((height, width, 3), 255, np.uint8)
+    page = np.clip(page.astype(np.float32) + rng.normal(0, 3, page.shape), 0, 255).astype(np.uint8)
+    sels = []
+    for i in range(n):
+        w, h = int(rng.integers(48, 320)), int(rng.integers(64, 480))
+        x, y = int(rng.integers(-10, width - w + 10)), int(rng.integers(-10, height - h + 10))
+        crop = make_crop(rng, h, w, tint=(i % 10 == 0))
+        y0, y1, x0, x1 = max(y, 0), min(y + h, height), max(x, 0), min(x + w, width)
+        page[y0:y1, x0:x1] = crop[y0 - y:y1 - y, x0 - x:x1 - x]
+        poly = None
+        if i % 4 != 3:
+            k = int(rng.integers(12, 41))
+            ang = np.sort(rng.uniform(0, 2 * np.pi, k))
+            rad = rng.uniform(0.8, 1.0, k)
+            poly = np.stack([x + w / 2 + (w / 2) * rad * np.cos(ang), y + h / 2 + (h / 2) * rad * np.sin(ang)], 1)
+            poly = np.round(poly).astype(np.int32)
+            bx, by = int(poly[:, 0].min()), int(poly[:, 1].min())
+            rect = (bx, by, int(poly[:, 0].max()) - bx + 1, int(poly[:, 1].max()) - by + 1)     # QPolygon.boundingRect()
+        else:
+            rect = (x, y, w, h)
+        orientation = None
+        if i % 5 == 4:
+            orientation = "Vertical" if rect[2] > rect[3] else "Horizontal"
+        sels.append((rect, poly, orientation))
+    return page, sels

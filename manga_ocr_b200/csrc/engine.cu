@@ -30,6 +30,7 @@
 #include "encoder_attn_tc.cuh"
 #include "gemm_tcgen05.cuh"
 #include "preprocess.cuh"
+#include "region_mask.cuh"
 #include "rowops.cuh"
 
 using namespace mocr;
@@ -189,6 +190,13 @@ struct mocr_handle {
   uint8_t* h_arena = nullptr;
   uint8_t* d_arena = nullptr;
   size_t arena_cap = 0;
+  // region staging (polygon masks rasterised on the device)
+  uint8_t* d_masks = nullptr;
+  size_t masks_cap = 0;
+  void* d_mask_meta = nullptr;        // jobs | edges | lines, one upload
+  size_t mask_meta_cap = 0;
+  std::vector<long long> region_mask_off;   // per staged region: mask offset or -1 (test hook)
+  std::vector<int> region_mask_hw;          // per staged region: source crop h, w
   CropDesc* h_descs = nullptr;        // pinned [max_batch]
   CropDesc* d_descs = nullptr;
   std::vector<int> h_coefs;
@@ -583,6 +591,7 @@ int stage_crops(mocr_handle* h, const mocr_crop_t* crops, int n, int order) {
   if (n < 1 || n > h->max_batch) return fail(h, MOCR_ERR_CAPACITY, "batch of %d crops, handle capacity is %d", n, h->max_batch);
   if (crops == nullptr) return fail(h, MOCR_ERR_INVALID, "crops is NULL");
   h->staged_ok = h->pre_ok = h->enc_ok = h->dec_ok = false;
+  h->region_mask_off.clear();
   size_t total = 0;
   int max_w = 0, tmp_rows = kPreStripRows;
   for (int i = 0; i < n; ++i) {
@@ -624,6 +633,13 @@ int stage_crops(mocr_handle* h, const mocr_crop_t* crops, int n, int order) {
     d.channels = c.channels;
     d.hcoef = d.vcoef = -1;
     d.hks = d.vks = 0;
+    d.region = 0;
+    d.rot = kRotNone;
+    d.ox = d.oy = 0;
+    d.ph = c.height;
+    d.pw = c.width;
+    d.sw = c.width;
+    d.mask = -1;
     mocr_handle::TableRef t;
     if (c.width != kImage) {
       TRY(table_for(h, c.width, &t));
@@ -668,6 +684,167 @@ int stage_crops(mocr_handle* h, const mocr_crop_t* crops, int n, int order) {
   return MOCR_OK;
 }
 
+// Region staging: ONE upload of the page, then every selection is a view of it -
+// crop box, optional polygon (rasterised on the device into a mask), optional 90-degree rotation -
+// resolved inside the preprocess kernel's reads.  Replaces, per selection, the reference's
+// PIL crop + RGB->BGR + fillPoly/bitwise_and/add composite + cv2.rotate + BGR->RGB host copies
+// (reference/src/ui/main_window.py:6497-6506, 9789-9800).
+int stage_regions(mocr_handle* h, const mocr_crop_t* page, const mocr_region_t* regions, int n, int order) {
+  if (!h->finalized) return fail(h, MOCR_ERR_INVALID, "weights are not finalized");
+  if (n < 1 || n > h->max_batch) return fail(h, MOCR_ERR_CAPACITY, "batch of %d regions, handle capacity is %d", n, h->max_batch);
+  if (page == nullptr || regions == nullptr) return fail(h, MOCR_ERR_INVALID, "page or regions is NULL");
+  const mocr_crop_t& pg = *page;
+  if (pg.data == nullptr || pg.height < 1 || pg.width < 1 || (pg.channels != 1 && pg.channels != 3 && pg.channels != 4) ||
+      pg.stride < pg.width * pg.channels)
+    return fail(h, MOCR_ERR_INVALID, "page is malformed (h=%d w=%d stride=%d channels=%d)", pg.height, pg.width, pg.stride, pg.channels);
+  h->staged_ok = h->pre_ok = h->enc_ok = h->dec_ok = false;
+  std::vector<MaskJob> jobs;
+  std::vector<MaskEdge> edges;
+  std::vector<MaskLine> lines;
+  std::vector<int32_t> rel;
+  size_t mask_bytes = 0;
+  int max_w = 0, tmp_rows = kPreStripRows, max_mask_h = 0;
+  h->region_mask_off.assign(n, -1);
+  h->region_mask_hw.assign(2 * n, 0);
+  for (int i = 0; i < n; ++i) {
+    const mocr_region_t& r = regions[i];
+    const long long sw = static_cast<long long>(r.right) - r.left, sh = static_cast<long long>(r.bottom) - r.top;
+    if (sw < 1 || sh < 1 || sw > 32768 || sh > 32768) return fail(h, MOCR_ERR_INVALID, "region %d has an empty or oversized box (%lld x %lld)", i, sw, sh);
+    if (r.rotate < 0 || r.rotate > 2) return fail(h, MOCR_ERR_INVALID, "region %d: rotate must be 0, 1 (clockwise) or 2 (counter-clockwise)", i);
+    if (r.n_points < 0 || r.n_points > kMaskMaxEdges || (r.n_points > 0 && r.polygon == nullptr))
+      return fail(h, r.n_points > kMaskMaxEdges ? MOCR_ERR_CAPACITY : MOCR_ERR_INVALID, "region %d: bad polygon (%d points, limit %d)", i, r.n_points, kMaskMaxEdges);
+    CropDesc& d = h->h_descs[i];
+    d.offset = 0;
+    d.h = static_cast<int>(r.rotate == kRotNone ? sh : sw);
+    d.w = static_cast<int>(r.rotate == kRotNone ? sw : sh);
+    d.stride = pg.width * pg.channels;      // the page is packed into the arena
+    d.channels = pg.channels;
+    d.hcoef = d.vcoef = -1;
+    d.hks = d.vks = 0;
+    d.region = 1;
+    d.rot = r.rotate;
+    d.ox = r.left;
+    d.oy = r.top;
+    d.ph = pg.height;
+    d.pw = pg.width;
+    d.sw = static_cast<int>(sw);
+    d.mask = -1;
+    h->region_mask_hw[2 * i] = static_cast<int>(sh);
+    h->region_mask_hw[2 * i + 1] = static_cast<int>(sw);
+    if (r.n_points > 0) {
+      rel.resize(2 * static_cast<size_t>(r.n_points));
+      for (int k = 0; k < r.n_points; ++k) {
+        rel[2 * k] = r.polygon[2 * k] - r.left;
+        rel[2 * k + 1] = r.polygon[2 * k + 1] - r.top;
+      }
+      MaskJob j;
+      j.mask_off = static_cast<long long>(mask_bytes);
+      j.h = static_cast<int>(sh);
+      j.w = static_cast<int>(sw);
+      j.edge0 = static_cast<int>(edges.size());
+      j.line0 = static_cast<int>(lines.size());
+      collect_poly_edges(j.h, j.w, rel.data(), r.n_points, edges, lines);
+      j.n_edges = static_cast<int>(edges.size()) - j.edge0;
+      j.n_lines = static_cast<int>(lines.size()) - j.line0;
+      jobs.push_back(j);
+      d.mask = j.mask_off;
+      h->region_mask_off[i] = j.mask_off;
+      mask_bytes += (static_cast<size_t>(sh) * sw + 15) & ~static_cast<size_t>(15);
+      max_mask_h = std::max(max_mask_h, j.h);
+    }
+    mocr_handle::TableRef t;
+    if (d.w != kImage) {
+      TRY(table_for(h, d.w, &t));
+      d.hcoef = t.offset;
+      d.hks = t.ksize;
+    }
+    if (d.h != kImage) {
+      TRY(table_for(h, d.h, &t));
+      d.vcoef = t.offset;
+      d.vks = t.ksize;
+      tmp_rows = std::max(tmp_rows, t.strip_rows);
+    }
+    max_w = std::max(max_w, d.w);
+  }
+  h->pre_pitch = round_up(max_w, 16);
+  h->pre_tmp_rows = tmp_rows;
+  h->pre_bgr = order == MOCR_BGR ? 1 : 0;
+  const size_t smem = static_cast<size_t>(kPreThreads / 32) * h->pre_pitch + static_cast<size_t>(tmp_rows) * kImage;
+  if (smem > 200 * 1024) return fail(h, MOCR_ERR_CAPACITY, "region extents need %zu B of shared memory (limit 204800)", smem);
+
+  CK(cudaStreamSynchronize(h->stream));     // the previous batch may still be reading the arena / tables / masks
+  const size_t rowb = static_cast<size_t>(pg.width) * pg.channels, total = rowb * pg.height;
+  if (total > h->arena_cap) {
+    if (h->h_arena) cudaFreeHost(h->h_arena);
+    if (h->d_arena) cudaFree(h->d_arena);
+    h->h_arena = nullptr;
+    h->d_arena = nullptr;
+    h->arena_cap = 0;
+    const size_t cap = std::max<size_t>(total + total / 4, 8u << 20);
+    CK(cudaMallocHost(reinterpret_cast<void**>(&h->h_arena), cap));
+    CK(cudaMalloc(reinterpret_cast<void**>(&h->d_arena), cap));
+    h->arena_cap = cap;
+  }
+  if (static_cast<size_t>(pg.stride) == rowb) memcpy(h->h_arena, pg.data, total);
+  else for (int y = 0; y < pg.height; ++y) memcpy(h->h_arena + y * rowb, pg.data + static_cast<size_t>(y) * pg.stride, rowb);
+  CK(cudaMemcpyAsync(h->d_arena, h->h_arena, total, cudaMemcpyHostToDevice, h->stream));
+  if (h->h_coefs.size() > h->d_coefs_cap) {
+    if (h->d_coefs) cudaFree(h->d_coefs);
+    h->d_coefs = nullptr;
+    h->d_coefs_cap = h->d_coefs_used = 0;
+    const size_t cap = std::max<size_t>(h->h_coefs.size() * 2, 1u << 20);
+    CK(cudaMalloc(reinterpret_cast<void**>(&h->d_coefs), cap * sizeof(int)));
+    h->d_coefs_cap = cap;
+  }
+  if (h->h_coefs.size() > h->d_coefs_used) {
+    CK(cudaMemcpyAsync(h->d_coefs + h->d_coefs_used, h->h_coefs.data() + h->d_coefs_used,
+                       (h->h_coefs.size() - h->d_coefs_used) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    h->d_coefs_used = h->h_coefs.size();
+  }
+  CK(cudaMemcpyAsync(h->d_descs, h->h_descs, sizeof(CropDesc) * n, cudaMemcpyHostToDevice, h->stream));
+  if (!jobs.empty()) {
+    if (mask_bytes > h->masks_cap) {
+      if (h->d_masks) cudaFree(h->d_masks);
+      h->d_masks = nullptr;
+      h->masks_cap = 0;
+      const size_t cap = std::max<size_t>(mask_bytes + mask_bytes / 4, 4u << 20);
+      CK(cudaMalloc(reinterpret_cast<void**>(&h->d_masks), cap));
+      h->masks_cap = cap;
+    }
+    // jobs | edges | lines in one pageable upload (staged synchronously by the runtime)
+    const size_t jb = round_up(static_cast<int>(jobs.size() * sizeof(MaskJob)), 16), eb = round_up(static_cast<int>(edges.size() * sizeof(MaskEdge)), 16),
+                 lb = round_up(static_cast<int>(lines.size() * sizeof(MaskLine)), 16), meta = jb + eb + lb + 16;
+    if (meta > h->mask_meta_cap) {
+      if (h->d_mask_meta) cudaFree(h->d_mask_meta);
+      h->d_mask_meta = nullptr;
+      h->mask_meta_cap = 0;
+      CK(cudaMalloc(&h->d_mask_meta, meta * 2));
+      h->mask_meta_cap = meta * 2;
+    }
+    std::vector<uint8_t> blob(meta, 0);
+    memcpy(blob.data(), jobs.data(), jobs.size() * sizeof(MaskJob));
+    if (!edges.empty()) memcpy(blob.data() + jb, edges.data(), edges.size() * sizeof(MaskEdge));
+    if (!lines.empty()) memcpy(blob.data() + jb + eb, lines.data(), lines.size() * sizeof(MaskLine));
+    CK(cudaMemcpyAsync(h->d_mask_meta, blob.data(), meta, cudaMemcpyHostToDevice, h->stream));
+    const MaskJob* dj = static_cast<const MaskJob*>(h->d_mask_meta);
+    const MaskEdge* de = reinterpret_cast<const MaskEdge*>(static_cast<const uint8_t*>(h->d_mask_meta) + jb);
+    const MaskLine* dl = reinterpret_cast<const MaskLine*>(static_cast<const uint8_t*>(h->d_mask_meta) + jb + eb);
+    dim3 grid((max_mask_h + kMaskRowsPerCta - 1) / kMaskRowsPerCta, static_cast<unsigned>(jobs.size()));
+    region_mask_fill_kernel<<<grid, 32 * kMaskRowsPerCta, 0, h->stream>>>(dj, de, h->d_masks);
+    CK(cudaGetLastError());
+    ++h->launches;
+    if (!lines.empty()) {
+      region_mask_lines_kernel<<<(static_cast<int>(lines.size()) + 127) / 128, 128, 0, h->stream>>>(dj, static_cast<int>(jobs.size()), dl,
+                                                                                                  static_cast<int>(lines.size()), h->d_masks);
+      CK(cudaGetLastError());
+      ++h->launches;
+    }
+  }
+  h->n = n;
+  h->staged_ok = true;
+  return MOCR_OK;
+}
+
 int preprocess(mocr_handle* h) {
   if (!h->staged_ok) return fail(h, MOCR_ERR_INVALID, "no crops staged");
   const size_t smem = static_cast<size_t>(kPreThreads / 32) * h->pre_pitch + static_cast<size_t>(h->pre_tmp_rows) * kImage;
@@ -678,7 +855,7 @@ int preprocess(mocr_handle* h) {
   }
   const bool tap = (h->taps & MOCR_TAP_PIXELS) != 0;
   dim3 grid(kImage / kPreStripRows, h->n);
-  preprocess_kernel<<<grid, kPreThreads, smem, h->stream>>>(h->d_arena, h->d_descs, h->d_coefs, h->pre_bgr, h->pre_pitch, h->patches.p,
+  preprocess_kernel<<<grid, kPreThreads, smem, h->stream>>>(h->d_arena, h->d_descs, h->d_coefs, h->pre_bgr, h->pre_pitch, h->d_masks, h->patches.p,
                                                            tap ? h->px_u8 : nullptr, tap ? h->px_f32 : nullptr, h->lut);
   CK(cudaGetLastError());
   ++h->launches;
@@ -1227,6 +1404,8 @@ int mocr_destroy(mocr_handle_t* h) {
     if (h->d_arena) cudaFree(h->d_arena);
     if (h->h_arena) cudaFreeHost(h->h_arena);
     if (h->d_coefs) cudaFree(h->d_coefs);
+    if (h->d_masks) cudaFree(h->d_masks);
+    if (h->d_mask_meta) cudaFree(h->d_mask_meta);
     if (h->h_flags) cudaFreeHost(h->h_flags);
     if (h->h_steps) cudaFreeHost(h->h_steps);
     if (h->h_descs) cudaFreeHost(h->h_descs);
@@ -1265,6 +1444,37 @@ int mocr_stage_crops(mocr_handle_t* h, const mocr_crop_t* crops, int n, int chan
   TRY(check_handle(h));
   std::lock_guard<std::mutex> lock(h->mu);
   return stage_crops(h, crops, n, channel_order);
+}
+
+int mocr_stage_regions(mocr_handle_t* h, const mocr_crop_t* page, const mocr_region_t* regions, int n, int channel_order) {
+  TRY(check_handle(h));
+  std::lock_guard<std::mutex> lock(h->mu);
+  return stage_regions(h, page, regions, n, channel_order);
+}
+
+int mocr_recognize_regions(mocr_handle_t* h, const mocr_crop_t* page, const mocr_region_t* regions, int n, int channel_order, int max_length,
+                           int32_t* out_ids, int32_t* out_lens) {
+  TRY(check_handle(h));
+  std::lock_guard<std::mutex> lock(h->mu);
+  if (n < 0 || (n > 0 && (page == nullptr || regions == nullptr || out_ids == nullptr))) return fail(h, MOCR_ERR_INVALID, "bad argument");
+  for (int i0 = 0; i0 < n; i0 += h->max_batch) {
+    const int m = std::min(h->max_batch, n - i0);
+    TRY(stage_regions(h, page, regions + i0, m, channel_order));
+    TRY(preprocess(h));
+    TRY(encode(h));
+    TRY(decode(h, max_length, nullptr));
+    TRY(fetch_ids(h, out_ids + static_cast<size_t>(i0) * max_length, out_lens ? out_lens + i0 : nullptr));
+  }
+  return MOCR_OK;
+}
+
+int mocr_get_region_mask(mocr_handle_t* h, int index, uint8_t* out) {
+  TRY(check_handle(h));
+  std::lock_guard<std::mutex> lock(h->mu);
+  if (!h->staged_ok || index < 0 || index >= static_cast<int>(h->region_mask_off.size()) || index >= h->n || out == nullptr)
+    return fail(h, MOCR_ERR_INVALID, "no staged region %d", index);
+  if (h->region_mask_off[index] < 0) return fail(h, MOCR_ERR_INVALID, "region %d has no polygon", index);
+  return d2h(h, out, h->d_masks + h->region_mask_off[index], static_cast<size_t>(h->region_mask_hw[2 * index]) * h->region_mask_hw[2 * index + 1]);
 }
 
 int mocr_preprocess(mocr_handle_t* h) {

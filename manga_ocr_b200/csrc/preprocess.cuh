@@ -26,14 +26,23 @@ constexpr int kPreStripRows = 8;      // output rows per CTA
 constexpr int kPreThreads = 256;
 constexpr int kResampleBits = 22;     // Pillow PRECISION_BITS = 32 - 8 - 2
 
+constexpr int kRotNone = 0, kRotCw = 1, kRotCcw = 2;
+
 struct CropDesc {
-  long long offset;   // byte offset of pixel (0,0) in the crop arena
-  int h, w;
-  int stride;         // bytes per row
+  long long offset;   // byte offset of source pixel (0,0) - the crop's, or the page's for a region - in the crop arena
+  int h, w;           // extent of the image handed to the resampler (after the optional rotation)
+  int stride;         // bytes per source row
   int hcoef;          // int32 offset of the horizontal table in the coefficient arena (-1: w == 224)
   int vcoef;          // same for the vertical table (-1: h == 224)
   int hks, vks;       // taps per output (table row width)
   int channels;       // bytes per pixel: 1 (luma), 3 (RGB/BGR) or 4 (RGBA/BGRA, alpha ignored)
+  // region staging (main_window.py:6497-6506, 9789-9795); a plain crop has region = 0
+  int region;         // 1: the fields below apply
+  int rot;            // kRotNone / kRotCw / kRotCcw (cv2.rotate of the composited crop)
+  int ox, oy;         // crop origin in the source image; pixels outside [0, sw_full) x [0, sh_full) read 0 (PIL crop)
+  int ph, pw;         // source image extent
+  int sw;             // crop width before rotation (the mask pitch)
+  long long mask;     // byte offset of the crop's [sh][sw] polygon mask in the mask arena, -1: none
 };
 
 // One table = xmin[224] | count[224] | k[224 * ksize]  (all int32)
@@ -95,7 +104,7 @@ inline ResampleTable make_resample_table(int in_size) {
 // dynamic smem = 8 * rowbuf_pitch + tmp_rows * 224 bytes.
 __global__ void __launch_bounds__(kPreThreads)
 preprocess_kernel(const uint8_t* __restrict__ arena, const CropDesc* __restrict__ crops, const int* __restrict__ coefs,
-                  int bgr, int rowbuf_pitch, __nv_bfloat16* __restrict__ patches /*[n*196,256]*/,
+                  int bgr, int rowbuf_pitch, const uint8_t* __restrict__ masks, __nv_bfloat16* __restrict__ patches /*[n*196,256]*/,
                   uint8_t* __restrict__ dbg_u8 /*[n,224,224] or null*/, float* __restrict__ dbg_f32 /*[n,224,224] or null*/,
                   const float* __restrict__ lut /*[256]*/) {
   extern __shared__ uint8_t pre_smem[];
@@ -121,7 +130,29 @@ preprocess_kernel(const uint8_t* __restrict__ arena, const CropDesc* __restrict_
     const uint8_t* src = arena + cd.offset + static_cast<long long>(r) * cd.stride;
     uint8_t* trow = tmp + (r - r_lo) * kImage;
     uint8_t* lrow = (cd.hcoef >= 0) ? rowbuf : trow;
-    if (cd.channels == 1) {
+    if (cd.region) {
+      // crop + polygon composite on white + rotation, folded into the read: image pixel (r, x) is source
+      // crop pixel (sy, sx); outside the polygon it is white, outside the page it is black (PIL crop)
+      const int pc = cd.channels;
+      const int sh = cd.rot == kRotNone ? cd.h : cd.w;
+      for (int x = lane; x < cd.w; x += 32) {
+        int sy = r, sx = x;
+        if (cd.rot == kRotCw) { sy = sh - 1 - x; sx = r; }            // dst(y, x) = src(H-1-x, y)
+        else if (cd.rot == kRotCcw) { sy = x; sx = cd.sw - 1 - r; }   // dst(y, x) = src(x, W-1-y)
+        unsigned c0 = 255u, c1 = 255u, c2 = 255u;
+        if (cd.mask < 0 || masks[cd.mask + static_cast<long long>(sy) * cd.sw + sx] != 0) {
+          const int py = cd.oy + sy, px = cd.ox + sx;
+          c0 = c1 = c2 = 0u;
+          if (py >= 0 && py < cd.ph && px >= 0 && px < cd.pw) {
+            const uint8_t* q = arena + cd.offset + static_cast<long long>(py) * cd.stride + static_cast<long long>(px) * pc;
+            c0 = q[0];
+            if (pc == 1) { c1 = c2 = c0; } else { c1 = q[1]; c2 = q[2]; }
+          }
+        }
+        // (for a 1-channel source the three equal "channels" give back the value itself: the weights sum to 65536)
+        lrow[x] = static_cast<uint8_t>((cr * c0 + 38470u * c1 + cb * c2 + 0x8000u) >> 16);
+      }
+    } else if (cd.channels == 1) {
       for (int x = lane; x < cd.w; x += 32) lrow[x] = src[x];
     } else {
       const int pc = cd.channels;

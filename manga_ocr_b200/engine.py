@@ -16,6 +16,7 @@ from . import _lib
 from .weights import D, ENC_TOKENS, IMAGE, VOCAB
 
 RGB, BGR = 0, 1
+ROT_NONE, ROT_CW, ROT_CCW = 0, 1, 2
 TAP_PIXELS, TAP_ENCODER, TAP_LOGITS = 1, 2, 4
 MAX_LENGTH = 300   # hard-coded by upstream MangaOcr.__call__
 
@@ -44,6 +45,55 @@ def _as_crop_array(crops: Sequence[np.ndarray]) -> Tuple[ctypes.Array, List[np.n
         arr[i].width = c.shape[1]
         arr[i].stride = c.strides[0]
         arr[i].channels = ch
+    return arr, keep
+
+
+class Region:
+    """One selection on a page, as the reference stages it in front of the engine
+    (reference/src/ui/main_window.py:6497-6506, 6429-6430, 9789-9795): ``box`` = the PIL crop box
+    (left, top, right, bottom), ``polygon`` = optional [n, 2] int points in PAGE coordinates (outside it
+    the crop is white), ``rotate`` = ROT_NONE / ROT_CW / ROT_CCW."""
+
+    __slots__ = ("box", "polygon", "rotate")
+
+    def __init__(self, box: Sequence[int], polygon: Optional[Sequence[Sequence[int]]] = None, rotate: int = ROT_NONE):
+        self.box = tuple(int(v) for v in box)
+        if len(self.box) != 4:
+            raise ValueError("box must be (left, top, right, bottom)")
+        self.polygon = None if polygon is None else np.ascontiguousarray(np.asarray(polygon).reshape(-1, 2), dtype=np.int32)
+        self.rotate = int(rotate)
+
+    @classmethod
+    def from_qt(cls, rect_xywh: Sequence[int], polygon: Optional[Sequence[Sequence[int]]] = None, orientation: Optional[str] = None) -> "Region":
+        """The reference's own numbers: the crop box is (x, y, QRect.right(), QRect.bottom()) with right = x + w - 1
+        (so the crop is one pixel short of the rectangle, main_window.py:6497), and a crop is rotated when the
+        text orientation disagrees with its aspect (:9789-9795)."""
+        x, y, w, h = (int(v) for v in rect_xywh)
+        box = (x, y, x + w - 1, y + h - 1)
+        ch, cw = box[3] - box[1], box[2] - box[0]
+        rot = ROT_NONE
+        if orientation == "Vertical" and cw > ch:
+            rot = ROT_CW
+        elif orientation == "Horizontal" and ch > cw:
+            rot = ROT_CCW
+        return cls(box, polygon, rot)
+
+
+def _as_region_array(regions: Sequence[Region]) -> Tuple[ctypes.Array, list]:
+    keep = []
+    arr = (_lib.mocr_region_t * len(regions))()
+    for i, r in enumerate(regions):
+        if not isinstance(r, Region):
+            r = Region(*r)
+        arr[i].left, arr[i].top, arr[i].right, arr[i].bottom = r.box
+        arr[i].rotate = r.rotate
+        if r.polygon is not None and len(r.polygon) > 0:
+            keep.append(r.polygon)
+            arr[i].polygon = r.polygon.ctypes.data_as(POINTER(c_int32))
+            arr[i].n_points = len(r.polygon)
+        else:
+            arr[i].polygon = None
+            arr[i].n_points = 0
     return arr, keep
 
 
@@ -131,6 +181,34 @@ class Engine:
         self._ck(self._lib.mocr_stage_crops(self._h, arr, len(crops), order))
         self.n = len(crops)
         del keep
+
+    def stage_regions(self, page: np.ndarray, regions: Sequence[Region], order: int = RGB) -> None:
+        """One page + its selections (crop box, polygon, rotation resolved on the device)."""
+        parr, keep = _as_crop_array([page])
+        rarr, rkeep = _as_region_array(regions)
+        self._ck(self._lib.mocr_stage_regions(self._h, parr, rarr, len(regions), order))
+        self.n = len(regions)
+        del keep, rkeep
+
+    def recognize_regions(self, page: np.ndarray, regions: Sequence[Region], order: int = RGB, max_length: Optional[int] = None):
+        T = max_length or self.max_length
+        n = len(regions)
+        ids = np.zeros((n, T), np.int32)
+        lens = np.zeros((n,), np.int32)
+        if n == 0:
+            return ids, lens
+        parr, keep = _as_crop_array([page])
+        rarr, rkeep = _as_region_array(regions)
+        self._ck(self._lib.mocr_recognize_regions(self._h, parr, rarr, n, order, T, ids.ctypes.data_as(POINTER(c_int32)),
+                                                  lens.ctypes.data_as(POINTER(c_int32))))
+        del keep, rkeep
+        return ids, lens
+
+    def region_mask(self, index: int, shape: Tuple[int, int]) -> np.ndarray:
+        """Polygon mask of staged region ``index`` as the device rasterised it (tests)."""
+        out = np.zeros(shape, np.uint8)
+        self._ck(self._lib.mocr_get_region_mask(self._h, index, out.ctypes.data_as(POINTER(c_uint8))))
+        return out
 
     def preprocess(self) -> None:
         self._ck(self._lib.mocr_preprocess(self._h))

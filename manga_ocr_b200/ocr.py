@@ -140,6 +140,37 @@ class MangaOcr:
         ids = self.recognize_ids(arrays, order)
         return ids_to_texts(self.vocab, ids)
 
+    def recognize_regions(self, page, regions: Sequence, order: int = RGB) -> List[str]:
+        """All selections of ONE page -> strings.  ``page``: PIL image or uint8 array; ``regions``: ``Region``
+        objects (``manga_ocr_b200.engine.Region``; ``Region.from_qt(rect, polygon, orientation)`` reproduces the
+        reference's numbers).  The page is uploaded once; crop, polygon composite on white and rotation
+        (reference/src/ui/main_window.py:6497-6506, 9789-9800) happen on the GPU."""
+        arr = page if isinstance(page, np.ndarray) else image_to_array(page)
+        regions = list(regions)
+        if len(self.engines) == 1 or len(regions) <= 1:
+            ids = self.engines[0].recognize_regions(arr, regions, order, self.max_length)[0]
+            return ids_to_texts(self.vocab, ids)
+        from .splitter import shard_bounds
+        out = np.zeros((len(regions), self.max_length), np.int32)
+        errs: List[BaseException] = []
+
+        def work(k: int) -> None:
+            lo, hi = shard_bounds(len(regions), len(self.engines), k)
+            try:
+                if hi > lo:
+                    out[lo:hi] = self.engines[k].recognize_regions(arr, regions[lo:hi], order, self.max_length)[0]
+            except BaseException as e:   # noqa: BLE001 - re-raised on the caller's thread
+                errs.append(e)
+
+        ts = [threading.Thread(target=work, args=(k,)) for k in range(len(self.engines))]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        if errs:
+            raise errs[0]
+        return ids_to_texts(self.vocab, out)
+
     def recognize_ids(self, arrays: Sequence[np.ndarray], order: int = RGB) -> np.ndarray:
         if len(self.engines) == 1 or len(arrays) <= 1:
             return self.engines[0].recognize(arrays, order, self.max_length)[0]
