@@ -284,6 +284,44 @@ def run_b200(args, rank, local_rank, world):
                     "traffic": None, "peak_source": peaks["source"], "ms_per_launch": k_ms, "algorithmic_bytes": k_bytes,
                     "note": "50 back-to-back launches with programmatic dependent launch, exactly as in the decode loop; L2 warm"}
 
+        if name == "dec_cross_attn" and BATCH == 64:
+            # dram__bytes_read.sum + dram__bytes_write.sum of pd_attention_kernel<0>, one `ncu --set full` capture of this
+            # command (profiles/r1_ncu_decode_kernels.txt): 39.355136 MB + 1.536 KB per launch, vs 38.93 MB algorithmic
+            roof["traffic"] = 39355136.0 + 1536.0
+            roof["traffic_source"] = "profiles/r1_ncu_decode_kernels.txt"
+
+    # ---- region staging: 64 selections of one page, crop + polygon composite + rotation on the device
+    regions_info = None
+    if rank == 0 and world == 1 and not args.no_regions:
+        from manga_ocr_b200.engine import Region
+        page, sels = C.page_with_selections(BATCH)
+        regions = [Region.from_qt(rect, poly, orient) for rect, poly, orient in sels]
+        ocr.recognize_regions(page, regions)
+        t0 = time.perf_counter()
+        for _ in range(2):
+            ocr.recognize_regions(page, regions)
+        reg_s = (time.perf_counter() - t0) / 2
+        def timed(f, n=5):
+            f()
+            t0 = time.perf_counter()
+            for _ in range(n):
+                f()
+            return (time.perf_counter() - t0) / n * 1e3
+        def dev_stage():
+            eng.stage_regions(page, regions)
+            eng.sync()
+        regions_info = {"selections": BATCH, "page": list(page.shape), "with_polygon": sum(r.polygon is not None for r in regions),
+                        "rotated": sum(r.rotate != 0 for r in regions), "e2e_crops_per_s": BATCH / reg_s,
+                        "device_staging_ms": timed(dev_stage), "api": "MangaOcr.recognize_regions (page + selections -> strings)"}
+        if not args.no_cpu_baseline:
+            try:
+                from oracle.make_golden_staging import reference_stage     # the reference's own PIL / cv2 call sequence
+                host_ms = timed(lambda: [reference_stage(page, r.box, r.polygon, r.rotate) for r in regions])
+                regions_info["host_staging_ms_reference_libs"] = host_ms
+            except Exception as e:      # noqa: BLE001 - cv2 missing on this box
+                regions_info["host_staging_ms_reference_libs"] = None
+                regions_info["host_staging_note"] = f"not measured: {e}"
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         n_calls = 8
@@ -305,7 +343,7 @@ def run_b200(args, rank, local_rank, world):
             "decode_tokens_per_s": BATCH * world * steps_decoded * args.steps / (ms_max * 1e-3),
             "e2e": {"value": total_crops / (e2e_ms_max * 1e-3), "unit": UNIT, "h2d_bytes_per_step": in_bytes + 40 * BATCH,
                     "d2h_bytes_per_step": BATCH * MAX_LENGTH * 4 + BATCH * 4, "api": "MangaOcr.recognize_batch (host uint8 crops -> strings)"},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "phases": phases, "kernels": kernels,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "phases": phases, "kernels": kernels, "regions": regions_info,
             "wall_s_timed_region": t_wall,
         }
         print(json.dumps(line), flush=True)
@@ -322,6 +360,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--roofline-kernel", default="dec_cross_attn")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-regions", action="store_true", help="skip the region-staging leg")
     ap.add_argument("--max-length", type=int, default=300, help="profiling only; the metric is defined at 300")
     args = ap.parse_args()
     rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
