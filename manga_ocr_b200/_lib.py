@@ -12,7 +12,7 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB_PATH = os.path.join(HERE, "libmocr_b200.so")
+LIB_PATH = os.environ.get("MOCR_LIB_PATH") or os.path.join(HERE, "libmocr_b200.so")   # (override: A/B runs of two builds)
 HEADER = os.path.join(os.path.dirname(HERE), "include", "mocr_b200.h")
 
 NVCC_FLAGS = [

@@ -35,7 +35,7 @@ constexpr int kPdWarps = kPdThreads / 32;
 constexpr int kPdRowsPerBlock = 64;          // activation rows per pass (4 m-tiles of 16)
 constexpr int kPdKSlices = 2;                // warps per m-tile: K is split in two inside a CTA
 constexpr int kPdGroups = kPdThreads / 128;  // attention groups of 4 warps
-constexpr int kPdKeySlots = 7;               // 7 * 16 = 112 keys per staged block (a 197-key unit = 2 blocks)
+constexpr int kPdKeySlots = 8;               // 8 * 16 = 128 keys per staged block (a 197-key unit = 2 blocks); each warp owns 32 consecutive keys
 constexpr int kPdStageBytes = 2 * kPdKeySlots * 128 * 16;          // K and V of one block, one group
 constexpr int kPdMaxNT = 48;
 constexpr int kPdRedFloats = kPdKSlices * kPdRowsPerBlock * (kPdMaxNT + 1);
@@ -663,29 +663,54 @@ __device__ __forceinline__ uint64_t l2_policy_evict_first() {
 __device__ __forceinline__ void cp_async16_cg_hint(void* smem_dst, const void* gsrc, uint64_t pol) {
   asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "l"(pol) : "memory");
 }
-__device__ __forceinline__ void pd_attn_request_stream(uint4* stage, const PdAttnUnit& a, int key_stride, int j0, int gt, uint64_t pol) {
-  const int gw = gt >> 5, sub = (gt & 31) >> 3;
+__device__ __forceinline__ void cp_async16_zero(void* smem_dst, const void* any_valid_gsrc) {   // src-size 0: writes 16 zero bytes
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, 0;" ::"r"(smem_u32(smem_dst)), "l"(any_valid_gsrc) : "memory");
+}
+// Stage one 128-key block: warp w of the group fetches - and later consumes, so a __syncwarp is all the
+// synchronisation the stream needs - keys [32w, 32w+32) of the block.  A key row is 128 bytes (64 dims);
+// its 16-byte chunks are XOR-swizzled with the key index so that ldmatrix (8 rows x 16 bytes) is
+// conflict-free.  V rows past the last key are zero-filled (their probabilities are 0, but 0 x garbage
+// could be NaN inside the MMA).  self: the row at index pos is this token's K/V, taken from the QKV buffer
+// and appended to the cache here (modeling_bert.py:190 re-concatenates the whole cache instead).
+template <bool HINT>
+__device__ __forceinline__ void pd_attn_request_t(uint4* stage, const PdAttnUnit& a, int key_stride, int j0, int gt, uint64_t pol) {
+  const int gw = gt >> 5, sub = (gt & 31) >> 3, ch = gt & 7;
+  if (j0 + 32 * gw >= a.n_keys) return;                 // warp-uniform: nothing of this warp's range exists
+  int fresh_j = -1;
 #pragma unroll 1
   for (int i = 0; i < kPdKeySlots; ++i) {
-    const int j = j0 + 16 * i + 4 * gw + sub;
+    const int kl = 32 * gw + 4 * i + sub;               // key index inside the block
+    const int j = j0 + kl;
+    uint4* kd = stage + kl * 8 + (ch ^ (kl & 7));
+    uint4* vd = kd + kPdKeySlots * 128;
     if (j < a.n_keys) {
       const bool fresh = j == a.ps;
-      cp_async16_cg_hint(stage + i * 128 + gt, fresh ? a.nk : a.kc + static_cast<size_t>(j) * key_stride, pol);
-      cp_async16_cg_hint(stage + (kPdKeySlots + i) * 128 + gt, fresh ? a.nv : a.vc + static_cast<size_t>(j) * key_stride, pol);
+      const __nv_bfloat16* ks = fresh ? a.nk : a.kc + static_cast<size_t>(j) * key_stride;
+      const __nv_bfloat16* vs = fresh ? a.nv : a.vc + static_cast<size_t>(j) * key_stride;
+      if (HINT) {
+        cp_async16_cg_hint(kd, ks, pol);
+        cp_async16_cg_hint(vd, vs, pol);
+      } else {
+        cp_async16_cg(kd, ks);
+        cp_async16_cg(vd, vs);
+      }
+      if (fresh) fresh_j = j;
+    } else {
+      cp_async16_zero(vd, a.vc);
     }
+  }
+  if (fresh_j >= 0) {    // append this token's row to the cache (8 lanes, 16 bytes each, per K and V) once the stream is issued
+    const uint4 kq = ldg_cg16(a.nk), vq = ldg_cg16(a.nv);
+    *reinterpret_cast<uint4*>(const_cast<__nv_bfloat16*>(a.kc) + static_cast<size_t>(fresh_j) * key_stride) = kq;
+    *reinterpret_cast<uint4*>(const_cast<__nv_bfloat16*>(a.vc) + static_cast<size_t>(fresh_j) * key_stride) = vq;
   }
 }
-__device__ __forceinline__ void pd_attn_request(uint4* stage, const PdAttnUnit& a, int key_stride, int j0, int gt) {
-  const int gw = gt >> 5, sub = (gt & 31) >> 3;
-#pragma unroll 1
-  for (int i = 0; i < kPdKeySlots; ++i) {
-    const int j = j0 + 16 * i + 4 * gw + sub;
-    if (j < a.n_keys) {
-      const bool fresh = j == a.ps;
-      cp_async16_cg(stage + i * 128 + gt, fresh ? a.nk : a.kc + static_cast<size_t>(j) * key_stride);
-      cp_async16_cg(stage + (kPdKeySlots + i) * 128 + gt, fresh ? a.nv : a.vc + static_cast<size_t>(j) * key_stride);
-    }
-  }
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr) : "memory");
 }
 
 template <bool SELF, class Bar>
@@ -695,10 +720,9 @@ __device__ __forceinline__ void pd_attention_stage(Bar& bar, uint8_t* smem, cons
   const int n_groups = blockDim.x >> 7;       // 2 in the persistent kernel, 1 in the stage kernel
   const int group = tid >> 7, gt = tid & 127;
   const int gw = gt >> 5, lane = gt & 31;
-  const int sub = lane >> 3, ch = lane & 7;
+  const int ch = lane & 7;
   uint4* stage0 = reinterpret_cast<uint4*>(smem + (group * 2) * kPdStageBytes);
   uint4* stage1 = reinterpret_cast<uint4*>(smem + (group * 2 + 1) * kPdStageBytes);
-  float* s_part = reinterpret_cast<float*>(smem + n_groups * 2 * kPdStageBytes) + group * 4 * (2 + kHeadDim);
   const PdLayer& L = p.layer[st.layer];
   // self: cache rows [B][t][768], a head is a 64-column slice; cross: one contiguous [197][64] block per (crop, layer, K|V, head)
   const __nv_bfloat16* kbase = SELF ? L.self_k : p.crosskv + static_cast<size_t>(st.layer * 2) * kHeads * kEncTokens * kHeadDim;
@@ -795,8 +819,8 @@ __device__ __forceinline__ void pd_attention_stage(Bar& bar, uint8_t* smem, cons
   const bool stream_kv = SELF ? (p.kv_evict_first & 2) != 0 : (p.kv_evict_first & 1) != 0;
   const uint64_t pol = stream_kv ? l2_policy_evict_first() : 0ull;
   auto request = [&](uint4* stage, const PdAttnUnit& a, int j0) {
-    if (stream_kv) pd_attn_request_stream(stage, a, key_stride, j0, gt, pol);
-    else pd_attn_request(stage, a, key_stride, j0, gt);
+    if (stream_kv) pd_attn_request_t<true>(stage, a, key_stride, j0, gt, pol);
+    else pd_attn_request_t<false>(stage, a, key_stride, j0, gt, 0ull);
   };
   PdAttnUnit cur = make_unit(u0 < units ? u0 : 0, 0, 0, false);
   bool pre2 = false;       // both blocks of the first unit were requested before the dependency wait
@@ -839,7 +863,13 @@ __device__ __forceinline__ void pd_attention_stage(Bar& bar, uint8_t* smem, cons
     }
   }
   int par = 0, j0 = 0;
-  float q[8], m = -INFINITY, l = 0.f, acc[8];
+  // Per-warp online-softmax state.  The attention of ONE query is a GEMV; it runs on mma.sync.m16n8k16 with the
+  // query in row 0 of the A operand (rows 1-15 are zero): 12x fewer instructions than the per-thread FMA/shuffle
+  // form, which had made the stage issue-bound.  Row 0 lives in lanes 0-3 (t = lane): score / output columns
+  // 2t, 2t+1 of every 8-wide tile.
+  float q[8], m = -INFINITY, l = 0.f;
+  float o[8][4];
+  uint32_t qa[4][2];                     // A fragments (a0, a2) of the four 16-dim k-steps; a1 = a3 = 0
 #pragma unroll 1
   while (u < units && cur.n_keys > 0) {
     uint4* stage = par ? stage1 : stage0;
@@ -868,96 +898,119 @@ __device__ __forceinline__ void pd_attention_stage(Bar& bar, uint8_t* smem, cons
       m = -INFINITY;
       l = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+      for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+      // lane c (< 8) holds the 8-dim chunk c of q; the row-0 quad needs, per 16-dim k-step ks,
+      // a0 = q[16ks + 2t, +1] (chunk 2ks, pair t) and a2 = q[16ks + 8 + 2t, +1] (chunk 2ks+1, pair t)
+      uint32_t pk[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) pk[e] = pack_bf16(q[2 * e], q[2 * e + 1]);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint32_t f = 0u;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const uint32_t v = __shfl_sync(0xffffffffu, pk[e], c);
+          if (lane == e) f = v;
+        }
+        qa[c >> 1][c & 1] = f;                          // lanes >= 4 keep 0: rows 1-15 of the A operand
+      }
     }
     if (nu != u && nu < units) issue_q(nu, raw_nxt);      // the next unit's query travels while this block is reduced
     cp_async_wait_group<1>();             // everything but the newest group (the next block) has landed
-    // ---- pass 1: the block's scores (independent dot products: the shuffles overlap)
-    float sc[kPdKeySlots];
-    float bm = -INFINITY;
-#pragma unroll
-    for (int i = 0; i < kPdKeySlots; ++i) {
-      const int j = j0 + 16 * i + 4 * gw + sub;
-      sc[i] = -INFINITY;
-      if (j0 + 16 * i < cur.n_keys) {         // warp-uniform: this slot holds at least one live key
-        const bool ok = j < cur.n_keys;       // uniform over the 8 lanes that share a key
-        const uint4 kq = ok ? stage[i * 128 + gt] : make_uint4(0, 0, 0, 0);
-        if (SELF && ok && j == cur.ps)        // append this token's K row to the cache
-          *reinterpret_cast<uint4*>(const_cast<__nv_bfloat16*>(cur.kc) + static_cast<size_t>(j) * key_stride) = kq;
-        float f[8];
-        pd_bf16x8(kq, f);
-        float d = 0.f;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) d = fmaf(q[e], f[e], d);
-        d += __shfl_xor_sync(0xffffffffu, d, 1);
-        d += __shfl_xor_sync(0xffffffffu, d, 2);
-        d += __shfl_xor_sync(0xffffffffu, d, 4);
-        if (ok) {
-          sc[i] = d;
-          bm = fmaxf(bm, d);
-        }
-      }
-    }
-    // ---- pass 2: one rescale of the running state per block, then independent exp / FMA per key
+    __syncwarp();                         // ... for every lane of this warp (a warp consumes only what it staged)
     {
-      const float mn = fmaxf(m, bm);
-      const float cs = mn == -INFINITY ? 0.f : __expf(m - mn);
-      l *= cs;
+      const int wk0 = 32 * gw;
+      const int valid = cur.n_keys - (j0 + wk0);       // keys of this warp's range that exist (warp-uniform)
+      if (valid > 0) {
+        const uint32_t kaddr = smem_u32(stage), vaddr = kaddr + kPdKeySlots * 128 * 16;
+        const int t2 = 2 * (lane & 3);
+        // ---- scores of up to 32 keys: S[0, key] = q . K[key]   (4 key tiles x 4 k-steps)
+        float sc[4][4];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) acc[e] *= cs;
-      m = mn;
+        for (int nt = 0; nt < 4; ++nt) {
+          sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+          if (8 * nt < valid) {
+            const int kr = wk0 + 8 * nt + (lane & 7);          // the key row whose address this lane supplies
 #pragma unroll
-      for (int i = 0; i < kPdKeySlots; ++i) {
-        const int j = j0 + 16 * i + 4 * gw + sub;
-        if (j < cur.n_keys) {
-          const uint4 vq = stage[(kPdKeySlots + i) * 128 + gt];
-          if (SELF && j == cur.ps)              // append this token's V row to the cache
-            *reinterpret_cast<uint4*>(const_cast<__nv_bfloat16*>(cur.vc) + static_cast<size_t>(j) * key_stride) = vq;
-          const float e0 = __expf(sc[i] - mn);
-          float f[8];
-          pd_bf16x8(vq, f);
-          l += e0;
+            for (int hf = 0; hf < 2; ++hf) {                   // dims 32 hf .. 32 hf + 31
+              uint32_t b[4];
+              ldmatrix_x4(b, kaddr + static_cast<uint32_t>(kr * 128 + (((4 * hf + (lane >> 3)) ^ (kr & 7)) << 4)));
+              mma16816(sc[nt], qa[2 * hf][0], 0u, qa[2 * hf][1], 0u, b[0], b[1]);
+              mma16816(sc[nt], qa[2 * hf + 1][0], 0u, qa[2 * hf + 1][1], 0u, b[2], b[3]);
+            }
+          }
+        }
+        float bm = -INFINITY;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) acc[e] = fmaf(e0, f[e], acc[e]);
+        for (int nt = 0; nt < 4; ++nt) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            if (8 * nt + t2 + e >= valid) sc[nt][e] = -INFINITY;
+            bm = fmaxf(bm, sc[nt][e]);
+          }
+        }
+        bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 1));
+        bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 2));   // key 0 of the range exists: finite on the row-0 quad
+        // ---- one rescale of the running state per block, then P = exp(S - m) as the A operand of O += P V
+        const float mn = fmaxf(m, bm);
+        const float cs = __expf(m - mn);                       // m = -inf on the first block: 0
+        l *= cs;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { o[i][0] *= cs; o[i][1] *= cs; }
+        m = mn;
+        uint32_t pa[2][2];
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          const float p0 = __expf(sc[2 * ks][0] - mn), p1 = __expf(sc[2 * ks][1] - mn);
+          const float p2 = __expf(sc[2 * ks + 1][0] - mn), p3 = __expf(sc[2 * ks + 1][1] - mn);
+          l += (p0 + p1) + (p2 + p3);
+          pa[ks][0] = lane < 4 ? pack_bf16(p0, p1) : 0u;       // rows 1-15 of P are unused: keep them exactly zero
+          pa[ks][1] = lane < 4 ? pack_bf16(p2, p3) : 0u;
+        }
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          if (16 * ks < valid) {
+            const int kr = wk0 + 16 * ks + ((lane >> 3) & 1) * 8 + (lane & 7);
+#pragma unroll
+            for (int dp = 0; dp < 4; ++dp) {                   // dims 16 dp .. 16 dp + 15 (two output tiles)
+              uint32_t b[4];
+              ldmatrix_x4_trans(b, vaddr + static_cast<uint32_t>(kr * 128 + (((2 * dp + (lane >> 4)) ^ (kr & 7)) << 4)));
+              mma16816(o[2 * dp], pa[ks][0], 0u, pa[ks][1], 0u, b[0], b[1]);
+              mma16816(o[2 * dp + 1], pa[ks][0], 0u, pa[ks][1], 0u, b[2], b[3]);
+            }
+          }
         }
       }
     }
-    // ---- last block of a unit: merge the 16 partial states in a fixed order and write the context
+    // ---- last block of a unit: merge the 4 warps' states in a fixed order and write the context
     if (j0 + kBlockKeys >= cur.n_keys) {
-      float mm = m, ll = l;
+      l += __shfl_xor_sync(0xffffffffu, l, 1);
+      l += __shfl_xor_sync(0xffffffffu, l, 2);
+      // (each warp parks its state in its own, fully consumed, 4 KB of the current block's K rows)
+      float* s_part = reinterpret_cast<float*>(stage);
+      constexpr int kPartStride = 32 * 128 / 4;          // floats between two warps' regions
+      __syncwarp();
+      if (lane < 4) {
+        float* dst = s_part + gw * kPartStride;
+        if (lane == 0) { dst[0] = m; dst[1] = l; }
 #pragma unroll
-      for (int o = 8; o <= 16; o <<= 1) {
-        const float m2 = __shfl_xor_sync(0xffffffffu, mm, o);
-        const float l2 = __shfl_xor_sync(0xffffffffu, ll, o);
-        const float mn = fmaxf(mm, m2);
-        const float c1 = mn == -INFINITY ? 0.f : __expf(mm - mn);
-        const float c2 = mn == -INFINITY ? 0.f : __expf(m2 - mn);
-        ll = ll * c1 + l2 * c2;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float a2 = __shfl_xor_sync(0xffffffffu, acc[e], o);
-          acc[e] = acc[e] * c1 + a2 * c2;
+        for (int i = 0; i < 8; ++i) {
+          dst[2 + 8 * i + 2 * lane] = o[i][0];
+          dst[2 + 8 * i + 2 * lane + 1] = o[i][1];
         }
-        mm = mn;
-      }
-      if (sub == 0) {
-        float* dst = s_part + gw * (2 + kHeadDim);
-        if (ch == 0) { dst[0] = mm; dst[1] = ll; }
-#pragma unroll
-        for (int e = 0; e < 8; ++e) dst[2 + ch * 8 + e] = acc[e];
       }
       group_sync(group);
       if (gt < kHeadDim) {
         float mx = -INFINITY;
 #pragma unroll
-        for (int w = 0; w < 4; ++w) mx = fmaxf(mx, s_part[w * (2 + kHeadDim)]);
+        for (int w = 0; w < 4; ++w) mx = fmaxf(mx, s_part[w * kPartStride]);
         float lt = 0.f, ot = 0.f;
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
-          const float mw = s_part[w * (2 + kHeadDim)];
+          const float mw = s_part[w * kPartStride];
           const float cw = mw == -INFINITY ? 0.f : __expf(mw - mx);
-          lt += s_part[w * (2 + kHeadDim) + 1] * cw;
-          ot += s_part[w * (2 + kHeadDim) + 2 + gt] * cw;
+          lt += s_part[w * kPartStride + 1] * cw;
+          ot += s_part[w * kPartStride + 2 + gt] * cw;
         }
         p.ctx[static_cast<size_t>(cur.b) * kD + cur.h * kHeadDim + gt] = __float2bfloat16(__fdividef(ot, lt));   // lt >= 1
       }
@@ -976,7 +1029,7 @@ __device__ __forceinline__ void pd_attention_stage(Bar& bar, uint8_t* smem, cons
 
 // ------------------------------------------------------------------ the kernel ---
 
-constexpr int kPdSmemBytes = kPdGroups * 2 * kPdStageBytes + kPdGroups * 4 * (2 + kHeadDim) * 4 + kPdMaxStages * static_cast<int>(sizeof(PdStage)) + 128;
+constexpr int kPdSmemBytes = kPdGroups * 2 * kPdStageBytes + kPdMaxStages * static_cast<int>(sizeof(PdStage)) + 128;
 static_assert(kPdRedFloats * 4 <= kPdGroups * 2 * kPdStageBytes, "reduction scratch must fit in the staging area it aliases");
 
 __host__ __device__ inline PdStage pd_gemm_desc(int type, int epi, const __nv_bfloat16* A, int K, const PdLinear& lin, int N, int ksplit,
@@ -1036,7 +1089,7 @@ __device__ __noinline__ void pd_next_call(GridBarrier& bar, const PdParams& p) {
 __global__ void __launch_bounds__(kPdThreads, 1) decode_persistent_kernel(const __grid_constant__ PdParams p) {
   extern __shared__ __align__(128) uint8_t pd_smem[];
   float* red = reinterpret_cast<float*>(pd_smem);     // aliases the attention staging area (stages never overlap)
-  PdStage* prog = reinterpret_cast<PdStage*>(pd_smem + kPdGroups * 2 * kPdStageBytes + kPdGroups * 4 * (2 + kHeadDim) * 4);
+  PdStage* prog = reinterpret_cast<PdStage*>(pd_smem + kPdGroups * 2 * kPdStageBytes);
   __shared__ int s_nstages;
   GridBarrier bar{p.barrier, 0u, p.prof, 0};
   const int B = p.B;
@@ -1166,6 +1219,9 @@ __global__ void __launch_bounds__(kPdThreads) pd_begin_kernel(const __grid_const
   }
 }
 
-constexpr int kPdAttnSmemBytes = 2 * kPdStageBytes + 4 * (2 + kHeadDim) * 4;     // one 128-thread group per CTA
+// one 128-thread group per CTA.  Exactly 64 KB: three CTAs (+1 KB each reserved by the system) fit the 196 KB shared-memory
+// carve-out; one more byte selects the 228 KB split, and a kernel whose L1/smem split differs from its neighbours' cannot
+// overlap them under programmatic dependent launch (measured: +13 us per token step).
+constexpr int kPdAttnSmemBytes = 2 * kPdStageBytes;
 
 }  // namespace mocr

@@ -122,6 +122,7 @@ struct mocr_handle {
   // tile widths (mocr_set_option)
   int enc_bn = 256;
   int attn_tc = 1;          // encoder attention on tcgen05 (0: the warp-level mma.sync kernel)
+  int carveout = -1;        // shared-memory carve-out (percent) forced on every decoder stage kernel; -1: driver default (set before the first decode)
   int kv_evict_first = 1;   // decoder cross-attention streams the encoder K/V through L2 with an evict-first policy
   int resid_tma = 1;        // encoder residual adds through the TMA reduce-add epilogue (0: per-thread f32 loads/stores)
   int gemm_pair = 0;        // 1: cta_group::2 GEMM (CTA pairs, 256-row tiles) for the large-M encoder GEMMs; parity-tested, measured no faster (K = 768 tiles are not smem-bound enough)
@@ -1121,6 +1122,17 @@ int decode_stage_step(mocr_handle* h, const PdParams& p) {
     CK(cudaFuncSetAttribute(pd_attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPdAttnSmemBytes));
     CK(cudaFuncSetAttribute(pd_attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPdAttnSmemBytes));
     CK(cudaFuncSetAttribute(pd_gemm_kernel<48, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pd_gemm_smem_bytes(48)));
+    if (h->carveout >= 0) {
+      // one shared-memory carve-out for every stage kernel: kernels with different L1/smem splits cannot overlap on an SM
+      CK(cudaFuncSetAttribute(pd_attention_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, h->carveout));
+      CK(cudaFuncSetAttribute(pd_attention_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, h->carveout));
+      CK(cudaFuncSetAttribute(pd_gemm_kernel<16, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, h->carveout));
+      CK(cudaFuncSetAttribute(pd_gemm_kernel<32, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, h->carveout));
+      CK(cudaFuncSetAttribute(pd_gemm_kernel<48, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, h->carveout));
+      CK(cudaFuncSetAttribute(pd_ln_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, h->carveout));
+      CK(cudaFuncSetAttribute(pd_next_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, h->carveout));
+      CK(cudaFuncSetAttribute(pd_begin_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, h->carveout));
+    }
     done[h->device & 15] = true;
   }
   PdStage prog[kPdMaxStages];
@@ -1595,6 +1607,7 @@ int mocr_set_option(mocr_handle_t* h, const char* key, int value) {
   else if (k == "use_graph") h->use_graph = value != 0;
   else if (k == "use_pdl") h->use_pdl = value != 0;
   else if (k == "resid_tma") h->resid_tma = value != 0;
+  else if (k == "carveout" && value >= -1 && value <= 100) h->carveout = value;
   else if (k == "kv_evict_first" && value >= 0 && value <= 3) h->kv_evict_first = value;
   else if (k == "attn_grid" && value >= 0) h->attn_grid = value;
   else if (k == "fuse_rows") h->fuse_rows = value != 0;
