@@ -122,6 +122,7 @@ struct mocr_handle {
   // tile widths (mocr_set_option)
   int enc_bn = 256;
   int attn_tc = 1;          // encoder attention on tcgen05 (0: the warp-level mma.sync kernel)
+  int row_warps = 2;        // warps (= rows) per CTA of the decoder's row-wise stage kernels
   int carveout = -1;        // shared-memory carve-out (percent) forced on every decoder stage kernel; -1: driver default (set before the first decode)
   int kv_evict_first = 1;   // decoder cross-attention streams the encoder K/V through L2 with an evict-first policy
   int resid_tma = 1;        // encoder residual adds through the TMA reduce-add epilogue (0: per-thread f32 loads/stores)
@@ -1137,7 +1138,10 @@ int decode_stage_step(mocr_handle* h, const PdParams& p) {
   }
   PdStage prog[kPdMaxStages];
   const int n_stages = pd_build_program(p, prog);
-  const int row_ctas = (p.B + kPdWarps - 1) / kPdWarps;
+  // row-wise stages (LayerNorm, next token): one warp per row; few warps per CTA so that the 64 rows spread over
+  // many SMs (8 CTAs of 8 warps made 8 SMs pull 98 KB each at ~75 GB/s per SM: 1.3 us of the stage's 2.6)
+  const int row_warps = std::max(1, std::min(h->row_warps, kPdWarps));
+  const int row_ctas = (p.B + row_warps - 1) / row_warps;
   const int tail_ctas = (p.B + 4 * kPdStageKS - 1) / (4 * kPdStageKS);      // 16 warps per GEMM CTA, one row each
   const int attn_grid = h->attn_grid > 0 ? std::min(h->attn_grid, p.B * kHeads) : p.B * kHeads;
   PdStage none{};
@@ -1163,9 +1167,9 @@ int decode_stage_step(mocr_handle* h, const PdParams& p) {
     } else if (st.type == PD_ATTN_CROSS) {
       CK(launch_pdl(h, pd_attention_kernel<false>, attn_grid, 128, kPdAttnSmemBytes, p, st));
     } else if (st.type == PD_LN) {
-      CK(launch_pdl(h, pd_ln_kernel, row_ctas, kPdThreads, 0, p, st));
+      CK(launch_pdl(h, pd_ln_kernel, row_ctas, 32 * row_warps, 0, p, st));
     } else {
-      CK(launch_pdl(h, pd_next_kernel, row_ctas, kPdThreads, 0, p));
+      CK(launch_pdl(h, pd_next_kernel, row_ctas, 32 * row_warps, 0, p));
     }
     ++h->launches;
   }
@@ -1607,6 +1611,7 @@ int mocr_set_option(mocr_handle_t* h, const char* key, int value) {
   else if (k == "use_graph") h->use_graph = value != 0;
   else if (k == "use_pdl") h->use_pdl = value != 0;
   else if (k == "resid_tma") h->resid_tma = value != 0;
+  else if (k == "row_warps" && value >= 1 && value <= 8) h->row_warps = value;
   else if (k == "carveout" && value >= -1 && value <= 100) h->carveout = value;
   else if (k == "kv_evict_first" && value >= 0 && value <= 3) h->kv_evict_first = value;
   else if (k == "attn_grid" && value >= 0) h->attn_grid = value;
