@@ -25,6 +25,7 @@ extern "C" {
 #define MOCR_ABI_VERSION 1
 
 typedef struct mocr_handle mocr_handle_t;
+typedef struct mocr_beam mocr_beam_t;   /* beam-search bookkeeping (host) */
 
 enum mocr_status {
   MOCR_OK = 0,
@@ -118,6 +119,30 @@ int mocr_decode_greedy(mocr_handle_t* h, int max_length, const int32_t* forced_i
 int mocr_fetch_ids(mocr_handle_t* h, int32_t* out_ids /*[n,max_length]*/, int32_t* out_lens /*[n]*/);
 /* stage_crops must have been called; runs preprocess + encode + decode with no host copies. */
 int mocr_run_resident(mocr_handle_t* h, int max_length);
+
+/* ---- beam search (the shipped checkpoint's generation config is believed to be
+ *      num_beams=4, no_repeat_ngram_size=3, length_penalty=2.0) -------------------------------------------
+ * Replaces GenerationMixin._beam_search (transformers generation/utils.py:3076-3370) with the
+ * NoRepeatNGramLogitsProcessor (logits_process.py:1012-1136) and the MaxLength / EOS stopping criteria.
+ * mocr_decode_beam runs on the encoded crops (n * num_beams <= max_batch): every step is the greedy path's
+ * stage kernels over n * num_beams rows that share their crop's cross-attention K/V, a device kernel that turns
+ * the step's logits into each row's 2 * num_beams best continuations (log-softmax, n-gram ban), and the host
+ * bookkeeping below; the self-attention cache follows the surviving beams.
+ * early_stopping: 0 = False (heuristic), 1 = True, 2 = "never".  out_ids [n, max_length] (best hypothesis per crop,
+ * filled with EOS past its end exactly as the reference does when the PAD id is 0), out_lens [n], out_scores [n] (sum of log-probabilities / length^length_penalty). */
+int mocr_decode_beam(mocr_handle_t* h, int num_beams, int max_length, int no_repeat_ngram_size, float length_penalty, int early_stopping,
+                     int32_t* out_ids, int32_t* out_lens, float* out_scores);
+/* The bookkeeping alone (no device needed): n crops, rows = n * num_beams, K = 2 * num_beams candidates per row. */
+int mocr_beam_create(int n, int num_beams, int max_length, int no_repeat_ngram_size, float length_penalty, int early_stopping,
+                     mocr_beam_t** out);
+int mocr_beam_destroy(mocr_beam_t* b);
+/* Tokens row `row` may not produce next (n-gram ban); returns their number (writes at most cap). */
+int mocr_beam_banned(const mocr_beam_t* b, int row, int32_t* out, int cap);
+/* cand_logprob / cand_token: [rows, K], every row sorted by descending log-probability (banned tokens excluded).
+ * next_tokens / parents: [rows] the token each running row consumes next and the row it continues.
+ * Returns 1 while the search goes on, 0 when it is finished, < 0 on error. */
+int mocr_beam_step(mocr_beam_t* b, const float* cand_logprob, const int32_t* cand_token, int32_t* next_tokens, int32_t* parents);
+int mocr_beam_result(const mocr_beam_t* b, int32_t* out_ids /*[n,max_length]*/, int32_t* out_lens /*[n]*/, float* out_scores /*[n]*/);
 
 /* ---- parity taps (tests only; enable before the stage they tap) ------------------------ */
 

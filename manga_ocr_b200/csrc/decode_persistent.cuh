@@ -62,6 +62,8 @@ struct PdParams {
   int B;                    // rows
   int max_len;              // this decode's max_length
   int cache_len;            // self-KV cache capacity per row (tokens)
+  int kv_div;               // decoder rows per crop (1; num_beams in beam mode: the beams of a crop share its cross-attention K/V)
+  int logits_cur;           // 1: the logits tap holds the CURRENT step only, [B, 6144] (beam mode)
   int kv_evict_first;       // 1: encoder K/V are streamed through L2 with an evict-first policy (the per-step weights stay resident)
   int eos_id;
   PdLayer layer[kDecLayers];
@@ -384,7 +386,8 @@ __device__ __forceinline__ void pd_gemm_stage(Bar& bar, float* red, const PdPara
           float* lg = nullptr;
           if (p.logits != nullptr) {
             const int stp = ldg_cg_s32(p.pos + r);
-            if (stp < p.max_len - 1) lg = p.logits + (static_cast<size_t>(r) * (p.max_len - 1) + stp) * N + n0;
+            if (p.logits_cur) lg = p.logits + static_cast<size_t>(r) * N + n0;
+            else if (stp < p.max_len - 1) lg = p.logits + (static_cast<size_t>(r) * (p.max_len - 1) + stp) * N + n0;
           }
 #pragma unroll 4
           for (int cc = 0; cc < NT; ++cc) {
@@ -742,8 +745,9 @@ __device__ __forceinline__ void pd_attention_stage(Bar& bar, uint8_t* smem, cons
     PdAttnUnit a;
     a.b = u / kHeads;
     a.h = u - a.b * kHeads;
-    a.kc = kbase + static_cast<size_t>(a.b) * b_stride + static_cast<size_t>(a.h) * head_stride + ch * 8;
-    a.vc = vbase + static_cast<size_t>(a.b) * b_stride + static_cast<size_t>(a.h) * head_stride + ch * 8;
+    const int kvb = SELF ? a.b : a.b / p.kv_div;                    // cross: the beams of a crop read the same K/V
+    a.kc = kbase + static_cast<size_t>(kvb) * b_stride + static_cast<size_t>(a.h) * head_stride + ch * 8;
+    a.vc = vbase + static_cast<size_t>(kvb) * b_stride + static_cast<size_t>(a.h) * head_stride + ch * 8;
     a.nk = a.nv = nullptr;
     a.n_keys = kEncTokens;
     a.ps = -1;

@@ -31,6 +31,8 @@
 #include "gemm_tcgen05.cuh"
 #include "preprocess.cuh"
 #include "region_mask.cuh"
+#include "beam_search.h"
+#include "beam_kernels.cuh"
 #include "rowops.cuh"
 
 using namespace mocr;
@@ -167,6 +169,10 @@ struct mocr_handle {
   __nv_bfloat16* d_q = nullptr;       // [brow_cap, 768]
   __nv_bfloat16* self_k[kDecLayers] = {nullptr, nullptr};   // [max_batch, max_length, 768]
   __nv_bfloat16* self_v[kDecLayers] = {nullptr, nullptr};
+  __nv_bfloat16* self_k2[kDecLayers] = {nullptr, nullptr};  // beam mode: second cache set (the gather that follows the beams ping-pongs)
+  __nv_bfloat16* self_v2[kDecLayers] = {nullptr, nullptr};
+  void* d_beam = nullptr;             // beam mode scratch: candidates, next tokens, parents, ban lists
+  size_t d_beam_bytes = 0;
   float* part_max = nullptr;
   int* part_idx = nullptr;
   int* d_ids = nullptr;               // [max_batch, max_length]
@@ -806,7 +812,8 @@ int stage_regions(mocr_handle* h, const mocr_crop_t* page, const mocr_region_t* 
   CK(cudaMemcpyAsync(h->d_descs, h->h_descs, sizeof(CropDesc) * n, cudaMemcpyHostToDevice, h->stream));
   if (!jobs.empty()) {
     if (mask_bytes > h->masks_cap) {
-      if (h->d_masks) cudaFree(h->d_masks);
+      if (h->d_beam) cudaFree(h->d_beam);
+    if (h->d_masks) cudaFree(h->d_masks);
       h->d_masks = nullptr;
       h->masks_cap = 0;
       const size_t cap = std::max<size_t>(mask_bytes + mask_bytes / 4, 4u << 20);
@@ -1040,6 +1047,8 @@ PdParams make_pd_params(mocr_handle* h, int n, int max_length, bool forced, bool
   p.B = n;
   p.max_len = max_length;
   p.cache_len = h->max_length;
+  p.kv_div = 1;
+  p.logits_cur = 0;
   p.kv_evict_first = h->kv_evict_first;
   p.eos_id = kSepId;
   for (int l = 0; l < kDecLayers; ++l) {
@@ -1117,7 +1126,7 @@ cudaError_t launch_pdl(mocr_handle* h, void (*kernel)(KArgs...), int grid, int b
 }
 
 // One greedy step as a sequence of stage kernels (decode_persistent.cuh), one launch per stage.
-int decode_stage_step(mocr_handle* h, const PdParams& p) {
+int decode_stage_step(mocr_handle* h, const PdParams& p, bool skip_next = false) {
   static bool done[16] = {};
   if (!done[h->device & 15]) {
     CK(cudaFuncSetAttribute(pd_attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPdAttnSmemBytes));
@@ -1169,6 +1178,7 @@ int decode_stage_step(mocr_handle* h, const PdParams& p) {
     } else if (st.type == PD_LN) {
       CK(launch_pdl(h, pd_ln_kernel, row_ctas, 32 * row_warps, 0, p, st));
     } else {
+      if (skip_next) continue;
       CK(launch_pdl(h, pd_next_kernel, row_ctas, 32 * row_warps, 0, p));
     }
     ++h->launches;
@@ -1539,6 +1549,162 @@ int mocr_recognize(mocr_handle_t* h, const mocr_crop_t* crops, int n, int channe
     TRY(decode(h, max_length, nullptr));
     TRY(fetch_ids(h, out_ids + static_cast<size_t>(i0) * max_length, out_lens ? out_lens + i0 : nullptr));
   }
+  return MOCR_OK;
+}
+
+// Beam search over the encoded crops (include/mocr_b200.h: mocr_decode_beam).
+int decode_beam(mocr_handle* h, int beams, int max_length, int ngram, float length_penalty, int early, int32_t* out_ids, int32_t* out_lens,
+                float* out_scores) {
+  if (!h->enc_ok) return fail(h, MOCR_ERR_INVALID, "encode has not run on the staged crops");
+  if (h->decode_mode != 2) return fail(h, MOCR_ERR_INVALID, "beam search runs on the stage kernels (decode_mode 2)");
+  if (beams < 1 || 2 * beams > kBeamMaxK || ngram < 0 || early < 0 || early > 2 || out_ids == nullptr)
+    return fail(h, MOCR_ERR_INVALID, "bad beam-search argument");
+  if (max_length < 2 || max_length > h->max_length) return fail(h, MOCR_ERR_CAPACITY, "max_length %d outside [2, %d]", max_length, h->max_length);
+  const int n = h->n, R = n * beams, K = 2 * beams;
+  if (R > h->max_batch) return fail(h, MOCR_ERR_CAPACITY, "%d crops x %d beams = %d rows, handle capacity is %d", n, beams, R, h->max_batch);
+  const size_t cache_elems = static_cast<size_t>(h->max_batch) * h->max_length * kD;
+  for (int l = 0; l < kDecLayers; ++l) {
+    if (h->self_k2[l] == nullptr) TRY(dmalloc(h, &h->self_k2[l], cache_elems));
+    if (h->self_v2[l] == nullptr) TRY(dmalloc(h, &h->self_v2[l], cache_elems));
+  }
+  const size_t need_tap = static_cast<size_t>(h->max_batch) * kVocab * sizeof(float);
+  if (need_tap > h->logits_tap_bytes) {
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->logits_tap) cudaFree(h->logits_tap);
+    h->logits_tap = nullptr;
+    h->logits_tap_bytes = 0;
+    CK(cudaMalloc(reinterpret_cast<void**>(&h->logits_tap), need_tap));
+    h->logits_tap_bytes = need_tap;
+    for (auto& g : h->graphs) cudaGraphExecDestroy(g.second.exec);   // they captured the old tap pointer
+    h->graphs.clear();
+  }
+  // scratch: cand_lp [R][K] f32 | cand_tok [R][K] | next [R] | parent [R] | ban_cnt [R] | ban_tok [R][max_length]
+  const size_t Rm = h->max_batch;
+  const size_t off_tok = Rm * kBeamMaxK * 4, off_next = off_tok + Rm * kBeamMaxK * 4, off_parent = off_next + Rm * 4, off_bcnt = off_parent + Rm * 4,
+               off_btok = off_bcnt + Rm * 4, total = off_btok + Rm * h->max_length * 4;
+  if (total > h->d_beam_bytes) {
+    if (h->d_beam) cudaFree(h->d_beam);
+    h->d_beam = nullptr;
+    h->d_beam_bytes = 0;
+    CK(cudaMalloc(&h->d_beam, total));
+    h->d_beam_bytes = total;
+  }
+  uint8_t* sb = static_cast<uint8_t*>(h->d_beam);
+  float* d_lp = reinterpret_cast<float*>(sb);
+  int* d_tok = reinterpret_cast<int*>(sb + off_tok);
+  int* d_next = reinterpret_cast<int*>(sb + off_next);
+  int* d_parent = reinterpret_cast<int*>(sb + off_parent);
+  int* d_bcnt = reinterpret_cast<int*>(sb + off_bcnt);
+  int* d_btok = reinterpret_cast<int*>(sb + off_btok);
+
+  BeamSearch bs;
+  bs.init(n, beams, max_length, ngram, length_penalty, early, kClsId);
+  std::vector<float> lp(static_cast<size_t>(R) * K);
+  std::vector<int32_t> tok(static_cast<size_t>(R) * K), next(R), parent(R), bcnt(R, 0), btok;
+  __nv_bfloat16 *ck[kDecLayers], *cv[kDecLayers], *ak[kDecLayers], *av[kDecLayers];    // current / alternate caches
+  for (int l = 0; l < kDecLayers; ++l) { ck[l] = h->self_k[l]; cv[l] = h->self_v[l]; ak[l] = h->self_k2[l]; av[l] = h->self_v2[l]; }
+  PdParams p = make_pd_params(h, R, max_length, false, true);
+  p.kv_div = beams;
+  p.logits_cur = 1;
+  CK(launch_pdl(h, pd_begin_kernel, (R + kPdWarps - 1) / kPdWarps, kPdThreads, 0, p));
+  ++h->launches;
+  CK(cudaMemsetAsync(d_bcnt, 0, sizeof(int) * R, h->stream));
+  int ban_cap = 1, steps = 0;
+  for (int t = 0; t < max_length - 1 && bs.unfinished; ++t) {
+    for (int l = 0; l < kDecLayers; ++l) { p.layer[l].self_k = ck[l]; p.layer[l].self_v = cv[l]; }
+    TRY(decode_stage_step(h, p, true));
+    beam_topk_kernel<<<R, 256, 0, h->stream>>>(h->logits_tap, d_btok, d_bcnt, ban_cap, K, d_lp, d_tok);
+    CK(cudaGetLastError());
+    ++h->launches;
+    CK(cudaMemcpyAsync(lp.data(), d_lp, sizeof(float) * R * K, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(tok.data(), d_tok, sizeof(int) * R * K, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    ++steps;
+    if (!bs.step(lp.data(), tok.data(), next.data(), parent.data())) break;
+    // ---- next step's inputs: tokens, cache rows, n-gram bans
+    bool moved = false;
+    for (int r = 0; r < R; ++r) moved = moved || parent[r] != r;
+    CK(cudaMemcpyAsync(d_next, next.data(), sizeof(int) * R, cudaMemcpyHostToDevice, h->stream));
+    if (moved) {
+      CK(cudaMemcpyAsync(d_parent, parent.data(), sizeof(int) * R, cudaMemcpyHostToDevice, h->stream));
+      BeamCaches bc;
+      for (int l = 0; l < kDecLayers; ++l) {
+        bc.src[2 * l] = ck[l]; bc.dst[2 * l] = ak[l];
+        bc.src[2 * l + 1] = cv[l]; bc.dst[2 * l + 1] = av[l];
+      }
+      beam_kv_gather_kernel<<<dim3(R, 2 * kDecLayers), 256, 0, h->stream>>>(bc, d_parent, t + 1, h->max_length);
+      CK(cudaGetLastError());
+      ++h->launches;
+      for (int l = 0; l < kDecLayers; ++l) { std::swap(ck[l], ak[l]); std::swap(cv[l], av[l]); }
+    }
+    int mx = 0;
+    if (ngram > 0) {
+      btok.assign(static_cast<size_t>(R) * max_length, 0);
+      for (int r = 0; r < R; ++r) {
+        bcnt[r] = bs.banned(r, &btok[static_cast<size_t>(r) * max_length], max_length);
+        mx = std::max(mx, bcnt[r]);
+      }
+    }
+    ban_cap = std::max(mx, 1);
+    if (mx > 0) {     // pack [R][ban_cap]
+      std::vector<int32_t> packed(static_cast<size_t>(R) * ban_cap, 0);
+      for (int r = 0; r < R; ++r) std::copy_n(&btok[static_cast<size_t>(r) * max_length], std::min(bcnt[r], ban_cap), &packed[static_cast<size_t>(r) * ban_cap]);
+      CK(cudaMemcpyAsync(d_btok, packed.data(), sizeof(int) * packed.size(), cudaMemcpyHostToDevice, h->stream));
+      CK(cudaMemcpyAsync(d_bcnt, bcnt.data(), sizeof(int) * R, cudaMemcpyHostToDevice, h->stream));
+      CK(cudaStreamSynchronize(h->stream));      // (pageable sources)
+    } else {
+      CK(cudaMemsetAsync(d_bcnt, 0, sizeof(int) * R, h->stream));
+    }
+    beam_advance_kernel<<<(R + 7) / 8, 256, 0, h->stream>>>(p, d_next, t + 1);
+    CK(cudaGetLastError());
+    ++h->launches;
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  bs.result(out_ids, out_lens, out_scores);
+  h->last_steps = steps;
+  h->cur_len = max_length;
+  h->dec_ok = false;        // the greedy-path getters (ids, step logits) do not describe this run
+  return MOCR_OK;
+}
+
+int mocr_decode_beam(mocr_handle_t* h, int num_beams, int max_length, int no_repeat_ngram_size, float length_penalty, int early_stopping,
+                     int32_t* out_ids, int32_t* out_lens, float* out_scores) {
+  TRY(check_handle(h));
+  std::lock_guard<std::mutex> lock(h->mu);
+  return decode_beam(h, num_beams, max_length, no_repeat_ngram_size, length_penalty, early_stopping, out_ids, out_lens, out_scores);
+}
+
+// ---- beam-search bookkeeping (host only; usable without a device: the CPU tests drive it with the oracle's logits)
+struct mocr_beam {
+  BeamSearch s;
+};
+
+int mocr_beam_create(int n, int num_beams, int max_length, int no_repeat_ngram, float length_penalty, int early_stopping, mocr_beam_t** out) {
+  if (out == nullptr || n < 1 || num_beams < 1 || num_beams > 16 || max_length < 2 || max_length > kMaxPos || no_repeat_ngram < 0 ||
+      early_stopping < 0 || early_stopping > 2)
+    return MOCR_ERR_INVALID;
+  mocr_beam* b = new (std::nothrow) mocr_beam();
+  if (b == nullptr) return MOCR_ERR_CAPACITY;
+  b->s.init(n, num_beams, max_length, no_repeat_ngram, length_penalty, early_stopping, 2 /*[CLS]*/);
+  *out = b;
+  return MOCR_OK;
+}
+int mocr_beam_destroy(mocr_beam_t* b) {
+  delete b;
+  return MOCR_OK;
+}
+int mocr_beam_banned(const mocr_beam_t* b, int row, int32_t* out, int cap) {
+  if (b == nullptr || row < 0 || row >= b->s.n * b->s.beams || (cap > 0 && out == nullptr) || cap < 0) return MOCR_ERR_INVALID;
+  return b->s.banned(row, out, cap);
+}
+int mocr_beam_step(mocr_beam_t* b, const float* cand_logprob, const int32_t* cand_token, int32_t* next_tokens, int32_t* parents) {
+  if (b == nullptr || cand_logprob == nullptr || cand_token == nullptr || next_tokens == nullptr || parents == nullptr) return MOCR_ERR_INVALID;
+  if (!b->s.unfinished) return 0;
+  return b->s.step(cand_logprob, cand_token, next_tokens, parents) ? 1 : 0;
+}
+int mocr_beam_result(const mocr_beam_t* b, int32_t* ids, int32_t* lens, float* scores) {
+  if (b == nullptr || ids == nullptr) return MOCR_ERR_INVALID;
+  b->s.result(ids, lens, scores);
   return MOCR_OK;
 }
 

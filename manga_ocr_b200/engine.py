@@ -232,6 +232,38 @@ class Engine:
         self._ck(self._lib.mocr_run_resident(self._h, T))
         self._cur_len = T
 
+    def decode_beam(self, num_beams: int = 4, max_length: Optional[int] = None, no_repeat_ngram_size: int = 3,
+                    length_penalty: float = 2.0, early_stopping=True):
+        """Beam search over the encoded crops (n * num_beams <= max_batch); the defaults are the generation config the
+        shipped checkpoint is believed to carry.  early_stopping: False / True / "never".
+        Returns (ids [n, T] best hypothesis, EOS-filled past its end as the reference does; lens [n]; scores [n])."""
+        T = max_length or self.max_length
+        ids = np.zeros((self.n, T), np.int32)
+        lens = np.zeros((self.n,), np.int32)
+        scores = np.zeros((self.n,), np.float32)
+        early = 2 if early_stopping == "never" else (1 if early_stopping else 0)
+        self._ck(self._lib.mocr_decode_beam(self._h, num_beams, T, no_repeat_ngram_size, length_penalty, early,
+                                            ids.ctypes.data_as(POINTER(c_int32)), lens.ctypes.data_as(POINTER(c_int32)),
+                                            scores.ctypes.data_as(POINTER(c_float))))
+        return ids, lens, scores
+
+    def recognize_beam(self, crops: Sequence[np.ndarray], order: int = RGB, max_length: Optional[int] = None, num_beams: int = 4,
+                       no_repeat_ngram_size: int = 3, length_penalty: float = 2.0, early_stopping=True):
+        """crops -> (ids, lens, scores) with beam search; chunks of max_batch // num_beams crops."""
+        T = max_length or self.max_length
+        per = max(1, self.max_batch // num_beams)
+        ids = np.zeros((len(crops), T), np.int32)
+        lens = np.zeros((len(crops),), np.int32)
+        scores = np.zeros((len(crops),), np.float32)
+        for lo in range(0, len(crops), per):
+            chunk = crops[lo:lo + per]
+            self.stage(chunk, order)
+            self.preprocess()
+            self.encode()
+            ids[lo:lo + len(chunk)], lens[lo:lo + len(chunk)], scores[lo:lo + len(chunk)] = self.decode_beam(
+                num_beams, T, no_repeat_ngram_size, length_penalty, early_stopping)
+        return ids, lens, scores
+
     def fetch_ids(self):
         ids = np.zeros((self.n, self._cur_len), np.int32)
         lens = np.zeros((self.n,), np.int32)
@@ -292,3 +324,59 @@ class Engine:
         out = np.zeros((n,), np.int64)
         self._ck(self._lib.mocr_get_decode_profile(self._h, out.ctypes.data_as(POINTER(c_int64)), n))
         return out
+
+
+class BeamScorer:
+    """The host bookkeeping of the beam search alone (mocr_beam_*; no device needed).  Rows = n * num_beams,
+    K = 2 * num_beams candidates per row and step."""
+
+    def __init__(self, n: int, num_beams: int = 4, max_length: int = MAX_LENGTH, no_repeat_ngram_size: int = 3,
+                 length_penalty: float = 2.0, early_stopping=True):
+        self._lib = _lib.load()
+        self._b = c_void_p()
+        self.n, self.beams, self.K, self.T = n, num_beams, 2 * num_beams, max_length
+        early = 2 if early_stopping == "never" else (1 if early_stopping else 0)
+        rc = self._lib.mocr_beam_create(n, num_beams, max_length, no_repeat_ngram_size, length_penalty, early, byref(self._b))
+        if rc != 0:
+            raise MocrError(rc, "mocr_beam_create: bad argument")
+
+    def banned(self, row: int) -> List[int]:
+        buf = np.zeros((self.T,), np.int32)
+        cnt = self._lib.mocr_beam_banned(self._b, row, buf.ctypes.data_as(POINTER(c_int32)), self.T)
+        if cnt < 0:
+            raise MocrError(cnt, "mocr_beam_banned")
+        return buf[:cnt].tolist()
+
+    def step(self, cand_logprob: np.ndarray, cand_token: np.ndarray):
+        """-> (unfinished, next_tokens [rows], parents [rows])"""
+        lp = np.ascontiguousarray(cand_logprob, np.float32)
+        tk = np.ascontiguousarray(cand_token, np.int32)
+        rows = self.n * self.beams
+        if lp.shape != (rows, self.K) or tk.shape != (rows, self.K):
+            raise ValueError(f"candidates must be [{rows}, {self.K}]")
+        nxt = np.zeros((rows,), np.int32)
+        par = np.zeros((rows,), np.int32)
+        rc = self._lib.mocr_beam_step(self._b, lp.ctypes.data_as(POINTER(c_float)), tk.ctypes.data_as(POINTER(c_int32)),
+                                      nxt.ctypes.data_as(POINTER(c_int32)), par.ctypes.data_as(POINTER(c_int32)))
+        if rc < 0:
+            raise MocrError(rc, "mocr_beam_step")
+        return rc == 1, nxt, par
+
+    def result(self):
+        ids = np.zeros((self.n, self.T), np.int32)
+        lens = np.zeros((self.n,), np.int32)
+        scores = np.zeros((self.n,), np.float32)
+        self._lib.mocr_beam_result(self._b, ids.ctypes.data_as(POINTER(c_int32)), lens.ctypes.data_as(POINTER(c_int32)),
+                                   scores.ctypes.data_as(POINTER(c_float)))
+        return ids, lens, scores
+
+    def close(self) -> None:
+        if self._b:
+            self._lib.mocr_beam_destroy(self._b)
+            self._b = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:      # noqa: BLE001 - interpreter shutdown
+            pass

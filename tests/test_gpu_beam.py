@@ -1,0 +1,109 @@
+"""Beam-search mode on the B200 against transformers' generate(num_beams=4,
+no_repeat_ngram_size=3, length_penalty=2.0) on the fp32 CPU oracle.  The selection logic is pinned exactly by
+tests/test_beam_host.py; here the bf16 device path supplies the log-probabilities, so a hypothesis may differ from the
+oracle's only where the two are near-ties: |score difference| <= 5e-2 (logits tolerance of the greedy path: 6e-2)."""
+import numpy as np
+import pytest
+
+from manga_ocr_b200 import crops as C
+from manga_ocr_b200 import weights as W
+
+pytestmark = pytest.mark.gpu
+T = 20
+
+
+@pytest.fixture(scope="module")
+def beam_setup():
+    import torch
+    from manga_ocr_b200.engine import Engine
+    from manga_ocr_b200.text import Vocab
+    from oracle.reference_ocr import ReferenceMangaOcr
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    w = W.random_init(0, gain=3.0, eos_bias=4.2)
+    eng = Engine(w, device=0, max_batch=16, max_length=T)
+    ocr = ReferenceMangaOcr(w, Vocab.synthetic().tokens, max_length=T)
+    crops = C.bubble_batch(6, seed=41)
+    yield eng, ocr, crops
+    eng.close()
+
+
+def _oracle_beam(ocr, crops, **kw):
+    import torch
+    x = torch.stack([ocr.pixel_values(c) for c in crops])
+    with torch.no_grad():
+        out = ocr.model.generate(x, max_length=T, do_sample=False, output_scores=True, return_dict_in_generate=True, **kw)
+    return out.sequences.numpy(), out.sequences_scores.numpy()
+
+
+def _oracle_score(ocr, crop, seq, lp):
+    """Sum of the fp32 oracle's log-probabilities of the generated tokens / (their number ** length_penalty): what
+    transformers reports as sequences_scores for a finished hypothesis."""
+    import torch
+    x = ocr.pixel_values(crop)[None]
+    with torch.no_grad():
+        enc = ocr.model.encoder(pixel_values=x).last_hidden_state
+        t = torch.tensor(seq[None, :-1].astype(np.int64))
+        logp = torch.nn.functional.log_softmax(ocr.model.decoder(input_ids=t, encoder_hidden_states=enc).logits[0].float(), dim=-1)
+    gen = seq[1:]
+    total = float(sum(logp[i, int(tok)] for i, tok in enumerate(gen)))
+    return total / (len(gen) ** lp)
+
+
+def _has_repeated_ngram(seq, n=3):
+    grams = [tuple(seq[i:i + n]) for i in range(len(seq) - n + 1)]
+    return len(grams) != len(set(grams))
+
+
+@pytest.mark.parametrize("early", [True, False])
+def test_beam_search_matches_oracle(beam_setup, early):
+    """Most crops: the oracle's hypothesis exactly.  bf16 log-probabilities can send the search down another branch at
+    a near-tie; such a hypothesis must still be legal (ends at EOS or max_length, no repeated 3-gram) and carry the
+    score the fp32 oracle assigns to it (the device's scoring is faithful) - and is never much worse than the
+    oracle's own result."""
+    eng, ocr, crops = beam_setup
+    ref_ids, ref_scores = _oracle_beam(ocr, crops, num_beams=4, no_repeat_ngram_size=3, length_penalty=2.0, early_stopping=early)
+    ids, lens, scores = eng.recognize_beam(crops, max_length=T, num_beams=4, no_repeat_ngram_size=3, length_penalty=2.0,
+                                           early_stopping=early)          # 6 crops x 4 beams > 16 rows: two chunks
+    assert ids.shape == (6, T) and (ids[:, 0] == 2).all()
+    same = 0
+    for i in range(6):
+        L = int(lens[i])
+        seq = ids[i, :L]
+        assert (ids[i, L:] == 3).all()
+        assert seq[-1] == 3 or L == T, (i, seq)
+        assert not _has_repeated_ngram(seq.tolist()), (i, seq)
+        assert abs(_oracle_score(ocr, crops[i], seq, 2.0) - scores[i]) <= 2e-2, (i, seq, scores[i])
+        ref = ref_ids[i]
+        ref_len = len(ref)
+        while ref_len > 1 and ref[ref_len - 1] == 3 and ref[ref_len - 2] == 3:
+            ref_len -= 1                                                   # the reference fills with EOS past the end
+        if L == ref_len and np.array_equal(seq, ref[:L]):
+            same += 1
+        else:
+            assert scores[i] >= ref_scores[i] - 0.25, (i, seq, ref, scores[i], ref_scores[i])
+    assert same >= 4, same
+
+
+def test_single_beam_without_penalties_is_the_greedy_path(beam_setup):
+    eng, ocr, crops = beam_setup
+    g_ids, g_lens = eng.recognize(crops[:4], max_length=T)
+    b_ids, b_lens, _ = eng.recognize_beam(crops[:4], max_length=T, num_beams=1, no_repeat_ngram_size=0, length_penalty=1.0,
+                                          early_stopping=True)
+    for i in range(4):
+        L = int(g_lens[i])
+        assert int(b_lens[i]) == L and np.array_equal(b_ids[i, :L], g_ids[i, :L]), i
+
+
+def test_beam_capacity_and_argument_errors(beam_setup):
+    from manga_ocr_b200.engine import MocrError
+    eng, _, crops = beam_setup
+    eng.stage(crops[:5]); eng.preprocess(); eng.encode()
+    with pytest.raises(MocrError) as e:
+        eng.decode_beam(4, T)                       # 5 x 4 = 20 rows > 16
+    assert e.value.code == -4
+    with pytest.raises(MocrError) as e:
+        eng.decode_beam(0, T)
+    assert e.value.code == -1
+    ids, lens, scores = eng.decode_beam(3, T)       # 15 rows: fine, handle still usable
+    assert ids.shape == (5, T) and np.isfinite(scores).all()
