@@ -50,6 +50,32 @@ def _find_checkpoint(name_or_path: str):
     return None
 
 
+GREEDY = {"num_beams": 1, "no_repeat_ngram_size": 0, "length_penalty": 1.0, "early_stopping": False}
+
+
+def _generation_config(weights_path: Optional[str]) -> Dict:
+    """``generate()`` reads the checkpoint's generation settings (generation_config.json, else the legacy fields of
+    config.json).  The shipped kha-white/manga-ocr-base is believed to carry num_beams=4, no_repeat_ngram_size=3,
+    length_penalty=2.0, early_stopping=true; without a file the path is greedy (BASELINE)."""
+    import json
+    gen = dict(GREEDY)
+    if not weights_path:
+        return gen
+    d = weights_path if os.path.isdir(weights_path) else os.path.dirname(weights_path)
+    for fn in ("config.json", "generation_config.json"):          # the generation config wins
+        fp = os.path.join(d, fn)
+        if os.path.exists(fp):
+            try:
+                with open(fp, encoding="utf-8") as f:
+                    cfg = json.load(f)
+            except (OSError, ValueError):
+                continue
+            for k in gen:
+                if cfg.get(k) is not None:
+                    gen[k] = cfg[k]
+    return gen
+
+
 def image_to_array(img) -> np.ndarray:
     """PIL image -> the uint8 array the engine reads.  The luma conversion itself
     (``img.convert("L")``) happens on the GPU; modes whose ``convert("L")`` is not the plain
@@ -76,9 +102,11 @@ class MangaOcr:
     def __init__(self, pretrained_model_name_or_path: str = DEFAULT_MODEL, force_cpu: bool = False, *,
                  weights: Optional[Dict[str, np.ndarray]] = None, vocab: Optional[Vocab] = None,
                  devices: Optional[Sequence[int]] = None, max_batch: int = 64, max_length: int = MAX_LENGTH,
-                 warmup: bool = True):
+                 warmup: bool = True, num_beams: Optional[int] = None, no_repeat_ngram_size: Optional[int] = None,
+                 length_penalty: Optional[float] = None, early_stopping=None):
         if force_cpu:
             raise RuntimeError("manga_ocr_b200 has no CPU path (force_cpu=True is not supported); it needs a B200 GPU")
+        gen = dict(GREEDY)
         if weights is None:
             name = pretrained_model_name_or_path
             env = os.environ.get("MOCR_WEIGHTS", "")
@@ -94,10 +122,18 @@ class MangaOcr:
                         f"no local checkpoint for {name!r}: pass a directory holding model.safetensors (+ vocab.txt), "
                         "set MOCR_WEIGHTS to one, or use 'random[:seed[:eos_bias]]' for random-init weights")
                 weights = W.load_weights(found[0])
+                gen = _generation_config(found[0])
                 if vocab is None and found[1]:
                     vocab = Vocab.from_file(found[1])
         else:
             weights = W.complete(weights)
+        for k, v in (("num_beams", num_beams), ("no_repeat_ngram_size", no_repeat_ngram_size), ("length_penalty", length_penalty),
+                     ("early_stopping", early_stopping)):
+            if v is not None:
+                gen[k] = v
+        if int(gen["num_beams"]) < 1 or int(gen["num_beams"]) > max_batch:
+            raise ValueError(f"num_beams={gen['num_beams']} outside [1, max_batch={max_batch}]")
+        self.generation = gen          # num_beams == 1 -> the greedy path; > 1 -> beam search
         self.vocab = vocab or Vocab.synthetic()
         self.max_length = max_length
         self.max_batch = max_batch
@@ -171,9 +207,17 @@ class MangaOcr:
             raise errs[0]
         return ids_to_texts(self.vocab, out)
 
+    def _engine_ids(self, engine: Engine, arrays: Sequence[np.ndarray], order: int) -> np.ndarray:
+        g = self.generation
+        if int(g["num_beams"]) <= 1:
+            return engine.recognize(arrays, order, self.max_length)[0]
+        ids = engine.recognize_beam(arrays, order, self.max_length, int(g["num_beams"]), int(g["no_repeat_ngram_size"]),
+                                    float(g["length_penalty"]), g["early_stopping"])[0]
+        return ids
+
     def recognize_ids(self, arrays: Sequence[np.ndarray], order: int = RGB) -> np.ndarray:
         if len(self.engines) == 1 or len(arrays) <= 1:
-            return self.engines[0].recognize(arrays, order, self.max_length)[0]
+            return self._engine_ids(self.engines[0], arrays, order)
         # host-side job splitter: contiguous blocks, one worker thread per GPU, no collective
         from .splitter import shard_bounds
         out = np.zeros((len(arrays), self.max_length), np.int32)
@@ -183,7 +227,7 @@ class MangaOcr:
             lo, hi = shard_bounds(len(arrays), len(self.engines), k)
             try:
                 if hi > lo:
-                    out[lo:hi] = self.engines[k].recognize(arrays[lo:hi], order, self.max_length)[0]
+                    out[lo:hi] = self._engine_ids(self.engines[k], arrays[lo:hi], order)
             except BaseException as e:   # noqa: BLE001 - re-raised on the caller's thread
                 errs.append(e)
 
@@ -206,7 +250,7 @@ class MangaOcr:
                     return
                 batch = [self._queue.popleft() for _ in range(min(len(self._queue), self.max_batch))]
             try:
-                ids, _ = engine.recognize([r.crop for r in batch], RGB, self.max_length)
+                ids = self._engine_ids(engine, [r.crop for r in batch], RGB)
                 for r, t in zip(batch, ids_to_texts(self.vocab, ids)):
                     r.text = t
             except BaseException as e:   # noqa: BLE001 - delivered to every waiting caller

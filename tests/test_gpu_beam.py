@@ -107,3 +107,31 @@ def test_beam_capacity_and_argument_errors(beam_setup):
     assert e.value.code == -1
     ids, lens, scores = eng.decode_beam(3, T)       # 15 rows: fine, handle still usable
     assert ids.shape == (5, T) and np.isfinite(scores).all()
+
+
+def test_manga_ocr_front_end_runs_the_checkpoint_generation_config(beam_setup, tmp_path):
+    """MangaOcr(...) picks num_beams / no_repeat_ngram_size / length_penalty up from the checkpoint directory, as
+    transformers' generate() does, and the single-image call returns the beam result."""
+    import json
+    from manga_ocr_b200.ocr import MangaOcr
+    from manga_ocr_b200.text import Vocab, ids_to_texts
+    eng, _, crops = beam_setup
+    w = W.random_init(0, gain=3.0, eos_bias=4.2)
+    np.savez(tmp_path / "weights.npz", **w)
+    (tmp_path / "generation_config.json").write_text(json.dumps(
+        {"num_beams": 4, "no_repeat_ngram_size": 3, "length_penalty": 2.0, "early_stopping": True, "max_length": 300}))
+    ocr = MangaOcr(str(tmp_path), max_batch=16, max_length=T, warmup=False)
+    try:
+        assert ocr.generation["num_beams"] == 4 and ocr.generation["no_repeat_ngram_size"] == 3
+        want = ids_to_texts(Vocab.synthetic(), eng.recognize_beam(crops[:3], max_length=T)[0])
+        assert ocr.recognize_batch(crops[:3]) == want
+        from PIL import Image
+        assert ocr(Image.fromarray(crops[1])) == want[1]
+    finally:
+        ocr.close()
+    greedy = MangaOcr(str(tmp_path), max_batch=16, max_length=T, warmup=False, num_beams=1)
+    try:
+        assert greedy.generation["num_beams"] == 1
+        assert greedy.recognize_batch(crops[:2]) == ids_to_texts(Vocab.synthetic(), eng.recognize(crops[:2], max_length=T)[0])
+    finally:
+        greedy.close()

@@ -106,3 +106,16 @@ def test_gather_ids_gloo_world2(n_total):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(res)
+
+
+def test_generation_config_is_read_from_the_checkpoint_directory(tmp_path):
+    """generate() uses the checkpoint's generation settings; no file -> greedy."""
+    import json
+    from manga_ocr_b200.ocr import GREEDY, _generation_config
+    assert _generation_config(None) == GREEDY
+    assert _generation_config(str(tmp_path / "model.safetensors")) == GREEDY
+    (tmp_path / "config.json").write_text(json.dumps({"num_beams": 2, "length_penalty": 1.5, "model_type": "vision-encoder-decoder"}))
+    assert _generation_config(str(tmp_path))["num_beams"] == 2
+    (tmp_path / "generation_config.json").write_text(json.dumps({"num_beams": 4, "no_repeat_ngram_size": 3, "early_stopping": True}))
+    g = _generation_config(str(tmp_path / "model.safetensors"))
+    assert g == {"num_beams": 4, "no_repeat_ngram_size": 3, "length_penalty": 1.5, "early_stopping": True}
