@@ -14,6 +14,14 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _library_present():
+    """The C-ABI library is built in-tree by __graft_entry__.build(); build it here only when it is missing."""
+    from manga_ocr_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        _lib.build()
+
+
 @pytest.fixture(scope="session")
 def golden_pre():
     return np.load(os.path.join(GOLDEN, "preprocess_kat.npz"))
