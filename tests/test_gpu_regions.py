@@ -139,3 +139,21 @@ def test_region_errors_are_reported_and_handle_survives(engine8):
         engine8.region_mask(0, (10, 10))                                         # no polygon on that region
     ids, _ = engine8.recognize_regions(page, [Region((-5, -5, 70, 60), [(0, 0), (59, 0), (30, 49)], 1)])
     assert ids.shape == (1, 24)
+
+
+def test_manga_ocr_recognize_regions_strings(weights0):
+    """The front-end call: page + Region.from_qt(...) selections -> the strings of the host-staged crops."""
+    from manga_ocr_b200.engine import Region
+    from manga_ocr_b200.ocr import MangaOcr
+    page, sels = C.page_with_selections(11, seed=5)
+    regions = [Region.from_qt(rect, poly, orient) for rect, poly, orient in sels]
+    ocr = MangaOcr(weights=weights0, max_batch=8, max_length=16, warmup=False)
+    try:
+        got = ocr.recognize_regions(page, regions)
+        want = ocr.recognize_batch([S.stage_region(page, r.box, r.polygon, r.rotate) for r in regions])
+        assert got == want and len(got) == 11 and all(isinstance(t, str) for t in got)
+        from PIL import Image
+        assert ocr.recognize_regions(Image.fromarray(page), regions[:3]) == want[:3]
+        assert ocr.recognize_regions(page, []) == []
+    finally:
+        ocr.close()
