@@ -56,22 +56,60 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md).  NVML is polled in-process
+    every 20 ms (the first sample is taken synchronously at start(), so even a 0.2 s region on an 8-GPU box is
+    covered); `nvidia-smi -lms` - whose start-up alone can exceed a short region - is the fallback."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index: int):
-        self.index = index
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        ids = [v for v in vis.split(",") if v.strip() != ""]
+        self.index = int(ids[index]) if ids and index < len(ids) and ids[index].strip().isdigit() else index
         self.proc = None
         self.lines = []
+        self.nvml = None
+        self.samples = []          # (sm_mhz, reason_bits)
+        self.max_mhz = None
+        self.stop_flag = threading.Event()
+        self.t = None
+
+    def _nvml_sample(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)
+        try:
+            bits = n.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:      # noqa: BLE001 - older bindings
+            bits = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        self.samples.append((float(sm), int(bits)))
+
+    def _nvml_loop(self):
+        while not self.stop_flag.wait(0.02):
+            try:
+                self._nvml_sample()
+            except Exception:  # noqa: BLE001
+                return
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self._nvml_sample()
+            self.t = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.t.start()
+            return
+        except Exception:      # noqa: BLE001 - no NVML bindings: nvidia-smi
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
-        except Exception:
+        except Exception:      # noqa: BLE001
             self.proc = None
 
     def _pump(self):
@@ -79,6 +117,21 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            try:
+                self._nvml_sample()      # one more while the last kernels of the region are still in flight / just done
+            except Exception:            # noqa: BLE001
+                pass
+            self.stop_flag.set()
+            if self.t is not None:
+                self.t.join(timeout=2)
+            sm = [s[0] for s in self.samples]
+            bits = 0
+            for _, b in self.samples:
+                bits |= b
+            reasons = sorted(name for bit, name in self.BITS.items() if bits & bit)
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                    "samples": len(sm), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -101,7 +154,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 # ------------------------------------------------------------------ CPU reference arm ---
