@@ -812,8 +812,7 @@ int stage_regions(mocr_handle* h, const mocr_crop_t* page, const mocr_region_t* 
   CK(cudaMemcpyAsync(h->d_descs, h->h_descs, sizeof(CropDesc) * n, cudaMemcpyHostToDevice, h->stream));
   if (!jobs.empty()) {
     if (mask_bytes > h->masks_cap) {
-      if (h->d_beam) cudaFree(h->d_beam);
-    if (h->d_masks) cudaFree(h->d_masks);
+      if (h->d_masks) cudaFree(h->d_masks);
       h->d_masks = nullptr;
       h->masks_cap = 0;
       const size_t cap = std::max<size_t>(mask_bytes + mask_bytes / 4, 4u << 20);
@@ -1432,6 +1431,7 @@ int mocr_destroy(mocr_handle_t* h) {
     if (h->d_coefs) cudaFree(h->d_coefs);
     if (h->d_masks) cudaFree(h->d_masks);
     if (h->d_mask_meta) cudaFree(h->d_mask_meta);
+    if (h->d_beam) cudaFree(h->d_beam);
     if (h->h_flags) cudaFreeHost(h->h_flags);
     if (h->h_steps) cudaFreeHost(h->h_steps);
     if (h->h_descs) cudaFreeHost(h->h_descs);

@@ -135,3 +135,20 @@ def test_manga_ocr_front_end_runs_the_checkpoint_generation_config(beam_setup, t
         assert greedy.recognize_batch(crops[:2]) == ids_to_texts(Vocab.synthetic(), eng.recognize(crops[:2], max_length=T)[0])
     finally:
         greedy.close()
+
+
+def test_beam_and_region_calls_interleave_on_one_handle(beam_setup):
+    """Scratch buffers of the two widened paths are independent: beam -> regions (growing mask arena) -> beam."""
+    from manga_ocr_b200.engine import Region
+    eng, _, crops = beam_setup
+    first = eng.recognize_beam(crops[:3], max_length=T)
+    page, sels = C.page_with_selections(12, seed=9, height=900, width=700)
+    regions = [Region.from_qt(r, p, o) for r, p, o in sels]
+    ids_a, _ = eng.recognize_regions(page, regions, max_length=T)
+    big = np.full((1500, 1200, 3), 200, np.uint8)
+    poly = np.array([[5, 5], [1190, 10], [1195, 1490], [10, 1495]], np.int32)
+    eng.recognize_regions(big, [Region((0, 0, 1200, 1500), poly)], max_length=T)       # a 1.8 MB mask: the arena grows
+    again = eng.recognize_beam(crops[:3], max_length=T)
+    assert all(np.array_equal(a, b) for a, b in zip(first, again))
+    ids_b, _ = eng.recognize_regions(page, regions, max_length=T)
+    assert np.array_equal(ids_a, ids_b)
