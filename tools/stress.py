@@ -12,7 +12,8 @@ pool = C.page_batch(96, seed=1003)
 page, sels = C.page_with_selections(24)
 regions = [Region.from_qt(r, p, o) for r, p, o in sels]
 t0 = time.time()
-for cycle in range(3):
+after = []
+for cycle in range(5):
     eng = Engine(w, device=0, max_batch=32, max_length=48)
     used = []
     for it in range(60):
@@ -31,8 +32,10 @@ for cycle in range(3):
         if it % 20 == 19:
             used.append(free0 - torch.cuda.mem_get_info()[0])
     eng.close()
+    after.append(free0 - torch.cuda.mem_get_info()[0])
     print(f"cycle {cycle}: in-use while alive (MB) {[round(u / 2**20) for u in used]}, after close {round((free0 - torch.cuda.mem_get_info()[0]) / 2**20)} MB, {time.time() - t0:.0f} s", flush=True)
-leak = free0 - torch.cuda.mem_get_info()[0]
-print("leaked MB:", round(leak / 2**20))
-assert leak < 64 * 2**20
+# (the first cycle loads the library's kernels and CUDA graphs' code: constant, not a leak)
+growth = after[-1] - after[0]
+print("after-close in-use per cycle (MB):", [round(a / 2**20) for a in after], "growth:", round(growth / 2**20, 1))
+assert growth < 8 * 2**20
 print("stress ok")
