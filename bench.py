@@ -280,13 +280,15 @@ def run_b200(args, rank, local_rank, world):
         ocr.recognize_batch(crops)
     barrier()
     t0 = time.perf_counter()
+    from manga_ocr_b200.text import ids_to_texts
     for _ in range(args.steps):
-        ids = ocr.recognize_ids(crops)
-        texts = [None] * len(ids)
-        from manga_ocr_b200.text import ids_to_texts
-        texts = ids_to_texts(ocr.vocab, ids)
-        if world > 1:
+        if world == 1:
+            texts = ocr.recognize_batch(crops)   # the public call: host uint8 crops -> strings
+        else:
+            ids = ocr.recognize_ids(crops)       # the same call in its two halves, to have the id rows for the gather
+            texts = ids_to_texts(ocr.vocab, ids)
             gather_ids(ids, BATCH * world)       # final result gather: NCCL all_gather of [64, 300] int32 per rank
+        assert len(texts) == BATCH
     barrier()
     e2e_s = time.perf_counter() - t0
 
