@@ -41,6 +41,7 @@ constexpr int kPdMaxNT = 48;
 constexpr int kPdRedFloats = kPdKSlices * kPdRowsPerBlock * (kPdMaxNT + 1);
 constexpr int kPdMaxStages = 32;
 constexpr int kPdVocabTiles = kVocab / kPdMaxNT;
+constexpr int kPdMaxPartials = 192;          // arg-max partials per row the next-token stage can merge
 constexpr int kPdSplit = 3;                  // CTA-level K split of the N = 768 projections
 
 struct PdLinear {
@@ -62,6 +63,7 @@ struct PdParams {
   int B;                    // rows
   int max_len;              // this decode's max_length
   int cache_len;            // self-KV cache capacity per row (tokens)
+  int n_partials;           // per-row (max, arg-max) partials of the vocabulary GEMM: kPdVocabTiles, or 2 * tiles of the tcgen05 kernel
   int kv_div;               // decoder rows per crop (1; num_beams in beam mode: the beams of a crop share its cross-attention K/V)
   int logits_cur;           // 1: the logits tap holds the CURRENT step only, [B, 6144] (beam mode)
   int kv_evict_first;       // 1: encoder K/V are streamed through L2 with an evict-first policy (the per-step weights stay resident)
@@ -395,8 +397,8 @@ __device__ __forceinline__ void pd_gemm_stage(Bar& bar, float* red, const PdPara
             if (v > best) { best = v; best_i = n0 + cc; }     // strict >: lowest index wins ties
             if (lg != nullptr) lg[cc] = v;
           }
-          p.part_max[static_cast<size_t>(r) * kPdVocabTiles + tile] = best;
-          p.part_idx[static_cast<size_t>(r) * kPdVocabTiles + tile] = best_i;
+          p.part_max[static_cast<size_t>(r) * p.n_partials + tile] = best;
+          p.part_idx[static_cast<size_t>(r) * p.n_partials + tile] = best_i;
         }
       } else {
 #pragma unroll
@@ -583,16 +585,16 @@ __device__ __forceinline__ void pd_next_token_stage(Bar& bar, const PdParams& p,
     // one round trip: state and the 128 per-tile (max, arg-max) partials together
     const int ps = ldg_cg_s32(p.pos + r);
     const int fin0 = ldg_cg_s32(p.finished + r);
-    float pv[(kPdVocabTiles + 31) / 32];
-    int pi[(kPdVocabTiles + 31) / 32];
+    float pv[kPdMaxPartials / 32];
+    int pi[kPdMaxPartials / 32];
 #pragma unroll
-    for (int j = 0; j < (kPdVocabTiles + 31) / 32; ++j) {
+    for (int j = 0; j < kPdMaxPartials / 32; ++j) {
       const int i = lane + 32 * j;
       pv[j] = -INFINITY;
       pi[j] = 0x7fffffff;
-      if (i < kPdVocabTiles) {
-        pv[j] = ldg_cg_f32(p.part_max + static_cast<size_t>(r) * kPdVocabTiles + i);
-        pi[j] = ldg_cg_s32(p.part_idx + static_cast<size_t>(r) * kPdVocabTiles + i);
+      if (i < p.n_partials) {
+        pv[j] = ldg_cg_f32(p.part_max + static_cast<size_t>(r) * p.n_partials + i);
+        pi[j] = ldg_cg_s32(p.part_idx + static_cast<size_t>(r) * p.n_partials + i);
       }
     }
     const bool was_finished = fin0 != 0;
@@ -600,7 +602,7 @@ __device__ __forceinline__ void pd_next_token_stage(Bar& bar, const PdParams& p,
     float bv = -INFINITY;
     int bi = 0x7fffffff;
 #pragma unroll
-    for (int j = 0; j < (kPdVocabTiles + 31) / 32; ++j)
+    for (int j = 0; j < kPdMaxPartials / 32; ++j)
       if (pv[j] > bv || (pv[j] == bv && pi[j] < bi)) { bv = pv[j]; bi = pi[j]; }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {

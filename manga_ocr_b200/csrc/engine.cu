@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -124,6 +125,7 @@ struct mocr_handle {
   // tile widths (mocr_set_option)
   int enc_bn = 256;
   int attn_tc = 1;          // encoder attention on tcgen05 (0: the warp-level mma.sync kernel)
+  int dec_tc = 1;           // decoder GEMM stages on the encoder's tcgen05 kernel (bit 0: vocabulary, bit 1: FFN1, bit 2: QKV)
   int row_warps = 2;        // warps (= rows) per CTA of the decoder's row-wise stage kernels
   int carveout = -1;        // shared-memory carve-out (percent) forced on every decoder stage kernel; -1: driver default (set before the first decode)
   int kv_evict_first = 1;   // decoder cross-attention streams the encoder K/V through L2 with an evict-first policy
@@ -1047,6 +1049,7 @@ PdParams make_pd_params(mocr_handle* h, int n, int max_length, bool forced, bool
   p.max_len = max_length;
   p.cache_len = h->max_length;
   p.kv_div = 1;
+  p.n_partials = ((h->dec_tc & 1) && h->decode_mode == 2 && !h->fuse_rows) ? 2 * (kVocab / 64) : kPdVocabTiles;
   p.logits_cur = 0;
   p.kv_evict_first = h->kv_evict_first;
   p.eos_id = kSepId;
@@ -1124,6 +1127,29 @@ cudaError_t launch_pdl(mocr_handle* h, void (*kernel)(KArgs...), int grid, int b
   return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
+// The encoder's tcgen05 GEMM as a decoder stage: launched with programmatic stream serialization (the kernel requests its
+// weight tiles before griddepcontrol.wait), A map clipped to the live rows (TMA zero-fills rows >= n without reading them).
+template <int BN, int EPI>
+int launch_gemm_stage_tc(mocr_handle* h, const __nv_bfloat16* a_ptr, int K, Linear& L, int rows, GemmArgs a) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_done[16] = {};
+  if (!attr_done[h->device & 15]) {
+    CK(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(Cfg::kSmemBytes, EPI)));
+    attr_done[h->device & 15] = true;
+  }
+  CUtensorMap ma;
+  TRY(make_map(h, &ma, a_ptr, rows, K, kGemmBM));
+  const CUtensorMap* mb;
+  TRY(linear_map(h, &L, BN, &mb));
+  a.M = rows;
+  a.N = L.N;
+  a.K = L.K;
+  a.bias = L.bias;
+  a.pdl = 1;
+  CK(launch_pdl(h, gemm_tcgen05_kernel<BN, EPI>, std::min(L.N / BN, h->sms), kGemmThreads, gemm_smem_bytes(Cfg::kSmemBytes, EPI), ma, *mb, a));
+  return MOCR_OK;
+}
+
 // One greedy step as a sequence of stage kernels (decode_persistent.cuh), one launch per stage.
 int decode_stage_step(mocr_handle* h, const PdParams& p, bool skip_next = false) {
   static bool done[16] = {};
@@ -1162,6 +1188,32 @@ int decode_stage_step(mocr_handle* h, const PdParams& p, bool skip_next = false)
       const PdStage* tail = &none;
       if (h->fuse_rows && i + 1 < n_stages && (prog[i + 1].type == PD_LN || prog[i + 1].type == PD_NEXT)) tail = &prog[i + 1];
       if (i == 0) st.epi |= kPdZeroCounters;
+      if (h->dec_tc && !h->fuse_rows) {
+        bool done_tc = false;
+        if ((h->dec_tc & 1) && (st.epi & 0xff) == PD_ARGMAX && !p.logits_cur) {
+          GemmArgs a{};
+          a.part_max = p.part_max;
+          a.part_idx = p.part_idx;
+          a.logits = p.logits;
+          a.step = p.pos;
+          a.tap_steps = p.max_len - 1;
+          TRY((launch_gemm_stage_tc<64, EPI_ARGMAX>(h, p.xb, kD, h->head_dec, p.B, a)));
+          done_tc = true;
+        }
+        for (int l = 0; l < kDecLayers && !done_tc; ++l) {
+          if ((h->dec_tc & 2) && st.W == h->dec[l].fc1.w) {
+            TRY((launch_gemm_stage_tc<32, EPI_BF16_GELU>(h, p.xb, kD, h->dec[l].fc1, p.B, out_bf16(p.ffn, kFFN))));
+            done_tc = true;
+          } else if ((h->dec_tc & 4) && st.W == h->dec[l].self_qkv.w) {
+            TRY((launch_gemm_stage_tc<32, EPI_BF16>(h, p.xb, kD, h->dec[l].self_qkv, p.B, out_bf16(p.qkv, 3 * kD))));
+            done_tc = true;
+          }
+        }
+        if (done_tc) {
+          ++h->launches;
+          continue;
+        }
+      }
       const int nt = st.type == PD_GEMM16 ? 16 : (st.type == PD_GEMM32 ? 32 : 48);
       const int grid = (st.N / nt) * st.ksplit;
       const int tc = std::min(tail_ctas, grid);
@@ -1326,6 +1378,7 @@ int create_impl(mocr_handle* h) {
     return fail(h, MOCR_ERR_NO_DEVICE, "device %d is sm_%d%d; the kernels are built for sm_100a (B200) only", h->device, prop.major, prop.minor);
   CK(cudaSetDevice(h->device));
   h->sms = prop.multiProcessorCount;
+  if (const char* e = getenv("MOCR_DEC_TC")) h->dec_tc = atoi(e) & 7;     // (A/B switch for the test-suite)
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   const int B = h->max_batch, T = h->max_length;
   h->rows_cap = round_up(B * kEncTokens, kGemmBM);
@@ -1778,6 +1831,7 @@ int mocr_set_option(mocr_handle_t* h, const char* key, int value) {
   else if (k == "use_pdl") h->use_pdl = value != 0;
   else if (k == "resid_tma") h->resid_tma = value != 0;
   else if (k == "row_warps" && value >= 1 && value <= 8) h->row_warps = value;
+  else if (k == "dec_tc" && value >= 0 && value <= 7) h->dec_tc = value;
   else if (k == "carveout" && value >= -1 && value <= 100) h->carveout = value;
   else if (k == "kv_evict_first" && value >= 0 && value <= 3) h->kv_evict_first = value;
   else if (k == "attn_grid" && value >= 0) h->attn_grid = value;

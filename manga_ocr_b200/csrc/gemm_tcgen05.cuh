@@ -46,6 +46,8 @@ struct GemmArgs {
   float* logits;         // EPI_ARGMAX: optional f32 tap for parity tests (may be null):
   const int* step;       //   row r writes logits[(r * tap_steps + step[r]) * N ...]
   int tap_steps;
+  int pdl;               // 1: launched with programmatic stream serialization (decoder stage): weights are requested before
+                         //    griddepcontrol.wait, the activations after it
   alignas(64) CUtensorMap tmap_out;   // EPI_F32_ACCUM: f32 [M, N] view of `out`, box 32 x 32, SWIZZLE_128B
 };
 
@@ -246,19 +248,37 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  if (args.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (warp == 0) {
     // ------------------------------------------------ TMA producer ----------
     int stage = 0;
     uint32_t phase = 0;
+    int pre = 0;        // k-blocks of the first tile whose weight tiles were requested before the dependency wait
+    if (args.pdl) {
+      pre = k_blocks < kStages ? k_blocks : kStages;
+      if (lane == 0) {
+        const int n0 = (static_cast<int>(blockIdx.x) % n_tiles) * BN;
+        for (int s = 0; s < pre; ++s) {
+          mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
+          tma_load_2d(smem_b + s * Cfg::kStageBytesB, &tmap_b, &full_bar[s], s * kGemmBK, n0);
+        }
+      }
+      __syncwarp();
+      asm volatile("griddepcontrol.wait;" ::: "memory");
+    }
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / n_tiles) * kGemmBM;
       const int n0 = (tile % n_tiles) * BN;
       for (int kb = 0; kb < k_blocks; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1u);
         if (lane == 0) {
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          tma_load_2d(smem_a + stage * Cfg::kStageBytesA, &tmap_a, &full_bar[stage], kb * kGemmBK, m0);
-          tma_load_2d(smem_b + stage * Cfg::kStageBytesB, &tmap_b, &full_bar[stage], kb * kGemmBK, n0);
+          if (tile == static_cast<int>(blockIdx.x) && kb < pre) {     // B is on its way already
+            tma_load_2d(smem_a + stage * Cfg::kStageBytesA, &tmap_a, &full_bar[stage], kb * kGemmBK, m0);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            tma_load_2d(smem_a + stage * Cfg::kStageBytesA, &tmap_a, &full_bar[stage], kb * kGemmBK, m0);
+            tma_load_2d(smem_b + stage * Cfg::kStageBytesB, &tmap_b, &full_bar[stage], kb * kGemmBK, n0);
+          }
         }
         __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1u; }
