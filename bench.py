@@ -341,8 +341,8 @@ def run_b200(args, rank, local_rank, world):
 
         if name == "dec_cross_attn" and BATCH == 64:
             # dram__bytes_read.sum + dram__bytes_write.sum of pd_attention_kernel<0>, one `ncu --set full` capture of this
-            # command (profiles/r1_ncu_decode_kernels.txt): 39.353088 MB + 22.272 KB per launch, vs 38.93 MB algorithmic
-            roof["traffic"] = 39353088.0 + 22272.0
+            # command (profiles/r1_ncu_decode_kernels.txt): 39.354368 MB + 4.864 KB per launch, vs 38.93 MB algorithmic
+            roof["traffic"] = 39354368.0 + 4864.0
             roof["traffic_source"] = "profiles/r1_ncu_decode_kernels.txt"
 
     # ---- region staging: 64 selections of one page, crop + polygon composite + rotation on the device

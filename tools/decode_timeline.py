@@ -16,8 +16,10 @@ eng.decode(T); eng.sync()
 prof = eng.decode_profile(4096)
 n = int(prof[0]); rec = prof[1:1 + 4 * min(n, 1000)].reshape(-1, 4)
 NAMES = {0: "gemm16", 1: "gemm32", 2: "gemm48", 3: "self_attn", 4: "cross_attn", 5: "ln", 6: "next"}
-per = 26 if not fuse else 18
-rec = rec[per * 8: per * 28]        # skip the first steps
+# a step ends with the next-token kernel (tag 6xx); the vocabulary GEMM runs on the tcgen05 kernel and leaves no record
+ends = [i for i, r in enumerate(rec) if int(r[0]) // 100 == 6]
+rec = rec[ends[7] + 1: ends[27] + 1]        # 20 steps, skipping the first ones
+per = len(rec) / 20
 t0 = rec[0, 1]
 agg = {}
 prev_done = None
@@ -27,7 +29,7 @@ for tag, te, tr, td in rec:
     a = agg.setdefault(name, [0, 0.0, 0.0, 0.0])
     a[0] += 1; a[1] += (tr - te); a[2] += (td - tr); a[3] += gap
     prev_done = td
-steps = len(rec) / per
+steps = 20.0
 print(f"B={B} fuse={fuse}: {len(rec)} records, {steps:.1f} steps, {(rec[-1,3]-rec[0,1])/steps/1e3:.1f} us/step")
 print("stage            n/step  entry->ready  ready->done  prev_done->entry   (us, CTA 0)")
 for k, (c, w, d, g) in agg.items():
