@@ -7,7 +7,7 @@
 //   beam_kv_gather      the self-attention cache follows the surviving beams (Cache.reorder_cache, :3345-3350)
 //   beam_advance_kernel position += 1, x = embed(next token)
 #pragma once
-#include "decode_persistent.cuh"
+#include "decode_stages.cuh"
 
 namespace mocr {
 

@@ -1,44 +1,35 @@
-// Persistent greedy decoder: ONE cooperative launch runs every decode step of a batch.
+// Greedy decoder: the per-token program of stage kernels (one launch per stage, CUDA graph + programmatic
+// dependent launch).
 //
 // Replaces the per-step host loop of GenerationMixin._sample (transformers/generation/utils.py:
-// 2743-2805: ~120 library launches and a host sync per token).  One CTA per SM stays resident and
-// interprets a small stage table (26 entries per token):
-//   BertLayer x2 [QKV -> self-attn -> out -> LN -> cross-q -> cross-attn -> out -> LN -> FFN1 -> FFN2 -> LN]
+// 2743-2805: ~120 library launches and a host sync per token).  A token step is a short program:
+//   BertLayer x2 [QKV -> self-attn -> out+LN -> cross-q -> cross-attn -> out+LN -> FFN1 -> FFN2 -> LN]
 //   (modeling_bert.py:143-421), LM head (:471-501), arg-max / EOS / append / embed (utils.py:2793-2805).
-// Stages are separated by a grid-wide barrier (one release-atomic + a poll, 1.1 us measured) and the
-// loop ends on the device when every row has produced [SEP] or reached max_length - no host round
-// trip per token.
 //
-// Design rules that came out of measurements on the B200 (tools/microbench.cu, tools/decode_prof.py):
+// Design rules that came out of measurements on the B200 (tools/microbench*.cu, tools/decode_timeline.py):
 //  * a token is latency/bandwidth-bound (M = batch rows, 46 MFLOP per row), so the small-M GEMMs use
 //    warp-level mma.sync fed straight from L2 with 16-byte loads in a k-permuted fragment order
 //    that needs no shared-memory staging;
 //  * what costs is the broadcast of the activation to all CTAs (98 KB per CTA = 1.3 us at the L2's
-//    ~11 TB/s aggregate): the N = 768 projections are therefore split over K as well as N
-//    (48 x 3 tiles), each CTA reads a third of the activation, and the raw fp32 partials are summed
-//    in a fixed order (no atomics: results are deterministic) by the LayerNorm / attention stage
-//    that consumes them, together with bias, GELU and residual;
+//    ~11 TB/s aggregate) and the ~1 us every kernel boundary adds to the dependent chain; the chain is
+//    therefore kept short: the projections that feed a LayerNorm run as 16-CTA clusters that own
+//    complete rows (16 x 48 columns), exchange the row statistics through distributed shared memory
+//    and write the normalised row themselves (no separate LayerNorm stage);
 //  * weights and the encoder K/V do not depend on the previous stage, so they are requested BEFORE
-//    waiting on the barrier; attention K/V travel through cp.async into per-thread shared-memory
-//    staging slots (no registers held, double-buffered across units);
-//  * the code is kept small (one instance per stage TYPE, rolled loops): the stage sequence does not
-//    fit in the instruction caches, and an earlier fully inlined version (247 KB of SASS) lost more
-//    to instruction fetch than it gained.
+//    the dependency wait (griddepcontrol.wait); attention K/V travel through cp.async into
+//    shared-memory staging (no registers held, double-buffered across units).
 #pragma once
 #include "common.cuh"
 #include "rowops.cuh"
 
 namespace mocr {
 
-constexpr int kPdThreads = 256;              // 8 warps, one CTA per SM
+constexpr int kPdThreads = 256;              // row-stage kernels: 8 warps per CTA at most
 constexpr int kPdWarps = kPdThreads / 32;
 constexpr int kPdRowsPerBlock = 64;          // activation rows per pass (4 m-tiles of 16)
-constexpr int kPdKSlices = 2;                // warps per m-tile: K is split in two inside a CTA
-constexpr int kPdGroups = kPdThreads / 128;  // attention groups of 4 warps
 constexpr int kPdKeySlots = 8;               // 8 * 16 = 128 keys per staged block (a 197-key unit = 2 blocks); each warp owns 32 consecutive keys
 constexpr int kPdStageBytes = 2 * kPdKeySlots * 128 * 16;          // K and V of one block, one group
 constexpr int kPdMaxNT = 48;
-constexpr int kPdRedFloats = kPdKSlices * kPdRowsPerBlock * (kPdMaxNT + 1);
 constexpr int kPdMaxStages = 32;
 constexpr int kPdVocabTiles = kVocab / kPdMaxNT;
 constexpr int kPdMaxPartials = 192;          // arg-max partials per row the next-token stage can merge
@@ -67,6 +58,9 @@ struct PdParams {
   int kv_div;               // decoder rows per crop (1; num_beams in beam mode: the beams of a crop share its cross-attention K/V)
   int logits_cur;           // 1: the logits tap holds the CURRENT step only, [B, 6144] (beam mode)
   int kv_evict_first;       // 1: encoder K/V are streamed through L2 with an evict-first policy (the per-step weights stay resident)
+  int fuse_ln;              // 1: the projections that feed a LayerNorm run as 16-CTA clusters that normalise the rows themselves
+  int kv_prefetch;          // 1: a layer's encoder K/V are requested into L2 (bulk prefetch) by the layer's first stage
+  int big;                  // 1: large-batch program - every Linear on the tcgen05 GEMM (128-row tiles, weights read once for all rows)
   int eos_id;
   PdLayer layer[kDecLayers];
   PdLinear head_t, head_dec;
@@ -80,6 +74,8 @@ struct PdParams {
   const int* forced;        // teacher forcing or null
   float* x;                 // [B, 768] post-LN hidden (fp32 residual)
   __nv_bfloat16* xb;        // [B, 768] bf16 copy (GEMM A operand)
+  __nv_bfloat16* tb;        // [B, 768] LM-head transform output (A operand of the vocabulary projection)
+  __nv_bfloat16* q;         // [B, 768] cross-attention query (large-batch program)
   float* y;                 // [3, B, 768] split-K partials of the projections that feed a LayerNorm
   float* yq;                // [3, B, 768] split-K partials of the cross-attention query
   __nv_bfloat16* qkv;       // [B, 2304]
@@ -88,30 +84,36 @@ struct PdParams {
   float* part_max;          // [B, kPdVocabTiles]
   int* part_idx;
   float* logits;            // tap or null: [B, max_len-1, 6144]
-  unsigned int* barrier;    // grid barrier counter (zeroed by the host before launch)
-  int* steps_done;          // out
   long long* prof;          // optional [4096] stage timeline of CTA 0 (debug / tuning), or null
 };
 
-enum PdStageType { PD_GEMM16 = 0, PD_GEMM32 = 1, PD_GEMM48 = 2, PD_ATTN_SELF = 3, PD_ATTN_CROSS = 4, PD_LN = 5, PD_NEXT = 6 };
+enum PdStageType { PD_GEMM16 = 0, PD_GEMM32 = 1, PD_GEMM48 = 2, PD_ATTN_SELF = 3, PD_ATTN_CROSS = 4, PD_LN = 5, PD_NEXT = 6, PD_PROJ_LN = 7, PD_TC = 8 };
+// the decoder's Linear layers, for the host (tensor maps of the tcgen05 stages)
+enum PdLinId { PD_LIN_QKV = 0, PD_LIN_SELF_OUT = 1, PD_LIN_CROSS_Q = 2, PD_LIN_CROSS_OUT = 3, PD_LIN_FC1 = 4, PD_LIN_FC2 = 5, PD_LIN_PER_LAYER = 6,
+               PD_LIN_HEAD_T = 2 * PD_LIN_PER_LAYER, PD_LIN_HEAD_DEC = 2 * PD_LIN_PER_LAYER + 1 };
 enum PdEpi { PD_BF16 = 0, PD_BF16_GELU = 1, PD_F32_PARTIAL = 2, PD_ARGMAX = 3 };
 
-// One entry of the per-token program, built once in shared memory.
+// One entry of the per-token program.
 struct PdStage {
   int type;
-  int epi;                  // GEMM: PdEpi.  LN: bit 0 = GELU before the norm (LM-head transform)
+  int epi;                  // GEMM: PdEpi.  LN / PROJ_LN: bit 0 = GELU before the norm (LM-head transform).  TC: GemmEpilogue
+  int lin;                  // TC: PdLinId of the weights
   int N, K, ksplit, ldo;
-  int parts;                // LN: number of split-K partials to add
+  int parts;                // LN / cross-attention query: number of split-K partials to add
   int layer;                // attention: decoder layer
-  const __nv_bfloat16* A;   // GEMM A operand [B, K]
+  const __nv_bfloat16* A;   // GEMM A operand [B, K]; cross-attention: the query rows [B, 768] when they are not split-K partials
   const __nv_bfloat16* W;   // GEMM weights [N, K]
-  const float* bias;        // GEMM bias (unsplit) / LN: bias of the producing projection / cross: query bias
+  const float* bias;        // GEMM bias (unsplit) / LN: bias of the producing projection (nullable) / cross: query bias
   __nv_bfloat16* ob;        // GEMM bf16 out / LN bf16 out
   float* of;                // GEMM fp32 partial out / LN fp32 out (nullable)
-  const float* src;         // LN: partials [parts][B][768]
+  const float* src;         // LN: partials [parts][B][768]; cross-attention: partials of the query projection
   const float* resid;       // LN: residual rows (nullable)
   const float* g;           // LN gamma / beta
   const float* b;
+  const __nv_bfloat16* pf;  // optional region to request into L2 before the dependency wait (the layer's encoder K/V), or null
+  long long pf_bytes;       // bytes per row block of that region
+  long long pf_stride;      // bytes between the row blocks
+  int pf_blocks;
 };
 
 // ------------------------------------------------------------------ primitives ---
@@ -141,16 +143,6 @@ __device__ __forceinline__ float4 ldg_cg_f4(const float* p) {
   asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p) : "memory");
   return r;
 }
-// Barrier poll.  Deliberately relaxed: an acquire load at gpu scope makes ptxas invalidate the
-// SM's whole L1 (CCTL.IVALL) at every barrier, evicting the cached LayerNorm / bias vectors.
-// Every datum that another CTA writes during the launch is read with ld.global.cg (L2, the
-// coherence point) and the writer publishes with red.release.gpu, so no L1 line can be stale; the
-// consuming loads are issued after the poll loop exits (control dependence + bar.sync).
-__device__ __forceinline__ unsigned int ld_poll_u32(const unsigned int* p) {
-  unsigned int r;
-  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
-  return r;
-}
 __device__ __forceinline__ void group_sync(int group) {      // 128-thread named barrier (ids 1..)
   asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");
 }
@@ -167,49 +159,16 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 
-// Grid barrier, split so that independent loads can be issued between arrive and wait.
-struct GridBarrier {
-  unsigned int* ctr;
-  unsigned int target;
-  long long* prof;        // optional stage timeline of CTA 0 (clock64 at every wait-exit and arrive), or null
-  int prof_n;
-  __device__ __forceinline__ void stamp() {
-    if (prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && prof_n < 4096) prof[prof_n] = clock64();
-    ++prof_n;
-  }
-  __device__ __forceinline__ void arrive() {
-    __syncthreads();                       // every thread's writes of this stage are done
-    stamp();
-    if (threadIdx.x == 0) {
-      // release at gpu scope: the CTA's writes (ordered before this by the barrier above) become
-      // visible to whoever observes the counter
-      asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(ctr), "r"(1u) : "memory");
-    }
-    target += gridDim.x;
-  }
-  __device__ __forceinline__ void wait() {
-    if (threadIdx.x == 0) {
-      const long long t0 = clock64();
-      while (ld_poll_u32(ctr) < target) {
-        if (clock64() - t0 > 8000000000LL) __trap();   // a lost arrival must not hang the GPU box
-      }
-    }
-    __syncthreads();
-    stamp();
-  }
-};
-
-// Stage kernels launched one by one (CUDA graph) use the same stage code with this no-op barrier:
-// stream order provides the dependency.
-// With programmatic dependent launch the next stage kernel is already resident while this one
-// runs: everything before wait() (weight / encoder-K/V prefetch, index arithmetic) overlaps the
-// previous stage, and wait() returns once the previous grid has completed and flushed.
+// Dependency of a stage kernel on its predecessor.  With programmatic dependent launch the next stage
+// kernel is already resident while this one runs: everything before wait() (weight / encoder-K/V
+// prefetch, index arithmetic) overlaps the previous stage, and wait() returns once the previous grid
+// has completed and flushed.
 __device__ __forceinline__ long long global_timer_ns() {
   long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-struct NullBarrier {
+struct StageDep {
   long long* prof;      // optional timeline (option decode_prof): prof[0] = entry count, then (tag, t_entry, t_ready, t_done) records
   int tag;
   long long t_entry, t_ready;
@@ -239,6 +198,24 @@ struct NullBarrier {
 };
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// Request a stage's prefetch region (PdStage::pf: the layer's encoder K/V, which never change during a decode) into
+// L2: 16 KB bulk prefetches, spread over the grid, one instruction per thread.  Issued BEFORE the dependency wait
+// by the first stage of a layer, so that HBM streams the K/V while the layer's GEMM stages (whose weights are L2
+// hits) run; the cross-attention stage, four stages later, then reads L2 instead of HBM.
+__device__ __forceinline__ void pd_prefetch_region(const void* base, long long block_bytes, long long block_stride, int blocks) {
+  if (base == nullptr) return;
+  constexpr long long kChunk = 16384;
+  const int per_block = static_cast<int>((block_bytes + kChunk - 1) / kChunk);
+  const int total = per_block * blocks;
+  for (int c = blockIdx.x + gridDim.x * threadIdx.x; c < total; c += gridDim.x * blockDim.x) {
+    const int b = c / per_block, k = c - b * per_block;
+    const long long off = static_cast<long long>(k) * kChunk;
+    const unsigned bytes = static_cast<unsigned>(block_bytes - off < kChunk ? block_bytes - off : kChunk);
+    const char* ptr = static_cast<const char*>(base) + b * block_stride + off;
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------ small-M GEMM stage ---
 //
 // out[r, n] = epilogue( sum_k A[r,k] * W[n,k] (+ bias[n]) ),  r < B; tile = (N-slice of NT columns,
@@ -250,7 +227,7 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 // 16-byte load per row gives a0/a2 (or b0/b1) of both k-steps.  A and W use the same mapping, so
 // the product is exact, every 32-byte sector fetched is fully used, and nothing is staged in smem.
 // Inside the CTA the warps are 4 m-tiles x KS K-slices, reduced through smem in a fixed order
-// (KS = 2 in the persistent kernel, 4 in the stage kernels: 512 threads keep ~130 KB in flight).
+// (KS = 4: 512 threads keep ~130 KB in flight).
 template <int NT, int CH, int KS, class Bar>
 __device__ __forceinline__ void pd_gemm_stage(Bar& bar, float* red, const PdParams& p, const PdStage& st) {
   constexpr int NTL = NT / 8;
@@ -293,6 +270,7 @@ __device__ __forceinline__ void pd_gemm_stage(Bar& bar, float* red, const PdPara
       }
     }
     if (!waited) {
+      pd_prefetch_region(st.pf, st.pf_bytes, st.pf_stride, st.pf_blocks);
       bar.wait();
       waited = true;
     }
@@ -465,7 +443,7 @@ __device__ __forceinline__ void pd_ln_stage(Bar& bar, const PdParams& p, const P
       const int c = (lane + 32 * i) * 4;
       gm[i] = __ldg(reinterpret_cast<const float4*>(st.g + c));
       bt[i] = __ldg(reinterpret_cast<const float4*>(st.b + c));
-      bs[i] = __ldg(reinterpret_cast<const float4*>(st.bias + c));
+      bs[i] = st.bias != nullptr ? __ldg(reinterpret_cast<const float4*>(st.bias + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
   bar.wait();
@@ -476,7 +454,8 @@ __device__ __forceinline__ void pd_ln_stage(Bar& bar, const PdParams& p, const P
 #pragma unroll
     for (int pt = 0; pt < kPdSplit; ++pt)
 #pragma unroll
-      for (int i = 0; i < 6; ++i) part[pt][i] = ldg_cg_f4(st.src + (static_cast<size_t>(pt) * B + r) * kD + (lane + 32 * i) * 4);
+      for (int i = 0; i < 6; ++i)
+        part[pt][i] = pt < st.parts ? ldg_cg_f4(st.src + (static_cast<size_t>(pt) * B + r) * kD + (lane + 32 * i) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     if (st.resid != nullptr) {
 #pragma unroll
       for (int i = 0; i < 6; ++i) rs[i] = ldg_cg_f4(st.resid + static_cast<size_t>(r) * kD + (lane + 32 * i) * 4);
@@ -628,6 +607,205 @@ __device__ __forceinline__ void pd_next_token_stage(Bar& bar, const PdParams& p,
   bar.arrive();
 }
 
+// ------------------------------------------------------------------ projection + residual + LayerNorm, one launch ---
+//
+// x, xb = LayerNorm( [gelu]( A W^T + bias ) + resid )  for the N = 768 projections that feed a LayerNorm
+// (BertSelfOutput / BertOutput: modeling_bert.py:287-298, 343-356; LM-head transform :471-486).
+//
+// A cluster of 16 CTAs owns 16 complete rows: CTA c computes columns [48 c, 48 c + 48) over the whole K
+// (8 or 16 warps = K slices, fixed-order reduction through shared memory), adds bias and residual, and the
+// row statistics are combined across the cluster through distributed shared memory (one exchange of
+// (sum, M2) per CTA and row, merged with Chan's formula: the two-pass variance of the reference, exactly).
+// Every CTA then normalises and writes its own 48 columns.  Compared with split-K partials + a separate
+// LayerNorm stage this removes a dependent launch (~1 us) and the partials' round trip through L2 per
+// LayerNorm; the CTA's whole weight slab (74 KB at K = 768) is requested into registers BEFORE the
+// dependency wait, so that only 16 rows of the activation (24 KB) are on the critical path.
+constexpr int kPlCluster = 16;
+constexpr int kPlCols = kD / kPlCluster;     // 48
+constexpr int kPlRows = 16;                  // one m16 tile per cluster
+constexpr int kPlNTL = kPlCols / 8;          // 6 n-tiles
+constexpr int pd_proj_ln_smem_bytes(int warps) { return warps * kPlRows * (kPlCols + 1) * 4 + kPlCluster * kPlRows * 8; }
+
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void st_cluster_f2(uint32_t cluster_addr, float a, float b) {
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(cluster_addr), "f"(a), "f"(b) : "memory");
+}
+
+// WARPS K-slices per CTA; CH 32-wide chunks per load batch; the K slice of a warp is NB batches: K = WARPS * NB * CH * 32.
+template <int WARPS, int CH, int NB>
+__global__ void __cluster_dims__(kPlCluster, 1, 1) __launch_bounds__(WARPS * 32, 1)
+pd_proj_ln_kernel(const __grid_constant__ PdParams p, const __grid_constant__ PdStage st) {
+  extern __shared__ __align__(16) float pl_smem[];
+  float* red = pl_smem;                                                             // [WARPS][16][49]
+  float2* stats = reinterpret_cast<float2*>(pl_smem + WARPS * kPlRows * (kPlCols + 1));   // [16 ranks][16 rows] (sum, M2)
+  StageDep bar;
+  bar.begin(p.prof, st.type * 100 + (st.K > 1000 ? 1 : 0));
+#ifdef MOCR_PL_STAMPS
+#define PL_STAMP(i) do { if (p.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.prof[3000 + (i)] = global_timer_ns(); } while (0)
+#else
+#define PL_STAMP(i) do { } while (0)
+#endif
+  PL_STAMP(0);
+  pdl_launch_dependents();
+  cluster_arrive_relaxed();                    // phase 0: every CTA of the cluster is running (its shared memory exists)
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const uint32_t rank = cluster_ctarank();
+  const int rg = blockIdx.x / kPlCluster;      // row group
+  const int n0 = static_cast<int>(rank) * kPlCols;
+  constexpr int K = WARPS * NB * CH * 32;
+  constexpr int kslice = K / WARPS;            // 96 (K = 768, 8 warps) or 192 (K = 3072, 16 warps)
+  const int B = p.B;
+  const int k0 = warp * kslice;
+  const int r_lo = rg * kPlRows + g, r_hi = r_lo + 8;
+  const bool lo_ok = r_lo < B, hi_ok = r_hi < B;
+
+  // ---- before the dependency wait: the first batch of weight fragments, bias / gamma / beta of this CTA's columns
+  const __nv_bfloat16* wbase = st.W + static_cast<size_t>(n0 + g) * K + k0 + 8 * t;
+  uint4 wf[2][CH][kPlNTL], af[2][CH][2];
+#pragma unroll
+  for (int c = 0; c < CH; ++c)
+#pragma unroll
+    for (int j = 0; j < kPlNTL; ++j) wf[0][c][j] = ldg_nc16(wbase + static_cast<size_t>(8 * j) * K + c * 32);
+  // epilogue mapping: warp w owns rows {w, w + WARPS, ..} < 16 of the tile, lane l columns l and l + 32 (< 48)
+  const int c0 = lane, c1 = lane + 32;
+  const bool c1_ok = c1 < kPlCols;
+  const float bias0 = __ldg(st.bias + n0 + c0), bias1 = c1_ok ? __ldg(st.bias + n0 + c1) : 0.f;
+  const float gm0 = __ldg(st.g + n0 + c0), gm1 = c1_ok ? __ldg(st.g + n0 + c1) : 0.f;
+  const float bt0 = __ldg(st.b + n0 + c0), bt1 = c1_ok ? __ldg(st.b + n0 + c1) : 0.f;
+  pd_prefetch_region(st.pf, st.pf_bytes, st.pf_stride, st.pf_blocks);
+  PL_STAMP(1);
+  bar.wait();
+  PL_STAMP(2);
+
+  // ---- the activation rows of this cluster and the residual elements this thread will need
+  const __nv_bfloat16* a_lo = st.A + static_cast<size_t>(lo_ok ? r_lo : 0) * K + k0 + 8 * t;
+  const __nv_bfloat16* a_hi = st.A + static_cast<size_t>(hi_ok ? r_hi : 0) * K + k0 + 8 * t;
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    af[0][c][0] = ldg_cg16(a_lo + c * 32);
+    af[0][c][1] = ldg_cg16(a_hi + c * 32);
+  }
+  constexpr int kRowsPerWarp = (kPlRows + WARPS - 1) / WARPS;     // 2 (8 warps) or 1 (16 warps)
+  float rs0[kRowsPerWarp], rs1[kRowsPerWarp];
+#pragma unroll
+  for (int i = 0; i < kRowsPerWarp; ++i) {
+    const int rl = warp + i * WARPS, r = rg * kPlRows + rl;
+    rs0[i] = rs1[i] = 0.f;
+    if (st.resid != nullptr && rl < kPlRows && r < B) {
+      rs0[i] = ldg_cg_f32(st.resid + static_cast<size_t>(r) * kD + n0 + c0);
+      if (c1_ok) rs1[i] = ldg_cg_f32(st.resid + static_cast<size_t>(r) * kD + n0 + c1);
+    }
+  }
+  float acc[kPlNTL][4];
+#pragma unroll
+  for (int j = 0; j < kPlNTL; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+#pragma unroll
+  for (int bt = 0; bt < NB; ++bt) {
+    const int cur = bt & 1, nxt = cur ^ 1;
+    if (bt + 1 < NB) {                         // the next batch is requested before the MMAs of this one are issued
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        af[nxt][c][0] = ldg_cg16(a_lo + ((bt + 1) * CH + c) * 32);
+        af[nxt][c][1] = ldg_cg16(a_hi + ((bt + 1) * CH + c) * 32);
+#pragma unroll
+        for (int j = 0; j < kPlNTL; ++j) wf[nxt][c][j] = ldg_nc16(wbase + static_cast<size_t>(8 * j) * K + ((bt + 1) * CH + c) * 32);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      uint4 a0 = af[cur][c][0], a1 = af[cur][c][1];
+      if (!lo_ok) a0 = make_uint4(0, 0, 0, 0);
+      if (!hi_ok) a1 = make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int j = 0; j < kPlNTL; ++j) {
+        mma16816(acc[j], a0.x, a1.x, a0.y, a1.y, wf[cur][c][j].x, wf[cur][c][j].y);
+        mma16816(acc[j], a0.z, a1.z, a0.w, a1.w, wf[cur][c][j].z, wf[cur][c][j].w);
+      }
+    }
+  }
+  // ---- fixed-order K reduction through shared memory
+  PL_STAMP(3);
+  {
+    float* rr = red + warp * kPlRows * (kPlCols + 1);
+#pragma unroll
+    for (int j = 0; j < kPlNTL; ++j) {
+      rr[g * (kPlCols + 1) + 8 * j + 2 * t] = acc[j][0];
+      rr[g * (kPlCols + 1) + 8 * j + 2 * t + 1] = acc[j][1];
+      rr[(g + 8) * (kPlCols + 1) + 8 * j + 2 * t] = acc[j][2];
+      rr[(g + 8) * (kPlCols + 1) + 8 * j + 2 * t + 1] = acc[j][3];
+    }
+  }
+  __syncthreads();
+  float v0[kRowsPerWarp], v1[kRowsPerWarp], sum_c[kRowsPerWarp], m2_c[kRowsPerWarp];
+#pragma unroll
+  for (int i = 0; i < kRowsPerWarp; ++i) {
+    const int rl = warp + i * WARPS;
+    float a = bias0, b = bias1;
+    if (rl < kPlRows) {
+#pragma unroll
+      for (int sl = 0; sl < WARPS; ++sl) {
+        a += red[(sl * kPlRows + rl) * (kPlCols + 1) + c0];
+        if (c1_ok) b += red[(sl * kPlRows + rl) * (kPlCols + 1) + c1];
+      }
+    }
+    if (st.epi & 1) { a = gelu_erf(a); b = gelu_erf(b); }
+    a += rs0[i];
+    b += rs1[i];
+    if (!c1_ok) b = 0.f;
+    v0[i] = a;
+    v1[i] = b;
+    // statistics of this CTA's 48 columns of the row: sum and M2 about their own mean
+    const float s = warp_sum(a + b);
+    const float mc = s * (1.0f / kPlCols);
+    const float d0 = a - mc, d1 = c1_ok ? b - mc : 0.f;
+    sum_c[i] = s;
+    m2_c[i] = warp_sum(d0 * d0 + d1 * d1);
+  }
+  PL_STAMP(4);
+  cluster_wait_acquire();                      // phase 0 complete: every peer's shared memory may be written
+  PL_STAMP(5);
+#pragma unroll
+  for (int i = 0; i < kRowsPerWarp; ++i) {
+    const int rl = warp + i * WARPS;
+    if (rl < kPlRows && lane < kPlCluster)     // lane j hands this CTA's (sum, M2) of the row to CTA j
+      st_cluster_f2(mapa_u32(&stats[rank * kPlRows + rl], static_cast<uint32_t>(lane)), sum_c[i], m2_c[i]);
+  }
+  cluster_arrive_release();                    // phase 1: the statistics of all 16 column slices have been delivered
+  cluster_wait_acquire();
+  PL_STAMP(6);
+#pragma unroll
+  for (int i = 0; i < kRowsPerWarp; ++i) {
+    const int rl = warp + i * WARPS, r = rg * kPlRows + rl;
+    if (rl >= kPlRows) continue;
+    const float2 sj = stats[(lane & (kPlCluster - 1)) * kPlRows + rl];   // lanes j and j + 16 read slice j
+    float tot = sj.x;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    const float mean = tot * (1.0f / kD);
+    const float dm = sj.x * (1.0f / kPlCols) - mean;
+    float m2 = sj.y + kPlCols * dm * dm;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) m2 += __shfl_xor_sync(0xffffffffu, m2, o);
+    const float rstd = rsqrtf(m2 * (1.0f / kD) + kLnEps);
+    if (r < B) {
+      const float y0 = (v0[i] - mean) * rstd * gm0 + bt0;
+      if (st.of != nullptr) st.of[static_cast<size_t>(r) * kD + n0 + c0] = y0;
+      st.ob[static_cast<size_t>(r) * kD + n0 + c0] = __float2bfloat16(y0);
+      if (c1_ok) {
+        const float y1 = (v1[i] - mean) * rstd * gm1 + bt1;
+        if (st.of != nullptr) st.of[static_cast<size_t>(r) * kD + n0 + c1] = y1;
+        st.ob[static_cast<size_t>(r) * kD + n0 + c1] = __float2bfloat16(y1);
+      }
+    }
+  }
+  PL_STAMP(7);
+  bar.arrive();
+}
+
 // ------------------------------------------------------------------ attention stage ---
 // Single-query attention for (row, head) units, 4 warps per unit.  Key j of a 208-key block is
 // owned by (warp gw, lane quarter sub, slot i): j = 16 i + 4 gw + sub; the 8 lanes of a quarter
@@ -722,7 +900,7 @@ template <bool SELF, class Bar>
 __device__ __forceinline__ void pd_attention_stage(Bar& bar, uint8_t* smem, const PdParams& p, const PdStage& st) {
   constexpr int kBlockKeys = 16 * kPdKeySlots;
   const int tid = threadIdx.x;
-  const int n_groups = blockDim.x >> 7;       // 2 in the persistent kernel, 1 in the stage kernel
+  const int n_groups = blockDim.x >> 7;       // 128-thread groups per CTA (1 in the stage kernel)
   const int group = tid >> 7, gt = tid & 127;
   const int gw = gt >> 5, lane = gt & 31;
   const int ch = lane & 7;
@@ -794,18 +972,20 @@ __device__ __forceinline__ void pd_attention_stage(Bar& bar, uint8_t* smem, cons
     const int b = u / kHeads, h = u - b * kHeads;
     if (SELF) {
       raw.qb = ldg_cg16(p.qkv + static_cast<size_t>(b) * 3 * kD + h * kHeadDim + ch * 8);
+    } else if (st.A != nullptr) {                   // complete bf16 query rows (large-batch program)
+      raw.qb = ldg_cg16(st.A + static_cast<size_t>(b) * kD + h * kHeadDim + ch * 8);
     } else {
       const int c = h * kHeadDim + ch * 8;
 #pragma unroll
       for (int pt = 0; pt < kPdSplit; ++pt) {
-        const float* src = p.yq + (static_cast<size_t>(pt) * p.B + b) * kD + c;
+        const float* src = st.src + (static_cast<size_t>(pt) * p.B + b) * kD + c;
         raw.e0[pt] = ldg_cg_f4(src);
         raw.e1[pt] = ldg_cg_f4(src + 4);
       }
     }
   };
   auto finish_q = [&](int u, const QRaw& raw, float (&qq)[8]) {
-    if (SELF) {
+    if (SELF || st.A != nullptr) {
       pd_bf16x8(raw.qb, qq);
     } else {
       const int c = (u % kHeads) * kHeadDim + ch * 8;
@@ -1035,8 +1215,6 @@ __device__ __forceinline__ void pd_attention_stage(Bar& bar, uint8_t* smem, cons
 
 // ------------------------------------------------------------------ the kernel ---
 
-constexpr int kPdSmemBytes = kPdGroups * 2 * kPdStageBytes + kPdMaxStages * static_cast<int>(sizeof(PdStage)) + 128;
-static_assert(kPdRedFloats * 4 <= kPdGroups * 2 * kPdStageBytes, "reduction scratch must fit in the staging area it aliases");
 
 __host__ __device__ inline PdStage pd_gemm_desc(int type, int epi, const __nv_bfloat16* A, int K, const PdLinear& lin, int N, int ksplit,
                                                 __nv_bfloat16* ob, float* of, int ldo) {
@@ -1050,160 +1228,130 @@ __host__ __device__ inline PdStage pd_ln_desc(const float* src, int parts, const
   s.type = PD_LN; s.epi = gelu; s.src = src; s.parts = parts; s.bias = bias; s.resid = resid; s.g = ln.g; s.b = ln.b; s.of = x; s.ob = xb;
   return s;
 }
+// x, xb = LayerNorm([gelu](A W^T + bias) + resid) in one launch (pd_proj_ln_kernel)
+__host__ __device__ inline PdStage pd_proj_ln_desc(const __nv_bfloat16* A, int K, const PdLinear& lin, int gelu, const float* resid, const PdLn& ln,
+                                                   float* x, __nv_bfloat16* xb) {
+  PdStage s{};
+  s.type = PD_PROJ_LN; s.epi = gelu; s.A = A; s.K = K; s.N = kD; s.W = lin.w; s.bias = lin.bias; s.resid = resid; s.g = ln.g; s.b = ln.b; s.of = x; s.ob = xb;
+  return s;
+}
+// a Linear on the tcgen05 GEMM (large-batch program); epi is a GemmEpilogue value
+__host__ __device__ inline PdStage pd_tc_desc(int lin, int epi, const __nv_bfloat16* A, int K, int N, __nv_bfloat16* ob, float* of, int ldo,
+                                              const float* resid) {
+  PdStage s{};
+  s.type = PD_TC; s.lin = lin; s.epi = epi; s.A = A; s.K = K; s.N = N; s.ob = ob; s.of = of; s.ldo = ldo; s.resid = resid;
+  return s;
+}
 
-// The per-token program (shared by the persistent kernel, which builds it in shared memory, and
-// by the host, which launches it stage by stage in the CUDA-graph mode).
+// The per-token program; the host launches it stage by stage (captured into a CUDA graph).
+//   small batches (p.big = 0): warp-level mma.sync stages; the N = 768 projections in front of a LayerNorm either as
+//     16-CTA clusters that normalise the rows themselves (p.fuse_ln) or as split-K partials + a LayerNorm stage;
+//   large batches (p.big = 1): every Linear on the tcgen05 kernel with 128-row tiles, LayerNorm as a row stage.
 __host__ __device__ inline int pd_build_program(const PdParams& p, PdStage* prog) {
   int n = 0;
+  const long long kv_layer_elems = 2ll * kHeads * kEncTokens * kHeadDim;      // K and V of one layer of one crop
   for (int l = 0; l < kDecLayers; ++l) {
     const PdLayer& L = p.layer[l];
+    const int lin0 = l * PD_LIN_PER_LAYER;
     PdStage a{};
     // self-attention block (modeling_bert.py:143-207, 287-298)
-    prog[n++] = pd_gemm_desc(PD_GEMM16, PD_BF16, p.xb, kD, L.qkv, 3 * kD, 1, p.qkv, nullptr, 3 * kD);
+    if (p.big) prog[n++] = pd_tc_desc(lin0 + PD_LIN_QKV, 0 /*EPI_BF16*/, p.xb, kD, 3 * kD, p.qkv, nullptr, 3 * kD, nullptr);
+    else prog[n++] = pd_gemm_desc(PD_GEMM16, PD_BF16, p.xb, kD, L.qkv, 3 * kD, 1, p.qkv, nullptr, 3 * kD);
+    if (p.kv_prefetch && !p.big) {           // this layer's encoder K/V start streaming into L2 now
+      PdStage& q = prog[n - 1];
+      q.pf = p.crosskv + static_cast<size_t>(l) * kv_layer_elems;
+      q.pf_bytes = kv_layer_elems * 2;
+      q.pf_stride = 2 * kDecLayers * kHeads * kEncTokens * kHeadDim * 2ll;
+      q.pf_blocks = (p.B + p.kv_div - 1) / p.kv_div;
+    }
     a = PdStage{}; a.type = PD_ATTN_SELF; a.layer = l; prog[n++] = a;
-    prog[n++] = pd_gemm_desc(PD_GEMM16, PD_F32_PARTIAL, p.ctx, kD, L.self_out, kD, kPdSplit, nullptr, p.y, kD);
-    prog[n++] = pd_ln_desc(p.y, kPdSplit, L.self_out.bias, 0, p.x, L.ln_self, p.x, p.xb);
+    if (p.big) {
+      prog[n++] = pd_tc_desc(lin0 + PD_LIN_SELF_OUT, 2 /*EPI_F32_RESID*/, p.ctx, kD, kD, nullptr, p.y, kD, p.x);
+      prog[n++] = pd_ln_desc(p.y, 1, nullptr, 0, nullptr, L.ln_self, p.x, p.xb);
+    } else if (p.fuse_ln) {
+      prog[n++] = pd_proj_ln_desc(p.ctx, kD, L.self_out, 0, p.x, L.ln_self, p.x, p.xb);
+    } else {
+      prog[n++] = pd_gemm_desc(PD_GEMM16, PD_F32_PARTIAL, p.ctx, kD, L.self_out, kD, kPdSplit, nullptr, p.y, kD);
+      prog[n++] = pd_ln_desc(p.y, kPdSplit, L.self_out.bias, 0, p.x, L.ln_self, p.x, p.xb);
+    }
     // cross-attention block (:210-284)
-    prog[n++] = pd_gemm_desc(PD_GEMM16, PD_F32_PARTIAL, p.xb, kD, L.cross_q, kD, kPdSplit, nullptr, p.yq, kD);
-    a = PdStage{}; a.type = PD_ATTN_CROSS; a.layer = l; a.bias = L.cross_q.bias; prog[n++] = a;
-    prog[n++] = pd_gemm_desc(PD_GEMM16, PD_F32_PARTIAL, p.ctx, kD, L.cross_out, kD, kPdSplit, nullptr, p.y, kD);
-    prog[n++] = pd_ln_desc(p.y, kPdSplit, L.cross_out.bias, 0, p.x, L.ln_cross, p.x, p.xb);
+    a = PdStage{}; a.type = PD_ATTN_CROSS; a.layer = l;
+    if (p.big) {
+      prog[n++] = pd_tc_desc(lin0 + PD_LIN_CROSS_Q, 0 /*EPI_BF16*/, p.xb, kD, kD, p.q, nullptr, kD, nullptr);
+      a.A = p.q;
+    } else {
+      prog[n++] = pd_gemm_desc(PD_GEMM16, PD_F32_PARTIAL, p.xb, kD, L.cross_q, kD, kPdSplit, nullptr, p.yq, kD);
+      a.src = p.yq; a.parts = kPdSplit; a.bias = L.cross_q.bias;
+    }
+    prog[n++] = a;
+    if (p.big) {
+      prog[n++] = pd_tc_desc(lin0 + PD_LIN_CROSS_OUT, 2 /*EPI_F32_RESID*/, p.ctx, kD, kD, nullptr, p.y, kD, p.x);
+      prog[n++] = pd_ln_desc(p.y, 1, nullptr, 0, nullptr, L.ln_cross, p.x, p.xb);
+    } else if (p.fuse_ln) {
+      prog[n++] = pd_proj_ln_desc(p.ctx, kD, L.cross_out, 0, p.x, L.ln_cross, p.x, p.xb);
+    } else {
+      prog[n++] = pd_gemm_desc(PD_GEMM16, PD_F32_PARTIAL, p.ctx, kD, L.cross_out, kD, kPdSplit, nullptr, p.y, kD);
+      prog[n++] = pd_ln_desc(p.y, kPdSplit, L.cross_out.bias, 0, p.x, L.ln_cross, p.x, p.xb);
+    }
     // feed-forward (:330-356)
-    prog[n++] = pd_gemm_desc(PD_GEMM32, PD_BF16_GELU, p.xb, kD, L.fc1, kFFN, 1, p.ffn, nullptr, kFFN);
-    prog[n++] = pd_gemm_desc(PD_GEMM16, PD_F32_PARTIAL, p.ffn, kFFN, L.fc2, kD, kPdSplit, nullptr, p.y, kD);
-    prog[n++] = pd_ln_desc(p.y, kPdSplit, L.fc2.bias, 0, p.x, L.ln_ffn, p.x, p.xb);
+    if (p.big) {
+      prog[n++] = pd_tc_desc(lin0 + PD_LIN_FC1, 1 /*EPI_BF16_GELU*/, p.xb, kD, kFFN, p.ffn, nullptr, kFFN, nullptr);
+      prog[n++] = pd_tc_desc(lin0 + PD_LIN_FC2, 2 /*EPI_F32_RESID*/, p.ffn, kFFN, kD, nullptr, p.y, kD, p.x);
+      prog[n++] = pd_ln_desc(p.y, 1, nullptr, 0, nullptr, L.ln_ffn, p.x, p.xb);
+    } else {
+      prog[n++] = pd_gemm_desc(PD_GEMM32, PD_BF16_GELU, p.xb, kD, L.fc1, kFFN, 1, p.ffn, nullptr, kFFN);
+      prog[n++] = pd_gemm_desc(PD_GEMM16, PD_F32_PARTIAL, p.ffn, kFFN, L.fc2, kD, kPdSplit, nullptr, p.y, kD);
+      prog[n++] = pd_ln_desc(p.y, kPdSplit, L.fc2.bias, 0, p.x, L.ln_ffn, p.x, p.xb);
+    }
   }
   // LM head (:471-501): dense -> GELU -> LayerNorm, then the vocabulary projection fused with the
   // per-tile arg-max: logits never leave the SM unless the parity tap is on
-  prog[n++] = pd_gemm_desc(PD_GEMM16, PD_F32_PARTIAL, p.xb, kD, p.head_t, kD, kPdSplit, nullptr, p.y, kD);
-  prog[n++] = pd_ln_desc(p.y, kPdSplit, p.head_t.bias, 1, nullptr, p.head_ln, nullptr, p.xb);
-  prog[n++] = pd_gemm_desc(PD_GEMM48, PD_ARGMAX, p.xb, kD, p.head_dec, kVocab, 1, nullptr, nullptr, 0);
+  if (p.big) {
+    prog[n++] = pd_tc_desc(PD_LIN_HEAD_T, 5 /*EPI_F32_GELU*/, p.xb, kD, kD, nullptr, p.y, kD, nullptr);
+    prog[n++] = pd_ln_desc(p.y, 1, nullptr, 0, nullptr, p.head_ln, nullptr, p.tb);
+  } else if (p.fuse_ln) {
+    prog[n++] = pd_proj_ln_desc(p.xb, kD, p.head_t, 1, nullptr, p.head_ln, nullptr, p.tb);
+  } else {
+    prog[n++] = pd_gemm_desc(PD_GEMM16, PD_F32_PARTIAL, p.xb, kD, p.head_t, kD, kPdSplit, nullptr, p.y, kD);
+    prog[n++] = pd_ln_desc(p.y, kPdSplit, p.head_t.bias, 1, nullptr, p.head_ln, nullptr, p.tb);
+  }
+  prog[n++] = pd_gemm_desc(PD_GEMM48, PD_ARGMAX, p.tb, kD, p.head_dec, kVocab, 1, nullptr, nullptr, 0);
   PdStage nx{};
   nx.type = PD_NEXT;
   prog[n++] = nx;
   return n;
 }
 
-// One out-of-line instance per stage type keeps the persistent kernel's code small.
-template <int NT, int CH>
-__device__ __noinline__ void pd_gemm_call(GridBarrier& bar, float* red, const PdParams& p, const PdStage& st) { pd_gemm_stage<NT, CH, kPdKSlices>(bar, red, p, st); }
-template <bool SELF>
-__device__ __noinline__ void pd_attention_call(GridBarrier& bar, uint8_t* smem, const PdParams& p, const PdStage& st) { pd_attention_stage<SELF>(bar, smem, p, st); }
-__device__ __noinline__ void pd_ln_call(GridBarrier& bar, const PdParams& p, const PdStage& st) { pd_ln_stage(bar, p, st, gridDim.x); }
-__device__ __noinline__ void pd_next_call(GridBarrier& bar, const PdParams& p) { pd_next_token_stage(bar, p, gridDim.x); }
-
-__global__ void __launch_bounds__(kPdThreads, 1) decode_persistent_kernel(const __grid_constant__ PdParams p) {
-  extern __shared__ __align__(128) uint8_t pd_smem[];
-  float* red = reinterpret_cast<float*>(pd_smem);     // aliases the attention staging area (stages never overlap)
-  PdStage* prog = reinterpret_cast<PdStage*>(pd_smem + kPdGroups * 2 * kPdStageBytes);
-  __shared__ int s_nstages;
-  GridBarrier bar{p.barrier, 0u, p.prof, 0};
-  const int B = p.B;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  if (threadIdx.x == 0) s_nstages = pd_build_program(p, prog);   // the per-token program
-
-  // step 0 input: ids[b][0] = [CLS] (generation/utils.py:806-863), PAD elsewhere; x = embed([CLS], 0)
-  for (int r = blockIdx.x * kPdWarps + warp; r < B; r += gridDim.x * kPdWarps) {
-    for (int i = lane; i < p.max_len; i += 32) p.ids[static_cast<size_t>(r) * p.max_len + i] = i == 0 ? 2 : 0;
-    if (lane == 0) {
-      p.pos[r] = 0;
-      p.finished[r] = p.max_len <= 1 ? 1 : 0;
-    }
-    PdEmbedConsts ek;
-    pd_embed_consts(p, lane, ek);
-    pd_embed_row_warp(p, ek, r, 2, 0, lane);
-  }
-  bar.arrive();       // (also orders the program table: arrive() starts with __syncthreads)
-  const int n_stages = s_nstages;
-
-  const int max_steps = p.max_len - 1;
-  int step = 0;
-#pragma unroll 1
-  for (; step < max_steps; ++step) {
-#pragma unroll 1
-    for (int si = 0; si < n_stages; ++si) {
-      const PdStage& st = prog[si];
-      switch (st.type) {
-        case PD_GEMM16: pd_gemm_call<16, 4>(bar, red, p, st); break;
-        case PD_GEMM32: pd_gemm_call<32, 2>(bar, red, p, st); break;
-        case PD_GEMM48: pd_gemm_call<48, 2>(bar, red, p, st); break;
-        case PD_ATTN_SELF: pd_attention_call<true>(bar, pd_smem, p, st); break;
-        case PD_ATTN_CROSS: pd_attention_call<false>(bar, pd_smem, p, st); break;
-        case PD_LN: pd_ln_call(bar, p, st); break;
-        default: pd_next_call(bar, p); break;
-      }
-    }
-    // device-side termination (generation/utils.py:2805 does this with a host sync per token)
-    bar.wait();
-    int live = 0;
-    for (int r = threadIdx.x; r < B; r += kPdThreads) live |= (ldg_cg_s32(p.finished + r) == 0) ? 1 : 0;
-    live = __syncthreads_or(live);      // no arrive: the next stage's wait() passes at once (same target)
-    if (!live && p.forced == nullptr) { ++step; break; }
-  }
-  if (blockIdx.x == 0 && threadIdx.x == 0) *p.steps_done = step;
-}
-
-
-// ------------------------------------------------------------------ stage kernels (CUDA-graph mode) ---
-// The same stage code, one launch per stage; grid = number of tiles / units so that every CTA has
-// exactly one piece of work and several CTAs share an SM (latency hiding the persistent kernel,
-// with 8 warps per SM, does not have).
+// ------------------------------------------------------------------ stage kernels ---
+// One launch per stage; grid = number of tiles / units so that every CTA has exactly one piece of
+// work and several CTAs share an SM.
 
 constexpr int kPdStageKS = 4;                  // K-slices (warps per m-tile) of the stage-kernel GEMMs: 512 threads
 constexpr int pd_gemm_smem_bytes(int nt) { return kPdStageKS * kPdRowsPerBlock * (nt + 1) * 4; }
-// `tail` (PD_LN or PD_NEXT, or type < 0 for none) is the row stage that consumes this GEMM: it is
-// fused into the same launch.  Every CTA publishes its tile with a release-add on `counter`; the
-// first `tail_ctas` CTAs then wait until all tiles have arrived and run the row stage.  All CTAs
-// of the grid are co-resident (grid <= SM count, one 512-thread CTA per SM), so the wait cannot
-// deadlock; it replaces a 3.5 us dependent launch by a ~1 us counter poll.  The counters are
-// zeroed by the first kernel of every token step (flag kPdZeroCounters).
-constexpr int kPdCounters = 16;
-constexpr int kPdZeroCounters = 0x100;          // PdStage::epi flag of the step's first GEMM
-
 template <int NT, int CH>
-__global__ void __launch_bounds__(128 * kPdStageKS, 1) pd_gemm_kernel(const __grid_constant__ PdParams p, const __grid_constant__ PdStage st,
-                                                                       const __grid_constant__ PdStage tail, unsigned int* counters, int slot,
-                                                                       int tail_ctas) {
+__global__ void __launch_bounds__(128 * kPdStageKS, 1) pd_gemm_kernel(const __grid_constant__ PdParams p, const __grid_constant__ PdStage st) {
   extern __shared__ __align__(16) float red[];      // kPdStageKS * 64 * (NT + 1) floats (pd_gemm_smem_bytes)
-  NullBarrier bar;
+  StageDep bar;
   bar.begin(p.prof, st.type * 100 + st.ksplit * 10 + (st.K > 1000 ? 1 : 0));
   pdl_launch_dependents();
-  PdStage mine = st;
-  mine.epi = st.epi & 0xff;
-  pd_gemm_stage<NT, CH, kPdStageKS>(bar, red, p, mine);
-  if ((st.epi & kPdZeroCounters) && blockIdx.x == 0 && threadIdx.x < kPdCounters && threadIdx.x != slot) counters[threadIdx.x] = 0u;
-  if (tail.type < 0) return;
-  __syncthreads();                                   // the whole tile is written
-  if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(counters + slot), "r"(1u) : "memory");
-  if (blockIdx.x >= tail_ctas) return;
-  if (threadIdx.x == 0) {
-    const long long t0 = clock64();
-    while (ld_poll_u32(counters + slot) < gridDim.x) {
-      if (clock64() - t0 > 8000000000LL) __trap();
-    }
-  }
-  __syncthreads();
-  struct Passed { __device__ __forceinline__ void arrive() {} __device__ __forceinline__ void wait() {} } done;
-  if (tail.type == PD_LN) pd_ln_stage(done, p, tail, tail_ctas);
-  else pd_next_token_stage(done, p, tail_ctas);
+  pd_gemm_stage<NT, CH, kPdStageKS>(bar, red, p, st);
 }
 template <bool SELF>
 __global__ void __launch_bounds__(128) pd_attention_kernel(const __grid_constant__ PdParams p, const __grid_constant__ PdStage st) {
   extern __shared__ __align__(128) uint8_t pd_smem[];
-  NullBarrier bar;
+  StageDep bar;
   bar.begin(p.prof, st.type * 100);
   pdl_launch_dependents();
   pd_attention_stage<SELF>(bar, pd_smem, p, st);
 }
 __global__ void __launch_bounds__(kPdThreads) pd_ln_kernel(const __grid_constant__ PdParams p, const __grid_constant__ PdStage st) {
-  NullBarrier bar;
+  StageDep bar;
   bar.begin(p.prof, st.type * 100);
   pdl_launch_dependents();
   pd_ln_stage(bar, p, st, gridDim.x);
 }
 __global__ void __launch_bounds__(kPdThreads) pd_next_kernel(const __grid_constant__ PdParams p) {
-  NullBarrier bar;
+  StageDep bar;
   bar.begin(p.prof, PD_NEXT * 100);
   pdl_launch_dependents();
   pd_next_token_stage(bar, p, gridDim.x);

@@ -25,8 +25,7 @@
 
 #include "../../include/mocr_b200.h"
 #include "common.cuh"
-#include "decode_attn.cuh"
-#include "decode_persistent.cuh"
+#include "decode_stages.cuh"
 #include "encoder_attn.cuh"
 #include "encoder_attn_tc.cuh"
 #include "gemm_tcgen05.cuh"
@@ -138,9 +137,10 @@ struct mocr_handle {
   int use_graph = 1;
   int use_pdl = 1;          // programmatic dependent launch between the decoder's stage kernels
   int steps_per_graph = 13; // decode steps captured in one CUDA graph (299 = 23 x 13)
-  int fuse_rows = 0;        // fuse LayerNorm / next-token row stages into the GEMM launch that feeds them
+  int fuse_ln = 1;          // decoder projections that feed a LayerNorm as 16-CTA clusters that normalise the rows themselves (0: split-K partials + LayerNorm stage)
+  int kv_prefetch = 0;      // 1: a layer's encoder K/V are requested into L2 by the layer's first stage (bulk prefetch before the dependency wait); measured 2.7 us per step SLOWER at 64 rows (the prefetch competes with the weights for L2)
+  int big_rows = 96;        // more decoder rows than this: the large-batch program (every Linear on the tcgen05 GEMM, 128-row tiles)
   int attn_grid = 384;      // CTAs of the decoder attention stage kernels (0 = one per (row, head) unit); 384 measured best at B = 64
-  int decode_mode = 2;   // 2 = stage kernels in a CUDA graph (default), 1 = persistent cooperative kernel, 0 = first version (tcgen05 GEMMs)
 
   // ---- weights
   Linear patch;
@@ -166,7 +166,6 @@ struct mocr_handle {
   __nv_bfloat16* crosskv = nullptr;   // [crop][layer][K|V][head][197][64]: cross-attention K/V, one contiguous block per (crop, layer, head)
   ActBuf d_xb, d_ctx, d_ffn, d_tb;
   float* d_x = nullptr;               // [brow_cap, 768]
-  float* d_tmp = nullptr;             // [brow_cap, 768]
   __nv_bfloat16* d_qkv = nullptr;     // [brow_cap, 2304]
   __nv_bfloat16* d_q = nullptr;       // [brow_cap, 768]
   __nv_bfloat16* self_k[kDecLayers] = {nullptr, nullptr};   // [max_batch, max_length, 768]
@@ -183,13 +182,9 @@ struct mocr_handle {
   int* d_forced = nullptr;
   int* d_zero = nullptr;              // [max_batch] zeros
   int* h_flags = nullptr;             // pinned [max_batch]
-  int* h_steps = nullptr;             // pinned [1]
-  unsigned int* d_barrier = nullptr;  // grid barrier counter of the persistent decoder
-  unsigned int* d_counters = nullptr; // arrival counters of the fused GEMM + row-stage kernels
-  int* d_steps = nullptr;
-  float* d_y = nullptr;               // [3, brow_cap, 768] split-K partials of the persistent decoder (projections feeding a LN)
+  float* d_y = nullptr;               // [3, brow_cap, 768] split-K partials of the projections feeding a LayerNorm
   float* d_yq = nullptr;              // [3, brow_cap, 768] split-K partials of the cross-attention query
-  long long* d_prof = nullptr;        // [4096] stage timeline of the persistent decoder (option decode_prof)
+  long long* d_prof = nullptr;        // [4096] stage timeline of the decoder (option decode_prof)
   int decode_prof = 0;
   float* logits_tap = nullptr;        // [n, max_length-1, 6144]
   size_t logits_tap_bytes = 0;
@@ -959,87 +954,6 @@ int encode(mocr_handle* h) {
 
 // ------------------------------------------------------------------ decoder ---
 
-DecodeState decode_state(mocr_handle* h, bool forced, int max_length) {
-  DecodeState st{};
-  st.ids = h->d_ids;
-  st.pos = h->d_pos;
-  st.finished = h->d_finished;
-  st.forced = forced ? h->d_forced : nullptr;
-  st.max_len = max_length;
-  st.x = h->d_x;
-  st.xb = h->d_xb.p;
-  return st;
-}
-
-int decode_attn(mocr_handle* h, int n, const DecodeAttnArgs& a) {
-  decode_attention_kernel<<<dim3(kHeads, n), kDecAttnThreads, 0, h->stream>>>(a);
-  CK(cudaGetLastError());
-  ++h->launches;
-  return MOCR_OK;
-}
-
-// One greedy step for all n rows (BertLayer x2 + LM head + arg-max / EOS / append / embed).
-int decode_step(mocr_handle* h, int n, int max_length, bool forced, bool tap) {
-  const int bn = h->dec_bn;
-  for (int l = 0; l < kDecLayers; ++l) {
-    DecLayer& L = h->dec[l];
-    // self-attention (modeling_bert.py:143-207) + BertSelfOutput (:287-298)
-    TRY(gemm(h, EPI_BF16, bn, h->d_xb, L.self_qkv, n, out_bf16(h->d_qkv, 3 * kD)));
-    DecodeAttnArgs sa{};
-    sa.q = h->d_qkv;
-    sa.ldq = 3 * kD;
-    sa.kcache = h->self_k[l];
-    sa.vcache = h->self_v[l];
-    sa.b_stride = static_cast<long long>(h->max_length) * kD;
-    sa.key_stride = kD;
-    sa.new_k = h->d_qkv + kD;
-    sa.new_v = h->d_qkv + 2 * kD;
-    sa.ld_new = 3 * kD;
-    sa.pos = h->d_pos;
-    sa.finished = h->d_finished;
-    sa.ctx = h->d_ctx.p;
-    TRY(decode_attn(h, n, sa));
-    TRY(gemm(h, EPI_F32_RESID, bn, h->d_ctx, L.self_out, n, out_f32(h->d_tmp, kD, h->d_x, kD)));
-    TRY(layernorm(h, h->d_tmp, n, L.ln_self, h->d_xb.p, h->d_x));
-    // cross-attention over the cached encoder K/V (:210-284)
-    TRY(gemm(h, EPI_BF16, bn, h->d_xb, L.cross_q, n, out_bf16(h->d_q, kD)));
-    DecodeAttnArgs ca{};
-    ca.q = h->d_q;
-    ca.ldq = kD;
-    ca.kcache = h->crosskv + static_cast<size_t>(l * 2) * kHeads * kEncTokens * kHeadDim;
-    ca.vcache = h->crosskv + static_cast<size_t>(l * 2 + 1) * kHeads * kEncTokens * kHeadDim;
-    ca.b_stride = static_cast<long long>(kEncTokens) * 4 * kD;
-    ca.key_stride = kHeadDim;
-    ca.head_stride = kEncTokens * kHeadDim;
-    ca.fixed_keys = kEncTokens;
-    ca.finished = h->d_finished;
-    ca.ctx = h->d_ctx.p;
-    TRY(decode_attn(h, n, ca));
-    TRY(gemm(h, EPI_F32_RESID, bn, h->d_ctx, L.cross_out, n, out_f32(h->d_tmp, kD, h->d_x, kD)));
-    TRY(layernorm(h, h->d_tmp, n, L.ln_cross, h->d_xb.p, h->d_x));
-    // feed-forward (:330-356)
-    TRY(gemm(h, EPI_BF16_GELU, bn, h->d_xb, L.fc1, n, out_bf16(h->d_ffn.p, kFFN)));
-    TRY(gemm(h, EPI_F32_RESID, bn, h->d_ffn, L.fc2, n, out_f32(h->d_tmp, kD, h->d_x, kD)));
-    TRY(layernorm(h, h->d_tmp, n, L.ln_ffn, h->d_xb.p, h->d_x));
-  }
-  // LM head (:471-501): dense + GELU + LayerNorm, then the vocabulary projection fused with
-  // the per-tile arg-max; logits only leave the SM when the parity tap is on.
-  TRY(gemm(h, EPI_F32_GELU, bn, h->d_xb, h->head_t, n, out_f32(h->d_tmp, kD)));
-  TRY(layernorm(h, h->d_tmp, n, h->head_ln, h->d_tb.p, nullptr));
-  GemmArgs a{};
-  a.part_max = h->part_max;
-  a.part_idx = h->part_idx;
-  a.logits = tap ? h->logits_tap : nullptr;
-  a.step = h->d_pos;
-  a.tap_steps = max_length - 1;
-  TRY(gemm(h, EPI_ARGMAX, h->head_bn, h->d_tb, h->head_dec, n, a));
-  next_token_kernel<<<n, 256, 0, h->stream>>>(decode_state(h, forced, max_length), h->emb, h->part_max, h->part_idx,
-                                              2 * (kVocab / h->head_bn), kSepId);
-  CK(cudaGetLastError());
-  ++h->launches;
-  return MOCR_OK;
-}
-
 PdLinear pd_lin(const Linear& L) { return PdLinear{L.w, L.bias}; }
 PdLn pd_ln(const LnParams& l) { return PdLn{l.g, l.b}; }
 
@@ -1049,9 +963,12 @@ PdParams make_pd_params(mocr_handle* h, int n, int max_length, bool forced, bool
   p.max_len = max_length;
   p.cache_len = h->max_length;
   p.kv_div = 1;
-  p.n_partials = ((h->dec_tc & 1) && h->decode_mode == 2 && !h->fuse_rows) ? 2 * (kVocab / 64) : kPdVocabTiles;
+  p.big = n > h->big_rows ? 1 : 0;
+  p.n_partials = (p.big || (h->dec_tc & 1)) ? 2 * (kVocab / 64) : kPdVocabTiles;
   p.logits_cur = 0;
   p.kv_evict_first = h->kv_evict_first;
+  p.fuse_ln = h->fuse_ln;
+  p.kv_prefetch = h->kv_prefetch;
   p.eos_id = kSepId;
   for (int l = 0; l < kDecLayers; ++l) {
     DecLayer& L = h->dec[l];
@@ -1079,6 +996,8 @@ PdParams make_pd_params(mocr_handle* h, int n, int max_length, bool forced, bool
   p.forced = forced ? h->d_forced : nullptr;
   p.x = h->d_x;
   p.xb = h->d_xb.p;
+  p.tb = h->d_tb.p;
+  p.q = h->d_q;
   p.y = h->d_y;
   p.yq = h->d_yq;
   p.qkv = h->d_qkv;
@@ -1087,27 +1006,8 @@ PdParams make_pd_params(mocr_handle* h, int n, int max_length, bool forced, bool
   p.part_max = h->part_max;
   p.part_idx = h->part_idx;
   p.logits = tap ? h->logits_tap : nullptr;
-  p.barrier = h->d_barrier;
-  p.steps_done = h->d_steps;
   p.prof = h->decode_prof ? h->d_prof : nullptr;
   return p;
-}
-
-// The whole greedy decode in one cooperative launch (decode_persistent.cuh).
-int decode_persistent(mocr_handle* h, int n, int max_length, bool forced, bool tap) {
-  static bool done[16] = {};
-  if (!done[h->device & 15]) {
-    CK(cudaFuncSetAttribute(decode_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPdSmemBytes));
-    done[h->device & 15] = true;
-  }
-  PdParams p = make_pd_params(h, n, max_length, forced, tap);
-  CK(cudaMemsetAsync(h->d_barrier, 0, sizeof(unsigned int), h->stream));
-  void* args[] = {&p};
-  CK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(decode_persistent_kernel), dim3(h->sms), dim3(kPdThreads), args,
-                                 static_cast<size_t>(kPdSmemBytes), h->stream));
-  ++h->launches;
-  CK(cudaMemcpyAsync(h->h_steps, h->d_steps, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-  return MOCR_OK;
 }
 
 // Launch with programmatic stream serialization: the kernel may start while its predecessor is
@@ -1146,17 +1046,51 @@ int launch_gemm_stage_tc(mocr_handle* h, const __nv_bfloat16* a_ptr, int K, Line
   a.K = L.K;
   a.bias = L.bias;
   a.pdl = 1;
-  CK(launch_pdl(h, gemm_tcgen05_kernel<BN, EPI>, std::min(L.N / BN, h->sms), kGemmThreads, gemm_smem_bytes(Cfg::kSmemBytes, EPI), ma, *mb, a));
+  const int tiles = ((rows + kGemmBM - 1) / kGemmBM) * (L.N / BN);
+  CK(launch_pdl(h, gemm_tcgen05_kernel<BN, EPI>, std::min(tiles, h->sms), kGemmThreads, gemm_smem_bytes(Cfg::kSmemBytes, EPI), ma, *mb, a));
   return MOCR_OK;
 }
 
-// One greedy step as a sequence of stage kernels (decode_persistent.cuh), one launch per stage.
+Linear* dec_linear(mocr_handle* h, int lin) {
+  if (lin == PD_LIN_HEAD_T) return &h->head_t;
+  if (lin == PD_LIN_HEAD_DEC) return &h->head_dec;
+  DecLayer& L = h->dec[lin / PD_LIN_PER_LAYER];
+  switch (lin % PD_LIN_PER_LAYER) {
+    case PD_LIN_QKV: return &L.self_qkv;
+    case PD_LIN_SELF_OUT: return &L.self_out;
+    case PD_LIN_CROSS_Q: return &L.cross_q;
+    case PD_LIN_CROSS_OUT: return &L.cross_out;
+    case PD_LIN_FC1: return &L.fc1;
+    default: return &L.fc2;
+  }
+}
+
+// A Linear of the large-batch program on the tcgen05 GEMM.  Tile widths: 64 columns for the N = 768 / 2304 / 6144 layers
+// (48 / 144 / 384 tiles at 512 rows), 128 for FFN1 (96 tiles).
+int launch_tc_stage(mocr_handle* h, const PdParams& p, const PdStage& st) {
+  Linear& L = *dec_linear(h, st.lin);
+  switch (st.epi) {
+    case EPI_BF16:
+      return launch_gemm_stage_tc<64, EPI_BF16>(h, st.A, st.K, L, p.B, out_bf16(st.ob, st.ldo));
+    case EPI_BF16_GELU:
+      return launch_gemm_stage_tc<128, EPI_BF16_GELU>(h, st.A, st.K, L, p.B, out_bf16(st.ob, st.ldo));
+    case EPI_F32_RESID:
+      return launch_gemm_stage_tc<64, EPI_F32_RESID>(h, st.A, st.K, L, p.B, out_f32(st.of, st.ldo, st.resid, kD));
+    case EPI_F32_GELU:
+      return launch_gemm_stage_tc<64, EPI_F32_GELU>(h, st.A, st.K, L, p.B, out_f32(st.of, st.ldo));
+    default:
+      return fail(h, MOCR_ERR_INVALID, "decoder stage with an unsupported tcgen05 epilogue %d", st.epi);
+  }
+}
+
+// One greedy step as a sequence of stage kernels (decode_stages.cuh), one launch per stage.
 int decode_stage_step(mocr_handle* h, const PdParams& p, bool skip_next = false) {
   static bool done[16] = {};
   if (!done[h->device & 15]) {
     CK(cudaFuncSetAttribute(pd_attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPdAttnSmemBytes));
     CK(cudaFuncSetAttribute(pd_attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPdAttnSmemBytes));
     CK(cudaFuncSetAttribute(pd_gemm_kernel<48, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pd_gemm_smem_bytes(48)));
+    CK(cudaFuncSetAttribute(pd_proj_ln_kernel<8, 3, 1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     if (h->carveout >= 0) {
       // one shared-memory carve-out for every stage kernel: kernels with different L1/smem splits cannot overlap on an SM
       CK(cudaFuncSetAttribute(pd_attention_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, h->carveout));
@@ -1164,6 +1098,7 @@ int decode_stage_step(mocr_handle* h, const PdParams& p, bool skip_next = false)
       CK(cudaFuncSetAttribute(pd_gemm_kernel<16, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, h->carveout));
       CK(cudaFuncSetAttribute(pd_gemm_kernel<32, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, h->carveout));
       CK(cudaFuncSetAttribute(pd_gemm_kernel<48, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, h->carveout));
+      CK(cudaFuncSetAttribute(pd_proj_ln_kernel<8, 3, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, h->carveout));
       CK(cudaFuncSetAttribute(pd_ln_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, h->carveout));
       CK(cudaFuncSetAttribute(pd_next_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, h->carveout));
       CK(cudaFuncSetAttribute(pd_begin_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, h->carveout));
@@ -1172,56 +1107,35 @@ int decode_stage_step(mocr_handle* h, const PdParams& p, bool skip_next = false)
   }
   PdStage prog[kPdMaxStages];
   const int n_stages = pd_build_program(p, prog);
-  // row-wise stages (LayerNorm, next token): one warp per row; few warps per CTA so that the 64 rows spread over
+  // row-wise stages (LayerNorm, next token): one warp per row; few warps per CTA so that the rows spread over
   // many SMs (8 CTAs of 8 warps made 8 SMs pull 98 KB each at ~75 GB/s per SM: 1.3 us of the stage's 2.6)
-  const int row_warps = std::max(1, std::min(h->row_warps, kPdWarps));
+  const int row_warps = p.big ? kPdWarps : std::max(1, std::min(h->row_warps, kPdWarps));
   const int row_ctas = (p.B + row_warps - 1) / row_warps;
-  const int tail_ctas = (p.B + 4 * kPdStageKS - 1) / (4 * kPdStageKS);      // 16 warps per GEMM CTA, one row each
-  const int attn_grid = h->attn_grid > 0 ? std::min(h->attn_grid, p.B * kHeads) : p.B * kHeads;
-  PdStage none{};
-  none.type = -1;
-  int slot = 0;
+  const int attn_grid = (h->attn_grid > 0 && !p.big) ? std::min(h->attn_grid, p.B * kHeads) : std::min(p.B * kHeads, 8 * h->sms);
   for (int i = 0; i < n_stages; ++i) {
-    PdStage st = prog[i];
-    if (st.type == PD_GEMM16 || st.type == PD_GEMM32 || st.type == PD_GEMM48) {
-      // fuse the row stage that consumes this GEMM (LayerNorm or next-token) into the same launch
-      const PdStage* tail = &none;
-      if (h->fuse_rows && i + 1 < n_stages && (prog[i + 1].type == PD_LN || prog[i + 1].type == PD_NEXT)) tail = &prog[i + 1];
-      if (i == 0) st.epi |= kPdZeroCounters;
-      if (h->dec_tc && !h->fuse_rows) {
-        bool done_tc = false;
-        if ((h->dec_tc & 1) && (st.epi & 0xff) == PD_ARGMAX && !p.logits_cur) {
-          GemmArgs a{};
-          a.part_max = p.part_max;
-          a.part_idx = p.part_idx;
-          a.logits = p.logits;
-          a.step = p.pos;
-          a.tap_steps = p.max_len - 1;
-          TRY((launch_gemm_stage_tc<64, EPI_ARGMAX>(h, p.xb, kD, h->head_dec, p.B, a)));
-          done_tc = true;
-        }
-        for (int l = 0; l < kDecLayers && !done_tc; ++l) {
-          if ((h->dec_tc & 2) && st.W == h->dec[l].fc1.w) {
-            TRY((launch_gemm_stage_tc<32, EPI_BF16_GELU>(h, p.xb, kD, h->dec[l].fc1, p.B, out_bf16(p.ffn, kFFN))));
-            done_tc = true;
-          } else if ((h->dec_tc & 4) && st.W == h->dec[l].self_qkv.w) {
-            TRY((launch_gemm_stage_tc<32, EPI_BF16>(h, p.xb, kD, h->dec[l].self_qkv, p.B, out_bf16(p.qkv, 3 * kD))));
-            done_tc = true;
-          }
-        }
-        if (done_tc) {
-          ++h->launches;
-          continue;
-        }
+    const PdStage& st = prog[i];
+    if (st.type == PD_TC) {
+      TRY(launch_tc_stage(h, p, st));
+    } else if (st.type == PD_GEMM16 || st.type == PD_GEMM32 || st.type == PD_GEMM48) {
+      if ((st.epi == PD_ARGMAX) && (p.big || (h->dec_tc & 1))) {
+        // vocabulary projection + per-tile arg-max on the tcgen05 kernel (96 CTAs, weights by TMA before the dependency wait)
+        GemmArgs a{};
+        a.part_max = p.part_max;
+        a.part_idx = p.part_idx;
+        a.logits = p.logits;
+        a.step = p.logits_cur ? h->d_zero : p.pos;          // beam mode taps the current step only: [B, 6144]
+        a.tap_steps = p.logits_cur ? 1 : p.max_len - 1;
+        TRY((launch_gemm_stage_tc<64, EPI_ARGMAX>(h, st.A, kD, h->head_dec, p.B, a)));
+      } else {
+        const int nt = st.type == PD_GEMM16 ? 16 : (st.type == PD_GEMM32 ? 32 : 48);
+        const int grid = (st.N / nt) * st.ksplit;
+        if (st.type == PD_GEMM16) CK(launch_pdl(h, pd_gemm_kernel<16, 2>, grid, 128 * kPdStageKS, pd_gemm_smem_bytes(16), p, st));
+        else if (st.type == PD_GEMM32) CK(launch_pdl(h, pd_gemm_kernel<32, 2>, grid, 128 * kPdStageKS, pd_gemm_smem_bytes(32), p, st));
+        else CK(launch_pdl(h, pd_gemm_kernel<48, 1>, grid, 128 * kPdStageKS, pd_gemm_smem_bytes(48), p, st));
       }
-      const int nt = st.type == PD_GEMM16 ? 16 : (st.type == PD_GEMM32 ? 32 : 48);
-      const int grid = (st.N / nt) * st.ksplit;
-      const int tc = std::min(tail_ctas, grid);
-      const int my_slot = tail->type >= 0 ? slot++ : kPdCounters - 1;
-      if (st.type == PD_GEMM16) CK(launch_pdl(h, pd_gemm_kernel<16, 2>, grid, 128 * kPdStageKS, pd_gemm_smem_bytes(16), p, st, *tail, h->d_counters, my_slot, tc));
-      else if (st.type == PD_GEMM32) CK(launch_pdl(h, pd_gemm_kernel<32, 2>, grid, 128 * kPdStageKS, pd_gemm_smem_bytes(32), p, st, *tail, h->d_counters, my_slot, tc));
-      else CK(launch_pdl(h, pd_gemm_kernel<48, 1>, grid, 128 * kPdStageKS, pd_gemm_smem_bytes(48), p, st, *tail, h->d_counters, my_slot, tc));
-      if (tail->type >= 0) ++i;
+    } else if (st.type == PD_PROJ_LN) {
+      const int groups = (p.B + kPlRows - 1) / kPlRows;
+      CK(launch_pdl(h, pd_proj_ln_kernel<8, 3, 1>, groups * kPlCluster, 256, pd_proj_ln_smem_bytes(8), p, st));
     } else if (st.type == PD_ATTN_SELF) {
       CK(launch_pdl(h, pd_attention_kernel<true>, attn_grid, 128, kPdAttnSmemBytes, p, st));
     } else if (st.type == PD_ATTN_CROSS) {
@@ -1259,31 +1173,21 @@ int decode(mocr_handle* h, int max_length, const int32_t* forced_ids) {
     }
     CK(cudaMemsetAsync(h->logits_tap, 0, need_b, h->stream));
   }
-  if (h->decode_mode == 1) {
-    TRY(decode_persistent(h, n, max_length, forced, tap));
-    h->last_steps = -1;       // read back lazily from the pinned counter
-    h->cur_len = max_length;
-    h->dec_ok = true;
-    return MOCR_OK;
-  }
-  const bool stage_mode = h->decode_mode == 2;
-  if (stage_mode && h->decode_prof) CK(cudaMemsetAsync(h->d_prof, 0, 8, h->stream));
+  if (h->decode_prof) CK(cudaMemsetAsync(h->d_prof, 0, 8, h->stream));
   const PdParams pdp = make_pd_params(h, n, max_length, forced, tap);
   auto begin = [&]() -> int {
-    if (stage_mode) CK(launch_pdl(h, pd_begin_kernel, (n + kPdWarps - 1) / kPdWarps, kPdThreads, 0, pdp));
-    else decode_begin_kernel<<<n, 256, 0, h->stream>>>(decode_state(h, forced, max_length), h->emb, kClsId, kPadId);
-    CK(cudaGetLastError());
+    CK(launch_pdl(h, pd_begin_kernel, (n + kPdWarps - 1) / kPdWarps, kPdThreads, 0, pdp));
     ++h->launches;
     return MOCR_OK;
   };
-  auto one_step = [&]() -> int { return stage_mode ? decode_stage_step(h, pdp) : decode_step(h, n, max_length, forced, tap); };
+  auto one_step = [&]() -> int { return decode_stage_step(h, pdp); };
   TRY(begin());
 
   const int steps = max_length - 1;
   cudaGraphExec_t exec = nullptr;
   int64_t per_step = 0;
   if (h->use_graph) {
-    const uint64_t key = (static_cast<uint64_t>(n) << 32) | (static_cast<uint64_t>(max_length) << 8) | (stage_mode ? 4u : 0u) | (forced ? 2u : 0u) | (tap ? 1u : 0u);
+    const uint64_t key = (static_cast<uint64_t>(n) << 32) | (static_cast<uint64_t>(max_length) << 8) | (forced ? 2u : 0u) | (tap ? 1u : 0u);
     const int spg = std::max(1, std::min(h->steps_per_graph, max_length - 1));
     auto it = h->graphs.find(key);
     if (it == h->graphs.end()) {
@@ -1398,7 +1302,6 @@ int create_impl(mocr_handle* h) {
   TRY(make_act(h, &h->d_ffn, h->brow_cap, kFFN));
   TRY(make_act(h, &h->d_tb, h->brow_cap, kD));
   TRY(dmalloc(h, &h->d_x, static_cast<size_t>(h->brow_cap) * kD));
-  TRY(dmalloc(h, &h->d_tmp, static_cast<size_t>(h->brow_cap) * kD));
   TRY(dmalloc(h, &h->d_y, static_cast<size_t>(h->brow_cap) * kD * kPdSplit));
   TRY(dmalloc(h, &h->d_yq, static_cast<size_t>(h->brow_cap) * kD * kPdSplit));
   TRY(dmalloc(h, &h->d_qkv, static_cast<size_t>(h->brow_cap) * 3 * kD));
@@ -1414,12 +1317,7 @@ int create_impl(mocr_handle* h) {
   TRY(dmalloc(h, &h->d_pos, static_cast<size_t>(B)));
   TRY(dmalloc(h, &h->d_finished, static_cast<size_t>(B)));
   TRY(dmalloc(h, &h->d_zero, static_cast<size_t>(B)));
-  TRY(dmalloc(h, &h->d_barrier, 4));
-  TRY(dmalloc(h, &h->d_counters, kPdCounters));
-  TRY(dmalloc(h, &h->d_steps, 4));
   TRY(dmalloc(h, &h->d_prof, 4096));
-  CK(cudaMallocHost(reinterpret_cast<void**>(&h->h_steps), sizeof(int)));
-  *h->h_steps = 0;
   TRY(dmalloc(h, &h->d_descs, static_cast<size_t>(B)));
   CK(cudaMallocHost(reinterpret_cast<void**>(&h->h_flags), sizeof(int) * B));
   CK(cudaMallocHost(reinterpret_cast<void**>(&h->h_descs), sizeof(CropDesc) * B));
@@ -1486,7 +1384,6 @@ int mocr_destroy(mocr_handle_t* h) {
     if (h->d_mask_meta) cudaFree(h->d_mask_meta);
     if (h->d_beam) cudaFree(h->d_beam);
     if (h->h_flags) cudaFreeHost(h->h_flags);
-    if (h->h_steps) cudaFreeHost(h->h_steps);
     if (h->h_descs) cudaFreeHost(h->h_descs);
     if (h->stream) cudaStreamDestroy(h->stream);
   }
@@ -1609,7 +1506,6 @@ int mocr_recognize(mocr_handle_t* h, const mocr_crop_t* crops, int n, int channe
 int decode_beam(mocr_handle* h, int beams, int max_length, int ngram, float length_penalty, int early, int32_t* out_ids, int32_t* out_lens,
                 float* out_scores) {
   if (!h->enc_ok) return fail(h, MOCR_ERR_INVALID, "encode has not run on the staged crops");
-  if (h->decode_mode != 2) return fail(h, MOCR_ERR_INVALID, "beam search runs on the stage kernels (decode_mode 2)");
   if (beams < 1 || 2 * beams > kBeamMaxK || ngram < 0 || early < 0 || early > 2 || out_ids == nullptr)
     return fail(h, MOCR_ERR_INVALID, "bad beam-search argument");
   if (max_length < 2 || max_length > h->max_length) return fail(h, MOCR_ERR_CAPACITY, "max_length %d outside [2, %d]", max_length, h->max_length);
@@ -1807,10 +1703,6 @@ int mocr_sync(mocr_handle_t* h) {
 int64_t mocr_launch_count(mocr_handle_t* h) { return h ? h->launches : 0; }
 int mocr_last_steps(mocr_handle_t* h) {
   if (h == nullptr) return 0;
-  if (h->last_steps < 0) {
-    if (cudaSetDevice(h->device) != cudaSuccess || cudaStreamSynchronize(h->stream) != cudaSuccess) return -1;
-    h->last_steps = *h->h_steps;
-  }
   return h->last_steps;
 }
 
@@ -1835,9 +1727,10 @@ int mocr_set_option(mocr_handle_t* h, const char* key, int value) {
   else if (k == "carveout" && value >= -1 && value <= 100) h->carveout = value;
   else if (k == "kv_evict_first" && value >= 0 && value <= 3) h->kv_evict_first = value;
   else if (k == "attn_grid" && value >= 0) h->attn_grid = value;
-  else if (k == "fuse_rows") h->fuse_rows = value != 0;
+  else if (k == "fuse_ln") h->fuse_ln = value != 0;
+  else if (k == "kv_prefetch") h->kv_prefetch = value != 0;
+  else if (k == "big_rows" && value >= 1) h->big_rows = value;
   else if (k == "steps_per_graph" && value >= 1 && value <= 64) h->steps_per_graph = value;
-  else if (k == "decode_mode" && value >= 0 && value <= 2) h->decode_mode = value;
   else if (k == "decode_prof") h->decode_prof = value != 0;
   else return fail(h, MOCR_ERR_INVALID, "unknown option or bad value: %s=%d", key, value);
   for (auto& g : h->graphs) cudaGraphExecDestroy(g.second.exec);
@@ -1892,28 +1785,44 @@ int mocr_time_kernel(mocr_handle_t* h, const char* kernel, int iters, float* ms_
       PdParams p = make_pd_params(h, n, h->cur_len, true, false);
       PdStage prog[kPdMaxStages];
       pd_build_program(p, prog);
-      // program order per layer: qkv, self_attn, self_out, ln, cross_q, cross_attn, cross_out, ln, fc1, fc2, ln; head: t, ln, vocab, next
+      // the first stage of the named kind in the per-token program
+      auto find_stage = [&](int type, int N, int K) {
+        for (int j = 0; j < kPdMaxStages && prog[j].type != PD_NEXT; ++j)
+          if (prog[j].type == type && (N == 0 || prog[j].N == N) && (K == 0 || prog[j].K == K)) return j;
+        return -1;
+      };
       int idx = -1;
       const double w768 = 2.0 * kD * kD, act = 2.0 * n * kD;
-      if (k == "dec_qkv") { idx = 0; bytes = 3 * w768 + act + 3 * act; }
-      else if (k == "dec_self_attn") { idx = 1; bytes = 0; }     // depends on the positions; reported by bench.py
-      else if (k == "dec_self_out") { idx = 2; bytes = w768 + act + kPdSplit * 2 * act; }
-      else if (k == "dec_ln") { idx = 3; bytes = (kPdSplit + 1) * 2 * act + 2 * act + act; }
-      else if (k == "dec_cross_attn") { idx = 5; bytes = static_cast<double>(n) * (2.0 * kEncTokens * kD * 2 + 2.0 * kD * 2); }
-      else if (k == "dec_fc1") { idx = 8; bytes = 4 * w768 + act + 4 * act; }
-      else if (k == "dec_fc2") { idx = 9; bytes = 4 * w768 + 4 * act + kPdSplit * 2 * act; }
-      else if (k == "dec_vocab") { idx = 24; bytes = 2.0 * kVocab * kD + act; }
-      if (idx < 0) { r = fail(h, MOCR_ERR_INVALID, "unknown kernel name %s", kernel); break; }
+      if (k == "dec_qkv") { idx = find_stage(p.big ? PD_TC : PD_GEMM16, 3 * kD, kD); bytes = 3 * w768 + act + 3 * act; }
+      else if (k == "dec_self_attn") { idx = find_stage(PD_ATTN_SELF, 0, 0); bytes = 0; }     // depends on the positions; reported by bench.py
+      else if (k == "dec_self_out") { idx = find_stage(p.big ? PD_TC : (p.fuse_ln ? PD_PROJ_LN : PD_GEMM16), kD, kD); bytes = w768 + act + (p.fuse_ln ? 3 * 2 * act : kPdSplit * 2 * act); }
+      else if (k == "dec_ln") { idx = find_stage(PD_LN, 0, 0); bytes = (kPdSplit + 1) * 2 * act + 2 * act + act; }
+      else if (k == "dec_cross_attn") { idx = find_stage(PD_ATTN_CROSS, 0, 0); bytes = static_cast<double>(n) * (2.0 * kEncTokens * kD * 2 + 2.0 * kD * 2); }
+      else if (k == "dec_fc1") { idx = find_stage(p.big ? PD_TC : PD_GEMM32, kFFN, kD); bytes = 4 * w768 + act + 4 * act; }
+      else if (k == "dec_fc2") { idx = find_stage(p.big ? PD_TC : PD_GEMM16, kD, kFFN); bytes = 4 * w768 + 4 * act + kPdSplit * 2 * act; }
+      else if (k == "dec_vocab") { idx = find_stage(PD_GEMM48, kVocab, kD); bytes = 2.0 * kVocab * kD + act; }
+      if (idx < 0) { r = fail(h, MOCR_ERR_INVALID, "no stage %s in the current decoder program", kernel); break; }
       const PdStage& st = prog[idx];
-      PdStage none{};
-      none.type = -1;
       cudaError_t le = cudaSuccess;
       // launched exactly as in the decode loop (programmatic dependent launch: the next launch's
       // constant / K-V prefetch overlaps the tail of the previous one)
       switch (st.type) {
-        case PD_GEMM16: le = launch_pdl(h, pd_gemm_kernel<16, 2>, (st.N / 16) * st.ksplit, 128 * kPdStageKS, pd_gemm_smem_bytes(16), p, st, none, h->d_counters, kPdCounters - 1, 0); break;
-        case PD_GEMM32: le = launch_pdl(h, pd_gemm_kernel<32, 2>, (st.N / 32) * st.ksplit, 128 * kPdStageKS, pd_gemm_smem_bytes(32), p, st, none, h->d_counters, kPdCounters - 1, 0); break;
-        case PD_GEMM48: le = launch_pdl(h, pd_gemm_kernel<48, 1>, (st.N / 48) * st.ksplit, 128 * kPdStageKS, pd_gemm_smem_bytes(48), p, st, none, h->d_counters, kPdCounters - 1, 0); break;
+        case PD_TC: r = launch_tc_stage(h, p, st); break;
+        case PD_GEMM16: le = launch_pdl(h, pd_gemm_kernel<16, 2>, (st.N / 16) * st.ksplit, 128 * kPdStageKS, pd_gemm_smem_bytes(16), p, st); break;
+        case PD_GEMM32: le = launch_pdl(h, pd_gemm_kernel<32, 2>, (st.N / 32) * st.ksplit, 128 * kPdStageKS, pd_gemm_smem_bytes(32), p, st); break;
+        case PD_GEMM48:
+          if (p.big || (h->dec_tc & 1)) {
+            GemmArgs ga{};
+            ga.part_max = p.part_max;
+            ga.part_idx = p.part_idx;
+            ga.step = p.pos;
+            ga.tap_steps = p.max_len - 1;
+            r = launch_gemm_stage_tc<64, EPI_ARGMAX>(h, st.A, kD, h->head_dec, p.B, ga);
+          } else {
+            le = launch_pdl(h, pd_gemm_kernel<48, 1>, (st.N / 48) * st.ksplit, 128 * kPdStageKS, pd_gemm_smem_bytes(48), p, st);
+          }
+          break;
+        case PD_PROJ_LN: le = launch_pdl(h, pd_proj_ln_kernel<8, 3, 1>, ((p.B + kPlRows - 1) / kPlRows) * kPlCluster, 256, pd_proj_ln_smem_bytes(8), p, st); break;
         case PD_ATTN_SELF: le = launch_pdl(h, pd_attention_kernel<true>, h->attn_grid > 0 ? std::min(h->attn_grid, p.B * kHeads) : p.B * kHeads, 128, kPdAttnSmemBytes, p, st); break;
         case PD_ATTN_CROSS: le = launch_pdl(h, pd_attention_kernel<false>, h->attn_grid > 0 ? std::min(h->attn_grid, p.B * kHeads) : p.B * kHeads, 128, kPdAttnSmemBytes, p, st); break;
         default: le = launch_pdl(h, pd_ln_kernel, (p.B + kPdWarps - 1) / kPdWarps, kPdThreads, 0, p, st); break;

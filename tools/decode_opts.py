@@ -5,7 +5,6 @@ from manga_ocr_b200.engine import Engine
 B, T = 64, 300
 eng = Engine(W.random_init(0), device=0, max_batch=B, max_length=T)
 eng.stage(C.bubble_batch(B)); eng.preprocess(); eng.encode()
-eng.set_option("decode_mode", 2)
 opts = [dict(kv_evict_first=0), dict(kv_evict_first=1), dict(kv_evict_first=3), dict(kv_evict_first=2), dict(kv_evict_first=1), dict(kv_evict_first=3)]
 for o in opts:
     for k, v in o.items(): eng.set_option(k, v)
