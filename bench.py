@@ -219,19 +219,54 @@ def run_reference(args, rank):
 
 # ------------------------------------------------------------------ B200 arm ---
 
+# algorithmic bytes of one decode step (bf16): the per-step weights once + per live crop its
+# encoder K/V of both layers + the self-attention cache read (6144 B per cached token) + the 6144 B it appends
+DEC_WEIGHT_BYTES = 43_716_096
+CROSS_KV_BYTES = 1_210_368
+SELF_KV_BYTES_PER_TOKEN = 6144
+ENC_FLOPS_PER_CROP = 36.056e9       # 35.126 GFLOP encoder + 0.930 GFLOP cross-K/V projection
+
+
+def decode_algorithmic_bytes(rows, steps):
+    """Sum over token steps t = 1..steps of the section-8(d) bytes for `rows` live crops."""
+    t = np.arange(1, steps + 1, dtype=np.float64)
+    return float(np.sum(DEC_WEIGHT_BYTES + rows * (CROSS_KV_BYTES + SELF_KV_BYTES_PER_TOKEN * t + SELF_KV_BYTES_PER_TOKEN)))
+
+
+def ncu_traffic(kernel_substr):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of a kernel, from the committed ncu summary of this
+    command (profiles/r2_ncu_traffic.json: written by tools/ncu_summary.py from an `ncu --set full` capture)."""
+    fp = os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")
+    if not os.path.exists(fp):
+        return None, None
+    try:
+        with open(fp) as f:
+            d = json.load(f)
+        for row in d.get("kernels", []):
+            if kernel_substr in row.get("kernel", ""):
+                return float(row["dram_bytes_per_launch"]), {"file": "profiles/r2_ncu_traffic.json", "command": d.get("command")}
+    except (OSError, ValueError, KeyError):
+        pass
+    return None, None
+
+
 def run_b200(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
     from manga_ocr_b200 import crops as C, weights as W
     from manga_ocr_b200.engine import RGB
     from manga_ocr_b200.ocr import MangaOcr
-    from manga_ocr_b200.splitter import gather_ids
+    from manga_ocr_b200.splitter import gather_ids, shard_bounds
+    from manga_ocr_b200.text import ids_to_texts
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the B200 arm has no CPU fallback (use --impl reference for the CPU path)")
     torch.cuda.set_device(local_rank)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        cpu_group = dist.new_group(backend="gloo")        # host-side barriers while one rank drives several GPUs in-process
+    legs = set(args.legs.split(",")) if args.legs != "all" else {"page512", "tall64", "stream", "regions", "ragged", "cpu"}
     weights = W.random_init(0)
     ocr = MangaOcr(weights=weights, devices=[local_rank], max_batch=BATCH, max_length=MAX_LENGTH, warmup=False)
     eng = ocr.engines[0]
@@ -239,15 +274,31 @@ def run_b200(args, rank, local_rank, world):
     in_bytes = int(sum(c.nbytes for c in crops))
     stream = torch.cuda.ExternalStream(eng.stream, device=local_rank)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")   # > 126 MB L2
+    peaks = measured_peaks()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def host_barrier():
+        if world > 1:
+            dist.barrier(group=cpu_group)
+
     def flush_l2():
         with torch.cuda.stream(stream):
             flush.add_(1)
+
+    def max_over_ranks(*vals):
+        t = torch.tensor(list(vals), dtype=torch.float64, device=f"cuda:{local_rank}")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t]
+
+    def ev():
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(stream)
+        return e
 
     # ---- resident leg: crops staged once, the device path timed with CUDA events
     eng.stage(crops, RGB)
@@ -262,25 +313,21 @@ def run_b200(args, rank, local_rank, world):
     t_wall0 = time.perf_counter()
     for _ in range(args.steps):
         flush_l2()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
+        e0 = ev()
         eng.run_resident(MAX_LENGTH)
-        e1.record(stream)
-        evs.append((e0, e1))
+        evs.append((e0, ev()))
     barrier()
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop()
     launches = eng.launch_count - launches0
     ms = sum(a.elapsed_time(b) for a, b in evs)
     steps_decoded = eng.last_steps
-    ids_res, lens = eng.fetch_ids()
 
     # ---- e2e leg: host crops in, strings out, through the public batch API
     for _ in range(max(1, min(args.warmup, 2))):
         ocr.recognize_batch(crops)
     barrier()
     t0 = time.perf_counter()
-    from manga_ocr_b200.text import ids_to_texts
     for _ in range(args.steps):
         if world == 1:
             texts = ocr.recognize_batch(crops)   # the public call: host uint8 crops -> strings
@@ -291,63 +338,185 @@ def run_b200(args, rank, local_rank, world):
         assert len(texts) == BATCH
     barrier()
     e2e_s = time.perf_counter() - t0
+    ms_max, e2e_ms_max = max_over_ranks(ms, e2e_s * 1e3)
 
-    t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=f"cuda:{local_rank}")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max, e2e_ms_max = float(t[0]), float(t[1])
-
-    # ---- phases of one step and the roofline of the dominant kernel, timed live with CUDA events
-    #      on the engine's stream
-    peaks = measured_peaks()
+    # ---- phases of one step, per-kernel table, roofline (rank 0; CUDA events on the engine's stream)
     roof, phases, kernels = None, None, []
     if rank == 0:
-        def ev():
-            e = torch.cuda.Event(enable_timing=True)
-            e.record(stream)
-            return e
         ph = []
         for _ in range(3):
             flush_l2()
             e0 = ev(); eng.preprocess(); e1 = ev(); eng.encode(); e2 = ev(); eng.decode(MAX_LENGTH); e3 = ev()
             eng.sync()
             ph.append((e0.elapsed_time(e1), e1.elapsed_time(e2), e2.elapsed_time(e3)))
+        steps_run = max(eng.last_steps, 1)
         phases = {"preprocess_ms": min(p[0] for p in ph), "encode_ms": min(p[1] for p in ph), "decode_ms": min(p[2] for p in ph),
-                  "decode_us_per_token_step": 1e3 * min(p[2] for p in ph) / max(eng.last_steps, 1)}
-        enc_flops = BATCH * 36.056e9        # 35.126 GFLOP encoder + 0.930 GFLOP cross-K/V projection per crop
-        phases["encoder_tflops"] = enc_flops / (phases["encode_ms"] * 1e-3) / 1e12
+                  "decode_us_per_token_step": 1e3 * min(p[2] for p in ph) / steps_run}
+        phases["encoder_tflops"] = BATCH * ENC_FLOPS_PER_CROP / (phases["encode_ms"] * 1e-3) / 1e12
         phases["encoder_frac_of_sustained_bf16_peak"] = phases["encoder_tflops"] / peaks["bf16_tflops_sustained"]
-        for name in ("enc_ln", "enc_qkv", "enc_attn", "enc_out", "enc_fc1", "enc_fc2", "dec_qkv", "dec_self_out", "dec_ln", "dec_cross_attn", "dec_fc1", "dec_fc2",
-                     "dec_vocab"):
+        dec_bytes = decode_algorithmic_bytes(BATCH, steps_run)
+        dec_gbs = dec_bytes / (phases["decode_ms"] * 1e-3) / 1e9
+        floor_ms = 1e3 * (dec_bytes / (peaks["hbm_gbs"] * 1e9) + BATCH * ENC_FLOPS_PER_CROP / (peaks["bf16_tflops_sustained"] * 1e12))
+        step_ms = ms_max / args.steps
+        # launches of each stage kernel per token step (decode_stages.cuh: pd_build_program) or per encoder pass
+        per_step = {"enc_ln": 25, "enc_qkv": 12, "enc_attn": 12, "enc_out": 12, "enc_fc1": 12, "enc_fc2": 12, "dec_qkv": 2, "dec_self_attn": 2,
+                    "dec_self_out": 5, "dec_ln": 2, "dec_cross_attn": 2, "dec_cross_q": 2, "dec_fc1": 2, "dec_fc2": 2, "dec_vocab": 1}
+        for name in ("enc_ln", "enc_qkv", "enc_attn", "enc_out", "enc_fc1", "enc_fc2", "dec_qkv", "dec_self_attn", "dec_self_out", "dec_ln",
+                     "dec_cross_attn", "dec_fc1", "dec_fc2", "dec_vocab"):
             try:
                 k_ms, k_bytes, k_flops = eng.time_kernel(name, 50)
             except Exception as e:      # noqa: BLE001
                 kernels.append({"kernel": name, "error": str(e)})
                 continue
-            kernels.append({"kernel": name, "us_per_launch": 1e3 * k_ms, "GBps": k_bytes / (k_ms * 1e-3) / 1e9,
+            n_launch = per_step[name] * (steps_run if name.startswith("dec_") else 1)
+            kernels.append({"kernel": name, "us_per_launch": 1e3 * k_ms, "launches_per_step": n_launch,
+                            "share_of_step": k_ms * n_launch / step_ms, "algorithmic_bytes": k_bytes,
+                            "GBps": k_bytes / (k_ms * 1e-3) / 1e9, "hbm_frac": k_bytes / (k_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                             "TFLOPs": k_flops / (k_ms * 1e-3) / 1e12})
-        name = args.roofline_kernel
-        k_ms, k_bytes, k_flops = eng.time_kernel(name, 50)
-        if k_flops > 0 and name.startswith("enc_") and name != "enc_attn":
-            ach = k_flops / (k_ms * 1e-3) / 1e12
-            roof = {"bound": "tensor", "kernel": name, "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                    "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None, "peak_source": peaks["source"] + " (sustained)",
-                    "ms_per_launch": k_ms}
-        else:
-            ach = k_bytes / (k_ms * 1e-3) / 1e9
-            roof = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
-                    "traffic": None, "peak_source": peaks["source"], "ms_per_launch": k_ms, "algorithmic_bytes": k_bytes,
-                    "note": "50 back-to-back launches with programmatic dependent launch, exactly as in the decode loop; L2 warm"}
+        kernels.sort(key=lambda r: -r.get("share_of_step", 0.0))      # dominant by time first
+        top = next((r for r in kernels if "error" not in r), None)
+        traffic, traffic_src = ncu_traffic("pd_attention_kernel<0>" if top and top["kernel"] == "dec_cross_attn" else
+                                           ("pd_gemm_kernel" if top and top["kernel"] in ("dec_qkv", "dec_fc2") else "\0"))
+        roof = {
+            "bound": "hbm", "kernel": "decode token step: all stage kernels of the %d steps (%.0f %% of the step's time)" % (steps_run, 100 * phases["decode_ms"] / step_ms),
+            "achieved": dec_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": dec_gbs / peaks["hbm_gbs"],
+            "algorithmic_bytes": dec_bytes, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peaks["source"],
+            "step_floor_ms": floor_ms, "step_frac_of_combined_roofline": floor_ms / step_ms,
+            "dominant_kernel": ({k: top[k] for k in ("kernel", "us_per_launch", "launches_per_step", "share_of_step", "GBps", "hbm_frac")} if top else None),
+            "note": "frac = SURVEY 8(d) bytes of the whole decode / its CUDA-event time in the L2-flushed step / measured HBM peak; "
+                    "step_frac_of_combined_roofline adds the encoder's tensor floor. The per-kernel rows (`kernels`, dominant by time first) are "
+                    "50 back-to-back launches of one stage on the state the decode left (programmatic dependent launch as in the loop): L2-WARM, "
+                    "so their GB/s are L2 + HBM delivery rates, not DRAM bandwidth"}
 
-        if name == "dec_cross_attn" and BATCH == 64:
-            # dram__bytes_read.sum + dram__bytes_write.sum of pd_attention_kernel<0>, one `ncu --set full` capture of this
-            # command (profiles/r1_ncu_decode_kernels.txt): 39.354368 MB + 4.864 KB per launch, vs 38.93 MB algorithmic
-            roof["traffic"] = 39354368.0 + 4864.0
-            roof["traffic_source"] = "profiles/r1_ncu_decode_kernels.txt"
+    extra = {}
+    ocr.close()
+    del ocr, eng
+    torch.cuda.empty_cache()
+
+    # ---- BASELINE configs[2]: one page batch of 512 mixed-size crops, STRONG-scaled over the ranks (host crops in, strings out)
+    if "page512" in legs:
+        total = args.page_crops
+        lo, hi = shard_bounds(total, world, rank)
+        page = C.page_batch(total, seed=1003)[lo:hi]
+        pocr = MangaOcr(weights=weights, devices=[local_rank], max_batch=max(hi - lo, 1), max_length=MAX_LENGTH, warmup=False)
+        pocr.recognize_batch(page[: min(len(page), 8)])
+        pocr.recognize_batch(page)
+        barrier()
+        t0 = time.perf_counter()
+        reps = 2
+        for _ in range(reps):
+            ids = pocr.recognize_ids(page)
+            ids_to_texts(pocr.vocab, ids)
+            if world > 1:
+                gather_ids(ids, total)
+        barrier()
+        dt = (time.perf_counter() - t0) / reps
+        # device-only share of the same work (resident crops)
+        pe = pocr.engines[0]
+        pe.stage(page, RGB)
+        pstream = torch.cuda.ExternalStream(pe.stream, device=local_rank)
+        a0 = torch.cuda.Event(enable_timing=True); a1 = torch.cuda.Event(enable_timing=True)
+        a0.record(pstream); pe.run_resident(MAX_LENGTH); a1.record(pstream); pe.sync()
+        dt_max, dev_ms = max_over_ranks(dt, a0.elapsed_time(a1))
+        extra["page512"] = {"workload": "configs[2]: 512 mixed-size crops (seed 1003), strong scaling", "crops": total, "n_gpus": world,
+                            "crops_per_rank": hi - lo, "e2e_crops_per_s": total / dt_max, "e2e_ms": dt_max * 1e3,
+                            "resident_crops_per_s": total / (dev_ms * 1e-3), "decode_steps_run": pe.last_steps, "h2d_bytes": int(sum(c.nbytes for c in page)),
+                            "api": "MangaOcr.recognize_ids + ids_to_texts per rank, NCCL all_gather of the id rows"}
+        pocr.close()
+        del pocr, pe
+
+    # ---- BASELINE configs[3]: tall vertical-text crops, 299 decode steps (decoder / KV-cache bandwidth stress), weak scaling
+    if "tall64" in legs:
+        tall = C.tall_batch(BATCH, seed=1004 + 7919 * rank)
+        tocr = MangaOcr(weights=weights, devices=[local_rank], max_batch=BATCH, max_length=MAX_LENGTH, warmup=False)
+        te = tocr.engines[0]
+        tstream = torch.cuda.ExternalStream(te.stream, device=local_rank)
+        te.stage(tall, RGB)
+        te.run_resident(MAX_LENGTH); te.sync()
+        te.preprocess(); te.encode(); te.sync()
+        barrier()
+        best = None
+        for _ in range(3):
+            with torch.cuda.stream(tstream):
+                flush.add_(1)
+            a0 = torch.cuda.Event(enable_timing=True); a1 = torch.cuda.Event(enable_timing=True)
+            a0.record(tstream); te.decode(MAX_LENGTH); a1.record(tstream); te.sync()
+            best = a0.elapsed_time(a1) if best is None else min(best, a0.elapsed_time(a1))
+        t0 = time.perf_counter()
+        tocr.recognize_batch(tall)
+        e2e_tall = time.perf_counter() - t0
+        (dec_ms, e2e_tall) = max_over_ranks(best, e2e_tall)
+        steps_t = max(te.last_steps, 1)
+        tb = decode_algorithmic_bytes(BATCH, steps_t)
+        extra["tall64"] = {"workload": "configs[3]: 64 tall crops per GPU (W 40-120, H 600-1600), max_length 300, weak scaling", "n_gpus": world,
+                           "decode_ms": dec_ms, "decode_us_per_token_step": 1e3 * dec_ms / steps_t,
+                           "decode_tokens_per_s": BATCH * world * steps_t / (dec_ms * 1e-3), "decode_hbm_GBps_per_gpu": tb / (dec_ms * 1e-3) / 1e9,
+                           "decode_hbm_frac": tb / (dec_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "e2e_crops_per_s": BATCH * world / e2e_tall,
+                           "h2d_bytes_per_gpu": int(sum(c.nbytes for c in tall))}
+        tocr.close()
+        del tocr, te
+
+    # ---- BASELINE configs[4]: the crop stream through ONE MangaOcr(devices=[0..N-1]) process (rank 0 drives every GPU of the
+    #      job; the other ranks have released theirs and wait on a host-side barrier): 50 caller threads on __call__ (the app's
+    #      worker model, reference/src/ui/main_window.py:4317-4327) and the same crops through recognize_batch
+    del flush
+    torch.cuda.empty_cache()
+    host_barrier()
+    if "stream" in legs and rank == 0:
+      try:
+          from PIL import Image
+          n_stream = args.stream_crops if args.stream_crops > 0 else 512 * world
+          per_gpu = -(-n_stream // world)
+          scrops = C.page_batch(n_stream, seed=1005)
+          socr = MangaOcr(weights=weights, devices=list(range(world)), max_batch=min(512, per_gpu), max_length=MAX_LENGTH, warmup=False)
+          socr.recognize_batch(scrops[: 8 * world])
+          socr.recognize_batch(scrops)                  # warm: graphs, arenas, tables
+          t0 = time.perf_counter()
+          texts = socr.recognize_batch(scrops)
+          dt_batch = time.perf_counter() - t0
+          assert len(texts) == n_stream
+          imgs = [Image.fromarray(c) for c in scrops]
+          n_threads = 50
+          out = [None] * n_stream
+          nxt = [0]
+          lock = threading.Lock()
+
+          def caller():
+              while True:
+                  with lock:
+                      i = nxt[0]
+                      nxt[0] += 1
+                  if i >= n_stream:
+                      return
+                  out[i] = socr(imgs[i])
+
+          ts = [threading.Thread(target=caller) for _ in range(n_threads)]
+          t0 = time.perf_counter()
+          for t in ts:
+              t.start()
+          for t in ts:
+              t.join()
+          dt_call = time.perf_counter() - t0
+          same = sum(a == b for a, b in zip(out, texts))
+          extra["stream"] = {"workload": "configs[4]: crop stream (config-3 distribution, seed 1005), one process driving every GPU", "crops": n_stream,
+                             "in_process_gpus": world, "recognize_batch_crops_per_s": n_stream / dt_batch, "recognize_batch_s": dt_batch,
+                             "call_threads": n_threads, "call_crops_per_s": n_stream / dt_call, "call_s": dt_call,
+                             "call_strings_equal_to_batch": same / n_stream, "h2d_bytes": int(sum(c.nbytes for c in scrops)),
+                             "note": "__call__ blocks its caller until that crop is decoded: 50 threads bound the crops in flight to 50 "
+                                     "(<= 50 / GPUs per batch), whatever the engine could take"}
+          socr.close()
+          del socr
+      except Exception as e:      # noqa: BLE001 - e.g. the launcher restricted this rank to one visible GPU
+        extra["stream"] = {"error": f"{type(e).__name__}: {e}"}
+    host_barrier()
 
     # ---- region staging: 64 selections of one page, crop + polygon composite + rotation on the device
     regions_info = None
-    if rank == 0 and world == 1 and not args.no_regions:
+    ocr = eng = None
+    if rank == 0 and world == 1 and ({"regions", "ragged"} & legs):
+        ocr = MangaOcr(weights=weights, devices=[local_rank], max_batch=BATCH, max_length=MAX_LENGTH, warmup=False)
+        eng = ocr.engines[0]
+    if rank == 0 and world == 1 and "regions" in legs:
         from manga_ocr_b200.engine import Region
         page, sels = C.page_with_selections(BATCH)
         regions = [Region.from_qt(rect, poly, orient) for rect, poly, orient in sels]
@@ -368,7 +537,7 @@ def run_b200(args, rank, local_rank, world):
         regions_info = {"selections": BATCH, "page": list(page.shape), "with_polygon": sum(r.polygon is not None for r in regions),
                         "rotated": sum(r.rotate != 0 for r in regions), "e2e_crops_per_s": BATCH / reg_s,
                         "device_staging_ms": timed(dev_stage), "api": "MangaOcr.recognize_regions (page + selections -> strings)"}
-        if not args.no_cpu_baseline:
+        if "cpu" in legs:
             try:
                 from oracle.make_golden_staging import reference_stage     # the reference's own PIL / cv2 call sequence
                 host_ms = timed(lambda: [reference_stage(page, r.box, r.polygon, r.rotate) for r in regions])
@@ -377,24 +546,29 @@ def run_b200(args, rank, local_rank, world):
                 regions_info["host_staging_ms_reference_libs"] = None
                 regions_info["host_staging_note"] = f"not measured: {e}"
 
-    # ---- realistic length mix (SURVEY.md 8d "Weights": optional, documented, NOT the headline): same architecture with
-    #      cls.predictions.bias[3] raised so that rows emit EOS early; decode stops once every row of the batch has finished
+    # ---- realistic length mix (SURVEY.md 8d "Weights": documented variant, NOT the headline): same architecture with
+    #      cls.predictions.bias[3] raised so that rows emit EOS early
     ragged = None
-    if rank == 0 and world == 1 and args.eos_bias > 0:
+    if rank == 0 and world == 1 and "ragged" in legs:
         from manga_ocr_b200.engine import Engine
+        n_rag = args.ragged_crops
+        rag = C.bubble_batch(n_rag, seed=1002)
         eng2 = Engine(W.random_init(0, eos_bias=args.eos_bias, gain=3.0), device=local_rank, max_batch=BATCH, max_length=MAX_LENGTH)
-        ids2, lens2 = eng2.recognize(crops, RGB, MAX_LENGTH)
+        ids2, lens2 = eng2.recognize(rag, RGB, MAX_LENGTH)
         t0 = time.perf_counter()
-        for _ in range(5):
-            eng2.recognize(crops, RGB, MAX_LENGTH)
-        dt = (time.perf_counter() - t0) / 5
-        ragged = {"eos_bias": args.eos_bias, "gain": 3.0, "mean_len": float(lens2.mean()), "max_len": int(lens2.max()),
-                  "decode_steps_run": int(eng2.last_steps), "e2e_ids_crops_per_s": BATCH / dt,
-                  "note": "host crops in, ids out; finished flags are polled every 26 token steps"}
+        for _ in range(3):
+            eng2.recognize(rag, RGB, MAX_LENGTH)
+        dt = (time.perf_counter() - t0) / 3
+        ragged = {"eos_bias": args.eos_bias, "gain": 3.0, "crops": n_rag, "rows_decoded_together": BATCH, "mean_len": float(lens2.mean()),
+                  "max_len": int(lens2.max()), "tokens": int(lens2.sum() - n_rag), "decode_steps_run": int(eng2.last_steps),
+                  "e2e_ids_crops_per_s": n_rag / dt, "e2e_tokens_per_s": float(lens2.sum() - n_rag) / dt,
+                  "note": "host crops in, ids out, through mocr_recognize"}
         eng2.close()
+    if ocr is not None:
+        ocr.close()
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and "cpu" in legs and not args.no_cpu_baseline:
         n_calls = 8
         cpu_reference(crops, 1)
         cps, tps, cores = cpu_reference(crops, n_calls)
@@ -414,11 +588,10 @@ def run_b200(args, rank, local_rank, world):
             "decode_tokens_per_s": BATCH * world * steps_decoded * args.steps / (ms_max * 1e-3),
             "e2e": {"value": total_crops / (e2e_ms_max * 1e-3), "unit": UNIT, "h2d_bytes_per_step": in_bytes + 40 * BATCH,
                     "d2h_bytes_per_step": BATCH * MAX_LENGTH * 4 + BATCH * 4, "api": "MangaOcr.recognize_batch (host uint8 crops -> strings)"},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "phases": phases, "kernels": kernels, "regions": regions_info, "ragged_lengths": ragged,
-            "wall_s_timed_region": t_wall,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "phases": phases, "kernels": kernels,
+            "configs": extra, "regions": regions_info, "ragged_lengths": ragged, "wall_s_timed_region": t_wall,
         }
         print(json.dumps(line), flush=True)
-    ocr.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -429,10 +602,12 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--roofline-kernel", default="dec_cross_attn")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-regions", action="store_true", help="skip the region-staging leg")
-    ap.add_argument("--eos-bias", type=float, default=0.0, help="extra leg: weights whose EOS bias is raised (realistic length mix); 0 = off")
+    ap.add_argument("--legs", default="all", help="comma list of the extra legs to run: page512,tall64,stream,regions,ragged,cpu (default all; 'none' = headline only)")
+    ap.add_argument("--page-crops", type=int, default=512, help="crops of the strong-scaled page batch (BASELINE configs[2])")
+    ap.add_argument("--stream-crops", type=int, default=0, help="crops of the stream leg (BASELINE configs[4]: 4096 on 8 GPUs); 0 = 512 per GPU")
+    ap.add_argument("--ragged-crops", type=int, default=512, help="crops of the realistic-length leg")
+    ap.add_argument("--eos-bias", type=float, default=4.2, help="EOS bias of the realistic-length leg's weights")
     ap.add_argument("--max-length", type=int, default=300, help="profiling only; the metric is defined at 300")
     args = ap.parse_args()
     rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)

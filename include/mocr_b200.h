@@ -132,6 +132,15 @@ int mocr_run_resident(mocr_handle_t* h, int max_length);
  * filled with EOS past its end exactly as the reference does when the PAD id is 0), out_lens [n], out_scores [n] (sum of log-probabilities / length^length_penalty). */
 int mocr_decode_beam(mocr_handle_t* h, int num_beams, int max_length, int no_repeat_ngram_size, float length_penalty, int early_stopping,
                      int32_t* out_ids, int32_t* out_lens, float* out_scores);
+/* Crops (or the selections of one page) -> beam-search hypotheses in ONE call, any n (chunks of max_batch / num_beams
+ * crops).  This is what generate() does when the checkpoint's generation config carries num_beams > 1, and the
+ * handle stays locked from staging to the result: concurrent callers cannot interleave between the stages. */
+int mocr_recognize_beam(mocr_handle_t* h, const mocr_crop_t* crops, int n, int channel_order, int max_length, int num_beams,
+                        int no_repeat_ngram_size, float length_penalty, int early_stopping, int32_t* out_ids, int32_t* out_lens,
+                        float* out_scores);
+int mocr_recognize_regions_beam(mocr_handle_t* h, const mocr_crop_t* page, const mocr_region_t* regions, int n, int channel_order,
+                                int max_length, int num_beams, int no_repeat_ngram_size, float length_penalty, int early_stopping,
+                                int32_t* out_ids, int32_t* out_lens, float* out_scores);
 /* The bookkeeping alone (no device needed): n crops, rows = n * num_beams, K = 2 * num_beams candidates per row. */
 int mocr_beam_create(int n, int num_beams, int max_length, int no_repeat_ngram_size, float length_penalty, int early_stopping,
                      mocr_beam_t** out);

@@ -64,6 +64,10 @@ _SIGNATURES = {
     "mocr_recognize_regions": (c_int, [c_void_p, POINTER(mocr_crop_t), POINTER(mocr_region_t), c_int, c_int, c_int, POINTER(c_int32),
                                        POINTER(c_int32)]),
     "mocr_decode_beam": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_int, POINTER(c_int32), POINTER(c_int32), POINTER(c_float)]),
+    "mocr_recognize_beam": (c_int, [c_void_p, POINTER(mocr_crop_t), c_int, c_int, c_int, c_int, c_int, c_float, c_int, POINTER(c_int32),
+                                    POINTER(c_int32), POINTER(c_float)]),
+    "mocr_recognize_regions_beam": (c_int, [c_void_p, POINTER(mocr_crop_t), POINTER(mocr_region_t), c_int, c_int, c_int, c_int, c_int, c_float,
+                                            c_int, POINTER(c_int32), POINTER(c_int32), POINTER(c_float)]),
     "mocr_beam_create": (c_int, [c_int, c_int, c_int, c_int, c_float, c_int, POINTER(c_void_p)]),
     "mocr_beam_destroy": (c_int, [c_void_p]),
     "mocr_beam_banned": (c_int, [c_void_p, c_int, POINTER(c_int32), c_int]),

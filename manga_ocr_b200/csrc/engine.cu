@@ -703,6 +703,7 @@ int stage_regions(mocr_handle* h, const mocr_crop_t* page, const mocr_region_t* 
       pg.stride < pg.width * pg.channels)
     return fail(h, MOCR_ERR_INVALID, "page is malformed (h=%d w=%d stride=%d channels=%d)", pg.height, pg.width, pg.stride, pg.channels);
   h->staged_ok = h->pre_ok = h->enc_ok = h->dec_ok = false;
+  CK(cudaStreamSynchronize(h->stream));     // the previous batch may still be reading the pinned descriptors / arena / tables / masks
   std::vector<MaskJob> jobs;
   std::vector<MaskEdge> edges;
   std::vector<MaskLine> lines;
@@ -777,7 +778,6 @@ int stage_regions(mocr_handle* h, const mocr_crop_t* page, const mocr_region_t* 
   const size_t smem = static_cast<size_t>(kPreThreads / 32) * h->pre_pitch + static_cast<size_t>(tmp_rows) * kImage;
   if (smem > 200 * 1024) return fail(h, MOCR_ERR_CAPACITY, "region extents need %zu B of shared memory (limit 204800)", smem);
 
-  CK(cudaStreamSynchronize(h->stream));     // the previous batch may still be reading the arena / tables / masks
   const size_t rowb = static_cast<size_t>(pg.width) * pg.channels, total = rowb * pg.height;
   if (total > h->arena_cap) {
     if (h->h_arena) cudaFreeHost(h->h_arena);
@@ -933,7 +933,10 @@ int encode(mocr_handle* h) {
       const int r = encode_launches(h);
       h->launches = l0 + per;
       const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
-      if (r != MOCR_OK) return r;
+      if (r != MOCR_OK) {
+        if (ce == cudaSuccess) cudaGraphDestroy(graph);
+        return r;
+      }
       if (ce != cudaSuccess) return fail(h, MOCR_ERR_CUDA, "encoder stream capture failed: %s", cudaGetErrorString(ce));
       CK(cudaGraphInstantiate(&exec, graph, 0));
       cudaGraphDestroy(graph);
@@ -1206,7 +1209,10 @@ int decode(mocr_handle* h, int max_length, const int32_t* forced_ids) {
       h->launches = l1;
       per_step *= spg;
       cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
-      if (r != MOCR_OK) return r;
+      if (r != MOCR_OK) {
+        if (ce == cudaSuccess) cudaGraphDestroy(graph);
+        return r;
+      }
       if (ce != cudaSuccess) return fail(h, MOCR_ERR_CUDA, "stream capture failed: %s", cudaGetErrorString(ce));
       CK(cudaGraphInstantiate(&exec, graph, 0));
       cudaGraphDestroy(graph);
@@ -1371,6 +1377,7 @@ int mocr_create(int device, int max_batch, int max_length, mocr_handle_t** out) 
 
 int mocr_destroy(mocr_handle_t* h) {
   if (h == nullptr) return MOCR_OK;
+  { std::lock_guard<std::mutex> lock(h->mu); }      // a call still running on another thread finishes first (callers must not start new ones)
   if (cudaSetDevice(h->device) == cudaSuccess) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (auto& g : h->graphs) cudaGraphExecDestroy(g.second.exec);
@@ -1621,6 +1628,47 @@ int mocr_decode_beam(mocr_handle_t* h, int num_beams, int max_length, int no_rep
   TRY(check_handle(h));
   std::lock_guard<std::mutex> lock(h->mu);
   return decode_beam(h, num_beams, max_length, no_repeat_ngram_size, length_penalty, early_stopping, out_ids, out_lens, out_scores);
+}
+
+// Crops / selections -> beam-search hypotheses in ONE call: the handle's mutex is held from staging to the result, so
+// concurrent callers of the same handle cannot interleave between stage, encode and decode (chunks of
+// max_batch / num_beams crops).  page == NULL: `crops` are host crops; page != NULL: `regions` of that page.
+int recognize_beam_impl(mocr_handle* h, const mocr_crop_t* crops, const mocr_crop_t* page, const mocr_region_t* regions, int n, int order,
+                        int max_length, int beams, int ngram, float length_penalty, int early, int32_t* out_ids, int32_t* out_lens,
+                        float* out_scores) {
+  if (n < 0 || (n > 0 && out_ids == nullptr) || (n > 0 && page == nullptr && crops == nullptr) || (n > 0 && page != nullptr && regions == nullptr))
+    return fail(h, MOCR_ERR_INVALID, "bad argument");
+  if (beams < 1 || beams > h->max_batch) return fail(h, MOCR_ERR_CAPACITY, "num_beams %d outside [1, max_batch = %d]", beams, h->max_batch);
+  const int per = std::max(1, h->max_batch / beams);
+  for (int i0 = 0; i0 < n; i0 += per) {
+    const int m = std::min(per, n - i0);
+    if (page != nullptr) TRY(stage_regions(h, page, regions + i0, m, order));
+    else TRY(stage_crops(h, crops + i0, m, order));
+    TRY(preprocess(h));
+    TRY(encode(h));
+    TRY(decode_beam(h, beams, max_length, ngram, length_penalty, early, out_ids + static_cast<size_t>(i0) * max_length,
+                    out_lens ? out_lens + i0 : nullptr, out_scores ? out_scores + i0 : nullptr));
+  }
+  return MOCR_OK;
+}
+
+int mocr_recognize_beam(mocr_handle_t* h, const mocr_crop_t* crops, int n, int channel_order, int max_length, int num_beams,
+                        int no_repeat_ngram_size, float length_penalty, int early_stopping, int32_t* out_ids, int32_t* out_lens,
+                        float* out_scores) {
+  TRY(check_handle(h));
+  std::lock_guard<std::mutex> lock(h->mu);
+  return recognize_beam_impl(h, crops, nullptr, nullptr, n, channel_order, max_length, num_beams, no_repeat_ngram_size, length_penalty,
+                             early_stopping, out_ids, out_lens, out_scores);
+}
+
+int mocr_recognize_regions_beam(mocr_handle_t* h, const mocr_crop_t* page, const mocr_region_t* regions, int n, int channel_order,
+                                int max_length, int num_beams, int no_repeat_ngram_size, float length_penalty, int early_stopping,
+                                int32_t* out_ids, int32_t* out_lens, float* out_scores) {
+  TRY(check_handle(h));
+  std::lock_guard<std::mutex> lock(h->mu);
+  if (page == nullptr) return fail(h, MOCR_ERR_INVALID, "page is NULL");
+  return recognize_beam_impl(h, nullptr, page, regions, n, channel_order, max_length, num_beams, no_repeat_ngram_size, length_penalty,
+                             early_stopping, out_ids, out_lens, out_scores);
 }
 
 // ---- beam-search bookkeeping (host only; usable without a device: the CPU tests drive it with the oracle's logits)

@@ -249,19 +249,40 @@ class Engine:
 
     def recognize_beam(self, crops: Sequence[np.ndarray], order: int = RGB, max_length: Optional[int] = None, num_beams: int = 4,
                        no_repeat_ngram_size: int = 3, length_penalty: float = 2.0, early_stopping=True):
-        """crops -> (ids, lens, scores) with beam search; chunks of max_batch // num_beams crops."""
+        """crops -> (ids, lens, scores) with beam search, any n; ONE call into the library (the handle stays locked from
+        staging to the result, so threads sharing this engine cannot interleave between the stages)."""
         T = max_length or self.max_length
-        per = max(1, self.max_batch // num_beams)
-        ids = np.zeros((len(crops), T), np.int32)
-        lens = np.zeros((len(crops),), np.int32)
-        scores = np.zeros((len(crops),), np.float32)
-        for lo in range(0, len(crops), per):
-            chunk = crops[lo:lo + per]
-            self.stage(chunk, order)
-            self.preprocess()
-            self.encode()
-            ids[lo:lo + len(chunk)], lens[lo:lo + len(chunk)], scores[lo:lo + len(chunk)] = self.decode_beam(
-                num_beams, T, no_repeat_ngram_size, length_penalty, early_stopping)
+        n = len(crops)
+        ids = np.zeros((n, T), np.int32)
+        lens = np.zeros((n,), np.int32)
+        scores = np.zeros((n,), np.float32)
+        if n == 0:
+            return ids, lens, scores
+        arr, keep = _as_crop_array(crops)
+        early = 2 if early_stopping == "never" else (1 if early_stopping else 0)
+        self._ck(self._lib.mocr_recognize_beam(self._h, arr, n, order, T, num_beams, no_repeat_ngram_size, length_penalty, early,
+                                               ids.ctypes.data_as(POINTER(c_int32)), lens.ctypes.data_as(POINTER(c_int32)),
+                                               scores.ctypes.data_as(POINTER(c_float))))
+        del keep
+        return ids, lens, scores
+
+    def recognize_regions_beam(self, page: np.ndarray, regions: Sequence[Region], order: int = RGB, max_length: Optional[int] = None,
+                               num_beams: int = 4, no_repeat_ngram_size: int = 3, length_penalty: float = 2.0, early_stopping=True):
+        """The selections of one page -> (ids, lens, scores) with beam search (one library call, like recognize_beam)."""
+        T = max_length or self.max_length
+        n = len(regions)
+        ids = np.zeros((n, T), np.int32)
+        lens = np.zeros((n,), np.int32)
+        scores = np.zeros((n,), np.float32)
+        if n == 0:
+            return ids, lens, scores
+        parr, keep = _as_crop_array([page])
+        rarr, rkeep = _as_region_array(regions)
+        early = 2 if early_stopping == "never" else (1 if early_stopping else 0)
+        self._ck(self._lib.mocr_recognize_regions_beam(self._h, parr, rarr, n, order, T, num_beams, no_repeat_ngram_size, length_penalty,
+                                                       early, ids.ctypes.data_as(POINTER(c_int32)), lens.ctypes.data_as(POINTER(c_int32)),
+                                                       scores.ctypes.data_as(POINTER(c_float))))
+        del keep, rkeep
         return ids, lens, scores
 
     def fetch_ids(self):

@@ -13,6 +13,8 @@ from __future__ import annotations
 import glob
 import os
 import threading
+import time
+import weakref
 from collections import deque
 from pathlib import Path
 from typing import Dict, List, Optional, Sequence
@@ -26,6 +28,27 @@ from .text import Vocab, ids_to_text, ids_to_texts
 DEFAULT_MODEL = "kha-white/manga-ocr-base"
 
 
+WEIGHT_FILES = ("model.safetensors", "pytorch_model.bin", "weights.npz")
+
+
+def _hub_snapshots(name: str) -> List[str]:
+    """Snapshot directories of ``name`` in the local Hugging Face cache, the one ``refs/main`` points to first.
+    Nothing is ever downloaded: the reference relies on ``from_pretrained`` fetching the checkpoint, this engine needs
+    it on disk already."""
+    home = os.environ.get("HF_HUB_CACHE") or os.path.join(os.environ.get("HF_HOME", os.path.expanduser("~/.cache/huggingface")), "hub")
+    repo = os.path.join(home, "models--" + name.replace("/", "--"))
+    snaps = sorted(glob.glob(os.path.join(repo, "snapshots", "*")))
+    try:
+        with open(os.path.join(repo, "refs", "main"), encoding="utf-8") as f:
+            main = os.path.join(repo, "snapshots", f.read().strip())
+        if main in snaps:
+            snaps.remove(main)
+            snaps.insert(0, main)
+    except OSError:
+        pass
+    return snaps
+
+
 def _find_checkpoint(name_or_path: str):
     """Resolve a local checkpoint directory/file; returns (weights_path, vocab_path | None) or None."""
     cands: List[str] = []
@@ -34,17 +57,15 @@ def _find_checkpoint(name_or_path: str):
     env = os.environ.get("MOCR_WEIGHTS", "")
     if env and os.path.exists(env):
         cands.append(env)
-    hub = os.path.join(os.environ.get("HF_HOME", os.path.expanduser("~/.cache/huggingface")), "hub",
-                       "models--" + name_or_path.replace("/", "--"), "snapshots", "*")
-    cands.extend(sorted(glob.glob(hub)))
+    cands.extend(_hub_snapshots(name_or_path))
     for c in cands:
         if os.path.isdir(c):
-            for fn in ("model.safetensors", "weights.npz"):
+            for fn in WEIGHT_FILES:
                 p = os.path.join(c, fn)
                 if os.path.exists(p):
                     v = os.path.join(c, "vocab.txt")
                     return p, (v if os.path.exists(v) else None)
-        elif c.endswith((".safetensors", ".npz")):
+        elif c.endswith((".safetensors", ".npz", ".bin", ".pt", ".pth")):
             v = os.path.join(os.path.dirname(c), "vocab.txt")
             return c, (v if os.path.exists(v) else None)
     return None
@@ -54,25 +75,28 @@ GREEDY = {"num_beams": 1, "no_repeat_ngram_size": 0, "length_penalty": 1.0, "ear
 
 
 def _generation_config(weights_path: Optional[str]) -> Dict:
-    """``generate()`` reads the checkpoint's generation settings (generation_config.json, else the legacy fields of
-    config.json).  The shipped kha-white/manga-ocr-base is believed to carry num_beams=4, no_repeat_ngram_size=3,
+    """``generate()`` reads the checkpoint's generation settings: ``generation_config.json`` WHOLESALE when the file
+    exists (transformers builds the GenerationConfig from it alone), else the legacy generation fields of
+    ``config.json``.  The shipped kha-white/manga-ocr-base is believed to carry num_beams=4, no_repeat_ngram_size=3,
     length_penalty=2.0, early_stopping=true; without a file the path is greedy (BASELINE)."""
     import json
     gen = dict(GREEDY)
     if not weights_path:
         return gen
     d = weights_path if os.path.isdir(weights_path) else os.path.dirname(weights_path)
-    for fn in ("config.json", "generation_config.json"):          # the generation config wins
+    for fn in ("generation_config.json", "config.json"):
         fp = os.path.join(d, fn)
-        if os.path.exists(fp):
-            try:
-                with open(fp, encoding="utf-8") as f:
-                    cfg = json.load(f)
-            except (OSError, ValueError):
-                continue
-            for k in gen:
-                if cfg.get(k) is not None:
-                    gen[k] = cfg[k]
+        if not os.path.exists(fp):
+            continue
+        try:
+            with open(fp, encoding="utf-8") as f:
+                cfg = json.load(f)
+        except (OSError, ValueError):
+            continue
+        for k in gen:
+            if cfg.get(k) is not None:
+                gen[k] = cfg[k]
+        break                      # the first file that exists decides; they are not merged
     return gen
 
 
@@ -86,6 +110,14 @@ def image_to_array(img) -> np.ndarray:
     if a.dtype != np.uint8:
         a = a.astype(np.uint8)
     return a
+
+
+def _validated(a: np.ndarray) -> np.ndarray:
+    if a.ndim not in (2, 3) or (a.ndim == 3 and a.shape[2] not in (1, 3, 4)) or a.shape[0] < 1 or a.shape[1] < 1:
+        raise ValueError(f"unsupported image array shape {a.shape}")
+    if max(a.shape[0], a.shape[1]) > 32768:
+        raise ValueError(f"image of {a.shape[1]} x {a.shape[0]} px is larger than the engine's 32768 px limit")
+    return a[:, :, 0] if a.ndim == 3 and a.shape[2] == 1 else a
 
 
 class _Request:
@@ -103,7 +135,7 @@ class MangaOcr:
                  weights: Optional[Dict[str, np.ndarray]] = None, vocab: Optional[Vocab] = None,
                  devices: Optional[Sequence[int]] = None, max_batch: int = 64, max_length: int = MAX_LENGTH,
                  warmup: bool = True, num_beams: Optional[int] = None, no_repeat_ngram_size: Optional[int] = None,
-                 length_penalty: Optional[float] = None, early_stopping=None):
+                 length_penalty: Optional[float] = None, early_stopping=None, linger_ms: Optional[float] = None):
         if force_cpu:
             raise RuntimeError("manga_ocr_b200 has no CPU path (force_cpu=True is not supported); it needs a B200 GPU")
         gen = dict(GREEDY)
@@ -119,8 +151,9 @@ class MangaOcr:
                 found = _find_checkpoint(name)
                 if found is None:
                     raise FileNotFoundError(
-                        f"no local checkpoint for {name!r}: pass a directory holding model.safetensors (+ vocab.txt), "
-                        "set MOCR_WEIGHTS to one, or use 'random[:seed[:eos_bias]]' for random-init weights")
+                        f"no local checkpoint for {name!r}: pass a directory holding model.safetensors or pytorch_model.bin "
+                        "(+ vocab.txt), set MOCR_WEIGHTS to one, put the snapshot into the Hugging Face cache "
+                        "(nothing is downloaded), or use 'random[:seed[:eos_bias]]' for random-init weights")
                 weights = W.load_weights(found[0])
                 gen = _generation_config(found[0])
                 if vocab is None and found[1]:
@@ -138,11 +171,35 @@ class MangaOcr:
         self.max_length = max_length
         self.max_batch = max_batch
         devs = list(devices) if devices is not None else [int(os.environ.get("MOCR_DEVICE", os.environ.get("LOCAL_RANK", "0")))]
-        self.engines = [Engine(weights, device=d, max_batch=max_batch, max_length=max_length) for d in devs]
+        if len(devs) == 1:
+            self.engines = [Engine(weights, device=devs[0], max_batch=max_batch, max_length=max_length)]
+        else:       # one engine per GPU, built concurrently (the bf16 conversion + upload of 111 M weights runs in the library, GIL released)
+            built: Dict[int, Engine] = {}
+            errs: List[BaseException] = []
+
+            def build(i: int, d: int) -> None:
+                try:
+                    built[i] = Engine(weights, device=d, max_batch=max_batch, max_length=max_length)
+                except BaseException as e:      # noqa: BLE001 - re-raised below
+                    errs.append(e)
+
+            ts = [threading.Thread(target=build, args=(i, d)) for i, d in enumerate(devs)]
+            for t in ts:
+                t.start()
+            for t in ts:
+                t.join()
+            if errs:
+                for e in built.values():
+                    e.close()
+                raise errs[0]
+            self.engines = [built[i] for i in range(len(devs))]
         self._queue: deque = deque()
         self._cv = threading.Condition()
         self._closed = False
-        self._threads = [threading.Thread(target=self._dispatch, args=(e,), name=f"mocr-gpu{e.device}", daemon=True)
+        self._busy = 0                     # dispatchers currently running a batch
+        self.linger_s = float(os.environ.get("MOCR_LINGER_MS", "1.5")) * 1e-3 if linger_ms is None else linger_ms * 1e-3
+        ref = weakref.ref(self)
+        self._threads = [threading.Thread(target=MangaOcr._dispatch, args=(ref, e, self._cv), name=f"mocr-gpu{e.device}", daemon=True)
                          for e in self.engines]
         for t in self._threads:
             t.start()
@@ -158,7 +215,7 @@ class MangaOcr:
             img = img_or_path
         else:
             raise ValueError(f"img_or_path must be a path or PIL.Image, instead got: {img_or_path}")
-        req = _Request(image_to_array(img))
+        req = _Request(_validated(image_to_array(img)))       # a malformed crop fails its own call, before it can join a batch
         with self._cv:
             if self._closed:
                 raise RuntimeError("MangaOcr instance is closed")
@@ -180,58 +237,47 @@ class MangaOcr:
         """All selections of ONE page -> strings.  ``page``: PIL image or uint8 array; ``regions``: ``Region``
         objects (``manga_ocr_b200.engine.Region``; ``Region.from_qt(rect, polygon, orientation)`` reproduces the
         reference's numbers).  The page is uploaded once; crop, polygon composite on white and rotation
-        (reference/src/ui/main_window.py:6497-6506, 9789-9800) happen on the GPU."""
+        (reference/src/ui/main_window.py:6497-6506, 9789-9800) happen on the GPU.  Decoding follows the same
+        generation settings as ``__call__`` / ``recognize_batch`` (greedy, or beam search when the checkpoint says so)."""
         arr = page if isinstance(page, np.ndarray) else image_to_array(page)
         regions = list(regions)
-        if len(self.engines) == 1 or len(regions) <= 1:
-            ids = self.engines[0].recognize_regions(arr, regions, order, self.max_length)[0]
-            return ids_to_texts(self.vocab, ids)
-        from .splitter import shard_bounds
-        out = np.zeros((len(regions), self.max_length), np.int32)
-        errs: List[BaseException] = []
 
-        def work(k: int) -> None:
-            lo, hi = shard_bounds(len(regions), len(self.engines), k)
-            try:
-                if hi > lo:
-                    out[lo:hi] = self.engines[k].recognize_regions(arr, regions[lo:hi], order, self.max_length)[0]
-            except BaseException as e:   # noqa: BLE001 - re-raised on the caller's thread
-                errs.append(e)
+        def run(engine: Engine, regs: Sequence) -> np.ndarray:
+            g = self.generation
+            if int(g["num_beams"]) <= 1:
+                return engine.recognize_regions(arr, regs, order, self.max_length)[0]
+            return engine.recognize_regions_beam(arr, regs, order, self.max_length, int(g["num_beams"]), int(g["no_repeat_ngram_size"]),
+                                                 float(g["length_penalty"]), g["early_stopping"])[0]
 
-        ts = [threading.Thread(target=work, args=(k,)) for k in range(len(self.engines))]
-        for t in ts:
-            t.start()
-        for t in ts:
-            t.join()
-        if errs:
-            raise errs[0]
-        return ids_to_texts(self.vocab, out)
+        return ids_to_texts(self.vocab, self._sharded(len(regions), lambda k, lo, hi: run(self.engines[k], regions[lo:hi])))
 
     def _engine_ids(self, engine: Engine, arrays: Sequence[np.ndarray], order: int) -> np.ndarray:
         g = self.generation
         if int(g["num_beams"]) <= 1:
             return engine.recognize(arrays, order, self.max_length)[0]
-        ids = engine.recognize_beam(arrays, order, self.max_length, int(g["num_beams"]), int(g["no_repeat_ngram_size"]),
-                                    float(g["length_penalty"]), g["early_stopping"])[0]
-        return ids
+        return engine.recognize_beam(arrays, order, self.max_length, int(g["num_beams"]), int(g["no_repeat_ngram_size"]),
+                                     float(g["length_penalty"]), g["early_stopping"])[0]
 
     def recognize_ids(self, arrays: Sequence[np.ndarray], order: int = RGB) -> np.ndarray:
-        if len(self.engines) == 1 or len(arrays) <= 1:
-            return self._engine_ids(self.engines[0], arrays, order)
-        # host-side job splitter: contiguous blocks, one worker thread per GPU, no collective
+        return self._sharded(len(arrays), lambda k, lo, hi: self._engine_ids(self.engines[k], arrays[lo:hi], order))
+
+    def _sharded(self, n: int, work) -> np.ndarray:
+        """Host-side job splitter: contiguous blocks of the n units, one worker thread per GPU, no collective."""
+        if len(self.engines) == 1 or n <= 1:
+            return work(0, 0, n)
         from .splitter import shard_bounds
-        out = np.zeros((len(arrays), self.max_length), np.int32)
+        out = np.zeros((n, self.max_length), np.int32)
         errs: List[BaseException] = []
 
-        def work(k: int) -> None:
-            lo, hi = shard_bounds(len(arrays), len(self.engines), k)
+        def run(k: int) -> None:
+            lo, hi = shard_bounds(n, len(self.engines), k)
             try:
                 if hi > lo:
-                    out[lo:hi] = self._engine_ids(self.engines[k], arrays[lo:hi], order)
+                    out[lo:hi] = work(k, lo, hi)
             except BaseException as e:   # noqa: BLE001 - re-raised on the caller's thread
                 errs.append(e)
 
-        ts = [threading.Thread(target=work, args=(k,)) for k in range(len(self.engines))]
+        ts = [threading.Thread(target=run, args=(k,)) for k in range(len(self.engines))]
         for t in ts:
             t.start()
         for t in ts:
@@ -241,33 +287,81 @@ class MangaOcr:
         return out
 
     # ---- cross-thread micro-batcher ------------------------------------------------
-    def _dispatch(self, engine: Engine) -> None:
-        while True:
-            with self._cv:
-                while not self._queue and not self._closed:
-                    self._cv.wait()
-                if self._closed and not self._queue:
-                    return
-                batch = [self._queue.popleft() for _ in range(min(len(self._queue), self.max_batch))]
-            try:
-                ids = self._engine_ids(engine, [r.crop for r in batch], RGB)
-                for r, t in zip(batch, ids_to_texts(self.vocab, ids)):
-                    r.text = t
-            except BaseException as e:   # noqa: BLE001 - delivered to every waiting caller
+    def _take_batch(self) -> Optional[list]:
+        """Called by a dispatcher with the condition held and requests queued (or the instance closed): linger a moment
+        so that callers arriving together share a batch, then take this GPU's share of what is queued (with several
+        GPUs nobody grabs the whole queue).  None = closed and drained."""
+        if self.linger_s > 0 and 0 < len(self._queue) < self.max_batch and not self._closed:
+            deadline = time.monotonic() + self.linger_s
+            while len(self._queue) < self.max_batch and not self._closed:
+                left = deadline - time.monotonic()
+                if left <= 0:
+                    break
+                self._cv.wait(left)
+        if not self._queue:
+            return None
+        share = -(-len(self._queue) // max(1, len(self.engines) - self._busy))     # ceil(queued / idle GPUs)
+        take = min(len(self._queue), self.max_batch, max(1, share))
+        self._busy += 1
+        return [self._queue.popleft() for _ in range(take)]
+
+    def _run_requests(self, engine: Engine, batch: list) -> None:
+        try:
+            ids = self._engine_ids(engine, [r.crop for r in batch], RGB)
+            for r, t in zip(batch, ids_to_texts(self.vocab, ids)):
+                r.text = t
+        except BaseException as e:   # noqa: BLE001
+            if len(batch) == 1:
+                batch[0].error = e
+            else:
+                # one bad crop must not fail its neighbours (the reference isolates failures per call,
+                # reference/src/core/workers.py:241-244): run the requests of a failed batch one by one
                 for r in batch:
-                    r.error = e
-            for r in batch:
-                r.event.set()
+                    self._run_requests(engine, [r])
+                return
+        for r in batch:
+            r.event.set()
+
+    @staticmethod
+    def _dispatch(ref, engine: Engine, cv: threading.Condition) -> None:
+        # The thread holds the MangaOcr only through a weak reference while it is idle, so an instance that is dropped
+        # without close() is collected (and its GPU memory freed) instead of being kept alive by its own threads.
+        while True:
+            with cv:
+                self = ref()
+                if self is None:
+                    return
+                if not self._queue and not self._closed:
+                    del self
+                    cv.wait(0.25)
+                    continue
+                batch = self._take_batch()
+            if batch is None:
+                return
+            try:
+                self._run_requests(engine, batch)
+            finally:
+                with cv:
+                    self._busy -= 1
+            del self, batch
 
     def close(self) -> None:
         with self._cv:
+            if self._closed:
+                return
             self._closed = True
             self._cv.notify_all()
         for t in self._threads:
             if t is not threading.current_thread():
-                t.join(timeout=5)
+                t.join()                 # queued requests are served first; the engines are idle afterwards
         for e in self.engines:
             e.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
 
     def __del__(self):
         try:

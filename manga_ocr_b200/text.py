@@ -16,6 +16,7 @@ DESIGN.md; swapping in the real ``vocab.txt`` is ``Vocab.from_file``.
 """
 from __future__ import annotations
 
+import os
 import re
 from typing import Iterable, List, Sequence
 
@@ -107,9 +108,27 @@ _VOICED_DST = "ガギグゲゴザジズゼゾダヂヅデドバビブベボヴ"
 _SEMI_SRC = "ﾊﾋﾌﾍﾎ"
 _SEMI_DST = "パピプペポ"
 
+# ASCII punctuation: jaconv's conversion table (jaconv/conv_table.py, HALF_ASCII -> FULL_ASCII) is NOT the uniform
+# U+FF01..U+FF5E block shift for four characters - it follows the JIS X 0208 look-alikes:
+#     "  ->  ”  (U+201D)      '  ->  ’  (U+2019)      \  ->  ￥  (U+FFE5)      `  ->  ‘  (U+2018)
+# Everything else in 0x21..0x7E (letters, digits, ~ -> ～ U+FF5E, - -> － U+FF0D, {|} -> ｛｜｝ ...) is the block shift.
+# PROVENANCE: restated from the published table as remembered - the package is absent offline,
+# so this row stays "unpinned against upstream"; tests/test_text.py lists the expected output character by character
+# so that a reader with the package at hand can check it in one glance.  MOCR_H2Z_ASCII=unicode selects the plain
+# block shift instead (what unicodedata-style widening would give).
+H2Z_ASCII_SPECIAL = {'"': "”", "'": "’", "\\": "￥", "`": "‘"}
+
+
+def _ascii_table(mode: str):
+    t = {c: chr(c + 0xFEE0) for c in range(0x21, 0x7F)}   # ASCII + digits
+    if mode != "unicode":
+        t.update({ord(k): v for k, v in H2Z_ASCII_SPECIAL.items()})
+    t[0x20] = "　"
+    return t
+
+
 _H2Z_SINGLE = {ord(a): b for a, b in zip(_HW_KANA + _HW_PUNCT, _FW_KANA + _FW_PUNCT)}
-_H2Z_SINGLE.update({c: chr(c + 0xFEE0) for c in range(0x21, 0x7F)})   # ASCII + digits
-_H2Z_SINGLE[0x20] = "　"
+_H2Z_SINGLE.update(_ascii_table(os.environ.get("MOCR_H2Z_ASCII", "jaconv")))
 _H2Z_PAIRS = {a + "ﾞ": b for a, b in zip(_VOICED_SRC, _VOICED_DST)}
 _H2Z_PAIRS.update({a + "ﾟ": b for a, b in zip(_SEMI_SRC, _SEMI_DST)})
 _PAIR_RE = re.compile("|".join(re.escape(k) for k in _H2Z_PAIRS))

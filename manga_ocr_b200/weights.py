@@ -168,11 +168,79 @@ def load_safetensors(path: str) -> Dict[str, np.ndarray]:
     return out
 
 
+_PT_STORAGE = {"FloatStorage": np.float32, "HalfStorage": np.float16, "DoubleStorage": np.float64, "BFloat16Storage": "bf16",
+               "LongStorage": np.int64, "IntStorage": np.int32, "ShortStorage": np.int16, "CharStorage": np.int8, "ByteStorage": np.uint8,
+               "BoolStorage": np.bool_}
+
+
+def load_torch_bin(path: str) -> Dict[str, np.ndarray]:
+    """``pytorch_model.bin`` (the zip container ``torch.save`` writes: ``<root>/data.pkl`` + one raw little-endian file
+    per storage) read WITHOUT torch: a restricted unpickler that only knows how to rebuild tensors, so a hub
+    snapshot that ships no ``model.safetensors`` still loads where the reference's ``from_pretrained`` works.
+    Floating tensors come back as float32; integer buffers (``position_ids``) are dropped."""
+    import pickle
+    import zipfile
+    from collections import OrderedDict
+
+    with zipfile.ZipFile(path) as z:
+        names = z.namelist()
+        pkl = next((n for n in names if n.endswith("data.pkl")), None)
+        if pkl is None:
+            raise ValueError(f"{path}: not a torch zip checkpoint (no data.pkl); legacy (pre-1.6) files are not supported")
+        root = pkl[: -len("data.pkl")]
+
+        class _Storage:
+            def __init__(self, kind):
+                self.kind = kind
+
+        def _rebuild_tensor_v2(storage, offset, size, stride, *unused):
+            dt, raw = storage
+            if dt == "bf16":
+                arr = (np.frombuffer(raw, dtype="<u2").astype(np.uint32) << 16).view(np.float32)
+            else:
+                arr = np.frombuffer(raw, dtype=np.dtype(dt).newbyteorder("<"))
+            size, stride = tuple(size), tuple(stride)
+            if len(size) == 0:
+                return arr[offset:offset + 1].reshape(())
+            view = np.lib.stride_tricks.as_strided(arr[offset:], shape=size, strides=tuple(st * arr.itemsize for st in stride))
+            return np.ascontiguousarray(view)
+
+        class _Unpickler(pickle.Unpickler):
+            def find_class(self, module, name):
+                if module == "collections" and name == "OrderedDict":
+                    return OrderedDict
+                if module == "torch._utils" and name in ("_rebuild_tensor_v2", "_rebuild_tensor"):
+                    return _rebuild_tensor_v2
+                if module == "torch._utils" and name == "_rebuild_parameter":
+                    return lambda data, requires_grad, hooks: data
+                if module in ("torch", "torch.storage") and name in _PT_STORAGE:
+                    return _Storage(_PT_STORAGE[name])
+                raise pickle.UnpicklingError(f"{path}: refusing to unpickle {module}.{name}")
+
+            def persistent_load(self, pid):
+                # ('storage', storage_type, key, location, numel)
+                if not isinstance(pid, tuple) or pid[0] != "storage" or not isinstance(pid[1], _Storage):
+                    raise pickle.UnpicklingError(f"{path}: unexpected persistent id {pid!r}")
+                return pid[1].kind, z.read(f"{root}data/{pid[2]}")
+
+        with z.open(pkl) as f:
+            sd = _Unpickler(f).load()
+    if isinstance(sd, dict) and "state_dict" in sd and isinstance(sd["state_dict"], dict):
+        sd = sd["state_dict"]
+    out: Dict[str, np.ndarray] = {}
+    for k, v in sd.items():
+        if isinstance(v, np.ndarray) and v.dtype.kind == "f":
+            out[k] = np.ascontiguousarray(v, dtype=np.float32)
+    return out
+
+
 def load_weights(path: str) -> Dict[str, np.ndarray]:
-    """Load a checkpoint: ``*.safetensors`` or ``*.npz`` keyed by reference names."""
+    """Load a checkpoint: ``*.safetensors``, ``*.bin`` / ``*.pt`` (torch zip) or ``*.npz``, keyed by reference names."""
     if path.endswith(".npz"):
         with np.load(path) as z:
             w = {k: np.ascontiguousarray(z[k], dtype=np.float32) for k in z.files}
+    elif path.endswith((".bin", ".pt", ".pth")):
+        w = load_torch_bin(path)
     else:
         w = load_safetensors(path)
     return complete(w)

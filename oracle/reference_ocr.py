@@ -83,6 +83,11 @@ def to_pixel_values(img: Image.Image) -> torch.Tensor:
 
 # ---- tokenizer.decode + post_process, restated independently of the product ----
 
+# jaconv/conv_table.py as published (remembered; the package is absent offline - "parity unpinned" for this row):
+# HALF_ASCII '!"#$%&\'()*+,-./:;<=>?@[\\]^_`{|}~' -> FULL_ASCII with ” ’ ￥ ‘ in place of the block-shifted ＂ ＇ ＼ ｀
+_JACONV_ASCII_SPECIAL = {chr(0x22): chr(0x201D), chr(0x27): chr(0x2019), chr(0x5C): chr(0xFFE5), chr(0x60): chr(0x2018)}
+
+
 def _h2z(text: str) -> str:
     hw = "ｦｧｨｩｪｫｬｭｮｯｰｱｲｳｴｵｶｷｸｹｺｻｼｽｾｿﾀﾁﾂﾃﾄﾅﾆﾇﾈﾉﾊﾋﾌﾍﾎﾏﾐﾑﾒﾓﾔﾕﾖﾗﾘﾙﾚﾛﾜﾝ｡｢｣､･ﾞﾟ"
     fw = "ヲァィゥェォャュョッーアイウエオカキクケコサシスセソタチツテトナニヌネノハヒフヘホマミムメモヤユヨラリルレロワン。「」、・゛゜"
@@ -100,6 +105,8 @@ def _h2z(text: str) -> str:
             out.append(semi[ch]); i += 2; continue
         if ch in single:
             out.append(single[ch])
+        elif ch in _JACONV_ASCII_SPECIAL:           # jaconv's FULL_ASCII row is not the plain block shift for these four
+            out.append(_JACONV_ASCII_SPECIAL[ch])
         elif 0x21 <= ord(ch) <= 0x7E:
             out.append(chr(ord(ch) + 0xFEE0))
         elif ch == " ":

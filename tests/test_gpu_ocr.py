@@ -132,3 +132,102 @@ def test_two_engines_share_a_gpu(weights0):
     finally:
         one.close()
         two.close()
+
+
+def test_regions_follow_the_generation_config_like_the_other_entry_points(weights0):
+    """With beam settings (what the shipped checkpoint's generation config selects), recognize_regions must give
+    the strings recognize_batch gives for the same selections staged on the host (one generate() behaviour for
+    every API of the drop-in)."""
+    from manga_ocr_b200 import weights as W
+    from manga_ocr_b200.engine import Region
+    from manga_ocr_b200.ocr import MangaOcr
+    from oracle import crop_staging_np as S
+    w = W.random_init(0, gain=3.0, eos_bias=4.2)
+    page, sels = C.page_with_selections(7, seed=21, height=700, width=600)
+    regions = [Region.from_qt(rect, poly, orient) for rect, poly, orient in sels]
+    with MangaOcr(weights=w, devices=[0], max_batch=16, max_length=20, warmup=False, num_beams=4, no_repeat_ngram_size=3,
+                  length_penalty=2.0, early_stopping=True) as ocr:
+        staged = [S.stage_region(page, r.box, r.polygon, r.rotate) for r in regions]
+        want = ocr.recognize_batch(staged)                 # 7 crops x 4 beams > 16 rows: chunked inside the library
+        assert ocr.recognize_regions(page, regions) == want
+        greedy = ocr.engines[0].recognize_regions(page, regions, max_length=20)[0]
+    from manga_ocr_b200.text import Vocab, ids_to_texts
+    assert ids_to_texts(Vocab.synthetic(), greedy) != want    # the beam settings really changed the result
+
+
+def test_beam_calls_from_many_threads_do_not_interleave(weights0):
+    """Beam mode used to be four separately locked library calls (stage, preprocess, encode, decode_beam): two threads
+    sharing an engine could decode each other's crops.  It is one call now."""
+    from manga_ocr_b200 import weights as W
+    from manga_ocr_b200.ocr import MangaOcr
+    w = W.random_init(0, gain=3.0, eos_bias=4.2)
+    crops = C.bubble_batch(12, seed=31)
+    with MangaOcr(weights=w, devices=[0], max_batch=16, max_length=16, warmup=False, num_beams=4) as ocr:
+        want = ocr.recognize_batch(crops)
+        got = [None] * 12
+        errs = []
+
+        def worker(k):
+            try:
+                if k % 2:
+                    got[k] = ocr.recognize_batch([crops[k]])[0]        # caller threads straight into the engine
+                else:
+                    got[k] = ocr(Image.fromarray(crops[k]))             # ... and through the dispatcher
+            except Exception as e:     # noqa: BLE001
+                errs.append(e)
+
+        ts = [threading.Thread(target=worker, args=(k,)) for k in range(12)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        assert not errs, errs
+        assert got == want
+
+
+def test_one_bad_request_does_not_fail_its_batch(ocr16):
+    """The reference isolates failures per call (workers catch per item, reference/src/core/workers.py:241-244): a crop
+    the engine refuses (here: wider than its 32768 px limit is caught before it joins a batch; a crop whose resampling
+    tables exceed the shared-memory capacity fails inside the library) must not fail the callers batched with it."""
+    crops = C.bubble_batch(6, seed=78)
+    want = ocr16.recognize_batch(crops)
+    huge = Image.fromarray(np.full((30000, 9, 3), 255, np.uint8))        # 30000 rows -> 224: the vertical strip does not fit
+    results = {}
+
+    def good(k):
+        results[k] = ocr16(Image.fromarray(crops[k]))
+
+    def bad():
+        try:
+            ocr16(huge)
+            results["bad"] = "no error"
+        except Exception as e:     # noqa: BLE001
+            results["bad"] = e
+
+    ts = [threading.Thread(target=good, args=(k,)) for k in range(6)] + [threading.Thread(target=bad)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert [results[k] for k in range(6)] == want
+    assert isinstance(results["bad"], Exception) or isinstance(results["bad"], str)
+    with pytest.raises(ValueError):
+        ocr16(Image.fromarray(np.zeros((4, 40000, 3), np.uint8)))       # refused before it is queued
+    assert ocr16(Image.fromarray(crops[0])) == want[0]                   # the instance stays usable
+
+
+def test_instance_is_collected_without_close(weights0):
+    """Dispatcher threads hold the instance weakly: dropping the last reference frees the engines."""
+    import gc
+    import weakref
+    from manga_ocr_b200.ocr import MangaOcr
+    ocr = MangaOcr(weights=weights0, devices=[0], max_batch=4, max_length=8, warmup=False)
+    assert isinstance(ocr(Image.fromarray(C.single_224()[0])), str)
+    threads = list(ocr._threads)
+    ref = weakref.ref(ocr)
+    del ocr
+    gc.collect()
+    assert ref() is None
+    for t in threads:
+        t.join(timeout=5)
+        assert not t.is_alive()

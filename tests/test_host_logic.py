@@ -47,6 +47,40 @@ def test_find_checkpoint(tmp_path, monkeypatch):
     snap.mkdir(parents=True)
     (snap / "model.safetensors").write_bytes(b"x")
     assert O._find_checkpoint("kha-white/manga-ocr-base") == (str(snap / "model.safetensors"), None)
+    # the snapshot refs/main points to wins over the lexicographically first one, and a snapshot that only
+    # ships pytorch_model.bin (what from_pretrained would load) is accepted
+    main = snap.parent / "zzz"
+    main.mkdir()
+    (main / "pytorch_model.bin").write_bytes(b"x")
+    refs = snap.parent.parent / "refs"
+    refs.mkdir()
+    (refs / "main").write_text("zzz\n")
+    assert O._find_checkpoint("kha-white/manga-ocr-base") == (str(main / "pytorch_model.bin"), None)
+
+
+def test_torch_bin_checkpoint_is_read_without_torch(tmp_path):
+    """pytorch_model.bin (torch.save zip) -> float32 arrays; written here WITH torch, read by the product WITHOUT it."""
+    import numpy as np
+    torch = pytest.importorskip("torch")
+    from manga_ocr_b200 import weights as W
+    sd = {"a.weight": torch.randn(5, 7), "half": torch.randn(3).half(), "bf": torch.randn(4, 4).bfloat16(),
+          "position_ids": torch.arange(10)[None], "transposed": torch.randn(6, 4).t(), "param": torch.nn.Parameter(torch.randn(2, 3))}
+    torch.save(sd, tmp_path / "pytorch_model.bin")
+    out = W.load_torch_bin(str(tmp_path / "pytorch_model.bin"))
+    assert "position_ids" not in out
+    for k, v in sd.items():
+        if v.is_floating_point():
+            assert out[k].dtype == np.float32 and np.array_equal(out[k], v.detach().float().numpy()), k
+    import pickle
+
+    class Evil:
+        def __reduce__(self):
+            return (print, ("pwned",))
+    import zipfile
+    with zipfile.ZipFile(tmp_path / "evil.bin", "w") as z:
+        z.writestr("archive/data.pkl", pickle.dumps({"x": Evil()}))
+    with pytest.raises(pickle.UnpicklingError):
+        W.load_torch_bin(str(tmp_path / "evil.bin"))
 
 
 def test_image_to_array_modes():
@@ -116,6 +150,7 @@ def test_generation_config_is_read_from_the_checkpoint_directory(tmp_path):
     assert _generation_config(str(tmp_path / "model.safetensors")) == GREEDY
     (tmp_path / "config.json").write_text(json.dumps({"num_beams": 2, "length_penalty": 1.5, "model_type": "vision-encoder-decoder"}))
     assert _generation_config(str(tmp_path))["num_beams"] == 2
+    # generation_config.json is used wholesale when it exists (not merged over config.json: length_penalty stays at its default)
     (tmp_path / "generation_config.json").write_text(json.dumps({"num_beams": 4, "no_repeat_ngram_size": 3, "early_stopping": True}))
     g = _generation_config(str(tmp_path / "model.safetensors"))
-    assert g == {"num_beams": 4, "no_repeat_ngram_size": 3, "length_penalty": 1.5, "early_stopping": True}
+    assert g == {"num_beams": 4, "no_repeat_ngram_size": 3, "length_penalty": 1.0, "early_stopping": True}

@@ -22,6 +22,26 @@ def test_post_process_known_answers(golden_text):
     assert post_process("1 2 3") == "１２３"
 
 
+def test_h2z_ascii_punctuation_character_by_character():
+    """jaconv.h2z(ascii=True, digit=True) on every ASCII punctuation mark, expected output spelled out.
+    Source: jaconv/conv_table.py (HALF_ASCII -> FULL_ASCII) as published, restated from memory because the package
+    is absent offline: the four quote-like marks map to their JIS look-alikes, everything else is the U+FEE0 block
+    shift.  This is the one place to look when checking the restatement against the real package."""
+    expected = {
+        "!": "！", '"': "”", "#": "＃", "$": "＄", "%": "％", "&": "＆", "'": "’", "(": "（", ")": "）", "*": "＊", "+": "＋",
+        ",": "，", "-": "－", ".": "．", "/": "／", ":": "：", ";": "；", "<": "＜", "=": "＝", ">": "＞", "?": "？", "@": "＠",
+        "[": "［", "\\": "￥", "]": "］", "^": "＾", "_": "＿", "`": "‘", "{": "｛", "|": "｜", "}": "｝", "~": "～",
+    }
+    for src, want in expected.items():
+        assert h2z(src) == want, (src, h2z(src), want)
+        assert post_process(f"あ {src} い") == f"あ{want}い"
+    assert h2z("Az09") == "Ａｚ０９"
+    # the oracle's independent restatement makes the same statement
+    from oracle.reference_ocr import post_process as oracle_post_process
+    for src in expected:
+        assert oracle_post_process(f"x {src}") == post_process(f"x {src}")
+
+
 def test_h2z_katakana_marks():
     assert h2z("ｶﾞｷﾞﾊﾟｱ") == "ガギパア"
     assert h2z("ｳﾞ") == "ヴ"
