@@ -1842,7 +1842,10 @@ int mocr_time_kernel(mocr_handle_t* h, const char* kernel, int iters, float* ms_
       int idx = -1;
       const double w768 = 2.0 * kD * kD, act = 2.0 * n * kD;
       if (k == "dec_qkv") { idx = find_stage(p.big ? PD_TC : PD_GEMM16, 3 * kD, kD); bytes = 3 * w768 + act + 3 * act; }
-      else if (k == "dec_self_attn") { idx = find_stage(PD_ATTN_SELF, 0, 0); bytes = 0; }     // depends on the positions; reported by bench.py
+      else if (k == "dec_self_attn") {     // on the state the last decode left: every row holds last_steps cached tokens (K and V rows of one layer)
+        idx = find_stage(PD_ATTN_SELF, 0, 0);
+        bytes = static_cast<double>(n) * std::max(h->last_steps, 1) * 2.0 * kD * 2 + 2.0 * act;
+      }
       else if (k == "dec_self_out") { idx = find_stage(p.big ? PD_TC : (p.fuse_ln ? PD_PROJ_LN : PD_GEMM16), kD, kD); bytes = w768 + act + (p.fuse_ln ? 3 * 2 * act : kPdSplit * 2 * act); }
       else if (k == "dec_ln") { idx = find_stage(PD_LN, 0, 0); bytes = (kPdSplit + 1) * 2 * act + 2 * act + act; }
       else if (k == "dec_cross_attn") { idx = find_stage(PD_ATTN_CROSS, 0, 0); bytes = static_cast<double>(n) * (2.0 * kEncTokens * kD * 2 + 2.0 * kD * 2); }
