@@ -172,6 +172,21 @@ int mocr_test_gemm(mocr_handle_t* h, int epi, int bn, int M, int N, int K, const
                    const float* resid, float* out, int32_t* out_argmax);
 int mocr_test_encoder_attention(mocr_handle_t* h, int n, const float* qkv /*[n*197,2304]*/, float* out /*[n*197,768]*/);
 
+/* Decoder stage kernels on caller-supplied host data (n_rows <= max_batch), inputs rounded to bf16 as the engine stores them.
+ * mocr_test_decode_attention: one query per row against its keys/values, ctx [n_rows, 768] out (q pre-scaled by 1/8).
+ *   mode 1 = self-attention (modeling_bert.py:143-207): k/v [n_rows, n_ctx, 768] is the row's cache, row b attends to its first
+ *            pos[b] cached keys plus this step's new_k/new_v [n_rows, 768], which the kernel also appends at index pos[b]
+ *            (returned in out_k_row / out_v_row when not NULL); n_ctx <= max_length
+ *   mode 0 = cross-attention (modeling_bert.py:210-284) over k/v [n_rows, 197, 768], query as fp32 split-K partials
+ *   mode 2 = the same with complete bf16 query rows (the large-batch program)
+ * mocr_test_stage_gemm: out[n_rows, N] of one small-M GEMM stage; kind 0 bf16, 1 bf16 + GELU, 2 split-K partials (summed + bias),
+ *   3 vocabulary arg-max (out = logits, N = 6144), 4 projection + residual + LayerNorm fused in the 16-CTA cluster kernel
+ *   (N = K = 768), 5 the same as split-K partials + the LayerNorm row stage. */
+int mocr_test_decode_attention(mocr_handle_t* h, int mode, int n_rows, int n_ctx, const int32_t* pos, const float* q, const float* k, const float* v,
+                               const float* new_k, const float* new_v, float* out_ctx, float* out_k_row, float* out_v_row);
+int mocr_test_stage_gemm(mocr_handle_t* h, int kind, int n_rows, int N, int K, const float* A, const float* Wt, const float* bias, const float* resid,
+                         const float* gamma, const float* beta, int gelu, float* out, int32_t* out_argmax);
+
 /* Host-only (no CUDA call): the Pillow-exact resampling table for one input extent, as the
  * preprocess kernel reads it: xmin[224] | count[224] | k[224*ksize] (int32).  Returns the number
  * of int32 written (or needed when out is NULL), negative on error. */

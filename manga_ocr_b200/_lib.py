@@ -95,6 +95,10 @@ _SIGNATURES = {
     "mocr_test_gemm": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, POINTER(c_float), POINTER(c_float), POINTER(c_float),
                                POINTER(c_float), POINTER(c_float), POINTER(c_int32)]),
     "mocr_test_encoder_attention": (c_int, [c_void_p, c_int, POINTER(c_float), POINTER(c_float)]),
+    "mocr_test_decode_attention": (c_int, [c_void_p, c_int, c_int, c_int, POINTER(c_int32), POINTER(c_float), POINTER(c_float), POINTER(c_float),
+                                           POINTER(c_float), POINTER(c_float), POINTER(c_float), POINTER(c_float), POINTER(c_float)]),
+    "mocr_test_stage_gemm": (c_int, [c_void_p, c_int, c_int, c_int, c_int, POINTER(c_float), POINTER(c_float), POINTER(c_float), POINTER(c_float),
+                                     POINTER(c_float), POINTER(c_float), c_int, POINTER(c_float), POINTER(c_int32)]),
     "mocr_resample_table": (c_int, [c_int, POINTER(c_int32), POINTER(c_int32), c_int]),
     "mocr_get_decode_profile": (c_int, [c_void_p, POINTER(c_int64), c_int]),
     "mocr_last_error": (c_char_p, [c_void_p]),

@@ -39,7 +39,7 @@ using namespace mocr;
 
 namespace {
 
-constexpr int kPadId = 0, kClsId = 2, kSepId = 3;
+constexpr int kClsId = 2, kSepId = 3;   // [CLS] starts a sequence, [SEP] ends it ([PAD] = 0 fills)
 constexpr float kQScale = 0.125f;   // 1/sqrt(64), folded into every query projection (exact in bf16)
 
 thread_local std::string g_create_error;
@@ -2011,6 +2011,243 @@ int mocr_test_encoder_attention(mocr_handle_t* h, int n, const float* qkv, float
   }
   h->pre_ok = h->enc_ok = h->dec_ok = false;   // scratch buffers were overwritten
   return MOCR_OK;
+}
+
+// ---- decoder stage kernels on caller-supplied data (tests only) ----
+
+namespace {
+std::vector<uint16_t> to_bf16(const float* src, size_t n) {
+  std::vector<uint16_t> out(n);
+  for (size_t i = 0; i < n; ++i) out[i] = f32_to_bf16(src[i]);
+  return out;
+}
+void from_bf16(const uint16_t* src, float* dst, size_t n) {
+  for (size_t i = 0; i < n; ++i) {
+    const uint32_t u = static_cast<uint32_t>(src[i]) << 16;
+    memcpy(&dst[i], &u, 4);
+  }
+}
+}  // namespace
+
+int mocr_test_decode_attention(mocr_handle_t* h, int mode, int n_rows, int n_ctx, const int32_t* pos, const float* q, const float* k, const float* v,
+                               const float* new_k, const float* new_v, float* out_ctx, float* out_k_row, float* out_v_row) {
+  TRY(check_handle(h));
+  std::lock_guard<std::mutex> lock(h->mu);
+  const bool self = mode == 1;
+  if (mode < 0 || mode > 2 || n_rows < 1 || n_rows > h->max_batch || q == nullptr || k == nullptr || v == nullptr || out_ctx == nullptr)
+    return fail(h, MOCR_ERR_INVALID, "bad test_decode_attention argument");
+  if (self && (pos == nullptr || new_k == nullptr || new_v == nullptr || n_ctx < 1 || n_ctx > h->max_length))
+    return fail(h, MOCR_ERR_INVALID, "self-attention test needs pos, new_k, new_v and 1 <= n_ctx <= max_length");
+  if (!self && n_ctx != kEncTokens) return fail(h, MOCR_ERR_INVALID, "cross-attention runs over %d keys", kEncTokens);
+  h->pre_ok = h->enc_ok = h->dec_ok = false;      // engine buffers are overwritten
+  PdParams p = make_pd_params(h, n_rows, h->max_length, false, false);
+  PdStage st{};
+  st.layer = 0;
+  std::vector<int> zeros(n_rows, 0);
+  CK(cudaMemcpyAsync(h->d_finished, zeros.data(), sizeof(int) * n_rows, cudaMemcpyHostToDevice, h->stream));
+  float* d_zero_bias = nullptr;
+  static bool done[16] = {};
+  if (!done[h->device & 15]) {
+    CK(cudaFuncSetAttribute(pd_attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPdAttnSmemBytes));
+    CK(cudaFuncSetAttribute(pd_attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPdAttnSmemBytes));
+    done[h->device & 15] = true;
+  }
+  const int grid = h->attn_grid > 0 ? std::min(h->attn_grid, n_rows * kHeads) : n_rows * kHeads;
+  int r = MOCR_OK;
+  auto body = [&]() -> int {
+    if (self) {
+      for (int b = 0; b < n_rows; ++b)
+        if (pos[b] < 0 || pos[b] >= n_ctx) return fail(h, MOCR_ERR_INVALID, "pos[%d] = %d outside [0, n_ctx)", b, pos[b]);
+      st.type = PD_ATTN_SELF;
+      // cache rows [b][j][768], j < n_ctx (the row at pos[b] is overwritten by the kernel with this step's K/V)
+      const std::vector<uint16_t> kb = to_bf16(k, static_cast<size_t>(n_rows) * n_ctx * kD), vb = to_bf16(v, static_cast<size_t>(n_rows) * n_ctx * kD);
+      for (int b = 0; b < n_rows; ++b) {
+        CK(cudaMemcpyAsync(h->self_k[0] + static_cast<size_t>(b) * h->max_length * kD, kb.data() + static_cast<size_t>(b) * n_ctx * kD,
+                           static_cast<size_t>(n_ctx) * kD * 2, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->self_v[0] + static_cast<size_t>(b) * h->max_length * kD, vb.data() + static_cast<size_t>(b) * n_ctx * kD,
+                           static_cast<size_t>(n_ctx) * kD * 2, cudaMemcpyHostToDevice, h->stream));
+      }
+      std::vector<uint16_t> qkv(static_cast<size_t>(n_rows) * 3 * kD);
+      for (int b = 0; b < n_rows; ++b)
+        for (int c = 0; c < kD; ++c) {
+          qkv[(static_cast<size_t>(b) * 3 + 0) * kD + c] = f32_to_bf16(q[static_cast<size_t>(b) * kD + c]);
+          qkv[(static_cast<size_t>(b) * 3 + 1) * kD + c] = f32_to_bf16(new_k[static_cast<size_t>(b) * kD + c]);
+          qkv[(static_cast<size_t>(b) * 3 + 2) * kD + c] = f32_to_bf16(new_v[static_cast<size_t>(b) * kD + c]);
+        }
+      CK(cudaMemcpyAsync(h->d_qkv, qkv.data(), qkv.size() * 2, cudaMemcpyHostToDevice, h->stream));
+      CK(cudaMemcpyAsync(h->d_pos, pos, sizeof(int) * n_rows, cudaMemcpyHostToDevice, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      CK(launch_pdl(h, pd_attention_kernel<true>, grid, 128, kPdAttnSmemBytes, p, st));
+    } else {
+      st.type = PD_ATTN_CROSS;
+      // [crop][layer][K|V][head][197][64]
+      std::vector<uint16_t> kv(static_cast<size_t>(n_rows) * 4 * kHeads * kEncTokens * kHeadDim, 0);
+      for (int b = 0; b < n_rows; ++b)
+        for (int j = 0; j < kEncTokens; ++j)
+          for (int c = 0; c < kD; ++c) {
+            const int hd = c / kHeadDim, d = c % kHeadDim;
+            const size_t src = (static_cast<size_t>(b) * kEncTokens + j) * kD + c;
+            const size_t base = static_cast<size_t>(b) * 4 * kHeads * kEncTokens * kHeadDim;
+            kv[base + ((0 * kHeads + hd) * kEncTokens + j) * kHeadDim + d] = f32_to_bf16(k[src]);
+            kv[base + ((1 * kHeads + hd) * kEncTokens + j) * kHeadDim + d] = f32_to_bf16(v[src]);
+          }
+      CK(cudaMemcpyAsync(h->crosskv, kv.data(), kv.size() * 2, cudaMemcpyHostToDevice, h->stream));
+      if (mode == 2) {         // complete bf16 query rows (the large-batch program)
+        const std::vector<uint16_t> qb = to_bf16(q, static_cast<size_t>(n_rows) * kD);
+        CK(cudaMemcpyAsync(h->d_q, qb.data(), qb.size() * 2, cudaMemcpyHostToDevice, h->stream));
+        st.A = h->d_q;
+      } else {                 // fp32 split-K partials + bias: the query is spread over the partials as 1/2, 1/4, 1/4
+        CK(cudaMalloc(reinterpret_cast<void**>(&d_zero_bias), kD * sizeof(float)));
+        CK(cudaMemsetAsync(d_zero_bias, 0, kD * sizeof(float), h->stream));
+        std::vector<float> parts(static_cast<size_t>(kPdSplit) * n_rows * kD);
+        for (size_t i = 0; i < static_cast<size_t>(n_rows) * kD; ++i) {
+          parts[i] = 0.5f * q[i];
+          parts[static_cast<size_t>(n_rows) * kD + i] = 0.25f * q[i];
+          parts[2 * static_cast<size_t>(n_rows) * kD + i] = 0.25f * q[i];
+        }
+        CK(cudaMemcpyAsync(h->d_yq, parts.data(), parts.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        st.src = h->d_yq;
+        st.parts = kPdSplit;
+        st.bias = d_zero_bias;
+      }
+      CK(cudaStreamSynchronize(h->stream));
+      CK(launch_pdl(h, pd_attention_kernel<false>, grid, 128, kPdAttnSmemBytes, p, st));
+    }
+    ++h->launches;
+    std::vector<uint16_t> cb(static_cast<size_t>(n_rows) * kD);
+    CK(cudaMemcpyAsync(cb.data(), h->d_ctx.p, cb.size() * 2, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    from_bf16(cb.data(), out_ctx, cb.size());
+    if (self && out_k_row != nullptr && out_v_row != nullptr) {
+      std::vector<uint16_t> row(kD);
+      for (int b = 0; b < n_rows; ++b) {
+        CK(cudaMemcpy(row.data(), h->self_k[0] + (static_cast<size_t>(b) * h->max_length + pos[b]) * kD, kD * 2, cudaMemcpyDeviceToHost));
+        from_bf16(row.data(), out_k_row + static_cast<size_t>(b) * kD, kD);
+        CK(cudaMemcpy(row.data(), h->self_v[0] + (static_cast<size_t>(b) * h->max_length + pos[b]) * kD, kD * 2, cudaMemcpyDeviceToHost));
+        from_bf16(row.data(), out_v_row + static_cast<size_t>(b) * kD, kD);
+      }
+    }
+    return MOCR_OK;
+  };
+  r = body();
+  cudaStreamSynchronize(h->stream);
+  if (d_zero_bias) cudaFree(d_zero_bias);
+  return r;
+}
+
+// kind: 0 bf16 (QKV-like, 16-column tiles), 1 bf16 + GELU (FFN1-like, 32-column tiles), 2 split-K fp32 partials (returned summed, + bias),
+// 3 vocabulary arg-max on the mma.sync kernel (out = logits), 4 projection + residual + LayerNorm in the cluster kernel (N = K = 768),
+// 5 the same projection as split-K partials + the LayerNorm row stage.  resid / gamma / beta: kinds 4, 5 (resid may be NULL); gelu: kinds 4, 5.
+int mocr_test_stage_gemm(mocr_handle_t* h, int kind, int n_rows, int N, int K, const float* A, const float* Wt, const float* bias, const float* resid,
+                         const float* gamma, const float* beta, int gelu, float* out, int32_t* out_argmax) {
+  TRY(check_handle(h));
+  std::lock_guard<std::mutex> lock(h->mu);
+  if (kind < 0 || kind > 5 || n_rows < 1 || n_rows > h->max_batch || A == nullptr || Wt == nullptr || bias == nullptr || out == nullptr)
+    return fail(h, MOCR_ERR_INVALID, "bad test_stage_gemm argument");
+  const int nt = kind == 1 ? 32 : (kind == 3 ? 48 : 16);
+  const int ksplit = (kind == 2 || kind == 5) ? kPdSplit : 1;
+  if (N % nt != 0 || K % (32 * kPdStageKS * ksplit * 2) != 0 || N > 3 * kFFN * 2 || K > kFFN)
+    return fail(h, MOCR_ERR_INVALID, "unsupported stage GEMM shape N=%d K=%d for kind %d", N, K, kind);
+  if ((kind == 4 || kind == 5) && (N != kD || (kind == 4 && K != kD) || gamma == nullptr || beta == nullptr))
+    return fail(h, MOCR_ERR_INVALID, "the LayerNorm kinds need N = 768 (K = 768 for the cluster kernel), gamma and beta");
+  if (kind == 3 && N > kVocab) return fail(h, MOCR_ERR_INVALID, "arg-max stage: N <= %d", kVocab);
+  h->pre_ok = h->enc_ok = h->dec_ok = false;
+  const size_t mn = static_cast<size_t>(n_rows) * N;
+  __nv_bfloat16 *d_a = nullptr, *d_w = nullptr, *d_ob = nullptr;
+  float *d_bias = nullptr, *d_of = nullptr, *d_res = nullptr, *d_g = nullptr, *d_b = nullptr, *d_x = nullptr;
+  int r = MOCR_OK;
+  static bool done[16] = {};
+  auto body = [&]() -> int {
+    if (!done[h->device & 15]) {
+      CK(cudaFuncSetAttribute(pd_gemm_kernel<48, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pd_gemm_smem_bytes(48)));
+      CK(cudaFuncSetAttribute(pd_proj_ln_kernel<8, 3, 1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      done[h->device & 15] = true;
+    }
+    const std::vector<uint16_t> ab = to_bf16(A, static_cast<size_t>(n_rows) * K), wb = to_bf16(Wt, static_cast<size_t>(N) * K);
+    CK(cudaMalloc(reinterpret_cast<void**>(&d_a), ab.size() * 2));
+    CK(cudaMalloc(reinterpret_cast<void**>(&d_w), wb.size() * 2));
+    CK(cudaMalloc(reinterpret_cast<void**>(&d_bias), N * sizeof(float)));
+    CK(cudaMalloc(reinterpret_cast<void**>(&d_ob), mn * 2));
+    CK(cudaMalloc(reinterpret_cast<void**>(&d_of), mn * sizeof(float) * kPdSplit));
+    CK(cudaMemcpy(d_a, ab.data(), ab.size() * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_w, wb.data(), wb.size() * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_bias, bias, N * sizeof(float), cudaMemcpyHostToDevice));
+    CK(cudaMemset(d_of, 0, mn * sizeof(float) * kPdSplit));
+    if (kind >= 4) {
+      CK(cudaMalloc(reinterpret_cast<void**>(&d_g), kD * sizeof(float)));
+      CK(cudaMalloc(reinterpret_cast<void**>(&d_b), kD * sizeof(float)));
+      CK(cudaMalloc(reinterpret_cast<void**>(&d_x), mn * sizeof(float)));
+      CK(cudaMemcpy(d_g, gamma, kD * sizeof(float), cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(d_b, beta, kD * sizeof(float), cudaMemcpyHostToDevice));
+      if (resid != nullptr) {
+        CK(cudaMalloc(reinterpret_cast<void**>(&d_res), mn * sizeof(float)));
+        CK(cudaMemcpy(d_res, resid, mn * sizeof(float), cudaMemcpyHostToDevice));
+      }
+    }
+    PdParams p = make_pd_params(h, n_rows, h->max_length, false, false);
+    p.n_partials = kPdVocabTiles;
+    if (kind == 3) {
+      std::vector<int> zeros(n_rows, 0);
+      CK(cudaMemcpy(h->d_pos, zeros.data(), sizeof(int) * n_rows, cudaMemcpyHostToDevice));
+      p.logits = d_of;
+      p.logits_cur = 1;
+      if (N != kVocab) return fail(h, MOCR_ERR_INVALID, "arg-max stage test runs at N = %d", kVocab);
+    }
+    const PdLinear lin{d_w, d_bias};
+    const PdLn ln{d_g, d_b};
+    if (kind == 4) {
+      const PdStage st = pd_proj_ln_desc(d_a, K, lin, gelu, d_res, ln, d_x, d_ob);
+      CK(launch_pdl(h, pd_proj_ln_kernel<8, 3, 1>, ((n_rows + kPlRows - 1) / kPlRows) * kPlCluster, 256, pd_proj_ln_smem_bytes(8), p, st));
+    } else {
+      const int epi = kind == 0 ? PD_BF16 : (kind == 1 ? PD_BF16_GELU : (kind == 3 ? PD_ARGMAX : PD_F32_PARTIAL));
+      const PdStage st = pd_gemm_desc(kind == 1 ? PD_GEMM32 : (kind == 3 ? PD_GEMM48 : PD_GEMM16), epi, d_a, K, lin, N, ksplit, d_ob, d_of, N);
+      const int grid = (N / nt) * ksplit;
+      if (nt == 16) CK(launch_pdl(h, pd_gemm_kernel<16, 2>, grid, 128 * kPdStageKS, pd_gemm_smem_bytes(16), p, st));
+      else if (nt == 32) CK(launch_pdl(h, pd_gemm_kernel<32, 2>, grid, 128 * kPdStageKS, pd_gemm_smem_bytes(32), p, st));
+      else CK(launch_pdl(h, pd_gemm_kernel<48, 1>, grid, 128 * kPdStageKS, pd_gemm_smem_bytes(48), p, st));
+      if (kind == 5) {
+        const PdStage lst = pd_ln_desc(d_of, kPdSplit, d_bias, gelu, d_res, ln, d_x, d_ob);
+        CK(launch_pdl(h, pd_ln_kernel, (n_rows + 1) / 2, 64, 0, p, lst));
+        ++h->launches;
+      }
+    }
+    ++h->launches;
+    CK(cudaStreamSynchronize(h->stream));
+    if (kind == 0 || kind == 1) {
+      std::vector<uint16_t> ob(mn);
+      CK(cudaMemcpy(ob.data(), d_ob, mn * 2, cudaMemcpyDeviceToHost));
+      from_bf16(ob.data(), out, mn);
+    } else if (kind == 2) {
+      std::vector<float> parts(mn * kPdSplit);
+      CK(cudaMemcpy(parts.data(), d_of, parts.size() * sizeof(float), cudaMemcpyDeviceToHost));
+      for (size_t i = 0; i < mn; ++i) out[i] = bias[i % N] + parts[i] + parts[mn + i] + parts[2 * mn + i];
+    } else if (kind == 3) {
+      CK(cudaMemcpy(out, d_of, mn * sizeof(float), cudaMemcpyDeviceToHost));
+      if (out_argmax != nullptr) {
+        std::vector<float> pm(static_cast<size_t>(n_rows) * kPdVocabTiles);
+        std::vector<int> pi(pm.size());
+        CK(cudaMemcpy(pm.data(), h->part_max, pm.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(pi.data(), h->part_idx, pi.size() * sizeof(int), cudaMemcpyDeviceToHost));
+        for (int m = 0; m < n_rows; ++m) {
+          float bv = -INFINITY;
+          int bi = 0x7fffffff;
+          for (int t = 0; t < kPdVocabTiles; ++t) {
+            const float vv = pm[static_cast<size_t>(m) * kPdVocabTiles + t];
+            const int ix = pi[static_cast<size_t>(m) * kPdVocabTiles + t];
+            if (vv > bv || (vv == bv && ix < bi)) { bv = vv; bi = ix; }
+          }
+          out_argmax[m] = bi;
+        }
+      }
+    } else {
+      CK(cudaMemcpy(out, d_x, mn * sizeof(float), cudaMemcpyDeviceToHost));
+    }
+    return MOCR_OK;
+  };
+  r = body();
+  cudaStreamSynchronize(h->stream);
+  cudaFree(d_a); cudaFree(d_w); cudaFree(d_bias); cudaFree(d_ob); cudaFree(d_of); cudaFree(d_res); cudaFree(d_g); cudaFree(d_b); cudaFree(d_x);
+  return r;
 }
 
 // Host-only: the Pillow-exact coefficient table the preprocess kernel reads for one input

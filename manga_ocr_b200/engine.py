@@ -341,6 +341,36 @@ class Engine:
         self._ck(self._lib.mocr_test_encoder_attention(self._h, n, qkv.ctypes.data_as(POINTER(c_float)), out.ctypes.data_as(POINTER(c_float))))
         return out
 
+    def test_decode_attention(self, mode: int, q: np.ndarray, k: np.ndarray, v: np.ndarray, pos: Optional[np.ndarray] = None,
+                              new_k: Optional[np.ndarray] = None, new_v: Optional[np.ndarray] = None):
+        """One decode-step attention stage on caller data (include/mocr_b200.h: mocr_test_decode_attention).
+        Returns ctx [n, 768] (and, for self-attention, the cache rows the kernel appended: (ctx, k_row, v_row))."""
+        f = lambda a: None if a is None else np.ascontiguousarray(a, np.float32)
+        q, k, v, new_k, new_v = f(q), f(k), f(v), f(new_k), f(new_v)
+        n, n_ctx = q.shape[0], k.shape[1]
+        fp = lambda a: None if a is None else a.ctypes.data_as(POINTER(c_float))
+        ctx = np.zeros((n, D), np.float32)
+        kr = np.zeros((n, D), np.float32)
+        vr = np.zeros((n, D), np.float32)
+        pp = None if pos is None else np.ascontiguousarray(pos, np.int32)
+        self._ck(self._lib.mocr_test_decode_attention(self._h, mode, n, n_ctx, None if pp is None else pp.ctypes.data_as(POINTER(c_int32)),
+                                                      fp(q), fp(k), fp(v), fp(new_k), fp(new_v), fp(ctx), fp(kr), fp(vr)))
+        return (ctx, kr, vr) if mode == 1 else ctx
+
+    def test_stage_gemm(self, kind: int, A: np.ndarray, Wt: np.ndarray, bias: np.ndarray, resid: Optional[np.ndarray] = None,
+                        gamma: Optional[np.ndarray] = None, beta: Optional[np.ndarray] = None, gelu: bool = False):
+        """One small-M decoder GEMM stage on caller data (mocr_test_stage_gemm); returns (out [n, N], argmax [n])."""
+        f = lambda a: None if a is None else np.ascontiguousarray(a, np.float32)
+        A, Wt, bias, resid, gamma, beta = f(A), f(Wt), f(bias), f(resid), f(gamma), f(beta)
+        n, K = A.shape
+        N = Wt.shape[0]
+        fp = lambda a: None if a is None else a.ctypes.data_as(POINTER(c_float))
+        out = np.zeros((n, N), np.float32)
+        am = np.zeros((n,), np.int32)
+        self._ck(self._lib.mocr_test_stage_gemm(self._h, kind, n, N, K, fp(A), fp(Wt), fp(bias), fp(resid), fp(gamma), fp(beta), int(gelu), fp(out),
+                                                am.ctypes.data_as(POINTER(c_int32))))
+        return out, am
+
     def decode_profile(self, n: int = 4096) -> np.ndarray:
         out = np.zeros((n,), np.int64)
         self._ck(self._lib.mocr_get_decode_profile(self._h, out.ctypes.data_as(POINTER(c_int64)), n))

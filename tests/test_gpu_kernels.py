@@ -110,3 +110,112 @@ def test_encoder_attention_mma_sync_variant(engine8):
     Q, K, V = (q[:, :, i].transpose(1, 2) for i in range(3))
     ref = (torch.softmax(Q @ K.transpose(-1, -2), dim=-1) @ V).transpose(1, 2).reshape(2 * 197, 768).numpy()
     assert np.abs(got - ref).max() < 2e-2
+
+
+# ---- decoder stage kernels (decode_stages.cuh) against fp64 references of the same op ----
+
+@pytest.fixture(scope="module")
+def engine_dec(weights0):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    from manga_ocr_b200.engine import Engine
+    e = Engine(weights0, device=0, max_batch=70, max_length=300)
+    yield e
+    e.close()
+
+
+def _attn_ref(q, k, v, n_keys):
+    """softmax(q_h . K_h^T) V_h per row and head over the first n_keys[b] keys, fp64 (q is pre-scaled)."""
+    import torch
+    n = q.shape[0]
+    out = np.zeros((n, 768))
+    for b in range(n):
+        nk = int(n_keys[b])
+        Q = torch.from_numpy(_bf16(q[b])).double().view(12, 1, 64)
+        K = torch.from_numpy(_bf16(k[b, :nk])).double().view(nk, 12, 64).transpose(0, 1)
+        V = torch.from_numpy(_bf16(v[b, :nk])).double().view(nk, 12, 64).transpose(0, 1)
+        out[b] = (torch.softmax(Q @ K.transpose(-1, -2), dim=-1) @ V).reshape(768).numpy()
+    return out
+
+
+@pytest.mark.parametrize("n_rows,pos", [(3, [0, 1, 5]), (5, [31, 32, 127, 128, 129]), (4, [255, 256, 257, 298]), (66, None)])
+def test_decode_self_attention_against_torch(engine_dec, n_rows, pos):
+    """One query over 1..299 cached keys (BertSelfAttention with a cache, modeling_bert.py:143-207): every staged-block
+    boundary (32-key warp ranges, 128-key blocks) and the append of this step's K/V row."""
+    rng = np.random.default_rng(n_rows)
+    pos = np.asarray(pos if pos is not None else rng.integers(0, 299, n_rows), np.int32)
+    n_ctx = int(pos.max()) + 1
+    q = rng.standard_normal((n_rows, 768), dtype=np.float32) * 0.3
+    k = rng.standard_normal((n_rows, n_ctx, 768), dtype=np.float32)
+    v = rng.standard_normal((n_rows, n_ctx, 768), dtype=np.float32)
+    nk = rng.standard_normal((n_rows, 768), dtype=np.float32)
+    nv = rng.standard_normal((n_rows, 768), dtype=np.float32)
+    ctx, k_row, v_row = engine_dec.test_decode_attention(1, q, k, v, pos=pos, new_k=nk, new_v=nv)
+    kk, vv = k.copy(), v.copy()
+    for b in range(n_rows):
+        kk[b, pos[b]] = nk[b]
+        vv[b, pos[b]] = nv[b]
+    ref = _attn_ref(q, kk, vv, pos + 1)
+    assert np.abs(ctx - ref).max() < 2e-2, float(np.abs(ctx - ref).max())
+    assert np.array_equal(k_row, _bf16(nk)) and np.array_equal(v_row, _bf16(nv))       # the cache append is exact
+
+
+@pytest.mark.parametrize("mode", [0, 2], ids=["f32_partial_query", "bf16_query"])
+def test_decode_cross_attention_against_torch(engine_dec, mode):
+    """One query over the 197 encoder keys (BertSelfAttention as cross-attention, modeling_bert.py:210-284), no mask."""
+    rng = np.random.default_rng(7 + mode)
+    n = 9
+    q = rng.standard_normal((n, 768), dtype=np.float32) * 0.3
+    k = rng.standard_normal((n, 197, 768), dtype=np.float32)
+    v = rng.standard_normal((n, 197, 768), dtype=np.float32)
+    ctx = engine_dec.test_decode_attention(mode, q, k, v)
+    ref = _attn_ref(q, k, v, np.full(n, 197))
+    assert np.abs(ctx - ref).max() < 2e-2, float(np.abs(ctx - ref).max())
+
+
+@pytest.mark.parametrize("kind,n_rows,N,K", [(0, 64, 2304, 768), (0, 5, 768, 768), (1, 64, 3072, 768), (1, 17, 3072, 768), (2, 64, 768, 768),
+                                             (2, 64, 768, 3072), (2, 70, 768, 3072), (3, 64, 6144, 768), (3, 3, 6144, 768)])
+def test_decode_stage_gemm_against_torch(engine_dec, kind, n_rows, N, K):
+    """The small-M mma.sync GEMM stages (BertSelfAttention / BertIntermediate / BertOutput Linear layers at M = batch rows)."""
+    import torch
+    rng = np.random.default_rng(kind * 1000 + n_rows + N + K)
+    A = rng.standard_normal((n_rows, K), dtype=np.float32)
+    Wt = rng.standard_normal((N, K), dtype=np.float32) * 0.05
+    b = rng.standard_normal((N,), dtype=np.float32)
+    got, am = engine_dec.test_stage_gemm(kind, A, Wt, b)
+    ref = torch.from_numpy(_bf16(A)).double() @ torch.from_numpy(_bf16(Wt)).double().T + torch.from_numpy(b).double()
+    if kind == 1:
+        ref = torch.nn.functional.gelu(ref)
+    ref = ref.numpy()
+    err = np.abs(got - ref).max()
+    if kind in (0, 1):
+        assert err <= 2.0 ** -8 * max(1.0, np.abs(ref).max()), err
+    else:
+        assert err <= 1e-3, err
+    if kind == 3:
+        assert np.array_equal(am, np.argmax(got, axis=1))
+
+
+@pytest.mark.parametrize("kind", [4, 5], ids=["cluster_proj_ln", "split_k_plus_ln_stage"])
+@pytest.mark.parametrize("n_rows,gelu,with_resid", [(64, False, True), (7, False, True), (33, True, False), (70, False, True)])
+def test_decode_projection_layernorm_against_torch(engine_dec, kind, n_rows, gelu, with_resid):
+    """LayerNorm([gelu](A W^T + b) + resid): BertSelfOutput / BertOutput (modeling_bert.py:287-298, 343-356) and the LM-head
+    transform (:471-486) - in the 16-CTA cluster kernel (row statistics exchanged through distributed shared memory) and as
+    split-K partials + the LayerNorm row stage; ragged last row group, rows beyond one cluster wave."""
+    import torch
+    rng = np.random.default_rng(100 * kind + n_rows)
+    A = rng.standard_normal((n_rows, 768), dtype=np.float32)
+    Wt = rng.standard_normal((768, 768), dtype=np.float32) * 0.05
+    b = rng.standard_normal((768,), dtype=np.float32)
+    R = rng.standard_normal((n_rows, 768), dtype=np.float32) + 0.5 if with_resid else None     # a non-zero row mean
+    g = (1.0 + 0.1 * rng.standard_normal(768)).astype(np.float32)
+    be = (0.1 * rng.standard_normal(768)).astype(np.float32)
+    got, _ = engine_dec.test_stage_gemm(kind, A, Wt, b, resid=R, gamma=g, beta=be, gelu=gelu)
+    y = torch.from_numpy(_bf16(A)).double() @ torch.from_numpy(_bf16(Wt)).double().T + torch.from_numpy(b).double()
+    if gelu:
+        y = torch.nn.functional.gelu(y)
+    if R is not None:
+        y = y + torch.from_numpy(R).double()
+    ref = torch.nn.functional.layer_norm(y, (768,), torch.from_numpy(g).double(), torch.from_numpy(be).double(), eps=1e-12).numpy()
+    assert np.abs(got - ref).max() <= 2e-3, float(np.abs(got - ref).max())
