@@ -66,9 +66,13 @@ struct PdParams {
   PdLinear head_t, head_dec;
   PdLn head_ln;
   EmbedWeights emb;
-  const __nv_bfloat16* crosskv;   // [B][layer][K|V][head][197][64]
+  const __nv_bfloat16* crosskv;   // [crop][layer][K|V][head][197][64]
   // state
-  int* ids;                 // [B, max_len]
+  int n_crops;              // crops of this decode (>= B: with more crops than rows, a row that finishes takes the next waiting crop)
+  int* ids;                 // [n_crops, max_len]
+  int* lens;                // [n_crops] valid ids per crop, written when the crop finishes
+  int* slot_crop;           // [B] crop each row is decoding (-1: idle)
+  int* queue;               // [0] next waiting crop, [1] crops whose encoder K/V are ready, [2] crops finished
   int* pos;                 // [B]
   int* finished;            // [B]
   const int* forced;        // teacher forcing or null
@@ -552,6 +556,24 @@ __device__ __forceinline__ void pd_embed_row_warp(const PdParams& p, const PdEmb
 
 // Greedy step tail (generation/utils.py:2793-2805, stopping_criteria.py:76,470): final arg-max over
 // the vocabulary tiles, EOS / max_length rules, append, embed the next input token.
+//
+// In-flight slot refill: the reference pads a finished row with [PAD] and keeps stepping it until EVERY row of the batch
+// has finished (utils.py:2797-2805).  Rows are independent, so here a row that finishes hands its slot to the next
+// waiting crop of the decode (p.queue, crops beyond the first B) and restarts at [CLS] - the ids of every crop are
+// exactly those of the padded scheme, but the step count follows the total number of tokens instead of
+// (crops / rows) x the longest sequence.
+__device__ __forceinline__ int pd_pop_waiting_crop(const PdParams& p) {      // one lane; -1: nothing is waiting
+  unsigned int head = static_cast<unsigned int>(ldg_cg_s32(p.queue));
+  while (true) {
+    int avail;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(avail) : "l"(p.queue + 1) : "memory");
+    if (static_cast<int>(head) >= avail) return -1;
+    const unsigned int seen = atomicCAS(reinterpret_cast<unsigned int*>(p.queue), head, head + 1u);
+    if (seen == head) return static_cast<int>(head);
+    head = seen;
+  }
+}
+
 template <class Bar>
 __device__ __forceinline__ void pd_next_token_stage(Bar& bar, const PdParams& p, int n_ctas) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -564,6 +586,7 @@ __device__ __forceinline__ void pd_next_token_stage(Bar& bar, const PdParams& p,
     // one round trip: state and the 128 per-tile (max, arg-max) partials together
     const int ps = ldg_cg_s32(p.pos + r);
     const int fin0 = ldg_cg_s32(p.finished + r);
+    const int crop = ldg_cg_s32(p.slot_crop + r);
     float pv[kPdMaxPartials / 32];
     int pi[kPdMaxPartials / 32];
 #pragma unroll
@@ -577,7 +600,22 @@ __device__ __forceinline__ void pd_next_token_stage(Bar& bar, const PdParams& p,
       }
     }
     const bool was_finished = fin0 != 0;
-    if (was_finished && (p.forced == nullptr || ps >= p.max_len - 1)) continue;
+    if (was_finished && (p.forced == nullptr || ps >= p.max_len - 1)) {
+      // an idle row (its crop is done and nothing was waiting then): crops whose encoder K/V arrive later are picked up here
+      if (p.forced == nullptr && p.n_crops > p.B) {
+        int c = lane == 0 ? pd_pop_waiting_crop(p) : 0;
+        c = __shfl_sync(0xffffffffu, c, 0);
+        if (c >= 0) {
+          if (lane == 0) {
+            p.slot_crop[r] = c;
+            p.pos[r] = 0;
+            p.finished[r] = 0;
+          }
+          pd_embed_row_warp(p, k, r, 2, 0, lane);
+        }
+      }
+      continue;
+    }
     float bv = -INFINITY;
     int bi = 0x7fffffff;
 #pragma unroll
@@ -595,12 +633,29 @@ __device__ __forceinline__ void pd_next_token_stage(Bar& bar, const PdParams& p,
     int fin = was_finished ? 1 : 0;
     if (tok == p.eos_id && p.forced == nullptr) fin = 1;
     if (np >= p.max_len - 1) fin = 1;
+    int next_crop = -1;
     if (lane == 0) {
-      if (np < p.max_len) p.ids[static_cast<size_t>(r) * p.max_len + np] = tok;
-      p.finished[r] = fin;
-      p.pos[r] = np;
+      if (np < p.max_len) p.ids[static_cast<size_t>(crop) * p.max_len + np] = tok;
+      if (fin && !was_finished) {            // the crop is complete
+        p.lens[crop] = np + 1 < p.max_len ? np + 1 : p.max_len;
+        atomicAdd(p.queue + 2, 1);
+        if (p.forced == nullptr && p.n_crops > p.B) next_crop = pd_pop_waiting_crop(p);
+      }
+      if (next_crop >= 0) {                  // the slot goes to the next waiting crop
+        p.slot_crop[r] = next_crop;
+        p.finished[r] = 0;
+        p.pos[r] = 0;
+      } else {
+        p.finished[r] = fin;
+        p.pos[r] = np;
+      }
     }
-    if (p.forced != nullptr && np < p.max_len) tok = p.forced[static_cast<size_t>(r) * p.max_len + np];
+    next_crop = __shfl_sync(0xffffffffu, next_crop, 0);
+    if (next_crop >= 0) {
+      pd_embed_row_warp(p, k, r, 2, 0, lane);        // [CLS] at position 0 (generation/utils.py:806-863)
+      continue;
+    }
+    if (p.forced != nullptr && np < p.max_len) tok = p.forced[static_cast<size_t>(crop) * p.max_len + np];
     if (np >= p.max_len - 1 || np >= kMaxPos) continue;
     pd_embed_row_warp(p, k, r, tok, np, lane);
   }
@@ -835,6 +890,7 @@ struct PdAttnUnit {
   const __nv_bfloat16* nk;     // self: this token's K / V row in the QKV buffer
   const __nv_bfloat16* nv;
   int b, h, n_keys, ps;
+  int crop;                    // cross: the crop whose encoder K/V the row reads
   bool skip;
 };
 
@@ -921,11 +977,12 @@ __device__ __forceinline__ void pd_attention_stage(Bar& bar, uint8_t* smem, cons
   // right after the dependency wait; together with the first unit's query they cost ONE L2 round trip.
   constexpr int kPre = 4;
   int pre_fin[kPre] = {0, 0, 0, 0}, pre_pos[kPre] = {0, 0, 0, 0};
-  auto make_unit = [&](int u, int fin, int pos, bool state_visible) {
+  auto make_unit = [&](int u, int fin, int pos, bool state_visible) {     // pos: self = the row's position; cross = the crop the row decodes
     PdAttnUnit a;
     a.b = u / kHeads;
     a.h = u - a.b * kHeads;
-    const int kvb = SELF ? a.b : a.b / p.kv_div;                    // cross: the beams of a crop read the same K/V
+    a.crop = SELF ? 0 : pos;
+    const int kvb = SELF ? a.b : (pos < 0 ? 0 : pos) / p.kv_div;    // cross: the beams of a crop read the same K/V
     a.kc = kbase + static_cast<size_t>(kvb) * b_stride + static_cast<size_t>(a.h) * head_stride + ch * 8;
     a.vc = vbase + static_cast<size_t>(kvb) * b_stride + static_cast<size_t>(a.h) * head_stride + ch * 8;
     a.nk = a.nv = nullptr;
@@ -958,7 +1015,7 @@ __device__ __forceinline__ void pd_attention_stage(Bar& bar, uint8_t* smem, cons
       }
     } else {
       fin = ldg_cg_s32(p.finished + u / kHeads);
-      pos = SELF ? ldg_cg_s32(p.pos + u / kHeads) : 0;
+      pos = ldg_cg_s32((SELF ? p.pos : p.slot_crop) + u / kHeads);
     }
     return make_unit(u, fin, pos, true);
   };
@@ -1008,10 +1065,13 @@ __device__ __forceinline__ void pd_attention_stage(Bar& bar, uint8_t* smem, cons
     if (stream_kv) pd_attn_request_t<true>(stage, a, key_stride, j0, gt, pol);
     else pd_attn_request_t<false>(stage, a, key_stride, j0, gt, 0ull);
   };
-  PdAttnUnit cur = make_unit(u0 < units ? u0 : 0, 0, 0, false);
+  // cross: which crop the first unit's row decodes is read speculatively before the dependency wait (it changes only when
+  // the row finishes and takes the next waiting crop) and checked again after it
+  const int spec_crop = (!SELF && u0 < units) ? ldg_cg_s32(p.slot_crop + u0 / kHeads) : 0;
+  PdAttnUnit cur = make_unit(u0 < units ? u0 : 0, 0, SELF ? 0 : spec_crop, false);
   bool pre2 = false;       // both blocks of the first unit were requested before the dependency wait
   if (!SELF) {   // encoder K/V never change during a decode: request the first unit (2 blocks) before the wait
-    if (u0 < units) {
+    if (u0 < units && spec_crop >= 0) {
       request(stage0, cur, 0);
       cp_async_commit();
       request(stage1, cur, kBlockKeys);
@@ -1028,7 +1088,7 @@ __device__ __forceinline__ void pd_attention_stage(Bar& bar, uint8_t* smem, cons
     pre_pos[k] = 0;
     if (uk < units) {
       pre_fin[k] = ldg_cg_s32(p.finished + uk / kHeads);
-      if (SELF) pre_pos[k] = ldg_cg_s32(p.pos + uk / kHeads);
+      pre_pos[k] = ldg_cg_s32((SELF ? p.pos : p.slot_crop) + uk / kHeads);
     }
   }
   if (u0 < units) issue_q(u0, raw_cur);
@@ -1041,8 +1101,8 @@ __device__ __forceinline__ void pd_attention_stage(Bar& bar, uint8_t* smem, cons
       cur = unit_state(u, uk_idx);
       issue_q(u, raw_cur);
     }
-    if (SELF || u != u0) {
-      if (!SELF) cp_async_wait_group<0>();          // (the prefetched blocks of a finished row are dropped)
+    if (SELF || u != u0 || !pre2 || cur.crop != spec_crop) {
+      if (!SELF) cp_async_wait_group<0>();          // (the prefetched blocks of a finished row, or of the crop the row has left, are dropped)
       pre2 = false;
       if (cur.n_keys > 0) request(stage0, cur, 0);
       cp_async_commit();
@@ -1356,20 +1416,29 @@ __global__ void __launch_bounds__(kPdThreads) pd_next_kernel(const __grid_consta
   pdl_launch_dependents();
   pd_next_token_stage(bar, p, gridDim.x);
 }
-// ids[b][0] = [CLS], pos = 0, finished = 0, x = embed([CLS], 0)
+// Every crop: ids[c][0] = [CLS], [PAD] elsewhere.  Rows 0..B-1 start on crops 0..B-1 (pos = 0, x = embed([CLS], 0)); the
+// crops beyond wait in the queue.
 __global__ void __launch_bounds__(kPdThreads) pd_begin_kernel(const __grid_constant__ PdParams p) {
   pdl_launch_dependents();
   asm volatile("griddepcontrol.wait;" ::: "memory");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int r = blockIdx.x * kPdWarps + warp; r < p.B; r += gridDim.x * kPdWarps) {
-    for (int i = lane; i < p.max_len; i += 32) p.ids[static_cast<size_t>(r) * p.max_len + i] = i == 0 ? 2 : 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    p.queue[0] = p.B;
+    p.queue[1] = p.n_crops;
+    p.queue[2] = 0;
+  }
+  for (int c = blockIdx.x * kPdWarps + warp; c < p.n_crops; c += gridDim.x * kPdWarps) {
+    for (int i = lane; i < p.max_len; i += 32) p.ids[static_cast<size_t>(c) * p.max_len + i] = i == 0 ? 2 : 0;
+    if (lane == 0) p.lens[c] = p.max_len <= 1 ? 1 : 0;
+    if (c >= p.B) continue;
     if (lane == 0) {
-      p.pos[r] = 0;
-      p.finished[r] = p.max_len <= 1 ? 1 : 0;
+      p.slot_crop[c] = c;
+      p.pos[c] = 0;
+      p.finished[c] = p.max_len <= 1 ? 1 : 0;
     }
     PdEmbedConsts ek;
     pd_embed_consts(p, lane, ek);
-    pd_embed_row_warp(p, ek, r, 2, 0, lane);
+    pd_embed_row_warp(p, ek, c, 2, 0, lane);
   }
 }
 

@@ -140,6 +140,9 @@ struct mocr_handle {
   int fuse_ln = 1;          // decoder projections that feed a LayerNorm as 16-CTA clusters that normalise the rows themselves (0: split-K partials + LayerNorm stage)
   int kv_prefetch = 0;      // 1: a layer's encoder K/V are requested into L2 by the layer's first stage (bulk prefetch before the dependency wait); measured 2.7 us per step SLOWER at 64 rows (the prefetch competes with the weights for L2)
   int big_rows = 96;        // more decoder rows than this: the large-batch program (every Linear on the tcgen05 GEMM, 128-row tiles)
+  int slots = 0;            // decoder rows of a greedy decode (0 = one per crop).  With fewer rows than crops a row that finishes takes
+                            // the next waiting crop (in-flight slot refill): worth it when lengths are ragged (real text); with random-init
+                            // weights, which never emit EOS, one row per crop on the large-batch program is faster
   int attn_grid = 384;      // CTAs of the decoder attention stage kernels (0 = one per (row, head) unit); 384 measured best at B = 64
 
   // ---- weights
@@ -181,6 +184,10 @@ struct mocr_handle {
   int* d_finished = nullptr;
   int* d_forced = nullptr;
   int* d_zero = nullptr;              // [max_batch] zeros
+  int* d_lens = nullptr;              // [max_batch] valid ids per crop of the last decode
+  int* d_slot_crop = nullptr;         // [max_batch] crop each decoder row is working on
+  int* d_queue = nullptr;             // [4] next waiting crop | crops ready | crops finished
+  int* h_queue = nullptr;             // pinned [4]
   int* h_flags = nullptr;             // pinned [max_batch]
   float* d_y = nullptr;               // [3, brow_cap, 768] split-K partials of the projections feeding a LayerNorm
   float* d_yq = nullptr;              // [3, brow_cap, 768] split-K partials of the cross-attention query
@@ -215,6 +222,7 @@ struct mocr_handle {
   int n = 0;              // crops of the current batch
   int cur_len = 0;        // max_length of the last decode
   int last_steps = 0;
+  int last_rows = 0;      // decoder rows of the last decode
   bool staged_ok = false, pre_ok = false, enc_ok = false, dec_ok = false;
 
   // ---- decode-step graphs keyed by (n, max_length, forced?, tap?)
@@ -960,9 +968,14 @@ int encode(mocr_handle* h) {
 PdLinear pd_lin(const Linear& L) { return PdLinear{L.w, L.bias}; }
 PdLn pd_ln(const LnParams& l) { return PdLn{l.g, l.b}; }
 
-PdParams make_pd_params(mocr_handle* h, int n, int max_length, bool forced, bool tap) {
+// n = decoder rows, n_crops = crops they work through (0: one crop per row)
+PdParams make_pd_params(mocr_handle* h, int n, int max_length, bool forced, bool tap, int n_crops = 0) {
   PdParams p{};
   p.B = n;
+  p.n_crops = n_crops > n ? n_crops : n;
+  p.lens = h->d_lens;
+  p.slot_crop = h->d_slot_crop;
+  p.queue = h->d_queue;
   p.max_len = max_length;
   p.cache_len = h->max_length;
   p.kv_div = 1;
@@ -1154,6 +1167,15 @@ int decode_stage_step(mocr_handle* h, const PdParams& p, bool skip_next = false)
   return MOCR_OK;
 }
 
+// slot_crop[r] = r for r < rows: rows that address their own crop (unit hooks, kernel timing, beam mode)
+int identity_slots(mocr_handle* h, int rows) {
+  std::vector<int> iota(rows);
+  for (int i = 0; i < rows; ++i) iota[i] = i;
+  CK(cudaMemcpyAsync(h->d_slot_crop, iota.data(), sizeof(int) * rows, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));      // (pageable source)
+  return MOCR_OK;
+}
+
 int decode(mocr_handle* h, int max_length, const int32_t* forced_ids) {
   if (!h->enc_ok) return fail(h, MOCR_ERR_INVALID, "encode has not run on the staged crops");
   if (max_length < 2 || max_length > h->max_length)
@@ -1177,20 +1199,25 @@ int decode(mocr_handle* h, int max_length, const int32_t* forced_ids) {
     CK(cudaMemsetAsync(h->logits_tap, 0, need_b, h->stream));
   }
   if (h->decode_prof) CK(cudaMemsetAsync(h->d_prof, 0, 8, h->stream));
-  const PdParams pdp = make_pd_params(h, n, max_length, forced, tap);
+  // decoder rows: one per crop, or fewer (option "slots"): a row that finishes then takes the next waiting crop.
+  // Teacher forcing and the logits tap address rows by crop, so they keep one row per crop.
+  const int rows = (h->slots > 0 && !forced && !tap) ? std::min(n, h->slots) : n;
+  const PdParams pdp = make_pd_params(h, rows, max_length, forced, tap, n);
   auto begin = [&]() -> int {
-    CK(launch_pdl(h, pd_begin_kernel, (n + kPdWarps - 1) / kPdWarps, kPdThreads, 0, pdp));
+    CK(launch_pdl(h, pd_begin_kernel, std::min((n + kPdWarps - 1) / kPdWarps, 4 * h->sms), kPdThreads, 0, pdp));
     ++h->launches;
     return MOCR_OK;
   };
   auto one_step = [&]() -> int { return decode_stage_step(h, pdp); };
   TRY(begin());
 
-  const int steps = max_length - 1;
+  // every crop takes at most max_length - 1 steps of one row: an upper bound of the step count for any length mix
+  const int steps = (max_length - 1) * ((n + rows - 1) / rows);
   cudaGraphExec_t exec = nullptr;
   int64_t per_step = 0;
   if (h->use_graph) {
-    const uint64_t key = (static_cast<uint64_t>(n) << 32) | (static_cast<uint64_t>(max_length) << 8) | (forced ? 2u : 0u) | (tap ? 1u : 0u);
+    const uint64_t key = (static_cast<uint64_t>(n) << 40) | (static_cast<uint64_t>(rows) << 20) | (static_cast<uint64_t>(max_length) << 8) |
+                         (forced ? 2u : 0u) | (tap ? 1u : 0u);
     const int spg = std::max(1, std::min(h->steps_per_graph, max_length - 1));
     auto it = h->graphs.find(key);
     if (it == h->graphs.end()) {
@@ -1244,15 +1271,14 @@ int decode(mocr_handle* h, int max_length, const int32_t* forced_ids) {
     }
     done_steps += ran;
     if (!forced && done_steps < steps) {
-      // every row finished? (generation/utils.py:2805 does this check, with a host sync, every step)
-      CK(cudaMemcpyAsync(h->h_flags, h->d_finished, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
+      // every crop finished? (generation/utils.py:2805 does this check, with a host sync, every step)
+      CK(cudaMemcpyAsync(h->h_queue, h->d_queue, sizeof(int) * 4, cudaMemcpyDeviceToHost, h->stream));
       CK(cudaStreamSynchronize(h->stream));
-      bool all = true;
-      for (int i = 0; i < n; ++i) all = all && h->h_flags[i] != 0;
-      if (all) break;
+      if (h->h_queue[2] >= n) break;
     }
   }
   h->last_steps = std::min(done_steps, steps);
+  h->last_rows = rows;
   h->cur_len = max_length;
   h->dec_ok = true;
   return MOCR_OK;
@@ -1262,10 +1288,15 @@ int fetch_ids(mocr_handle* h, int32_t* out_ids, int32_t* out_lens) {
   if (!h->dec_ok) return fail(h, MOCR_ERR_INVALID, "no decode result to fetch");
   const int n = h->n, T = h->cur_len;
   CK(cudaMemcpyAsync(out_ids, h->d_ids, sizeof(int) * n * T, cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaMemcpyAsync(h->h_flags, h->d_pos, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(h->h_flags, h->d_lens, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(h->h_flags + n, h->d_pos, sizeof(int) * std::min(n, std::max(h->last_rows, 1)), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   if (out_lens != nullptr)
-    for (int i = 0; i < n; ++i) out_lens[i] = std::min(h->h_flags[i] + 1, T);
+    for (int i = 0; i < n; ++i) {
+      // a crop that finished has its length recorded; a teacher-forced row never "finishes" before max_length: position + 1
+      const int by_pos = i < h->last_rows ? std::min(h->h_flags[n + i] + 1, T) : T;
+      out_lens[i] = h->h_flags[i] > 0 ? h->h_flags[i] : by_pos;
+    }
   return MOCR_OK;
 }
 
@@ -1323,9 +1354,13 @@ int create_impl(mocr_handle* h) {
   TRY(dmalloc(h, &h->d_pos, static_cast<size_t>(B)));
   TRY(dmalloc(h, &h->d_finished, static_cast<size_t>(B)));
   TRY(dmalloc(h, &h->d_zero, static_cast<size_t>(B)));
+  TRY(dmalloc(h, &h->d_lens, static_cast<size_t>(B)));
+  TRY(dmalloc(h, &h->d_slot_crop, static_cast<size_t>(B)));
+  TRY(dmalloc(h, &h->d_queue, 4));
+  CK(cudaMallocHost(reinterpret_cast<void**>(&h->h_queue), sizeof(int) * 4));
   TRY(dmalloc(h, &h->d_prof, 4096));
   TRY(dmalloc(h, &h->d_descs, static_cast<size_t>(B)));
-  CK(cudaMallocHost(reinterpret_cast<void**>(&h->h_flags), sizeof(int) * B));
+  CK(cudaMallocHost(reinterpret_cast<void**>(&h->h_flags), sizeof(int) * 2 * B));
   CK(cudaMallocHost(reinterpret_cast<void**>(&h->h_descs), sizeof(CropDesc) * B));
   CK(cudaStreamSynchronize(h->stream));
   return MOCR_OK;
@@ -1392,6 +1427,7 @@ int mocr_destroy(mocr_handle_t* h) {
     if (h->d_beam) cudaFree(h->d_beam);
     if (h->h_flags) cudaFreeHost(h->h_flags);
     if (h->h_descs) cudaFreeHost(h->h_descs);
+    if (h->h_queue) cudaFreeHost(h->h_queue);
     if (h->stream) cudaStreamDestroy(h->stream);
   }
   delete h;
@@ -1775,6 +1811,7 @@ int mocr_set_option(mocr_handle_t* h, const char* key, int value) {
   else if (k == "carveout" && value >= -1 && value <= 100) h->carveout = value;
   else if (k == "kv_evict_first" && value >= 0 && value <= 3) h->kv_evict_first = value;
   else if (k == "attn_grid" && value >= 0) h->attn_grid = value;
+  else if (k == "slots" && value >= 0) h->slots = value;
   else if (k == "fuse_ln") h->fuse_ln = value != 0;
   else if (k == "kv_prefetch") h->kv_prefetch = value != 0;
   else if (k == "big_rows" && value >= 1) h->big_rows = value;
@@ -1830,7 +1867,9 @@ int mocr_time_kernel(mocr_handle_t* h, const char* kernel, int iters, float* ms_
       // one stage kernel of the decoder's per-token program, on the state the last decode left
       // (finished flags cleared through a forced-decoding view so that every row is processed)
       if (!h->dec_ok) { r = fail(h, MOCR_ERR_INVALID, "run a decode first"); break; }
-      PdParams p = make_pd_params(h, n, h->cur_len, true, false);
+      const int rows = std::max(1, h->last_rows);
+      PdParams p = make_pd_params(h, rows, h->cur_len, true, false);
+      if (i == -2 && (r = identity_slots(h, rows)) != MOCR_OK) break;
       PdStage prog[kPdMaxStages];
       pd_build_program(p, prog);
       // the first stage of the named kind in the per-token program
@@ -2045,6 +2084,7 @@ int mocr_test_decode_attention(mocr_handle_t* h, int mode, int n_rows, int n_ctx
   st.layer = 0;
   std::vector<int> zeros(n_rows, 0);
   CK(cudaMemcpyAsync(h->d_finished, zeros.data(), sizeof(int) * n_rows, cudaMemcpyHostToDevice, h->stream));
+  TRY(identity_slots(h, n_rows));
   float* d_zero_bias = nullptr;
   static bool done[16] = {};
   if (!done[h->device & 15]) {

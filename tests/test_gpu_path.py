@@ -256,3 +256,44 @@ def test_large_ragged_batch_matches_small_batches(weights0):
     finally:
         big.close()
         small.close()
+
+
+def test_slot_refill_gives_the_same_ids_in_fewer_steps():
+    """In-flight slot refill (option "slots"): with fewer decoder rows than crops, a row that finishes takes the next
+    waiting crop.  The reference instead pads finished rows and steps the whole batch until its longest sequence ends
+    (generation/utils.py:2797-2805); rows are independent, so ids and lengths must be EXACTLY those of one row per crop,
+    in a number of steps that follows the total token count."""
+    from manga_ocr_b200 import weights as W
+    from manga_ocr_b200.engine import Engine
+    T = 40
+    w = W.random_init(0, gain=3.0, eos_bias=3.7)        # on these crops: a mix of very short rows and rows that never emit EOS
+    crops = C.bubble_batch(45, seed=91)
+    eng = Engine(w, device=0, max_batch=48, max_length=T)
+    try:
+        eng.set_option("check_every", 4)
+        ids_ref, lens_ref = eng.recognize(crops)
+        steps_ref = eng.last_steps
+        print("lens:", sorted(lens_ref.tolist()))
+        assert int(lens_ref.max()) == T and int(lens_ref.min()) < T // 2 and len(set(lens_ref.tolist())) >= 3      # ragged lengths
+        for slots in (8, 13, 44, 64):
+            eng.set_option("slots", slots)
+            ids, lens = eng.recognize(crops)
+            assert np.array_equal(lens, lens_ref), slots
+            assert np.array_equal(ids, ids_ref), slots
+            if slots == 8:
+                tokens = int(lens_ref.sum() - len(crops))
+                assert eng.last_steps < (T - 1) * 6                  # the padded scheme in chunks of 8 rows: 6 x 39 steps
+                print("slot refill: 45 crops,", tokens, "tokens, 8 rows:", eng.last_steps, "steps; one row per crop:", steps_ref, "steps")
+        # weights that never emit EOS: every crop runs to max_length, rows are handed over at the length limit
+        eng.set_option("slots", 0)
+    finally:
+        eng.close()
+    eng = Engine(W.random_init(0), device=0, max_batch=20, max_length=12)
+    try:
+        ids_ref, lens_ref = eng.recognize(crops[:20])
+        eng.set_option("slots", 6)
+        ids, lens = eng.recognize(crops[:20])
+        assert np.array_equal(ids, ids_ref) and np.array_equal(lens, lens_ref) and (lens == 12).all()
+        assert eng.last_steps == 11 * 4                              # ceil(20 / 6) rounds of 11 steps
+    finally:
+        eng.close()
