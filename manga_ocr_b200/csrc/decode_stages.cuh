@@ -68,6 +68,7 @@ struct PdParams {
   EmbedWeights emb;
   const __nv_bfloat16* crosskv;   // [crop][layer][K|V][head][197][64]
   // state
+  int ext_queue;            // 1: the queue is initialised and fed by the host's encoder stream (crops become ready while the decode runs)
   int n_crops;              // crops of this decode (>= B: with more crops than rows, a row that finishes takes the next waiting crop)
   int* ids;                 // [n_crops, max_len]
   int* lens;                // [n_crops] valid ids per crop, written when the crop finishes
@@ -1422,7 +1423,7 @@ __global__ void __launch_bounds__(kPdThreads) pd_begin_kernel(const __grid_const
   pdl_launch_dependents();
   asm volatile("griddepcontrol.wait;" ::: "memory");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
+  if (blockIdx.x == 0 && threadIdx.x == 0 && !p.ext_queue) {
     p.queue[0] = p.B;
     p.queue[1] = p.n_crops;
     p.queue[2] = 0;
@@ -1439,6 +1440,20 @@ __global__ void __launch_bounds__(kPdThreads) pd_begin_kernel(const __grid_const
     PdEmbedConsts ek;
     pd_embed_consts(p, lane, ek);
     pd_embed_row_warp(p, ek, c, 2, 0, lane);
+  }
+}
+
+// Encoder stream -> decoder: the encoder K/V of crops [0, ready) are complete (the launch is ordered after the kernels that
+// wrote them); rows that finish, or idle rows, may now take those crops.
+__global__ void pd_publish_kernel(int* queue, int head, int ready) {
+  if (head >= 0) {           // first publication of a decode: reset the queue
+    queue[0] = head;
+    queue[2] = 0;
+    __threadfence();
+    queue[1] = ready;
+  } else {
+    __threadfence();
+    atomicMax(queue + 1, ready);
   }
 }
 

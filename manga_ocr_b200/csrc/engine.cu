@@ -113,6 +113,9 @@ struct mocr_handle {
   int max_length = 0;
   int sms = 148;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream_enc = nullptr;  // lower priority: encoder of the crops that are still waiting while the decoder already runs (slot refill)
+  cudaStream_t stream_enc_hi = nullptr;   // the same at the decoder's priority (option pipeline = 2)
+  cudaEvent_t ev_first = nullptr;     // first sub-chunk encoded and published
   std::mutex mu;
   std::string error;
   int64_t launches = 0;
@@ -140,6 +143,10 @@ struct mocr_handle {
   int fuse_ln = 1;          // decoder projections that feed a LayerNorm as 16-CTA clusters that normalise the rows themselves (0: split-K partials + LayerNorm stage)
   int kv_prefetch = 0;      // 1: a layer's encoder K/V are requested into L2 by the layer's first stage (bulk prefetch before the dependency wait); measured 2.7 us per step SLOWER at 64 rows (the prefetch competes with the weights for L2)
   int big_rows = 96;        // more decoder rows than this: the large-batch program (every Linear on the tcgen05 GEMM, 128-row tiles)
+  int pipeline = 0;         // with slot refill, 1 (2: equal stream priorities): encode the waiting crops in sub-chunks on a second stream while the decoder
+                            // already runs.  Measured on the ragged 512-crop leg: 116 ms (80 ms at equal priorities) against 75 ms with the encoder
+                            // serialised in front - the 200 KB GEMM CTAs and the decoder's stage kernels do not share SMs well - so it is off
+  int sub_i0 = 0, sub_n = 0;   // sub-range of the staged crops that preprocess / encode work on (sub_n = 0: all of them)
   int slots = 0;            // decoder rows of a greedy decode (0 = one per crop).  With fewer rows than crops a row that finishes takes
                             // the next waiting crop (in-flight slot refill): worth it when lengths are ragged (real text); with random-init
                             // weights, which never emit EOS, one row per crop on the large-batch program is faster
@@ -867,8 +874,9 @@ int preprocess(mocr_handle* h) {
     smem_set[h->device & 15] = 200 * 1024;
   }
   const bool tap = (h->taps & MOCR_TAP_PIXELS) != 0;
-  dim3 grid(kImage / kPreStripRows, h->n);
-  preprocess_kernel<<<grid, kPreThreads, smem, h->stream>>>(h->d_arena, h->d_descs, h->d_coefs, h->pre_bgr, h->pre_pitch, h->d_masks, h->patches.p,
+  const int i0 = h->sub_n > 0 ? h->sub_i0 : 0, cnt = h->sub_n > 0 ? h->sub_n : h->n;
+  dim3 grid(kImage / kPreStripRows, cnt);
+  preprocess_kernel<<<grid, kPreThreads, smem, h->stream>>>(h->d_arena, h->d_descs + i0, h->d_coefs, h->pre_bgr, h->pre_pitch, h->d_masks, h->patches.p,
                                                            tap ? h->px_u8 : nullptr, tap ? h->px_f32 : nullptr, h->lut);
   CK(cudaGetLastError());
   ++h->launches;
@@ -896,7 +904,8 @@ int attention197(mocr_handle* h, int n) {
 }
 
 int encode_launches(mocr_handle* h) {
-  const int n = h->n, M = n * kEncTokens, bn = h->enc_bn, bn7 = h->enc_bn768;
+  const int i0 = h->sub_n > 0 ? h->sub_i0 : 0;
+  const int n = h->sub_n > 0 ? h->sub_n : h->n, M = n * kEncTokens, bn = h->enc_bn, bn7 = h->enc_bn768;
   // embeddings: patch rows -> h[b*197+1+p] = conv + pos ; h[b*197] = cls + pos[0]   (modeling_vit.py:100-128)
   {
     GemmArgs a = out_f32(h->hres, kD);
@@ -918,7 +927,7 @@ int encode_launches(mocr_handle* h) {
   }
   TRY(layernorm(h, h->hres, M, h->enc_ln, h->enc_out.p, (h->taps & MOCR_TAP_ENCODER) ? h->enc_f32 : nullptr));   // :455
   // cross-attention K/V of both decoder layers, once per crop (modeling_bert.py:252-267)
-  TRY(gemm(h, EPI_CROSSKV, bn, h->enc_out, h->cross_kv, M, out_bf16(h->crosskv, 4 * kD)));
+  TRY(gemm(h, EPI_CROSSKV, bn, h->enc_out, h->cross_kv, M, out_bf16(h->crosskv + static_cast<size_t>(i0) * kEncTokens * 4 * kD, 4 * kD)));
   return MOCR_OK;
 }
 
@@ -929,7 +938,8 @@ int encode(mocr_handle* h) {
   if (!h->use_graph) {
     TRY(encode_launches(h));
   } else {
-    const uint64_t key = (static_cast<uint64_t>(h->n) << 8) | ((h->taps & MOCR_TAP_ENCODER) ? 1u : 0u);
+    const uint64_t key = (static_cast<uint64_t>(h->sub_n > 0 ? h->sub_n : h->n) << 32) | (static_cast<uint64_t>(h->sub_n > 0 ? h->sub_i0 : 0) << 8) |
+                         ((h->taps & MOCR_TAP_ENCODER) ? 1u : 0u);
     auto it = h->enc_graphs.find(key);
     if (it == h->enc_graphs.end()) {
       const int64_t l0 = h->launches;
@@ -1176,6 +1186,106 @@ int identity_slots(mocr_handle* h, int rows) {
   return MOCR_OK;
 }
 
+int decode_begin(mocr_handle* h, const PdParams& pdp) {
+  CK(launch_pdl(h, pd_begin_kernel, std::min((pdp.n_crops + kPdWarps - 1) / kPdWarps, 4 * h->sms), kPdThreads, 0, pdp));
+  ++h->launches;
+  return MOCR_OK;
+}
+
+// The CUDA graph of steps_per_graph token steps for this (crops, rows, length, mode), created on first use.  Creation
+// runs one step outside capture (function attributes, tensor maps) on throw-away state and re-runs decode_begin.
+int decode_step_graph(mocr_handle* h, const PdParams& pdp, bool forced, bool tap, cudaGraphExec_t* exec, int64_t* per_step) {
+  *exec = nullptr;
+  *per_step = 0;
+  if (!h->use_graph) return MOCR_OK;
+  const int n = pdp.n_crops, rows = pdp.B, max_length = pdp.max_len;
+  const uint64_t key = (static_cast<uint64_t>(n) << 40) | (static_cast<uint64_t>(rows) << 20) | (static_cast<uint64_t>(max_length) << 8) |
+                       (forced ? 2u : 0u) | (tap ? 1u : 0u);
+  const int spg = std::max(1, std::min(h->steps_per_graph, max_length - 1));
+  auto it = h->graphs.find(key);
+  if (it != h->graphs.end()) {
+    *exec = it->second.exec;
+    *per_step = it->second.launches;
+    return MOCR_OK;
+  }
+  PdParams warm = pdp;
+  warm.ext_queue = 0;
+  const int64_t l0 = h->launches;
+  TRY(decode_stage_step(h, pdp));
+  *per_step = h->launches - l0;
+  TRY(decode_begin(h, warm));
+  if (tap) CK(cudaMemsetAsync(h->logits_tap, 0, static_cast<size_t>(n) * (max_length - 1) * kVocab * sizeof(float), h->stream));
+  cudaGraph_t graph;
+  CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+  const int64_t l1 = h->launches;
+  int r = MOCR_OK;
+  for (int s = 0; s < spg && r == MOCR_OK; ++s) r = decode_stage_step(h, pdp);
+  h->launches = l1;
+  *per_step *= spg;
+  cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+  if (r != MOCR_OK) {
+    if (ce == cudaSuccess) cudaGraphDestroy(graph);
+    return r;
+  }
+  if (ce != cudaSuccess) return fail(h, MOCR_ERR_CUDA, "stream capture failed: %s", cudaGetErrorString(ce));
+  CK(cudaGraphInstantiate(exec, graph, 0));
+  cudaGraphDestroy(graph);
+  if (h->graphs.size() >= 64) {
+    for (auto& g : h->graphs) cudaGraphExecDestroy(g.second.exec);
+    h->graphs.clear();
+  }
+  h->graphs[key] = mocr_handle::StepGraph{*exec, static_cast<int>(*per_step)};
+  return MOCR_OK;
+}
+
+// Decoder rows for n crops: one per crop, or fewer (option "slots"): a row that finishes then takes the next waiting crop.
+// Teacher forcing and the logits tap address rows by crop, so they keep one row per crop.
+int decode_rows(const mocr_handle* h, int n, bool forced, bool tap) { return (h->slots > 0 && !forced && !tap) ? std::min(n, h->slots) : n; }
+
+// Token steps until every crop of the decode has finished (polled every check_every steps).
+int decode_loop(mocr_handle* h, const PdParams& pdp, bool forced, cudaGraphExec_t exec, int64_t per_step, cudaStream_t feeder = nullptr) {
+  const int n = pdp.n_crops, rows = pdp.B, max_length = pdp.max_len;
+  // every crop takes at most max_length - 1 steps of one row: an upper bound of the step count for any length mix
+  const int steps = (max_length - 1) * ((n + rows - 1) / rows) + (pdp.ext_queue ? 4 * h->check_every : 0);
+  // A graph replays steps_per_graph steps; steps past the end are no-ops for the result
+  // (every row is finished by then: no id, position or cache row is written).
+  const int spg = exec != nullptr ? std::max(1, std::min(h->steps_per_graph, max_length - 1)) : 1;
+  int done_steps = 0, budget = steps;
+  bool finished = false, extended = false;
+  while (!finished) {
+    if (done_steps >= budget) {
+      // fed by the encoder stream: the bound only holds once every crop has been published (idle steps before that do not count)
+      if (!pdp.ext_queue || extended) break;
+      if (feeder != nullptr) CK(cudaStreamSynchronize(feeder));
+      budget = done_steps + steps;
+      extended = true;
+    }
+    const int chunk = forced ? budget - done_steps : std::min(std::max(h->check_every, spg), budget - done_steps);
+    int ran = 0;
+    while (ran < chunk) {
+      if (exec != nullptr) {
+        CK(cudaGraphLaunch(exec, h->stream));
+        h->launches += per_step;
+      } else {
+        TRY(decode_stage_step(h, pdp));
+      }
+      ran += spg;
+    }
+    done_steps += ran;
+    if (!forced && (done_steps < budget || pdp.ext_queue)) {
+      // every crop finished? (generation/utils.py:2805 does this check, with a host sync, every step)
+      CK(cudaMemcpyAsync(h->h_queue, h->d_queue, sizeof(int) * 4, cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      finished = h->h_queue[2] >= n;
+    }
+  }
+  h->last_steps = std::min(done_steps, budget);
+  h->last_rows = rows;
+  h->cur_len = max_length;
+  h->dec_ok = true;
+  return MOCR_OK;
+}
+
 int decode(mocr_handle* h, int max_length, const int32_t* forced_ids) {
   if (!h->enc_ok) return fail(h, MOCR_ERR_INVALID, "encode has not run on the staged crops");
   if (max_length < 2 || max_length > h->max_length)
@@ -1199,88 +1309,59 @@ int decode(mocr_handle* h, int max_length, const int32_t* forced_ids) {
     CK(cudaMemsetAsync(h->logits_tap, 0, need_b, h->stream));
   }
   if (h->decode_prof) CK(cudaMemsetAsync(h->d_prof, 0, 8, h->stream));
-  // decoder rows: one per crop, or fewer (option "slots"): a row that finishes then takes the next waiting crop.
-  // Teacher forcing and the logits tap address rows by crop, so they keep one row per crop.
-  const int rows = (h->slots > 0 && !forced && !tap) ? std::min(n, h->slots) : n;
-  const PdParams pdp = make_pd_params(h, rows, max_length, forced, tap, n);
-  auto begin = [&]() -> int {
-    CK(launch_pdl(h, pd_begin_kernel, std::min((n + kPdWarps - 1) / kPdWarps, 4 * h->sms), kPdThreads, 0, pdp));
-    ++h->launches;
-    return MOCR_OK;
-  };
-  auto one_step = [&]() -> int { return decode_stage_step(h, pdp); };
-  TRY(begin());
-
-  // every crop takes at most max_length - 1 steps of one row: an upper bound of the step count for any length mix
-  const int steps = (max_length - 1) * ((n + rows - 1) / rows);
+  const PdParams pdp = make_pd_params(h, decode_rows(h, n, forced, tap), max_length, forced, tap, n);
+  TRY(decode_begin(h, pdp));
   cudaGraphExec_t exec = nullptr;
   int64_t per_step = 0;
-  if (h->use_graph) {
-    const uint64_t key = (static_cast<uint64_t>(n) << 40) | (static_cast<uint64_t>(rows) << 20) | (static_cast<uint64_t>(max_length) << 8) |
-                         (forced ? 2u : 0u) | (tap ? 1u : 0u);
-    const int spg = std::max(1, std::min(h->steps_per_graph, max_length - 1));
-    auto it = h->graphs.find(key);
-    if (it == h->graphs.end()) {
-      // warm every kernel variant once outside capture (function attributes, tensor maps),
-      // on throw-away state: re-run decode_begin afterwards.
-      const int64_t l0 = h->launches;
-      TRY(one_step());
-      per_step = h->launches - l0;
-      TRY(begin());
-      if (tap) CK(cudaMemsetAsync(h->logits_tap, 0, static_cast<size_t>(n) * (max_length - 1) * kVocab * sizeof(float), h->stream));
-      cudaGraph_t graph;
-      CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-      const int64_t l1 = h->launches;
-      int r = MOCR_OK;
-      for (int s = 0; s < spg && r == MOCR_OK; ++s) r = one_step();
-      h->launches = l1;
-      per_step *= spg;
-      cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
-      if (r != MOCR_OK) {
-        if (ce == cudaSuccess) cudaGraphDestroy(graph);
-        return r;
-      }
-      if (ce != cudaSuccess) return fail(h, MOCR_ERR_CUDA, "stream capture failed: %s", cudaGetErrorString(ce));
-      CK(cudaGraphInstantiate(&exec, graph, 0));
-      cudaGraphDestroy(graph);
-      if (h->graphs.size() >= 64) {
-        for (auto& g : h->graphs) cudaGraphExecDestroy(g.second.exec);
-        h->graphs.clear();
-      }
-      h->graphs[key] = mocr_handle::StepGraph{exec, static_cast<int>(per_step)};
-    } else {
-      exec = it->second.exec;
-      per_step = it->second.launches;
+  TRY(decode_step_graph(h, pdp, forced, tap, &exec, &per_step));
+  return decode_loop(h, pdp, forced, exec, per_step);
+}
+
+// Slot refill with the encoder overlapped: all m crops are staged at once; the first sub-chunk is preprocessed and encoded,
+// then the decoder starts on its own (higher-priority) stream while the encoder stream works through the remaining
+// sub-chunks and publishes them to the device-side queue; rows that finish (or idle rows) pick them up.
+int recognize_pipelined(mocr_handle* h, const mocr_crop_t* crops, int m, int order, int max_length) {
+  if (max_length < 2 || max_length > h->max_length)
+    return fail(h, MOCR_ERR_CAPACITY, "max_length %d outside [2, %d]", max_length, h->max_length);
+  const int rows = std::min(m, h->slots);
+  const int sub = std::max(rows, 64);                   // crops per encoder sub-chunk
+  // the decode graph first: creating it runs a warm-up step that may not touch the live queue
+  PdParams pdp = make_pd_params(h, rows, max_length, false, false, m);
+  cudaGraphExec_t exec = nullptr;
+  int64_t per_step = 0;
+  h->n = m;
+  TRY(decode_begin(h, pdp));
+  TRY(decode_step_graph(h, pdp, false, false, &exec, &per_step));
+  CK(cudaStreamSynchronize(h->stream));
+  cudaStream_t dec_stream = h->stream;
+  struct Restore {
+    mocr_handle* h; cudaStream_t s;
+    ~Restore() { h->stream = s; h->sub_i0 = 0; h->sub_n = 0; }
+  } restore{h, dec_stream};
+  cudaStream_t enc_stream = h->pipeline == 2 ? h->stream_enc_hi : h->stream_enc;
+  h->stream = enc_stream;                               // everything encoder-side goes to the encoder stream
+  TRY(stage_crops(h, crops, m, order));
+  for (int i0 = 0; i0 < m; i0 += sub) {
+    h->sub_i0 = i0;
+    h->sub_n = std::min(sub, m - i0);
+    TRY(preprocess(h));
+    TRY(encode(h));
+    pd_publish_kernel<<<1, 1, 0, h->stream>>>(h->d_queue, i0 == 0 ? rows : -1, i0 + h->sub_n);
+    CK(cudaGetLastError());
+    ++h->launches;
+    if (i0 == 0) {
+      CK(cudaEventRecord(h->ev_first, h->stream));
+      // the decoder starts as soon as the first sub-chunk is ready; its launches are issued from here on while the
+      // host keeps feeding the encoder stream below
+      CK(cudaStreamWaitEvent(dec_stream, h->ev_first, 0));
     }
   }
-  // A graph replays steps_per_graph steps; steps past max_length - 1 are no-ops for the result
-  // (every row is finished by then: no id, position or cache row is written).
-  const int spg = exec != nullptr ? std::max(1, std::min(h->steps_per_graph, max_length - 1)) : 1;
-  int done_steps = 0;
-  while (done_steps < steps) {
-    const int chunk = forced ? steps - done_steps : std::min(std::max(h->check_every, spg), steps - done_steps);
-    int ran = 0;
-    while (ran < chunk) {
-      if (exec != nullptr) {
-        CK(cudaGraphLaunch(exec, h->stream));
-        h->launches += per_step;
-      } else {
-        TRY(one_step());
-      }
-      ran += spg;
-    }
-    done_steps += ran;
-    if (!forced && done_steps < steps) {
-      // every crop finished? (generation/utils.py:2805 does this check, with a host sync, every step)
-      CK(cudaMemcpyAsync(h->h_queue, h->d_queue, sizeof(int) * 4, cudaMemcpyDeviceToHost, h->stream));
-      CK(cudaStreamSynchronize(h->stream));
-      if (h->h_queue[2] >= n) break;
-    }
-  }
-  h->last_steps = std::min(done_steps, steps);
-  h->last_rows = rows;
-  h->cur_len = max_length;
-  h->dec_ok = true;
+  h->stream = dec_stream;
+  h->sub_i0 = h->sub_n = 0;
+  pdp.ext_queue = 1;
+  TRY(decode_begin(h, pdp));
+  TRY(decode_loop(h, pdp, false, exec, per_step, enc_stream));
+  CK(cudaStreamSynchronize(enc_stream));
   return MOCR_OK;
 }
 
@@ -1320,7 +1401,14 @@ int create_impl(mocr_handle* h) {
   CK(cudaSetDevice(h->device));
   h->sms = prop.multiProcessorCount;
   if (const char* e = getenv("MOCR_DEC_TC")) h->dec_tc = atoi(e) & 7;     // (A/B switch for the test-suite)
-  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  {
+    int lo = 0, hi = 0;     // (numerically lower = higher priority)
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CK(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, hi));
+    CK(cudaStreamCreateWithPriority(&h->stream_enc, cudaStreamNonBlocking, lo));
+    CK(cudaStreamCreateWithPriority(&h->stream_enc_hi, cudaStreamNonBlocking, hi));
+    CK(cudaEventCreateWithFlags(&h->ev_first, cudaEventDisableTiming));
+  }
   const int B = h->max_batch, T = h->max_length;
   h->rows_cap = round_up(B * kEncTokens, kGemmBM);
   h->brow_cap = round_up(B, kGemmBM);
@@ -1415,6 +1503,7 @@ int mocr_destroy(mocr_handle_t* h) {
   { std::lock_guard<std::mutex> lock(h->mu); }      // a call still running on another thread finishes first (callers must not start new ones)
   if (cudaSetDevice(h->device) == cudaSuccess) {
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->stream_enc) cudaStreamSynchronize(h->stream_enc);
     for (auto& g : h->graphs) cudaGraphExecDestroy(g.second.exec);
     for (auto& g : h->enc_graphs) cudaGraphExecDestroy(g.second.exec);
     for (void* p : h->allocs) cudaFree(p);
@@ -1428,6 +1517,9 @@ int mocr_destroy(mocr_handle_t* h) {
     if (h->h_flags) cudaFreeHost(h->h_flags);
     if (h->h_descs) cudaFreeHost(h->h_descs);
     if (h->h_queue) cudaFreeHost(h->h_queue);
+    if (h->stream_enc) cudaStreamDestroy(h->stream_enc);
+    if (h->stream_enc_hi) cudaStreamDestroy(h->stream_enc_hi);
+    if (h->ev_first) cudaEventDestroy(h->ev_first);
     if (h->stream) cudaStreamDestroy(h->stream);
   }
   delete h;
@@ -1536,10 +1628,14 @@ int mocr_recognize(mocr_handle_t* h, const mocr_crop_t* crops, int n, int channe
   if (n < 0 || (n > 0 && (crops == nullptr || out_ids == nullptr))) return fail(h, MOCR_ERR_INVALID, "bad argument");
   for (int i0 = 0; i0 < n; i0 += h->max_batch) {
     const int m = std::min(h->max_batch, n - i0);
-    TRY(stage_crops(h, crops + i0, m, channel_order));
-    TRY(preprocess(h));
-    TRY(encode(h));
-    TRY(decode(h, max_length, nullptr));
+    if (h->slots > 0 && h->pipeline && m > h->slots && h->taps == 0) {
+      TRY(recognize_pipelined(h, crops + i0, m, channel_order, max_length));
+    } else {
+      TRY(stage_crops(h, crops + i0, m, channel_order));
+      TRY(preprocess(h));
+      TRY(encode(h));
+      TRY(decode(h, max_length, nullptr));
+    }
     TRY(fetch_ids(h, out_ids + static_cast<size_t>(i0) * max_length, out_lens ? out_lens + i0 : nullptr));
   }
   return MOCR_OK;
@@ -1812,6 +1908,7 @@ int mocr_set_option(mocr_handle_t* h, const char* key, int value) {
   else if (k == "kv_evict_first" && value >= 0 && value <= 3) h->kv_evict_first = value;
   else if (k == "attn_grid" && value >= 0) h->attn_grid = value;
   else if (k == "slots" && value >= 0) h->slots = value;
+  else if (k == "pipeline" && value >= 0 && value <= 2) h->pipeline = value;
   else if (k == "fuse_ln") h->fuse_ln = value != 0;
   else if (k == "kv_prefetch") h->kv_prefetch = value != 0;
   else if (k == "big_rows" && value >= 1) h->big_rows = value;

@@ -135,7 +135,8 @@ class MangaOcr:
                  weights: Optional[Dict[str, np.ndarray]] = None, vocab: Optional[Vocab] = None,
                  devices: Optional[Sequence[int]] = None, max_batch: int = 64, max_length: int = MAX_LENGTH,
                  warmup: bool = True, num_beams: Optional[int] = None, no_repeat_ngram_size: Optional[int] = None,
-                 length_penalty: Optional[float] = None, early_stopping=None, linger_ms: Optional[float] = None):
+                 length_penalty: Optional[float] = None, early_stopping=None, linger_ms: Optional[float] = None,
+                 slots: Optional[int] = None):
         if force_cpu:
             raise RuntimeError("manga_ocr_b200 has no CPU path (force_cpu=True is not supported); it needs a B200 GPU")
         gen = dict(GREEDY)
@@ -193,6 +194,9 @@ class MangaOcr:
                     e.close()
                 raise errs[0]
             self.engines = [built[i] for i in range(len(devs))]
+        if slots is not None:      # greedy decode with fewer decoder rows than crops: in-flight slot refill (ragged real-text lengths)
+            for e in self.engines:
+                e.set_option("slots", int(slots))
         self._queue: deque = deque()
         self._cv = threading.Condition()
         self._closed = False

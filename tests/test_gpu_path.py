@@ -284,6 +284,19 @@ def test_slot_refill_gives_the_same_ids_in_fewer_steps():
                 tokens = int(lens_ref.sum() - len(crops))
                 assert eng.last_steps < (T - 1) * 6                  # the padded scheme in chunks of 8 rows: 6 x 39 steps
                 print("slot refill: 45 crops,", tokens, "tokens, 8 rows:", eng.last_steps, "steps; one row per crop:", steps_ref, "steps")
+        # the same with the encoder serialised in front of the decode (no second stream)
+        eng.set_option("slots", 8)
+        eng.set_option("pipeline", 0)
+        ids, lens = eng.recognize(crops)
+        assert np.array_equal(ids, ids_ref) and np.array_equal(lens, lens_ref)
+        eng.set_option("pipeline", 1)
+        # more crops than the handle takes at once: chunks of 48, each with its own queue
+        many = crops + C.bubble_batch(30, seed=92)
+        eng.set_option("slots", 0)
+        ids_many_ref, lens_many_ref = eng.recognize(many)
+        eng.set_option("slots", 8)
+        ids_many, lens_many = eng.recognize(many)
+        assert np.array_equal(ids_many, ids_many_ref) and np.array_equal(lens_many, lens_many_ref)
         # weights that never emit EOS: every crop runs to max_length, rows are handed over at the length limit
         eng.set_option("slots", 0)
     finally:
@@ -292,8 +305,12 @@ def test_slot_refill_gives_the_same_ids_in_fewer_steps():
     try:
         ids_ref, lens_ref = eng.recognize(crops[:20])
         eng.set_option("slots", 6)
+        eng.set_option("pipeline", 0)
         ids, lens = eng.recognize(crops[:20])
         assert np.array_equal(ids, ids_ref) and np.array_equal(lens, lens_ref) and (lens == 12).all()
         assert eng.last_steps == 11 * 4                              # ceil(20 / 6) rounds of 11 steps
+        eng.set_option("pipeline", 1)                                # a decode far shorter than the encoder of the waiting crops
+        ids, lens = eng.recognize(crops[:20])
+        assert np.array_equal(ids, ids_ref) and np.array_equal(lens, lens_ref)
     finally:
         eng.close()
