@@ -233,21 +233,20 @@ def decode_algorithmic_bytes(rows, steps):
     return float(np.sum(DEC_WEIGHT_BYTES + rows * (CROSS_KV_BYTES + SELF_KV_BYTES_PER_TOKEN * t + SELF_KV_BYTES_PER_TOKEN)))
 
 
-def ncu_traffic(kernel_substr):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of a kernel, from the committed ncu summary of this
-    command (profiles/r2_ncu_traffic.json: written by tools/ncu_summary.py from an `ncu --set full` capture)."""
+NCU_KERNEL_OF = {"dec_qkv": "pd_gemm_kernel<16", "dec_fc2": "pd_gemm_kernel<16", "dec_fc1": "pd_gemm_kernel<32", "dec_self_out": "pd_proj_ln_kernel",
+                 "dec_ln": "pd_ln_kernel", "dec_self_attn": "pd_attention_kernel<1>", "dec_cross_attn": "pd_attention_kernel<0>"}
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of each decoder stage kernel, from the committed ncu summary
+    (profiles/r2_ncu_traffic.json, written from one `ncu --set full` capture; its command is inside).  {} when absent."""
     fp = os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")
-    if not os.path.exists(fp):
-        return None, None
     try:
         with open(fp) as f:
             d = json.load(f)
-        for row in d.get("kernels", []):
-            if kernel_substr in row.get("kernel", ""):
-                return float(row["dram_bytes_per_launch"]), {"file": "profiles/r2_ncu_traffic.json", "command": d.get("command")}
+        return {row["kernel"]: float(row["dram_bytes_per_launch"]) for row in d.get("kernels", [])}, d.get("command")
     except (OSError, ValueError, KeyError):
-        pass
-    return None, None
+        return {}, None
 
 
 def run_b200(args, rank, local_rank, world):
@@ -387,14 +386,29 @@ def run_b200(args, rank, local_rank, world):
             pass
         kernels.sort(key=lambda r: -r.get("share_of_step", 0.0))      # dominant by time first
         top = next((r for r in kernels if "error" not in r), None)
-        traffic, traffic_src = ncu_traffic("pd_attention_kernel<0>" if top and top["kernel"] == "dec_cross_attn" else
-                                           ("pd_gemm_kernel" if top and top["kernel"] in ("dec_qkv", "dec_fc2") else "\0"))
+        ncu_bytes, ncu_cmd = ncu_traffic()
+        step_traffic = 0.0
+        for r in kernels:
+            pat = NCU_KERNEL_OF.get(r.get("kernel", ""))
+            hit = next((v for k, v in ncu_bytes.items() if pat and pat in k), None)
+            r["dram_bytes_per_launch_ncu"] = hit
+            if hit is not None and r["kernel"].startswith("dec_"):
+                step_traffic += hit * per_step[r["kernel"]]
+        traffic = step_traffic if step_traffic > 0 else None
+        traffic_src = None
+        if traffic is not None:
+            traffic += 2.0 * 6144 * 768 + 2 * 2.0 * 768 * 768    # + vocabulary projection and the two cross-q weights (not in the capture): algorithmic
+            traffic_src = {"file": "profiles/r2_ncu_traffic.json", "command": ncu_cmd,
+                           "what": "DRAM bytes of ONE token step = sum over the stage kernels of (cold-cache bytes per launch x launches per step), "
+                                   "captured at ~20 cached tokens; compare with algorithmic_bytes_per_step_t20"}
         roof = {
             "bound": "hbm", "kernel": "decode token step: all stage kernels of the %d steps (%.0f %% of the step's time)" % (steps_run, 100 * phases["decode_ms"] / step_ms),
             "achieved": dec_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": dec_gbs / peaks["hbm_gbs"],
-            "algorithmic_bytes": dec_bytes, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peaks["source"],
+            "algorithmic_bytes": dec_bytes, "algorithmic_bytes_per_step_t20": DEC_WEIGHT_BYTES + BATCH * (CROSS_KV_BYTES + SELF_KV_BYTES_PER_TOKEN * 21),
+            "traffic": traffic, "traffic_source": traffic_src, "peak_source": peaks["source"],
             "step_floor_ms": floor_ms, "step_frac_of_combined_roofline": floor_ms / step_ms,
-            "dominant_kernel": ({k: top[k] for k in ("kernel", "us_per_launch", "launches_per_step", "share_of_step", "GBps", "hbm_frac")} if top else None),
+            "dominant_kernel": ({k: top.get(k) for k in ("kernel", "us_per_launch", "launches_per_step", "share_of_step", "algorithmic_bytes", "GBps", "hbm_frac",
+                                                           "dram_bytes_per_launch_ncu")} if top else None),
             "note": "frac = SURVEY 8(d) bytes of the whole decode / its CUDA-event time in the L2-flushed step / measured HBM peak; "
                     "step_frac_of_combined_roofline adds the encoder's tensor floor. The per-kernel rows (`kernels`, dominant by time first) are "
                     "50 back-to-back launches of one stage on the state the decode left (programmatic dependent launch as in the loop): L2-WARM, "

@@ -142,6 +142,8 @@ struct mocr_handle {
   int steps_per_graph = 13; // decode steps captured in one CUDA graph (299 = 23 x 13)
   int fuse_ln = 1;          // decoder projections that feed a LayerNorm as 16-CTA clusters that normalise the rows themselves (0: split-K partials + LayerNorm stage)
   int kv_prefetch = 0;      // 1: a layer's encoder K/V are requested into L2 by the layer's first stage (bulk prefetch before the dependency wait); measured 2.7 us per step SLOWER at 64 rows (the prefetch competes with the weights for L2)
+  int big_bn768 = 32;       // tile width of the large-batch program's N = 768 GEMMs (32 or 64)
+  int big_vocab_bn = 64;    // tile width of its vocabulary projection (64 or 128)
   int big_rows = 96;        // more decoder rows than this: the large-batch program (every Linear on the tcgen05 GEMM, 128-row tiles)
   int pipeline = 0;         // with slot refill, 1 (2: equal stream priorities): encode the waiting crops in sub-chunks on a second stream while the decoder
                             // already runs.  Measured on the ragged 512-crop leg: 116 ms (80 ms at equal priorities) against 75 ms with the encoder
@@ -990,7 +992,7 @@ PdParams make_pd_params(mocr_handle* h, int n, int max_length, bool forced, bool
   p.cache_len = h->max_length;
   p.kv_div = 1;
   p.big = n > h->big_rows ? 1 : 0;
-  p.n_partials = (p.big || (h->dec_tc & 1)) ? 2 * (kVocab / 64) : kPdVocabTiles;
+  p.n_partials = (p.big || (h->dec_tc & 1)) ? 2 * (kVocab / ((p.big && h->big_vocab_bn == 128) ? 128 : 64)) : kPdVocabTiles;
   p.logits_cur = 0;
   p.kv_evict_first = h->kv_evict_first;
   p.fuse_ln = h->fuse_ln;
@@ -1091,18 +1093,23 @@ Linear* dec_linear(mocr_handle* h, int lin) {
   }
 }
 
-// A Linear of the large-batch program on the tcgen05 GEMM.  Tile widths: 64 columns for the N = 768 / 2304 / 6144 layers
-// (48 / 144 / 384 tiles at 512 rows), 128 for FFN1 (96 tiles).
+// A Linear of the large-batch program on the tcgen05 GEMM.  Tile widths are chosen for the tile count at a few hundred rows
+// (128-row tiles): 32 columns for the N = 768 layers (96 tiles at 512 rows; 64-column tiles left 100 SMs idle: 16 us per
+// launch), 64 for QKV (144 tiles), 128 for FFN1 (96 tiles).
 int launch_tc_stage(mocr_handle* h, const PdParams& p, const PdStage& st) {
   Linear& L = *dec_linear(h, st.lin);
+  const bool wide = h->big_bn768 == 64;
   switch (st.epi) {
     case EPI_BF16:
+      if (st.N == kD && !wide) return launch_gemm_stage_tc<32, EPI_BF16>(h, st.A, st.K, L, p.B, out_bf16(st.ob, st.ldo));
       return launch_gemm_stage_tc<64, EPI_BF16>(h, st.A, st.K, L, p.B, out_bf16(st.ob, st.ldo));
     case EPI_BF16_GELU:
       return launch_gemm_stage_tc<128, EPI_BF16_GELU>(h, st.A, st.K, L, p.B, out_bf16(st.ob, st.ldo));
     case EPI_F32_RESID:
+      if (!wide) return launch_gemm_stage_tc<32, EPI_F32_RESID>(h, st.A, st.K, L, p.B, out_f32(st.of, st.ldo, st.resid, kD));
       return launch_gemm_stage_tc<64, EPI_F32_RESID>(h, st.A, st.K, L, p.B, out_f32(st.of, st.ldo, st.resid, kD));
     case EPI_F32_GELU:
+      if (!wide) return launch_gemm_stage_tc<32, EPI_F32_GELU>(h, st.A, st.K, L, p.B, out_f32(st.of, st.ldo));
       return launch_gemm_stage_tc<64, EPI_F32_GELU>(h, st.A, st.K, L, p.B, out_f32(st.of, st.ldo));
     default:
       return fail(h, MOCR_ERR_INVALID, "decoder stage with an unsupported tcgen05 epilogue %d", st.epi);
@@ -1151,7 +1158,8 @@ int decode_stage_step(mocr_handle* h, const PdParams& p, bool skip_next = false)
         a.logits = p.logits;
         a.step = p.logits_cur ? h->d_zero : p.pos;          // beam mode taps the current step only: [B, 6144]
         a.tap_steps = p.logits_cur ? 1 : p.max_len - 1;
-        TRY((launch_gemm_stage_tc<64, EPI_ARGMAX>(h, st.A, kD, h->head_dec, p.B, a)));
+        if (p.big && h->big_vocab_bn == 128) TRY((launch_gemm_stage_tc<128, EPI_ARGMAX>(h, st.A, kD, h->head_dec, p.B, a)));
+        else TRY((launch_gemm_stage_tc<64, EPI_ARGMAX>(h, st.A, kD, h->head_dec, p.B, a)));
       } else {
         const int nt = st.type == PD_GEMM16 ? 16 : (st.type == PD_GEMM32 ? 32 : 48);
         const int grid = (st.N / nt) * st.ksplit;
@@ -1912,6 +1920,8 @@ int mocr_set_option(mocr_handle_t* h, const char* key, int value) {
   else if (k == "fuse_ln") h->fuse_ln = value != 0;
   else if (k == "kv_prefetch") h->kv_prefetch = value != 0;
   else if (k == "big_rows" && value >= 1) h->big_rows = value;
+  else if (k == "big_bn768" && (value == 32 || value == 64)) h->big_bn768 = value;
+  else if (k == "big_vocab_bn" && (value == 64 || value == 128)) h->big_vocab_bn = value;
   else if (k == "steps_per_graph" && value >= 1 && value <= 64) h->steps_per_graph = value;
   else if (k == "decode_prof") h->decode_prof = value != 0;
   else return fail(h, MOCR_ERR_INVALID, "unknown option or bad value: %s=%d", key, value);
