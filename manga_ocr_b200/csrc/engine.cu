@@ -683,7 +683,7 @@ int stage_crops(mocr_handle* h, const mocr_crop_t* crops, int n, int order) {
   h->pre_pitch = round_up(max_w, 16);
   h->pre_tmp_rows = tmp_rows;
   h->pre_bgr = order == MOCR_BGR ? 1 : 0;
-  const size_t smem = static_cast<size_t>(kPreThreads / 32) * h->pre_pitch + static_cast<size_t>(tmp_rows) * kImage;
+  const size_t smem = pre_smem_bytes(h->pre_pitch, tmp_rows);
   if (smem > 200 * 1024) return fail(h, MOCR_ERR_CAPACITY, "crop extents need %zu B of shared memory (limit 204800)", smem);
   if (h->h_coefs.size() > h->d_coefs_cap) {
     if (h->d_coefs) cudaFree(h->d_coefs);
@@ -792,7 +792,7 @@ int stage_regions(mocr_handle* h, const mocr_crop_t* page, const mocr_region_t* 
   h->pre_pitch = round_up(max_w, 16);
   h->pre_tmp_rows = tmp_rows;
   h->pre_bgr = order == MOCR_BGR ? 1 : 0;
-  const size_t smem = static_cast<size_t>(kPreThreads / 32) * h->pre_pitch + static_cast<size_t>(tmp_rows) * kImage;
+  const size_t smem = pre_smem_bytes(h->pre_pitch, tmp_rows);
   if (smem > 200 * 1024) return fail(h, MOCR_ERR_CAPACITY, "region extents need %zu B of shared memory (limit 204800)", smem);
 
   const size_t rowb = static_cast<size_t>(pg.width) * pg.channels, total = rowb * pg.height;
@@ -869,7 +869,7 @@ int stage_regions(mocr_handle* h, const mocr_crop_t* page, const mocr_region_t* 
 
 int preprocess(mocr_handle* h) {
   if (!h->staged_ok) return fail(h, MOCR_ERR_INVALID, "no crops staged");
-  const size_t smem = static_cast<size_t>(kPreThreads / 32) * h->pre_pitch + static_cast<size_t>(h->pre_tmp_rows) * kImage;
+  const size_t smem = pre_smem_bytes(h->pre_pitch, h->pre_tmp_rows);
   static size_t smem_set[16] = {};
   if (smem > 48 * 1024 && smem > smem_set[h->device & 15]) {
     CK(cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

@@ -26,7 +26,15 @@ constexpr int kPreStripRows = 8;      // output rows per CTA
 constexpr int kPreThreads = 256;
 constexpr int kResampleBits = 22;     // Pillow PRECISION_BITS = 32 - 8 - 2
 
+constexpr int kPreChunkPx = 1024;     // pixels of a source row staged per pass of the vectorised read
+constexpr int kPreRawBytes = kPreChunkPx * 4 + 32;     // per warp: the chunk's bytes (<= 4 per pixel) + alignment slack, 16-byte loads
+
 constexpr int kRotNone = 0, kRotCw = 1, kRotCcw = 2;
+
+// dynamic shared memory of the preprocess kernel: per-warp luma row | per-warp raw staging | the strip's resampled rows
+constexpr size_t pre_smem_bytes(int rowbuf_pitch, int tmp_rows) {
+  return static_cast<size_t>(kPreThreads / 32) * (rowbuf_pitch + kPreRawBytes) + static_cast<size_t>(tmp_rows) * 224;
+}
 
 struct CropDesc {
   long long offset;   // byte offset of source pixel (0,0) - the crop's, or the page's for a region - in the crop arena
@@ -100,8 +108,9 @@ inline ResampleTable make_resample_table(int in_size) {
   return t;
 }
 
-// grid = (224 / kPreStripRows, n_crops), block = kPreThreads.
-// dynamic smem = 8 * rowbuf_pitch + tmp_rows * 224 bytes.
+// grid = (224 / kPreStripRows, n_crops), block = kPreThreads; dynamic smem = pre_smem_bytes(rowbuf_pitch, tmp_rows).
+// HBM access: a warp reads its source row in 16-byte vectors (aligned span of the row, staged in shared memory and
+// converted to luma from there) and the strip is written as 16-byte patch-row pieces (8 bf16 pixels per store).
 __global__ void __launch_bounds__(kPreThreads)
 preprocess_kernel(const uint8_t* __restrict__ arena, const CropDesc* __restrict__ crops, const int* __restrict__ coefs,
                   int bgr, int rowbuf_pitch, const uint8_t* __restrict__ masks, __nv_bfloat16* __restrict__ patches /*[n*196,256]*/,
@@ -112,7 +121,8 @@ preprocess_kernel(const uint8_t* __restrict__ arena, const CropDesc* __restrict_
   const int y0 = blockIdx.x * kPreStripRows;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* rowbuf = pre_smem + warp * rowbuf_pitch;
-  uint8_t* tmp = pre_smem + (kPreThreads / 32) * rowbuf_pitch;      // [rows][224]
+  uint8_t* raw = pre_smem + (kPreThreads / 32) * rowbuf_pitch + warp * kPreRawBytes;      // 16-byte aligned (pitch is a multiple of 16)
+  uint8_t* tmp = pre_smem + (kPreThreads / 32) * (rowbuf_pitch + kPreRawBytes);           // [rows][224]
 
   const int* vmin = nullptr; const int* vcnt = nullptr; const int* vk = nullptr;
   int r_lo = y0, r_hi = y0 + kPreStripRows;
@@ -152,13 +162,28 @@ preprocess_kernel(const uint8_t* __restrict__ arena, const CropDesc* __restrict_
         // (for a 1-channel source the three equal "channels" give back the value itself: the weights sum to 65536)
         lrow[x] = static_cast<uint8_t>((cr * c0 + 38470u * c1 + cb * c2 + 0x8000u) >> 16);
       }
-    } else if (cd.channels == 1) {
-      for (int x = lane; x < cd.w; x += 32) lrow[x] = src[x];
     } else {
+      // plain crop: the row is one contiguous run of w * channels bytes; it is fetched in chunks of 1024 pixels as the
+      // 16-byte-aligned span that covers it (the arena is 16-byte aligned and padded, so the span stays inside it)
       const int pc = cd.channels;
-      for (int x = lane; x < cd.w; x += 32) {
-        const unsigned c0 = src[pc * x], c1 = src[pc * x + 1], c2 = src[pc * x + 2];
-        lrow[x] = static_cast<uint8_t>((cr * c0 + 38470u * c1 + cb * c2 + 0x8000u) >> 16);
+      for (int x0 = 0; x0 < cd.w; x0 += kPreChunkPx) {
+        const int npx = min(kPreChunkPx, cd.w - x0);
+        const uint8_t* s = src + static_cast<long long>(x0) * pc;
+        const int head = static_cast<int>(reinterpret_cast<uintptr_t>(s) & 15u);
+        const uint4* s16 = reinterpret_cast<const uint4*>(s - head);
+        const int nvec = (head + npx * pc + 15) >> 4;
+        __syncwarp();                                   // the previous chunk's readers are done with `raw`
+        for (int v = lane; v < nvec; v += 32) reinterpret_cast<uint4*>(raw)[v] = __ldg(s16 + v);
+        __syncwarp();
+        const uint8_t* q = raw + head;
+        if (pc == 1) {
+          for (int x = lane; x < npx; x += 32) lrow[x0 + x] = q[x];
+        } else {
+          for (int x = lane; x < npx; x += 32) {
+            const unsigned c0 = q[pc * x], c1 = q[pc * x + 1], c2 = q[pc * x + 2];
+            lrow[x0 + x] = static_cast<uint8_t>((cr * c0 + 38470u * c1 + cb * c2 + 0x8000u) >> 16);
+          }
+        }
       }
     }
     if (cd.hcoef >= 0) {
@@ -176,27 +201,58 @@ preprocess_kernel(const uint8_t* __restrict__ arena, const CropDesc* __restrict_
   }
   __syncthreads();
 
-  // Phase 2: vertical pass + emit.
-  for (int i = threadIdx.x; i < kPreStripRows * kImage; i += kPreThreads) {
-    const int yy = i / kImage, x = i - yy * kImage;
+  // Phase 2: vertical pass + emit, 8 consecutive pixels per thread: one 8-byte shared-memory read per tap and one
+  // 16-byte store of the 8 bf16 values (a patch row is 16 pixels = 32 bytes: two stores).
+  for (int i = threadIdx.x; i < kPreStripRows * (kImage / 8); i += kPreThreads) {
+    const int yy = i / (kImage / 8), x = (i - yy * (kImage / 8)) * 8;
     const int y = y0 + yy;
-    int val;
+    int val[8];
     if (cd.vcoef >= 0) {
       const int ym = vmin[y] - r_lo, n = vcnt[y];
       const int* k = vk + y * cd.vks;
-      int acc = 1 << (kResampleBits - 1);
-      for (int j = 0; j < n; ++j) acc += static_cast<int>(tmp[(ym + j) * kImage + x]) * k[j];
-      acc >>= kResampleBits;
-      val = acc < 0 ? 0 : (acc > 255 ? 255 : acc);
+      int acc[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = 1 << (kResampleBits - 1);
+      for (int j = 0; j < n; ++j) {
+        const uint2 px = *reinterpret_cast<const uint2*>(tmp + (ym + j) * kImage + x);
+        const int kj = k[j];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          acc[e] += static_cast<int>((px.x >> (8 * e)) & 0xffu) * kj;
+          acc[4 + e] += static_cast<int>((px.y >> (8 * e)) & 0xffu) * kj;
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int a = acc[e] >> kResampleBits;
+        val[e] = a < 0 ? 0 : (a > 255 ? 255 : a);
+      }
     } else {
-      val = tmp[yy * kImage + x];
+      const uint2 px = *reinterpret_cast<const uint2*>(tmp + yy * kImage + x);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        val[e] = static_cast<int>((px.x >> (8 * e)) & 0xffu);
+        val[4 + e] = static_cast<int>((px.y >> (8 * e)) & 0xffu);
+      }
     }
     const int patch = (y >> 4) * 14 + (x >> 4);
-    patches[(static_cast<size_t>(blockIdx.y) * kPatches + patch) * kPatchK + (y & 15) * 16 + (x & 15)] =
-        __float2bfloat16(static_cast<float>(val - 128));
+    uint4 out;
+    out.x = pack_bf16(static_cast<float>(val[0] - 128), static_cast<float>(val[1] - 128));
+    out.y = pack_bf16(static_cast<float>(val[2] - 128), static_cast<float>(val[3] - 128));
+    out.z = pack_bf16(static_cast<float>(val[4] - 128), static_cast<float>(val[5] - 128));
+    out.w = pack_bf16(static_cast<float>(val[6] - 128), static_cast<float>(val[7] - 128));
+    *reinterpret_cast<uint4*>(patches + (static_cast<size_t>(blockIdx.y) * kPatches + patch) * kPatchK + (y & 15) * 16 + (x & 15)) = out;
     const size_t o = (static_cast<size_t>(blockIdx.y) * kImage + y) * kImage + x;
-    if (dbg_u8) dbg_u8[o] = static_cast<uint8_t>(val);
-    if (dbg_f32) dbg_f32[o] = lut[val];
+    if (dbg_u8) {
+      uint2 b;
+      b.x = static_cast<unsigned>(val[0]) | (static_cast<unsigned>(val[1]) << 8) | (static_cast<unsigned>(val[2]) << 16) | (static_cast<unsigned>(val[3]) << 24);
+      b.y = static_cast<unsigned>(val[4]) | (static_cast<unsigned>(val[5]) << 8) | (static_cast<unsigned>(val[6]) << 16) | (static_cast<unsigned>(val[7]) << 24);
+      *reinterpret_cast<uint2*>(dbg_u8 + o) = b;
+    }
+    if (dbg_f32) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) dbg_f32[o + e] = lut[val[e]];
+    }
   }
 }
 
