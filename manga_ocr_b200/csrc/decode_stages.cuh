@@ -73,6 +73,7 @@ struct PdParams {
   int* ids;                 // [n_crops, max_len]
   int* lens;                // [n_crops] valid ids per crop, written when the crop finishes
   int* slot_crop;           // [B] crop each row is decoding (-1: idle)
+  const int* kv_row;        // [B] physical self-attention cache row of each row (beam search: the cache follows the beams), or null: row r uses row r
   int* queue;               // [0] next waiting crop, [1] crops whose encoder K/V are ready, [2] crops finished
   int* pos;                 // [B]
   int* finished;            // [B]
@@ -977,13 +978,14 @@ __device__ __forceinline__ void pd_attention_stage(Bar& bar, uint8_t* smem, cons
   // Row state (finished flag, position) of the first kPre units of this group is requested in one go
   // right after the dependency wait; together with the first unit's query they cost ONE L2 round trip.
   constexpr int kPre = 4;
-  int pre_fin[kPre] = {0, 0, 0, 0}, pre_pos[kPre] = {0, 0, 0, 0};
-  auto make_unit = [&](int u, int fin, int pos, bool state_visible) {     // pos: self = the row's position; cross = the crop the row decodes
+  int pre_fin[kPre] = {0, 0, 0, 0}, pre_pos[kPre] = {0, 0, 0, 0}, pre_kvr[kPre] = {0, 0, 0, 0};
+  auto make_unit = [&](int u, int fin, int pos, bool state_visible, int kvr) {     // pos: self = the row's position; cross = the crop the row decodes
     PdAttnUnit a;
     a.b = u / kHeads;
     a.h = u - a.b * kHeads;
     a.crop = SELF ? 0 : pos;
-    const int kvb = SELF ? a.b : (pos < 0 ? 0 : pos) / p.kv_div;    // cross: the beams of a crop read the same K/V
+    // self: the row's cache row (kvr: its own, or the one the beam-search row table gives); cross: the beams of a crop read the same K/V
+    const int kvb = SELF ? kvr : (pos < 0 ? 0 : pos) / p.kv_div;
     a.kc = kbase + static_cast<size_t>(kvb) * b_stride + static_cast<size_t>(a.h) * head_stride + ch * 8;
     a.vc = vbase + static_cast<size_t>(kvb) * b_stride + static_cast<size_t>(a.h) * head_stride + ch * 8;
     a.nk = a.nv = nullptr;
@@ -1003,22 +1005,25 @@ __device__ __forceinline__ void pd_attention_stage(Bar& bar, uint8_t* smem, cons
     return a;
   };
   auto unit_state = [&](int u, int k) {             // k = index of u in this group's unit sequence
-    int fin, pos;
+    int fin, pos, kvr;
     if (k < kPre) {
       fin = pre_fin[0];
       pos = pre_pos[0];
+      kvr = pre_kvr[0];
 #pragma unroll
       for (int i = 1; i < kPre; ++i) {              // (select chain: the arrays stay in registers)
         if (k == i) {
           fin = pre_fin[i];
           pos = pre_pos[i];
+          kvr = pre_kvr[i];
         }
       }
     } else {
       fin = ldg_cg_s32(p.finished + u / kHeads);
       pos = ldg_cg_s32((SELF ? p.pos : p.slot_crop) + u / kHeads);
+      kvr = (SELF && p.kv_row != nullptr) ? ldg_cg_s32(p.kv_row + u / kHeads) : u / kHeads;
     }
-    return make_unit(u, fin, pos, true);
+    return make_unit(u, fin, pos, true, kvr);
   };
   // The query of a unit, requested (raw) one unit ahead and summed when the unit starts:
   // self: bf16 row of the QKV buffer; cross: bias + split-K partials of the cross-q projection.
@@ -1069,7 +1074,7 @@ __device__ __forceinline__ void pd_attention_stage(Bar& bar, uint8_t* smem, cons
   // cross: which crop the first unit's row decodes is read speculatively before the dependency wait (it changes only when
   // the row finishes and takes the next waiting crop) and checked again after it
   const int spec_crop = (!SELF && u0 < units) ? ldg_cg_s32(p.slot_crop + u0 / kHeads) : 0;
-  PdAttnUnit cur = make_unit(u0 < units ? u0 : 0, 0, SELF ? 0 : spec_crop, false);
+  PdAttnUnit cur = make_unit(u0 < units ? u0 : 0, 0, SELF ? 0 : spec_crop, false, 0);
   bool pre2 = false;       // both blocks of the first unit were requested before the dependency wait
   if (!SELF) {   // encoder K/V never change during a decode: request the first unit (2 blocks) before the wait
     if (u0 < units && spec_crop >= 0) {
@@ -1090,6 +1095,7 @@ __device__ __forceinline__ void pd_attention_stage(Bar& bar, uint8_t* smem, cons
     if (uk < units) {
       pre_fin[k] = ldg_cg_s32(p.finished + uk / kHeads);
       pre_pos[k] = ldg_cg_s32((SELF ? p.pos : p.slot_crop) + uk / kHeads);
+      pre_kvr[k] = (SELF && p.kv_row != nullptr) ? ldg_cg_s32(p.kv_row + uk / kHeads) : uk / kHeads;
     }
   }
   if (u0 < units) issue_q(u0, raw_cur);

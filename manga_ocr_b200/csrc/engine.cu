@@ -33,6 +33,7 @@
 #include "region_mask.cuh"
 #include "beam_search.h"
 #include "beam_kernels.cuh"
+#include "beam_device.cuh"
 #include "rowops.cuh"
 
 using namespace mocr;
@@ -149,6 +150,8 @@ struct mocr_handle {
                             // already runs.  Measured on the ragged 512-crop leg: 116 ms (80 ms at equal priorities) against 75 ms with the encoder
                             // serialised in front - the 200 KB GEMM CTAs and the decoder's stage kernels do not share SMs well - so it is off
   int sub_i0 = 0, sub_n = 0;   // sub-range of the staged crops that preprocess / encode work on (sub_n = 0: all of them)
+  int beam_device = 1;      // beam search with the selection on the device and the steps in a CUDA graph (0: host bookkeeping, one round trip per step)
+  int beam_steps_per_graph = 8;
   int slots = 0;            // decoder rows of a greedy decode (0 = one per crop).  With fewer rows than crops a row that finishes takes
                             // the next waiting crop (in-flight slot refill): worth it when lengths are ragged (real text); with random-init
                             // weights, which never emit EOS, one row per crop on the large-batch program is faster
@@ -186,6 +189,9 @@ struct mocr_handle {
   __nv_bfloat16* self_v2[kDecLayers] = {nullptr, nullptr};
   void* d_beam = nullptr;             // beam mode scratch: candidates, next tokens, parents, ban lists
   size_t d_beam_bytes = 0;
+  void* d_beam_dev = nullptr;         // device-resident beam search: token rows, scores, control block (beam_device.cuh)
+  size_t d_beam_dev_bytes = 0;
+  int* h_beam_ctl = nullptr;          // pinned [8]
   float* part_max = nullptr;
   int* part_idx = nullptr;
   int* d_ids = nullptr;               // [max_batch, max_length]
@@ -238,6 +244,7 @@ struct mocr_handle {
   struct StepGraph { cudaGraphExec_t exec; int launches; };
   std::map<uint64_t, StepGraph> graphs;
   std::map<uint64_t, StepGraph> enc_graphs;   // encoder launches per (batch size, tap)
+  std::map<uint64_t, StepGraph> beam_graphs;  // device-resident beam search: steps per (crops, beams, length, n-gram, early stopping, penalty)
 };
 
 namespace {
@@ -1514,7 +1521,10 @@ int mocr_destroy(mocr_handle_t* h) {
     if (h->stream_enc) cudaStreamSynchronize(h->stream_enc);
     for (auto& g : h->graphs) cudaGraphExecDestroy(g.second.exec);
     for (auto& g : h->enc_graphs) cudaGraphExecDestroy(g.second.exec);
+    for (auto& g : h->beam_graphs) cudaGraphExecDestroy(g.second.exec);
     for (void* p : h->allocs) cudaFree(p);
+    if (h->d_beam_dev) cudaFree(h->d_beam_dev);
+    if (h->h_beam_ctl) cudaFreeHost(h->h_beam_ctl);
     if (h->logits_tap) cudaFree(h->logits_tap);
     if (h->d_arena) cudaFree(h->d_arena);
     if (h->h_arena) cudaFreeHost(h->h_arena);
@@ -1649,6 +1659,9 @@ int mocr_recognize(mocr_handle_t* h, const mocr_crop_t* crops, int n, int channe
   return MOCR_OK;
 }
 
+int decode_beam_device(mocr_handle* h, int beams, int max_length, int ngram, float length_penalty, int early, int32_t* out_ids, int32_t* out_lens,
+                       float* out_scores);
+
 // Beam search over the encoded crops (include/mocr_b200.h: mocr_decode_beam).
 int decode_beam(mocr_handle* h, int beams, int max_length, int ngram, float length_penalty, int early, int32_t* out_ids, int32_t* out_lens,
                 float* out_scores) {
@@ -1658,6 +1671,22 @@ int decode_beam(mocr_handle* h, int beams, int max_length, int ngram, float leng
   if (max_length < 2 || max_length > h->max_length) return fail(h, MOCR_ERR_CAPACITY, "max_length %d outside [2, %d]", max_length, h->max_length);
   const int n = h->n, R = n * beams, K = 2 * beams;
   if (R > h->max_batch) return fail(h, MOCR_ERR_CAPACITY, "%d crops x %d beams = %d rows, handle capacity is %d", n, beams, R, h->max_batch);
+  if (h->beam_device) {
+    const size_t need_tap_dev = static_cast<size_t>(h->max_batch) * kVocab * sizeof(float);
+    if (need_tap_dev > h->logits_tap_bytes) {
+      CK(cudaStreamSynchronize(h->stream));
+      if (h->logits_tap) cudaFree(h->logits_tap);
+      h->logits_tap = nullptr;
+      h->logits_tap_bytes = 0;
+      CK(cudaMalloc(reinterpret_cast<void**>(&h->logits_tap), need_tap_dev));
+      h->logits_tap_bytes = need_tap_dev;
+      for (auto& g : h->graphs) cudaGraphExecDestroy(g.second.exec);   // they captured the old tap pointer
+      h->graphs.clear();
+      for (auto& g : h->beam_graphs) cudaGraphExecDestroy(g.second.exec);
+      h->beam_graphs.clear();
+    }
+    return decode_beam_device(h, beams, max_length, ngram, length_penalty, early, out_ids, out_lens, out_scores);
+  }
   const size_t cache_elems = static_cast<size_t>(h->max_batch) * h->max_length * kD;
   for (int l = 0; l < kDecLayers; ++l) {
     if (h->self_k2[l] == nullptr) TRY(dmalloc(h, &h->self_k2[l], cache_elems));
@@ -1760,6 +1789,143 @@ int decode_beam(mocr_handle* h, int beams, int max_length, int ngram, float leng
   h->last_steps = steps;
   h->cur_len = max_length;
   h->dec_ok = false;        // the greedy-path getters (ids, step logits) do not describe this run
+  return MOCR_OK;
+}
+
+// Beam search with the selection on the device (beam_device.cuh): a step = the greedy path's stage kernels (all but the
+// next-token stage) + top-k with the n-gram ban + selection + cache-row fix-up + embed, captured beam_steps_per_graph steps
+// at a time; the host only reads the 32-byte control block after every graph.
+int decode_beam_device(mocr_handle* h, int beams, int max_length, int ngram, float length_penalty, int early, int32_t* out_ids, int32_t* out_lens,
+                       float* out_scores) {
+  const int n = h->n, R = n * beams, K = 2 * beams, T = max_length;
+  const size_t Rm = h->max_batch, Tm = h->max_length;
+  // scratch layout (ints / floats of 4 bytes)
+  size_t off = 0;
+  auto take = [&](size_t count) { const size_t o = off; off += (count * 4 + 255) & ~static_cast<size_t>(255); return o; };
+  const size_t o_run0 = take(Rm * Tm), o_run1 = take(Rm * Tm), o_fin0 = take(Rm * Tm), o_fin1 = take(Rm * Tm), o_rs = take(Rm), o_fs = take(Rm),
+               o_fl = take(Rm), o_if = take(Rm), o_un = take(Rm), o_ctl = take(8), o_clp = take(Rm * kBeamMaxK), o_ctk = take(Rm * kBeamMaxK),
+               o_nx = take(Rm), o_pa = take(Rm), o_ph = take(Rm), o_cs = take(Rm), o_cd = take(Rm);
+  if (off > h->d_beam_dev_bytes) {
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->d_beam_dev) cudaFree(h->d_beam_dev);
+    h->d_beam_dev = nullptr;
+    h->d_beam_dev_bytes = 0;
+    CK(cudaMalloc(&h->d_beam_dev, off));
+    h->d_beam_dev_bytes = off;
+    for (auto& g : h->beam_graphs) cudaGraphExecDestroy(g.second.exec);
+    h->beam_graphs.clear();
+  }
+  if (h->h_beam_ctl == nullptr) CK(cudaMallocHost(reinterpret_cast<void**>(&h->h_beam_ctl), 8 * sizeof(int)));
+  uint8_t* base = static_cast<uint8_t*>(h->d_beam_dev);
+  BeamDev d{};
+  d.n = n; d.beams = beams; d.K = K; d.T = T; d.ngram = ngram; d.early = early; d.length_penalty = length_penalty;
+  d.eos = kSepId; d.fill = kSepId;      // pad id 0 is falsy in the reference: finished rows are filled with EOS (beam_search.h)
+  d.prompt_len = 1; d.start_token = kClsId;
+  d.run[0] = reinterpret_cast<int*>(base + o_run0); d.run[1] = reinterpret_cast<int*>(base + o_run1);
+  d.fin[0] = reinterpret_cast<int*>(base + o_fin0); d.fin[1] = reinterpret_cast<int*>(base + o_fin1);
+  d.run_score = reinterpret_cast<float*>(base + o_rs); d.fin_score = reinterpret_cast<float*>(base + o_fs);
+  d.fin_len = reinterpret_cast<int*>(base + o_fl); d.is_fin = reinterpret_cast<int*>(base + o_if); d.unsat = reinterpret_cast<int*>(base + o_un);
+  d.ctl = reinterpret_cast<int*>(base + o_ctl);
+  d.cand_lp = reinterpret_cast<float*>(base + o_clp); d.cand_tok = reinterpret_cast<int*>(base + o_ctk);
+  d.next = reinterpret_cast<int*>(base + o_nx); d.parent = reinterpret_cast<int*>(base + o_pa); d.phys = reinterpret_cast<int*>(base + o_ph);
+  d.copy_src = reinterpret_cast<int*>(base + o_cs); d.copy_dst = reinterpret_cast<int*>(base + o_cd);
+
+  PdParams p = make_pd_params(h, R, max_length, false, true);
+  p.kv_div = beams;
+  p.logits_cur = 1;
+  p.kv_row = d.phys;
+  BeamCaches bc;
+  for (int l = 0; l < kDecLayers; ++l) {
+    bc.src[2 * l] = bc.dst[2 * l] = h->self_k[l];
+    bc.src[2 * l + 1] = bc.dst[2 * l + 1] = h->self_v[l];
+  }
+  auto one_step = [&]() -> int {
+    TRY(decode_stage_step(h, p, true));
+    beam_topk_dev_kernel<<<R, 256, 0, h->stream>>>(d, h->logits_tap);
+    beam_select_kernel<<<n, 128, 0, h->stream>>>(d);
+    beam_kv_copy_kernel<<<dim3(R, 2 * kDecLayers), 256, 0, h->stream>>>(d, bc, h->max_length);
+    beam_advance_dev_kernel<<<(R + 7) / 8, 256, 0, h->stream>>>(p, d);
+    CK(cudaGetLastError());
+    h->launches += 4;
+    return MOCR_OK;
+  };
+  auto begin = [&]() -> int {
+    CK(launch_pdl(h, pd_begin_kernel, (R + kPdWarps - 1) / kPdWarps, kPdThreads, 0, p));
+    beam_init_kernel<<<std::min(2 * h->sms, (R * T + 255) / 256), 256, 0, h->stream>>>(d);
+    CK(cudaGetLastError());
+    h->launches += 2;
+    return MOCR_OK;
+  };
+  TRY(begin());
+  const int spg = std::max(1, std::min(h->beam_steps_per_graph, max_length - 1));
+  cudaGraphExec_t exec = nullptr;
+  int64_t per_graph = 0;
+  if (h->use_graph) {
+    uint32_t lp_bits;
+    memcpy(&lp_bits, &length_penalty, 4);
+    const uint64_t key = (static_cast<uint64_t>(n) << 52) ^ (static_cast<uint64_t>(beams) << 44) ^ (static_cast<uint64_t>(max_length) << 34) ^
+                         (static_cast<uint64_t>(ngram) << 30) ^ (static_cast<uint64_t>(early) << 28) ^ (static_cast<uint64_t>(lp_bits) >> 4);
+    auto it = h->beam_graphs.find(key);
+    if (it == h->beam_graphs.end()) {
+      const int64_t l0 = h->launches;
+      TRY(one_step());                        // warm: function attributes, tensor maps
+      per_graph = (h->launches - l0) * spg;
+      TRY(begin());
+      cudaGraph_t graph;
+      CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+      const int64_t l1 = h->launches;
+      int r = MOCR_OK;
+      for (int s = 0; s < spg && r == MOCR_OK; ++s) r = one_step();
+      h->launches = l1;
+      const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+      if (r != MOCR_OK) {
+        if (ce == cudaSuccess) cudaGraphDestroy(graph);
+        return r;
+      }
+      if (ce != cudaSuccess) return fail(h, MOCR_ERR_CUDA, "beam-search stream capture failed: %s", cudaGetErrorString(ce));
+      CK(cudaGraphInstantiate(&exec, graph, 0));
+      cudaGraphDestroy(graph);
+      if (h->beam_graphs.size() >= 16) {
+        for (auto& g : h->beam_graphs) cudaGraphExecDestroy(g.second.exec);
+        h->beam_graphs.clear();
+      }
+      h->beam_graphs[key] = mocr_handle::StepGraph{exec, static_cast<int>(per_graph)};
+    } else {
+      exec = it->second.exec;
+      per_graph = it->second.launches;
+    }
+  }
+  int launched = 0;
+  while (launched < max_length - 1) {
+    if (exec != nullptr) {
+      CK(cudaGraphLaunch(exec, h->stream));
+      h->launches += per_graph;
+      launched += spg;
+    } else {
+      TRY(one_step());
+      launched += 1;
+    }
+    CK(cudaMemcpyAsync(h->h_beam_ctl, d.ctl, 8 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->h_beam_ctl[BC_UNFINISHED] == 0) break;
+  }
+  if (h->h_beam_ctl[BC_UNFINISHED] != 0) return fail(h, MOCR_ERR_CUDA, "beam search did not terminate within max_length steps");
+  const int par = h->h_beam_ctl[BC_PARITY];
+  std::vector<int> fl(R);
+  std::vector<float> fs(R);
+  CK(cudaMemcpyAsync(fl.data(), d.fin_len, sizeof(int) * R, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(fs.data(), d.fin_score, sizeof(float) * R, cudaMemcpyDeviceToHost, h->stream));
+  // best hypothesis of every crop = row 0 of its finished set
+  CK(cudaMemcpy2DAsync(out_ids, sizeof(int) * T, d.fin[par], sizeof(int) * T * beams, sizeof(int) * T, n, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  for (int b = 0; b < n; ++b) {
+    if (out_lens) out_lens[b] = 1 + fl[static_cast<size_t>(b) * beams];
+    if (out_scores) out_scores[b] = fs[static_cast<size_t>(b) * beams];
+  }
+  h->last_steps = h->h_beam_ctl[BC_STEPS];
+  h->last_rows = R;
+  h->cur_len = max_length;
+  h->dec_ok = false;
   return MOCR_OK;
 }
 
@@ -1916,6 +2082,8 @@ int mocr_set_option(mocr_handle_t* h, const char* key, int value) {
   else if (k == "kv_evict_first" && value >= 0 && value <= 3) h->kv_evict_first = value;
   else if (k == "attn_grid" && value >= 0) h->attn_grid = value;
   else if (k == "slots" && value >= 0) h->slots = value;
+  else if (k == "beam_device") h->beam_device = value != 0;
+  else if (k == "beam_steps_per_graph" && value >= 1 && value <= 64) h->beam_steps_per_graph = value;
   else if (k == "pipeline" && value >= 0 && value <= 2) h->pipeline = value;
   else if (k == "fuse_ln") h->fuse_ln = value != 0;
   else if (k == "kv_prefetch") h->kv_prefetch = value != 0;
@@ -1929,6 +2097,8 @@ int mocr_set_option(mocr_handle_t* h, const char* key, int value) {
   h->graphs.clear();
   for (auto& g : h->enc_graphs) cudaGraphExecDestroy(g.second.exec);
   h->enc_graphs.clear();
+  for (auto& g : h->beam_graphs) cudaGraphExecDestroy(g.second.exec);
+  h->beam_graphs.clear();
   return MOCR_OK;
 }
 

@@ -152,3 +152,41 @@ def test_beam_and_region_calls_interleave_on_one_handle(beam_setup):
     assert all(np.array_equal(a, b) for a, b in zip(first, again))
     ids_b, _ = eng.recognize_regions(page, regions, max_length=T)
     assert np.array_equal(ids_a, ids_b)
+
+
+@pytest.mark.parametrize("early", [True, False, "never"])
+@pytest.mark.parametrize("ngram,lp", [(3, 2.0), (0, 1.0), (2, 0.5)])
+def test_device_resident_beam_search_equals_host_bookkeeping(beam_setup, early, ngram, lp):
+    """The selection kernels (beam_device.cuh) restate beam_search.h, which tests/test_beam_host.py pins exactly against
+    transformers: on the same device logits both must return the same hypotheses - including the n-gram ban computed on the
+    device and the cache rows that follow the beams through the row table instead of the per-step gather."""
+    eng, _, crops = beam_setup
+    kw = dict(max_length=T, num_beams=4, no_repeat_ngram_size=ngram, length_penalty=lp, early_stopping=early)
+    eng.set_option("beam_device", 0)
+    try:
+        ids_h, lens_h, scores_h = eng.recognize_beam(crops, **kw)
+    finally:
+        eng.set_option("beam_device", 1)
+    ids_d, lens_d, scores_d = eng.recognize_beam(crops, **kw)
+    assert np.array_equal(lens_d, lens_h), (lens_d, lens_h)
+    assert np.array_equal(ids_d, ids_h)
+    assert np.allclose(scores_d, scores_h, rtol=1e-6, atol=1e-7)
+    eng.set_option("use_graph", 0)                 # the same steps launched one by one
+    try:
+        ids_n, lens_n, _ = eng.recognize_beam(crops, **kw)
+    finally:
+        eng.set_option("use_graph", 1)
+    assert np.array_equal(ids_n, ids_d) and np.array_equal(lens_n, lens_d)
+
+
+def test_device_beam_other_widths(beam_setup):
+    eng, _, crops = beam_setup
+    for beams in (1, 2, 3, 8):
+        kw = dict(max_length=T, num_beams=beams, no_repeat_ngram_size=3, length_penalty=2.0, early_stopping=True)
+        eng.set_option("beam_device", 0)
+        try:
+            want = eng.recognize_beam(crops[:2], **kw)
+        finally:
+            eng.set_option("beam_device", 1)
+        got = eng.recognize_beam(crops[:2], **kw)
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]), beams
