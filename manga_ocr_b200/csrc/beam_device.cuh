@@ -74,11 +74,13 @@ __global__ void __launch_bounds__(256) beam_init_kernel(BeamDev d) {
 // log-softmax + n-gram ban + the row's K best continuations (beam_topk_kernel with the ban list computed here from the
 // row's running tokens).  grid = rows, block = 256.
 __global__ void __launch_bounds__(256) beam_topk_dev_kernel(BeamDev d, const float* __restrict__ logits) {
+  pdl_launch_dependents();
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   if (d.ctl[BC_UNFINISHED] == 0) return;
   constexpr int kPer = kVocab / 256;   // 24
   __shared__ float s_val[8];
-  __shared__ int s_idx[8];
-  __shared__ int s_bidx;
+  __shared__ float s_rv[2][8];
+  __shared__ int s_ri[2][8];
   __shared__ int s_ban[kMaxPos];
   __shared__ int s_nban;
   const int r = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -132,7 +134,8 @@ __global__ void __launch_bounds__(256) beam_topk_dev_kernel(BeamDev d, const flo
     }
   }
   __syncthreads();
-  // K rounds of (max, lowest index) over the block
+  // K rounds of (max, lowest index) over the block; the warps' partial results are double-buffered by round, every thread
+  // merges them itself: one barrier per round
   for (int k = 0; k < K; ++k) {
     float best = -INFINITY;
     int bi = 0x7fffffff;
@@ -147,116 +150,113 @@ __global__ void __launch_bounds__(256) beam_topk_dev_kernel(BeamDev d, const flo
       const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
       if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
     }
-    if (lane == 0) { s_val[warp] = best; s_idx[warp] = bi; }
+    if (lane == 0) { s_rv[k & 1][warp] = best; s_ri[k & 1][warp] = bi; }
     __syncthreads();
+    float bb = s_rv[k & 1][0];
+    int ix = s_ri[k & 1][0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) {
+      const float wv = s_rv[k & 1][w];
+      const int wi = s_ri[k & 1][w];
+      if (wv > bb || (wv == bb && wi < ix)) { bb = wv; ix = wi; }
+    }
     if (tid == 0) {
-      float b = s_val[0];
-      int ix = s_idx[0];
-      for (int w = 1; w < 8; ++w)
-        if (s_val[w] > b || (s_val[w] == b && s_idx[w] < ix)) { b = s_val[w]; ix = s_idx[w]; }
-      s_bidx = ix;
-      d.cand_lp[static_cast<size_t>(r) * K + k] = b - lse;
+      d.cand_lp[static_cast<size_t>(r) * K + k] = bb - lse;
       d.cand_tok[static_cast<size_t>(r) * K + k] = ix;
     }
-    __syncthreads();
-    const int ix = s_bidx;
     if ((ix & 255) == tid) {
 #pragma unroll
       for (int i = 0; i < kPer; ++i)
         if (i == (ix >> 8)) v[i] = -INFINITY;      // taken
     }
-    __syncthreads();
   }
 }
 
-// One selection step for crop blockIdx.x (BeamSearch::step of beam_search.h); the last CTA to finish closes the step
-// (global "unfinished", current length, parity).  block = 128.
-__global__ void __launch_bounds__(128) beam_select_kernel(BeamDev d) {
+// One selection step for crop blockIdx.x (BeamSearch::step of beam_search.h) and the embedding of the tokens its beams
+// consume next; the last CTA to finish closes the step (global "unfinished", current length, parity).  block = 128.
+// The three sorts of the host code (stable, by descending value) are done as rank computations: element x goes to position
+// #{y : y sorts before x}, every thread ranking its own elements - the comparators are strict total orders, so the result is
+// the stable sort's.
+__global__ void __launch_bounds__(128) beam_select_kernel(const __grid_constant__ PdParams p, BeamDev d) {
+  pdl_launch_dependents();
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   if (d.ctl[BC_UNFINISHED] == 0) return;
   constexpr int MB = kBeamMaxBeams, MK = kBeamMaxK;
-  __shared__ int s_top_beam[MK], s_top_tok[MK], s_sel[MB], s_midx[MB];
-  __shared__ float s_run_lp[MK], s_mscore[MB + MK];
-  __shared__ int s_mfin[MB + MK], s_mlen[MB + MK];
-  const int b = blockIdx.x, tid = threadIdx.x;
-  const int beams = d.beams, K = d.K, T = d.T;
+  __shared__ float s_acc[MB * MK], s_top_lp[MK], s_run_lp[MK], s_mscore[MB + MK], s_denom;
+  __shared__ int s_tok[MB * MK], s_order[MK], s_top_beam[MK], s_top_tok[MK], s_hit[MK], s_sel[MB], s_midx[MB], s_mfin[MB + MK], s_mlen[MB + MK];
+  __shared__ int s_full, s_unsat;
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int beams = d.beams, K = d.K, T = d.T, nc = beams * K;
   const int cur_len = d.ctl[BC_CUR_LEN], par = d.ctl[BC_PARITY];
   const int* run_old = d.run[par];
   int* run_new = d.run[par ^ 1];
   const int* fin_old = d.fin[par];
   int* fin_new = d.fin[par ^ 1];
   const int row0 = b * beams;
+  // accumulated log-probabilities of the beams * K candidates
+  for (int i = tid; i < nc; i += blockDim.x) {
+    const int j = i / K;
+    s_acc[i] = d.cand_lp[static_cast<size_t>(row0 + j) * K + i % K] + d.run_score[row0 + j];
+    s_tok[i] = d.cand_tok[static_cast<size_t>(row0 + j) * K + i % K];
+  }
   if (tid == 0) {
-    float acc[MB * MK];
-    int order[MB * MK];
-    for (int j = 0; j < beams; ++j)
-      for (int k = 0; k < K; ++k) acc[j * K + k] = d.cand_lp[(static_cast<size_t>(row0) + j) * K + k] + d.run_score[row0 + j];
-    // stable sort by (value desc, beam asc, token asc): torch.topk over the flattened [beams * vocab] scores
-    const int nc = beams * K;
-    for (int i = 0; i < nc; ++i) {
-      int x = i, p = i;
-      while (p > 0) {
-        const int y = order[p - 1];
-        bool before;     // does x come before y?
-        if (acc[x] != acc[y]) before = acc[x] > acc[y];
-        else if (x / K != y / K) before = x / K < y / K;
-        else before = d.cand_tok[(static_cast<size_t>(row0) + x / K) * K + x % K] < d.cand_tok[(static_cast<size_t>(row0) + y / K) * K + y % K];
-        if (!before) break;
-        order[p] = y;
-        --p;
-      }
-      order[p] = x;
-    }
-    float top_lp[MK], fin_lp[MK];
-    int hit[MK];
-    bool all_hit = true;
-    for (int k = 0; k < K; ++k) {
-      const int c = order[k];
-      top_lp[k] = acc[c];
-      s_top_beam[k] = c / K;
-      s_top_tok[k] = d.cand_tok[(static_cast<size_t>(row0) + c / K) * K + c % K];
-      hit[k] = (cur_len + 1 >= T) || s_top_tok[k] == d.eos;
-      all_hit = all_hit && hit[k];
-      s_run_lp[k] = top_lp[k] + (hit[k] ? 1.0f : 0.0f) * -1.0e9f;
-    }
-    // running beams of the next iteration: the best `beams` candidates that did not stop (stable by candidate rank)
-    int top[MK];
-    for (int i = 0; i < K; ++i) {
-      int p = i;
-      while (p > 0 && s_run_lp[i] > s_run_lp[top[p - 1]]) { top[p] = top[p - 1]; --p; }
-      top[p] = i;
-    }
-    for (int j = 0; j < beams; ++j) s_sel[j] = top[j];
-    // finished beams: candidates among the first `beams` that stopped, length-penalised, merged with the previous set
-    const float denom = static_cast<float>(pow(static_cast<double>(cur_len + 1 - d.prompt_len), static_cast<double>(d.length_penalty)));
+    s_denom = static_cast<float>(pow(static_cast<double>(cur_len + 1 - d.prompt_len), static_cast<double>(d.length_penalty)));
     bool full = d.early == 1;
     for (int j = 0; j < beams; ++j) full = full && d.is_fin[row0 + j] != 0;
-    const bool unsat_b = d.unsat[b] != 0;
-    for (int k = 0; k < K; ++k) {
-      const bool did = hit[k] && k < beams;
-      float v = top_lp[k] / denom;
-      v += (full ? 1.0f : 0.0f) * -1.0e9f;
-      v += (unsat_b ? 0.0f : 1.0f) * -1.0e9f;
-      v += (did ? 0.0f : 1.0f) * -1.0e9f;
-      fin_lp[k] = v;
+    s_full = full ? 1 : 0;
+    s_unsat = d.unsat[b] != 0 ? 1 : 0;
+  }
+  __syncthreads();
+  // top K of them: (value desc, beam asc, token asc) = torch.topk over the flattened [beams * vocab] scores
+  for (int x = tid; x < nc; x += blockDim.x) {
+    int rank = 0;
+    const float ax = s_acc[x];
+    for (int y = 0; y < nc; ++y) {
+      const float ay = s_acc[y];
+      bool before;
+      if (ay != ax) before = ay > ax;
+      else if (y / K != x / K) before = y / K < x / K;
+      else before = s_tok[y] < s_tok[x];
+      rank += (y != x && before) ? 1 : 0;
     }
-    for (int j = 0; j < beams; ++j) {
-      s_mscore[j] = d.fin_score[row0 + j];
-      s_mfin[j] = d.is_fin[row0 + j];
-      s_mlen[j] = d.fin_len[row0 + j];
-    }
-    for (int k = 0; k < K; ++k) {
-      s_mscore[beams + k] = fin_lp[k];
-      s_mfin[beams + k] = (hit[k] && k < beams) ? 1 : 0;
-      s_mlen[beams + k] = cur_len + 1 - d.prompt_len;
-    }
-    int midx[MB + MK];
-    for (int i = 0; i < beams + K; ++i) {
-      int p = i;
-      while (p > 0 && s_mscore[i] > s_mscore[midx[p - 1]]) { midx[p] = midx[p - 1]; --p; }
-      midx[p] = i;
-    }
-    for (int j = 0; j < beams; ++j) s_midx[j] = midx[j];
-    if (!all_hit) atomicAnd(d.ctl + BC_ALL_HIT, 0);
+    if (rank < K) s_order[rank] = x;
+  }
+  __syncthreads();
+  if (tid < K) {
+    const int c = s_order[tid];
+    s_top_lp[tid] = s_acc[c];
+    s_top_beam[tid] = c / K;
+    s_top_tok[tid] = s_tok[c];
+    const int hit = ((cur_len + 1 >= T) || s_tok[c] == d.eos) ? 1 : 0;
+    s_hit[tid] = hit;
+    s_run_lp[tid] = s_acc[c] + (hit ? 1.0f : 0.0f) * -1.0e9f;
+  }
+  __syncthreads();
+  if (tid < K) {
+    // running beams of the next iteration: the best `beams` candidates that did not stop (stable by candidate rank)
+    int rank = 0;
+    for (int y = 0; y < K; ++y) rank += (s_run_lp[y] > s_run_lp[tid] || (s_run_lp[y] == s_run_lp[tid] && y < tid)) ? 1 : 0;
+    if (rank < beams) s_sel[rank] = tid;
+    // finished beams: candidates among the first `beams` that stopped, length-penalised
+    const bool did = s_hit[tid] && tid < beams;
+    float v = s_top_lp[tid] / s_denom;
+    v += (s_full ? 1.0f : 0.0f) * -1.0e9f;
+    v += (s_unsat ? 0.0f : 1.0f) * -1.0e9f;
+    v += (did ? 0.0f : 1.0f) * -1.0e9f;
+    s_mscore[beams + tid] = v;
+    s_mfin[beams + tid] = did ? 1 : 0;
+    s_mlen[beams + tid] = cur_len + 1 - d.prompt_len;
+  } else if (tid >= 64 && tid < 64 + beams) {        // ... merged with the previous finished set
+    const int j = tid - 64;
+    s_mscore[j] = d.fin_score[row0 + j];
+    s_mfin[j] = d.is_fin[row0 + j];
+    s_mlen[j] = d.fin_len[row0 + j];
+  }
+  __syncthreads();
+  if (tid < beams + K) {
+    int rank = 0;
+    for (int y = 0; y < beams + K; ++y) rank += (s_mscore[y] > s_mscore[tid] || (s_mscore[y] == s_mscore[tid] && y < tid)) ? 1 : 0;
+    if (rank < beams) s_midx[rank] = tid;
   }
   __syncthreads();
   // ---- token rows (read the old parity, write the new one)
@@ -276,25 +276,36 @@ __global__ void __launch_bounds__(128) beam_select_kernel(BeamDev d) {
     int* rdst = run_new + static_cast<size_t>(row0 + j) * T;
     for (int c = tid; c < T; c += blockDim.x) rdst[c] = c == cur_len ? s_top_tok[k] : rsrc[c];
   }
-  __syncthreads();
+  // ---- every running row of the crop consumes its next token at position cur_len (one warp per row)
+  {
+    PdEmbedConsts ek;
+    pd_embed_consts(p, lane, ek);
+    for (int j = warp; j < beams; j += blockDim.x >> 5) {
+      const int r = row0 + j;
+      if (lane == 0) {
+        p.pos[r] = cur_len;
+        p.finished[r] = 0;
+      }
+      pd_embed_row_warp(p, ek, r, s_top_tok[s_sel[j]], cur_len, lane);
+    }
+  }
   if (tid == 0) {
-    float fs[MB];
-    int ff[MB], fl[MB], old_phys[MB], new_phys[MB], claimed[MB];
+    float fs[MB], new_score[MB];
+    int ff[MB], old_phys[MB], new_phys[MB], claimed[MB];
+    bool all_hit = true;
+    for (int k = 0; k < K; ++k) all_hit = all_hit && s_hit[k] != 0;
+    if (!all_hit) atomicAnd(d.ctl + BC_ALL_HIT, 0);
     for (int j = 0; j < beams; ++j) {
       const int i = s_midx[j];
       fs[j] = s_mscore[i];
       ff[j] = s_mfin[i];
-      fl[j] = s_mlen[i];
-    }
-    for (int j = 0; j < beams; ++j) {
       d.fin_score[row0 + j] = fs[j];
       d.is_fin[row0 + j] = ff[j];
-      d.fin_len[row0 + j] = fl[j];
+      d.fin_len[row0 + j] = s_mlen[i];
     }
-    float new_score[MB];
-    for (int j = 0; j < beams; ++j) new_score[j] = s_run_lp[s_sel[j]];
     for (int j = 0; j < beams; ++j) {
       const int k = s_sel[j];
+      new_score[j] = s_run_lp[k];
       d.run_score[row0 + j] = new_score[j];
       d.next[row0 + j] = s_top_tok[k];
       d.parent[row0 + j] = row0 + s_top_beam[k];
@@ -329,16 +340,19 @@ __global__ void __launch_bounds__(128) beam_select_kernel(BeamDev d) {
       any = any || best_possible > worst;
       all_fin = all_fin && ff[j] != 0;
     }
-    const int us = (d.unsat[b] != 0 && any) ? 1 : 0;
+    const int us = (s_unsat && any) ? 1 : 0;
     d.unsat[b] = us;
     if (us) atomicOr(d.ctl + BC_ANY_UNSAT, 1);
     if (!all_fin) atomicAnd(d.ctl + BC_ALL_FIN, 0);
+  }
+  __syncthreads();                                          // every thread's writes of this crop are issued
+  if (tid == 0) {
     __threadfence();
     if (atomicAdd(d.ctl + BC_ARRIVED, 1) == d.n - 1) {      // the last crop closes the step
       __threadfence();
       const int all_hit = atomicAdd(d.ctl + BC_ALL_HIT, 0), any_unsat = atomicAdd(d.ctl + BC_ANY_UNSAT, 0), allf = atomicAdd(d.ctl + BC_ALL_FIN, 0);
       d.ctl[BC_UNFINISHED] = (any_unsat && !(allf && d.early == 1) && !all_hit) ? 1 : 0;
-      d.ctl[BC_CUR_LEN] = len1;
+      d.ctl[BC_CUR_LEN] = cur_len + 1;
       d.ctl[BC_PARITY] = par ^ 1;
       d.ctl[BC_STEPS] = d.ctl[BC_STEPS] + 1;
       d.ctl[BC_ALL_HIT] = 1;
@@ -351,6 +365,8 @@ __global__ void __launch_bounds__(128) beam_select_kernel(BeamDev d) {
 
 // The children of a parent that several beams continue get a copy of its cache rows [0, len).  grid = (rows, 2 * layers).
 __global__ void __launch_bounds__(256) beam_kv_copy_kernel(BeamDev d, BeamCaches c, int cache_len) {
+  pdl_launch_dependents();
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   if (d.ctl[BC_UNFINISHED] == 0) return;
   const int r = blockIdx.x, which = blockIdx.y;
   const int src_row = d.copy_src[r], dst_row = d.copy_dst[r];
@@ -360,23 +376,6 @@ __global__ void __launch_bounds__(256) beam_kv_copy_kernel(BeamDev d, BeamCaches
   uint4* t = reinterpret_cast<uint4*>(c.dst[which] + static_cast<size_t>(dst_row) * cache_len * kD);
   const int n16 = len * (kD * 2 / 16);
   for (int i = threadIdx.x; i < n16; i += 256) t[i] = s[i];
-}
-
-// Every running row consumes its next token at position cur_len - 1.  One warp per row.
-__global__ void __launch_bounds__(256) beam_advance_dev_kernel(const __grid_constant__ PdParams p, BeamDev d) {
-  if (d.ctl[BC_UNFINISHED] == 0) return;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int r = blockIdx.x * 8 + warp;
-  if (r >= p.B) return;
-  const int position = d.ctl[BC_CUR_LEN] - 1;
-  PdEmbedConsts ek;
-  pd_embed_consts(p, lane, ek);
-  const int tok = d.next[r];
-  if (lane == 0) {
-    p.pos[r] = position;
-    p.finished[r] = 0;
-  }
-  pd_embed_row_warp(p, ek, r, tok, position, lane);
 }
 
 }  // namespace mocr

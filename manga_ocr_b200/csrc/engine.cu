@@ -1062,6 +1062,20 @@ cudaError_t launch_pdl(mocr_handle* h, void (*kernel)(KArgs...), int grid, int b
   return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl_grid(mocr_handle* h, void (*kernel)(KArgs...), dim3 grid, int block, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(block);
+  cfg.stream = h->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = h->use_pdl ? 1 : 0;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 // The encoder's tcgen05 GEMM as a decoder stage: launched with programmatic stream serialization (the kernel requests its
 // weight tiles before griddepcontrol.wait), A map clipped to the live rows (TMA zero-fills rows >= n without reading them).
 template <int BN, int EPI>
@@ -1841,12 +1855,11 @@ int decode_beam_device(mocr_handle* h, int beams, int max_length, int ngram, flo
   }
   auto one_step = [&]() -> int {
     TRY(decode_stage_step(h, p, true));
-    beam_topk_dev_kernel<<<R, 256, 0, h->stream>>>(d, h->logits_tap);
-    beam_select_kernel<<<n, 128, 0, h->stream>>>(d);
-    beam_kv_copy_kernel<<<dim3(R, 2 * kDecLayers), 256, 0, h->stream>>>(d, bc, h->max_length);
-    beam_advance_dev_kernel<<<(R + 7) / 8, 256, 0, h->stream>>>(p, d);
-    CK(cudaGetLastError());
-    h->launches += 4;
+    // (programmatic dependent launch like the stage kernels: each waits for its predecessor with griddepcontrol.wait)
+    CK(launch_pdl(h, beam_topk_dev_kernel, R, 256, 0, d, static_cast<const float*>(h->logits_tap)));
+    CK(launch_pdl(h, beam_select_kernel, n, 128, 0, p, d));
+    CK(launch_pdl_grid(h, beam_kv_copy_kernel, dim3(R, 2 * kDecLayers), 256, d, bc, h->max_length));
+    h->launches += 3;
     return MOCR_OK;
   };
   auto begin = [&]() -> int {
