@@ -4,60 +4,60 @@
 // Reference: transformers/models/vit/modeling_vit.py:199-251 (non-causal, no mask); 1/sqrt(64) is
 // folded into W_q at load time.
 //
-// One CTA = (head, crop), 256 threads = two warpgroups, each owning one 128-row query tile.  Q (2 tiles of 128 rows), K and V (208 rows each) of the head
-// are fetched straight from the [n*197, 2304] QKV buffer by four TMA loads (128-byte swizzle; rows
-// past the crop's 197 belong to the next crop or are zero-filled - they are masked).  Thread 0 issues
-// the S MMAs, the first thread of each warpgroup its P V MMAs; every thread owns one query row (= one TMEM lane): two passes over the 208 score columns
-// (max, then exp / sum), P written as bf16 into the swizzled K-major layout UMMA expects, and the
-// normalisation by 1 / sum applied to the 64 output columns in the epilogue.
+// One CTA = one 128-row query tile of a (head, crop): 128 threads, every thread owns one query row (= one TMEM lane).
+// Q (128 rows), K and V (208 rows each) of the head are fetched straight from the [n*197, 2304] QKV buffer by three TMA
+// loads (128-byte swizzle; rows past the crop's 197 belong to the next crop or are zero-filled - they are masked).
+// Thread 0 issues the MMAs.  Two passes over the 208 score columns (max, then exp / sum); P is written as bf16 into the
+// swizzled K-major layout UMMA expects, INTO THE SHARED MEMORY OF Q AND K (dead once S is complete), and the
+// normalisation by 1 / sum is applied to the 64 output columns in the epilogue.
+// Footprint: 92 KB of shared memory and 256 TMEM columns, so TWO CTAs share an SM and the serial chain of one
+// (TMA -> S -> softmax -> P V -> epilogue) overlaps the other's; the first version (both query tiles in one 218 KB,
+// 512-column CTA, one per SM) ran the same chain unoverlapped: 54 us per layer at 64 crops.
 #pragma once
 #include "common.cuh"
 
 namespace mocr {
 
-constexpr int kAtcThreads = 256;                    // two warpgroups, one 128-row query tile each
+constexpr int kAtcThreads = 128;                    // one warpgroup = one 128-row query tile
 constexpr int kAtcKeys = 208;                       // 197 keys padded to a multiple of 16 (UMMA N and K granularity)
-constexpr int kAtcQBytes = 2 * 128 * 128;           // two 128-row Q tiles, 64 bf16 = 128 B per row
+constexpr int kAtcQBytes = 128 * 128;               // one 128-row Q tile, 64 bf16 = 128 B per row
 constexpr int kAtcKVBytes = kAtcKeys * 128;         // 26 624 B = 26 swizzle atoms of 1 KB
-constexpr int kAtcPBytes = 4 * 128 * 128;           // P of one tile: 4 K-atoms (256 keys) x 128 rows x 128 B
-constexpr int kAtcSmemBytes = kAtcQBytes + 2 * kAtcKVBytes + 2 * kAtcPBytes + 1024 /*align*/ + 64 /*barriers*/;
-constexpr int kAtcTmemCols = 512;
-constexpr uint32_t kAtcColS0 = 0, kAtcColS1 = 256;   // O_t overwrites the first 64 columns of S_t once the softmax has consumed it
+constexpr int kAtcPBytes = 4 * 128 * 128;           // P of the tile: 4 K-atoms (256 keys) x 128 rows x 128 B; aliases Q and K
+constexpr int kAtcSmemBytes = kAtcPBytes + kAtcKVBytes + 1024 /*align*/ + 64 /*barriers*/;
+static_assert(kAtcQBytes + kAtcKVBytes <= kAtcPBytes, "P reuses the shared memory of Q and K");
+constexpr int kAtcTmemCols = 256;                   // S: 208 fp32 columns; O overwrites its first 64 once the softmax has consumed it
 
 // kind::f16 instruction descriptor with an MN-major B operand (bit 16)
 __host__ __device__ constexpr uint32_t umma_idesc_bf16_bmn(int m, int n) { return umma_idesc_bf16(m, n) | (1u << 16); }
 
-// grid = (12 heads, n crops), block = 256
-__global__ void __launch_bounds__(kAtcThreads, 1)
+// grid = (2 query tiles, 12 heads, n crops), block = 128
+__global__ void __launch_bounds__(kAtcThreads, 2)
 encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q /*box 64 x 128*/, const __grid_constant__ CUtensorMap tmap_kv /*box 64 x 208*/,
                             __nv_bfloat16* __restrict__ ctx /*[n*197, 768]*/) {
   extern __shared__ uint8_t atc_raw[];
   const uint32_t raw_addr = smem_u32(atc_raw);
   uint8_t* smem = atc_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + kAtcQBytes;
-  uint8_t* sV = sK + kAtcKVBytes;
-  uint8_t* sP = sV + kAtcKVBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kAtcPBytes);
+  uint8_t* sP = smem;                    // [4 atoms][128 rows][128 B], written after S is complete ...
+  uint8_t* sQ = smem;                    // ... over Q
+  uint8_t* sK = sQ + kAtcQBytes;         // ... and K
+  uint8_t* sV = smem + kAtcPBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kAtcKVBytes);
   uint64_t* bar_load = bars;            // TMA -> issuer
-  uint64_t* bar_s = bars + 1;           // [2] S tile complete
-  uint64_t* bar_o = bars + 3;           // [2] P V of a tile complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  uint64_t* bar_s = bars + 1;           // S tile complete
+  uint64_t* bar_o = bars + 2;           // P V complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
 
-  const int head = blockIdx.x, crop = blockIdx.y;
+  const int t = blockIdx.x, head = blockIdx.y, crop = blockIdx.z;
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int t = tid >> 7;               // query tile of this warpgroup
-  const int r = tid & 127;              // row within the tile = TMEM lane
+  const int r = tid;                    // row within the tile = TMEM lane
   const int row0 = crop * kEncTokens;
 
   if (tid == 0) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_kv);
     mbar_init(bar_load, 1);
-    mbar_init(&bar_s[0], 1);
-    mbar_init(&bar_s[1], 1);
-    mbar_init(&bar_o[0], 1);
-    mbar_init(&bar_o[1], 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_o, 1);
     fence_barrier_init();
   }
   if (warp == 0) {
@@ -71,32 +71,27 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q /*box 64 
 
   if (tid == 0) {
     mbar_arrive_expect_tx(bar_load, kAtcQBytes + 2 * kAtcKVBytes);
-    tma_load_2d(sQ, &tmap_q, bar_load, head * kHeadDim, row0);
-    tma_load_2d(sQ + 128 * 128, &tmap_q, bar_load, head * kHeadDim, row0 + 128);
+    tma_load_2d(sQ, &tmap_q, bar_load, head * kHeadDim, row0 + t * 128);
     tma_load_2d(sK, &tmap_kv, bar_load, kD + head * kHeadDim, row0);
     tma_load_2d(sV, &tmap_kv, bar_load, 2 * kD + head * kHeadDim, row0);
     mbar_wait(bar_load, 0);
     tc_fence_after();
-    // S_t = Q_t K^T : M = 128, N = 208, K = 64 (4 steps of 16), both operands K-major
+    // S = Q K^T : M = 128, N = 208, K = 64 (4 steps of 16), both operands K-major
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, kAtcKeys);
     const uint64_t dk = umma_desc_k_sw128(smem_u32(sK));
+    const uint64_t dq = umma_desc_k_sw128(smem_u32(sQ));
 #pragma unroll
-    for (int tt = 0; tt < 2; ++tt) {
-      const uint64_t dq = umma_desc_k_sw128(smem_u32(sQ + tt * 128 * 128));
-      const uint32_t ts = tmem_base + (tt == 0 ? kAtcColS0 : kAtcColS1);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) umma_bf16(ts, dq + static_cast<uint64_t>(2 * k), dk + static_cast<uint64_t>(2 * k), idesc_s, k != 0);
-      umma_commit(&bar_s[tt]);
-    }
+    for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, dq + static_cast<uint64_t>(2 * k), dk + static_cast<uint64_t>(2 * k), idesc_s, k != 0);
+    umma_commit(bar_s);
   }
 
   constexpr float kLog2e = 1.4426950408889634f;
   const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;      // this warp's TMEM lane quadrant
   const int q = t * 128 + r;                           // query row owned by this thread
-  const uint32_t ts = tmem_base + lane_sel + (t == 0 ? kAtcColS0 : kAtcColS1);
-  uint8_t* sPt = sP + t * kAtcPBytes;
-  if (t == 0 || 128 < kEncTokens) {                    // (both tiles hold live rows for 197 tokens)
-    mbar_wait(&bar_s[t], 0);
+  const uint32_t ts = tmem_base + lane_sel;
+  uint8_t* sPt = sP;
+  {
+    mbar_wait(bar_s, 0);                               // S is complete: Q and K have been read, their memory is free for P
     tc_fence_after();
     // ---- pass 1: row maximum over the 197 valid keys
     float mx = -INFINITY;
@@ -142,22 +137,22 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q /*box 64 
     }
     fence_proxy_async_smem();                          // generic-proxy writes of P -> visible to the tensor core
     tc_fence_before();
-    asm volatile("bar.sync %0, 128;" ::"r"(t + 1) : "memory");   // the warpgroup's P tile is complete, S_t fully read
+    __syncthreads();                                   // the P tile is complete, S fully read
     if (r == 0) {
       tc_fence_after();
       // O_t = P V : M = 128, N = 64, K = 208 (13 steps of 16); A = P (K-major), B = V as stored [key][d] = MN-major:
       // 8 key rows of 128 B form one 1 KB swizzle atom (SBO = 1024), a 16-key step advances 2 KB.
-      // O_t goes to the first 64 columns of S_t (consumed above).
+      // O goes to the first 64 columns of S (consumed above).
       constexpr uint32_t idesc_o = umma_idesc_bf16_bmn(128, kHeadDim);
 #pragma unroll
       for (int s2 = 0; s2 < kAtcKeys / 16; ++s2) {
         const uint64_t dp = umma_desc_k_sw128(smem_u32(sPt + (s2 >> 2) * (128 * 128))) + static_cast<uint64_t>(2 * (s2 & 3));
         const uint64_t dv = umma_desc_k_sw128(smem_u32(sV + s2 * 2048));
-        umma_bf16(tmem_base + (t == 0 ? kAtcColS0 : kAtcColS1), dp, dv, idesc_o, s2 != 0);
+        umma_bf16(tmem_base, dp, dv, idesc_o, s2 != 0);
       }
-      umma_commit(&bar_o[t]);
+      umma_commit(bar_o);
     }
-    mbar_wait(&bar_o[t], 0);
+    mbar_wait(bar_o, 0);
     tc_fence_after();
     // ---- epilogue: O / sum -> bf16 -> ctx[row, head * 64 ..]
     const float inv = __fdividef(1.0f, sum);           // sum >= 1 (the maximum contributes exp(0))

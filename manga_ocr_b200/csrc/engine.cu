@@ -904,7 +904,7 @@ int attention197(mocr_handle* h, int n) {
     done[h->device & 15] = true;
   }
   if (h->attn_tc)
-    encoder_attention_tc_kernel<<<dim3(kHeads, n), kAtcThreads, kAtcSmemBytes, h->stream>>>(h->map_qkv_q, h->map_qkv_kv, h->ctx.p);
+    encoder_attention_tc_kernel<<<dim3(2, kHeads, n), kAtcThreads, kAtcSmemBytes, h->stream>>>(h->map_qkv_q, h->map_qkv_kv, h->ctx.p);
   else
     encoder_attention_kernel<<<dim3(kAttnQTiles, kHeads, n), kAttnThreads, kAttnSmemBytes, h->stream>>>(h->qkv, h->ctx.p);
   CK(cudaGetLastError());
