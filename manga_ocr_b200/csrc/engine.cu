@@ -26,7 +26,6 @@
 #include "../../include/mocr_b200.h"
 #include "common.cuh"
 #include "decode_stages.cuh"
-#include "encoder_attn.cuh"
 #include "encoder_attn_tc.cuh"
 #include "gemm_tcgen05.cuh"
 #include "preprocess.cuh"
@@ -127,14 +126,12 @@ struct mocr_handle {
 
   // tile widths (mocr_set_option)
   int enc_bn = 256;
-  int attn_tc = 1;          // encoder attention on tcgen05 (0: the warp-level mma.sync kernel)
   int dec_tc = 1;           // decoder GEMM stages on the encoder's tcgen05 kernel (bit 0: vocabulary, bit 1: FFN1, bit 2: QKV)
   int row_warps = 2;        // warps (= rows) per CTA of the decoder's row-wise stage kernels
   int carveout = -1;        // shared-memory carve-out (percent) forced on every decoder stage kernel; -1: driver default (set before the first decode)
   int kv_evict_first = 1;   // decoder cross-attention streams the encoder K/V through L2 with an evict-first policy
   int resid_tma = 1;        // encoder residual adds through the TMA reduce-add epilogue (0: per-thread f32 loads/stores)
-  int gemm_pair = 0;        // 1: cta_group::2 GEMM (CTA pairs, 256-row tiles) for the large-M encoder GEMMs; parity-tested, measured no faster (K = 768 tiles are not smem-bound enough)
-  int enc_bn768 = 256;      // tile width of the N = 768 encoder GEMMs (192 gives 2.68 waves instead of 2.007 but measured 3 % slower: the tiles are smem-bandwidth-bound)
+  int enc_bn768 = 256;      // tile width of the N = 768 encoder GEMMs (128 or 256; 192 would give 2.68 waves instead of 2.007, measured 3 % slower)
   int dec_bn = 32;
   int head_bn = 64;
   int check_every = 26;
@@ -377,7 +374,7 @@ int linear_map(mocr_handle* h, Linear* L, int bn, const CUtensorMap** out) {
   auto it = L->maps.find(bn);
   if (it == L->maps.end()) {
     CUtensorMap m;
-    TRY(make_map(h, &m, L->w, L->N, L->K, bn < 0 ? -bn / 2 : bn));
+    TRY(make_map(h, &m, L->w, L->N, L->K, bn));
     it = L->maps.emplace(bn, m).first;
   }
   *out = &it->second;
@@ -511,22 +508,6 @@ int launch_gemm_t(mocr_handle* h, const CUtensorMap& ma, const CUtensorMap& mb, 
   return MOCR_OK;
 }
 
-template <int BN, int EPI>
-int launch_gemm_pair_t(mocr_handle* h, const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& a) {
-  using Cfg = GemmPairCfg<BN>;
-  static bool attr_done[16] = {};
-  if (!attr_done[h->device & 15]) {
-    CK(cudaFuncSetAttribute(gemm_tcgen05_pair_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_done[h->device & 15] = true;
-  }
-  const int tiles = ((a.M + 2 * kGemmBM - 1) / (2 * kGemmBM)) * (a.N / BN);
-  const int pairs = std::min(tiles, h->sms / 2);
-  gemm_tcgen05_pair_kernel<BN, EPI><<<2 * pairs, kGemmThreads, Cfg::kSmemBytes, h->stream>>>(ma, mb, a);
-  CK(cudaGetLastError());
-  ++h->launches;
-  return MOCR_OK;
-}
-
 template <int EPI>
 int launch_gemm_bn(mocr_handle* h, int bn, const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& a) {
   switch (bn) {
@@ -547,19 +528,6 @@ int gemm(mocr_handle* h, int epi, int bn, const ActBuf& A, Linear& L, int M, Gem
   a.N = L.N;
   a.K = L.K;
   a.bias = L.bias;
-  if (h->gemm_pair && bn == 256 && M >= 2 * kGemmBM && epi != EPI_ARGMAX && epi != EPI_F32_GELU && epi != EPI_F32_ACCUM) {
-    // CTA-pair kernel: each CTA loads half of the B tile -> the B descriptor's box is bn/2 rows (cached under key -bn)
-    const CUtensorMap* mbh;
-    TRY(linear_map(h, &L, -bn, &mbh));
-    switch (epi) {
-      case EPI_BF16: return launch_gemm_pair_t<256, EPI_BF16>(h, A.map, *mbh, a);
-      case EPI_BF16_GELU: return launch_gemm_pair_t<256, EPI_BF16_GELU>(h, A.map, *mbh, a);
-      case EPI_F32_RESID: return launch_gemm_pair_t<256, EPI_F32_RESID>(h, A.map, *mbh, a);
-      case EPI_PATCH: return launch_gemm_pair_t<256, EPI_PATCH>(h, A.map, *mbh, a);
-      case EPI_CROSSKV: return launch_gemm_pair_t<256, EPI_CROSSKV>(h, A.map, *mbh, a);
-      default: break;
-    }
-  }
   const CUtensorMap* mb;
   TRY(linear_map(h, &L, bn, &mb));
   if (epi == EPI_F32_ACCUM) {
@@ -899,14 +867,10 @@ int preprocess(mocr_handle* h) {
 int attention197(mocr_handle* h, int n) {
   static bool done[16] = {};
   if (!done[h->device & 15]) {
-    CK(cudaFuncSetAttribute(encoder_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
     CK(cudaFuncSetAttribute(encoder_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtcSmemBytes));
     done[h->device & 15] = true;
   }
-  if (h->attn_tc)
-    encoder_attention_tc_kernel<<<dim3(2, kHeads, n), kAtcThreads, kAtcSmemBytes, h->stream>>>(h->map_qkv_q, h->map_qkv_kv, h->ctx.p);
-  else
-    encoder_attention_kernel<<<dim3(kAttnQTiles, kHeads, n), kAttnThreads, kAttnSmemBytes, h->stream>>>(h->qkv, h->ctx.p);
+  encoder_attention_tc_kernel<<<dim3(2, kHeads, n), kAtcThreads, kAtcSmemBytes, h->stream>>>(h->map_qkv_q, h->map_qkv_kv, h->ctx.p);
   CK(cudaGetLastError());
   ++h->launches;
   return MOCR_OK;
@@ -2080,9 +2044,7 @@ int mocr_set_option(mocr_handle_t* h, const char* key, int value) {
   const std::string k = key;
   auto bn_ok = [](int v) { return v == 32 || v == 64 || v == 128 || v == 192 || v == 256; };
   if (k == "enc_bn" && bn_ok(value) && kD % value == 0) h->enc_bn = value;
-  else if (k == "enc_bn768" && bn_ok(value) && kD % value == 0) h->enc_bn768 = value;
-  else if (k == "gemm_pair") h->gemm_pair = value != 0;
-  else if (k == "attn_tc") h->attn_tc = value != 0;
+  else if (k == "enc_bn768" && (value == 128 || value == 256)) h->enc_bn768 = value;
   else if (k == "dec_bn" && bn_ok(value) && kD % value == 0) h->dec_bn = value;
   else if (k == "head_bn" && bn_ok(value) && kVocab % value == 0) h->head_bn = value;
   else if (k == "check_every" && value >= 1) h->check_every = value;

@@ -349,156 +349,4 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
 }
 
-// ------------------------------------------------------------------ CTA-pair variant ---
-// Same GEMM on `tcgen05.mma.cta_group::2`: two CTAs of a cluster (the two SMs of a TPC) compute one
-// 256 x BN tile.  Each CTA stages its own 128 rows of A and HALF of the B tile (BN/2 rows), the
-// leader CTA issues UMMA 256 x BN x 16 for the pair, and the tensor cores of both SMs read the
-// two B halves from both shared memories.  Per SM and k-block that is 32 KB of TMA writes instead
-// of 48 KB and half the B reads: the single-CTA 128 x 256 tile needs ~187 B/clk of shared-memory
-// bandwidth against the 128 B/clk an SM has (measured: tensor pipe active 42-47 %), the pair
-// needs ~125 B/clk.
-template <int BN>
-struct GemmPairCfg {
-  static constexpr int kStageBytesA = kGemmBM * kGemmBK * 2;
-  static constexpr int kStageBytesB = (BN / 2) * kGemmBK * 2;
-  static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
-  static constexpr int kStagesFit = (200 * 1024) / kStageBytes;
-  static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
-  static constexpr int kTmemCols = 2 * BN <= 32 ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
-};
-
-template <int BN, int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
-gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmArgs args) {
-  using Cfg = GemmPairCfg<BN>;
-  constexpr int kStages = Cfg::kStages;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + kStages * Cfg::kStageBytesA;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
-  uint64_t* full_bar = bars;                    // [kStages]  used in the leader: TMA of both CTAs -> MMA
-  uint64_t* empty_bar = bars + kStages;         // [kStages]  in each CTA: MMA (multicast commit) -> its TMA producer
-  uint64_t* acc_full = bars + 2 * kStages;      // [2]        in each CTA: MMA (multicast commit) -> its epilogue
-  uint64_t* acc_empty = bars + 2 * kStages + 2; // [2]        used in the leader: epilogues of both CTAs -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();      // 0 = leader
-  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
-  const int m_tiles = (args.M + 2 * kGemmBM - 1) / (2 * kGemmBM);
-  const int n_tiles = args.N / BN;
-  const int num_tiles = m_tiles * n_tiles;
-  const int k_blocks = args.K / kGemmBK;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmap_a);
-    tma_prefetch_desc(&tmap_b);
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-    }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 2 * kGemmEpiThreads);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 1) {
-    tmem_alloc2(tmem_slot, Cfg::kTmemCols);
-    tmem_relinquish2();
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();                           // barrier inits and TMEM of both CTAs are in place
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    // ------------------------------------------------ TMA producer (both CTAs) ----------
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int tile = pair; tile < num_tiles; tile += n_pairs) {
-      const int m0 = (tile / n_tiles) * 2 * kGemmBM + static_cast<int>(rank) * kGemmBM;
-      const int n0 = (tile % n_tiles) * BN + static_cast<int>(rank) * (BN / 2);
-      for (int kb = 0; kb < k_blocks; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1u);
-        if (lane == 0) {
-          const uint32_t leader_full = mapa_u32(&full_bar[stage], 0);
-          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);   // bytes of both CTAs
-          tma_load_2d_pair(smem_a + stage * Cfg::kStageBytesA, &tmap_a, leader_full, kb * kGemmBK, m0);
-          tma_load_2d_pair(smem_b + stage * Cfg::kStageBytesB, &tmap_b, leader_full, kb * kGemmBK, n0);
-        }
-        __syncwarp();
-        if (++stage == kStages) { stage = 0; phase ^= 1u; }
-      }
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------ MMA issuer (leader CTA only) ------
-    if (rank == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(2 * kGemmBM, BN);
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int tile = pair; tile < num_tiles; tile += n_pairs, ++it) {
-        const int as = it & 1;
-        const uint32_t aphase = (it >> 1) & 1u;
-        mbar_wait(&acc_empty[as], aphase ^ 1u);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * BN);
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          if (lane == 0) {
-            const uint64_t da = umma_desc_k_sw128(smem_u32(smem_a + stage * Cfg::kStageBytesA));
-            const uint64_t db = umma_desc_k_sw128(smem_u32(smem_b + stage * Cfg::kStageBytesB));
-#pragma unroll
-            for (int k = 0; k < kGemmBK / 16; ++k)
-              umma_bf16_pair(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
-                             static_cast<uint32_t>((kb | k) != 0));
-            umma_commit_pair(&empty_bar[stage]);                      // frees the slot in BOTH CTAs
-            if (kb == k_blocks - 1) umma_commit_pair(&acc_full[as]);  // accumulators complete in both CTAs
-          }
-          __syncwarp();
-          if (++stage == kStages) { stage = 0; phase ^= 1u; }
-        }
-      }
-    }
-  } else {
-    // ------------------------------------------------ epilogue (each CTA drains its 128 rows) ----
-    const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;
-    const uint32_t leader_acc_empty0 = mapa_u32(&acc_empty[0], 0), leader_acc_empty1 = mapa_u32(&acc_empty[1], 0);
-    int it = 0;
-    for (int tile = pair; tile < num_tiles; tile += n_pairs, ++it) {
-      const int as = it & 1;
-      const uint32_t aphase = (it >> 1) & 1u;
-      const int m0 = (tile / n_tiles) * 2 * kGemmBM + static_cast<int>(rank) * kGemmBM;
-      const int nt = tile % n_tiles;
-      const int n0 = nt * BN;
-      const int row = m0 + quad * 32 + lane;
-      const bool row_ok = row < args.M;
-      GemmBiasLanes<BN> bias;
-      gemm_load_bias<BN>(args, n0, half, lane, bias);
-      mbar_wait(&acc_full[as], aphase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * BN);
-      gemm_epilogue_tile<BN, EPI>(args, taddr, row, row_ok, n0, nt, n_tiles, half, bias);
-      tc_fence_before();
-      mbar_arrive_cluster(as == 0 ? leader_acc_empty0 : leader_acc_empty1);
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();                           // the peer may still be reading this CTA's smem / signalling its barriers
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc2(tmem_base, Cfg::kTmemCols);
-  }
-}
-
 }  // namespace mocr

@@ -72,46 +72,6 @@ def test_encoder_attention_against_torch(engine8, n):
     assert np.abs(got - ref).max() < 2e-2
 
 
-@pytest.mark.parametrize("M,N,K,epi", [(256, 768, 256, 0), (333, 768, 768, 0), (1576, 2304, 768, 0), (1576, 3072, 768, 1), (1000, 768, 3072, 2)])
-def test_pair_gemm_cta_group2_against_torch(engine8, M, N, K, epi):
-    """The cta_group::2 variant (two CTAs of a cluster share one 256 x 256 tile) against the same reference."""
-    import torch
-    rng = np.random.default_rng(M + N + K + epi)
-    A = rng.standard_normal((M, K), dtype=np.float32)
-    Wt = rng.standard_normal((N, K), dtype=np.float32) * 0.05
-    b = rng.standard_normal((N,), dtype=np.float32)
-    R = rng.standard_normal((M, N), dtype=np.float32) if epi == 2 else None
-    engine8.set_option("gemm_pair", 1)
-    try:
-        got, _ = engine8.test_gemm(epi, 256, A, Wt, b, R)
-    finally:
-        engine8.set_option("gemm_pair", 0)
-    ref = torch.from_numpy(_bf16(A)).double() @ torch.from_numpy(_bf16(Wt)).double().T + torch.from_numpy(b).double()
-    if epi == 1:
-        ref = torch.nn.functional.gelu(ref)
-    if epi == 2:
-        ref = ref + torch.from_numpy(R).double()
-    err = np.abs(got - ref.numpy()).max()
-    assert err <= (2.0 ** -8 * max(1.0, float(ref.abs().max())) if epi in (0, 1) else 1e-3), err
-
-
-def test_encoder_attention_mma_sync_variant(engine8):
-    """The warp-level mma.sync attention kernel (option attn_tc = 0) stays covered."""
-    import torch
-    rng = np.random.default_rng(9)
-    qkv = rng.standard_normal((2 * 197, 2304), dtype=np.float32)
-    qkv[:, :768] *= 0.25
-    engine8.set_option("attn_tc", 0)
-    try:
-        got = engine8.test_encoder_attention(qkv)
-    finally:
-        engine8.set_option("attn_tc", 1)
-    q = torch.from_numpy(_bf16(qkv)).double().view(2, 197, 3, 12, 64)
-    Q, K, V = (q[:, :, i].transpose(1, 2) for i in range(3))
-    ref = (torch.softmax(Q @ K.transpose(-1, -2), dim=-1) @ V).transpose(1, 2).reshape(2 * 197, 768).numpy()
-    assert np.abs(got - ref).max() < 2e-2
-
-
 # ---- decoder stage kernels (decode_stages.cuh) against fp64 references of the same op ----
 
 @pytest.fixture(scope="module")

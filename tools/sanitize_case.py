@@ -25,7 +25,7 @@ for dev in (1, 0):
     eng.set_option("beam_device", dev)
     ids, lens, scores = eng.recognize_beam(crops[:3], max_length=T, num_beams=2)
     print("beam device", dev, lens.tolist())
-page, sels = C.page_with_selections(4, seed=9, height=300, width=260)
+page, sels = C.page_with_selections(4, seed=9, height=900, width=700)
 ids, lens = eng.recognize_regions(page, [Region.from_qt(r, p, o) for r, p, o in sels], max_length=T)
 print("regions", lens.tolist())
 eng.close()
