@@ -20,6 +20,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -149,6 +150,7 @@ struct mocr_handle {
   int sub_i0 = 0, sub_n = 0;   // sub-range of the staged crops that preprocess / encode work on (sub_n = 0: all of them)
   int beam_device = 1;      // beam search with the selection on the device and the steps in a CUDA graph (0: host bookkeeping, one round trip per step)
   int beam_steps_per_graph = 8;
+  int stage_threads = 6;    // host threads that copy a large batch of crops into the pinned arena (one per 8 MB, at most this many)
   int slots = 0;            // decoder rows of a greedy decode (0 = one per crop).  With fewer rows than crops a row that finishes takes
                             // the next waiting crop (in-flight slot refill): worth it when lengths are ragged (real text); with random-init
                             // weights, which never emit EOS, one row per crop on the large-batch program is faster
@@ -613,15 +615,12 @@ int stage_crops(mocr_handle* h, const mocr_crop_t* crops, int n, int order) {
     CK(cudaMalloc(reinterpret_cast<void**>(&h->d_arena), cap));
     h->arena_cap = cap;
   }
-  size_t off = 0, sent = 0;
+  // descriptors + arena offsets
+  std::vector<size_t> offs(static_cast<size_t>(n) + 1, 0);
+  size_t off = 0;
   for (int i = 0; i < n; ++i) {
     const mocr_crop_t& c = crops[i];
     const size_t rowb = static_cast<size_t>(c.width) * c.channels;
-    if (static_cast<size_t>(c.stride) == rowb) {
-      memcpy(h->h_arena + off, c.data, rowb * c.height);
-    } else {
-      for (int y = 0; y < c.height; ++y) memcpy(h->h_arena + off + y * rowb, c.data + static_cast<size_t>(y) * c.stride, rowb);
-    }
     CropDesc& d = h->h_descs[i];
     d.offset = static_cast<long long>(off);
     d.h = c.height;
@@ -649,11 +648,53 @@ int stage_crops(mocr_handle* h, const mocr_crop_t* crops, int n, int order) {
       d.vks = t.ksize;
       tmp_rows = std::max(tmp_rows, t.strip_rows);
     }
+    offs[i] = off;
     off += (rowb * c.height + 15) & ~static_cast<size_t>(15);
-    if (off - sent >= (1u << 20)) {   // the upload of the crops staged so far overlaps the host copy of the next ones
-      CK(cudaMemcpyAsync(h->d_arena + sent, h->h_arena + sent, off - sent, cudaMemcpyHostToDevice, h->stream));
-      sent = off;
+  }
+  offs[n] = off;
+  // pixels -> pinned arena -> device.  Workers take contiguous runs of crops of about equal bytes; each uploads its run
+  // as soon as it is copied (slices of >= 1 MB), so host copy and H2D overlap and a page batch (100+ MB) is not bound by
+  // one core's memcpy rate.
+  auto copy_run = [&](int lo, int hi) -> cudaError_t {
+    size_t sent = offs[lo];
+    for (int i = lo; i < hi; ++i) {
+      const mocr_crop_t& c = crops[i];
+      const size_t rowb = static_cast<size_t>(c.width) * c.channels;
+      if (static_cast<size_t>(c.stride) == rowb) {
+        memcpy(h->h_arena + offs[i], c.data, rowb * c.height);
+      } else {
+        for (int y = 0; y < c.height; ++y) memcpy(h->h_arena + offs[i] + y * rowb, c.data + static_cast<size_t>(y) * c.stride, rowb);
+      }
+      if (offs[i + 1] - sent >= (1u << 20) || i + 1 == hi) {
+        const cudaError_t e = cudaMemcpyAsync(h->d_arena + sent, h->h_arena + sent, offs[i + 1] - sent, cudaMemcpyHostToDevice, h->stream);
+        if (e != cudaSuccess) return e;
+        sent = offs[i + 1];
+      }
     }
+    return cudaSuccess;
+  };
+  const int workers = static_cast<int>(std::min<size_t>(h->stage_threads, std::max<size_t>(1, off >> 23)));     // one per 8 MB, at most stage_threads
+  if (workers <= 1) {
+    CK(copy_run(0, n));
+  } else {
+    std::vector<std::thread> pool;
+    std::vector<cudaError_t> errs(workers, cudaSuccess);
+    int lo = 0;
+    for (int w = 0; w < workers; ++w) {
+      const size_t target = off * (w + 1) / workers;
+      int hi = lo;
+      while (hi < n && (offs[hi + 1] <= target || w == workers - 1)) ++hi;
+      if (w == workers - 1) hi = n;
+      const int device = h->device;
+      pool.emplace_back([&, w, lo, hi, device]() {
+        cudaSetDevice(device);
+        errs[w] = copy_run(lo, hi);
+      });
+      lo = hi;
+    }
+    for (auto& th : pool) th.join();
+    for (cudaError_t e : errs)
+      if (e != cudaSuccess) return fail(h, MOCR_ERR_CUDA, "crop upload failed: %s", cudaGetErrorString(e));
   }
   h->pre_pitch = round_up(max_w, 16);
   h->pre_tmp_rows = tmp_rows;
@@ -674,7 +715,6 @@ int stage_crops(mocr_handle* h, const mocr_crop_t* crops, int n, int order) {
     // h_coefs is pageable: the copy above is staged synchronously by the runtime, safe to reuse
     h->d_coefs_used = h->h_coefs.size();
   }
-  if (off > sent) CK(cudaMemcpyAsync(h->d_arena + sent, h->h_arena + sent, off - sent, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->d_descs, h->h_descs, sizeof(CropDesc) * n, cudaMemcpyHostToDevice, h->stream));
   h->n = n;
   h->staged_ok = true;
@@ -2057,6 +2097,7 @@ int mocr_set_option(mocr_handle_t* h, const char* key, int value) {
   else if (k == "kv_evict_first" && value >= 0 && value <= 3) h->kv_evict_first = value;
   else if (k == "attn_grid" && value >= 0) h->attn_grid = value;
   else if (k == "slots" && value >= 0) h->slots = value;
+  else if (k == "stage_threads" && value >= 1 && value <= 64) h->stage_threads = value;
   else if (k == "beam_device") h->beam_device = value != 0;
   else if (k == "beam_steps_per_graph" && value >= 1 && value <= 64) h->beam_steps_per_graph = value;
   else if (k == "pipeline" && value >= 0 && value <= 2) h->pipeline = value;
