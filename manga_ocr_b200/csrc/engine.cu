@@ -138,12 +138,15 @@ struct mocr_handle {
   int check_every = 26;
   int use_graph = 1;
   int use_pdl = 1;          // programmatic dependent launch between the decoder's stage kernels
+  int pdl_mask = 0x1ff;     // ... per stage type (bit = PdStageType): kernels of a type whose bit is clear are launched in plain stream order
+  int pdl_now = 1;          // (set per launch by decode_stage_step)
   int steps_per_graph = 13; // decode steps captured in one CUDA graph (299 = 23 x 13)
   int fuse_ln = 1;          // decoder projections that feed a LayerNorm as 16-CTA clusters that normalise the rows themselves (0: split-K partials + LayerNorm stage)
   int kv_prefetch = 0;      // 1: a layer's encoder K/V are requested into L2 by the layer's first stage (bulk prefetch before the dependency wait); measured 2.7 us per step SLOWER at 64 rows (the prefetch competes with the weights for L2)
+  int big_attn_grid = 444;  // CTAs of the attention stages in the large-batch program (0 = one per (row, head) unit): 3 resident per SM measured best (444: 399 us per 512-row step, 1184: 416, one per unit: 432)
   int big_bn768 = 32;       // tile width of the large-batch program's N = 768 GEMMs (32 or 64)
   int big_vocab_bn = 64;    // tile width of its vocabulary projection (64 or 128)
-  int big_rows = 96;        // more decoder rows than this: the large-batch program (every Linear on the tcgen05 GEMM, 128-row tiles)
+  int big_rows = 144;       // more decoder rows than this (measured crossover: 128 rows 207 vs 226 us per step, 160 rows 248 vs 240): the large-batch program (every Linear on the tcgen05 GEMM, 128-row tiles)
   int pipeline = 0;         // with slot refill, 1 (2: equal stream priorities): encode the waiting crops in sub-chunks on a second stream while the decoder
                             // already runs.  Measured on the ragged 512-crop leg: 116 ms (80 ms at equal priorities) against 75 ms with the encoder
                             // serialised in front - the 200 KB GEMM CTAs and the decoder's stage kernels do not share SMs well - so it is off
@@ -1060,7 +1063,7 @@ cudaError_t launch_pdl(mocr_handle* h, void (*kernel)(KArgs...), int grid, int b
   cfg.stream = h->stream;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = h->use_pdl ? 1 : 0;
+  at[0].val.programmaticStreamSerializationAllowed = (h->use_pdl && h->pdl_now) ? 1 : 0;
   cfg.attrs = at;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kernel, args...);
@@ -1074,7 +1077,7 @@ cudaError_t launch_pdl_grid(mocr_handle* h, void (*kernel)(KArgs...), dim3 grid,
   cfg.stream = h->stream;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = h->use_pdl ? 1 : 0;
+  at[0].val.programmaticStreamSerializationAllowed = (h->use_pdl && h->pdl_now) ? 1 : 0;
   cfg.attrs = at;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kernel, args...);
@@ -1169,9 +1172,12 @@ int decode_stage_step(mocr_handle* h, const PdParams& p, bool skip_next = false)
   // many SMs (8 CTAs of 8 warps made 8 SMs pull 98 KB each at ~75 GB/s per SM: 1.3 us of the stage's 2.6)
   const int row_warps = p.big ? kPdWarps : std::max(1, std::min(h->row_warps, kPdWarps));
   const int row_ctas = (p.B + row_warps - 1) / row_warps;
-  const int attn_grid = (h->attn_grid > 0 && !p.big) ? std::min(h->attn_grid, p.B * kHeads) : std::min(p.B * kHeads, 8 * h->sms);
+  const int attn_grid = p.big ? std::min(p.B * kHeads, h->big_attn_grid > 0 ? h->big_attn_grid : p.B * kHeads)
+                              : (h->attn_grid > 0 ? std::min(h->attn_grid, p.B * kHeads) : p.B * kHeads);
+  struct PdlReset { mocr_handle* h; ~PdlReset() { h->pdl_now = 1; } } pdl_reset{h};
   for (int i = 0; i < n_stages; ++i) {
     const PdStage& st = prog[i];
+    h->pdl_now = (h->pdl_mask >> st.type) & 1;
     if (st.type == PD_TC) {
       TRY(launch_tc_stage(h, p, st));
     } else if (st.type == PD_GEMM16 || st.type == PD_GEMM32 || st.type == PD_GEMM48) {
@@ -2090,6 +2096,7 @@ int mocr_set_option(mocr_handle_t* h, const char* key, int value) {
   else if (k == "check_every" && value >= 1) h->check_every = value;
   else if (k == "use_graph") h->use_graph = value != 0;
   else if (k == "use_pdl") h->use_pdl = value != 0;
+  else if (k == "pdl_mask" && value >= 0) h->pdl_mask = value;
   else if (k == "resid_tma") h->resid_tma = value != 0;
   else if (k == "row_warps" && value >= 1 && value <= 8) h->row_warps = value;
   else if (k == "dec_tc" && value >= 0 && value <= 7) h->dec_tc = value;
@@ -2104,6 +2111,7 @@ int mocr_set_option(mocr_handle_t* h, const char* key, int value) {
   else if (k == "fuse_ln") h->fuse_ln = value != 0;
   else if (k == "kv_prefetch") h->kv_prefetch = value != 0;
   else if (k == "big_rows" && value >= 1) h->big_rows = value;
+  else if (k == "big_attn_grid" && value >= 0) h->big_attn_grid = value;
   else if (k == "big_bn768" && (value == 32 || value == 64)) h->big_bn768 = value;
   else if (k == "big_vocab_bn" && (value == 64 || value == 128)) h->big_vocab_bn = value;
   else if (k == "steps_per_graph" && value >= 1 && value <= 64) h->steps_per_graph = value;
