@@ -689,10 +689,14 @@ int stage_crops(mocr_handle* h, const mocr_crop_t* crops, int n, int order) {
       while (hi < n && (offs[hi + 1] <= target || w == workers - 1)) ++hi;
       if (w == workers - 1) hi = n;
       const int device = h->device;
-      pool.emplace_back([&, w, lo, hi, device]() {
-        cudaSetDevice(device);
+      try {
+        pool.emplace_back([&, w, lo, hi, device]() {
+          cudaSetDevice(device);
+          errs[w] = copy_run(lo, hi);
+        });
+      } catch (...) {          // no thread to be had: this run is copied here (nothing may cross the C ABI as an exception)
         errs[w] = copy_run(lo, hi);
-      });
+      }
       lo = hi;
     }
     for (auto& th : pool) th.join();
@@ -1373,11 +1377,11 @@ int recognize_pipelined(mocr_handle* h, const mocr_crop_t* crops, int m, int ord
   TRY(decode_step_graph(h, pdp, false, false, &exec, &per_step));
   CK(cudaStreamSynchronize(h->stream));
   cudaStream_t dec_stream = h->stream;
-  struct Restore {
-    mocr_handle* h; cudaStream_t s;
-    ~Restore() { h->stream = s; h->sub_i0 = 0; h->sub_n = 0; }
-  } restore{h, dec_stream};
   cudaStream_t enc_stream = h->pipeline == 2 ? h->stream_enc_hi : h->stream_enc;
+  struct Restore {      // also on an error path: the handle's stream is the decoder stream again and the encoder stream has drained
+    mocr_handle* h; cudaStream_t s; cudaStream_t e;
+    ~Restore() { h->stream = s; h->sub_i0 = 0; h->sub_n = 0; cudaStreamSynchronize(e); }
+  } restore{h, dec_stream, enc_stream};
   h->stream = enc_stream;                               // everything encoder-side goes to the encoder stream
   TRY(stage_crops(h, crops, m, order));
   for (int i0 = 0; i0 < m; i0 += sub) {
@@ -1509,6 +1513,20 @@ int d2h(mocr_handle* h, void* dst, const void* src, size_t bytes) {
   return MOCR_OK;
 }
 
+// No C++ exception may cross the C ABI (std::bad_alloc from a staging vector, std::system_error from a thread).
+template <class F>
+int guarded(mocr_handle* h, F&& f) {
+  try {
+    return f();
+  } catch (const std::bad_alloc&) {
+    return fail(h, MOCR_ERR_CAPACITY, "out of host memory");
+  } catch (const std::exception& e) {
+    return fail(h, MOCR_ERR_INVALID, "unexpected exception: %s", e.what());
+  } catch (...) {
+    return fail(h, MOCR_ERR_INVALID, "unexpected exception");
+  }
+}
+
 }  // namespace
 
 // ===================================================================== C ABI ===
@@ -1596,13 +1614,13 @@ int mocr_finalize_weights(mocr_handle_t* h) {
 int mocr_stage_crops(mocr_handle_t* h, const mocr_crop_t* crops, int n, int channel_order) {
   TRY(check_handle(h));
   std::lock_guard<std::mutex> lock(h->mu);
-  return stage_crops(h, crops, n, channel_order);
+  return guarded(h, [&]() -> int { return stage_crops(h, crops, n, channel_order); });
 }
 
 int mocr_stage_regions(mocr_handle_t* h, const mocr_crop_t* page, const mocr_region_t* regions, int n, int channel_order) {
   TRY(check_handle(h));
   std::lock_guard<std::mutex> lock(h->mu);
-  return stage_regions(h, page, regions, n, channel_order);
+  return guarded(h, [&]() -> int { return stage_regions(h, page, regions, n, channel_order); });
 }
 
 int mocr_recognize_regions(mocr_handle_t* h, const mocr_crop_t* page, const mocr_region_t* regions, int n, int channel_order, int max_length,
@@ -1610,15 +1628,17 @@ int mocr_recognize_regions(mocr_handle_t* h, const mocr_crop_t* page, const mocr
   TRY(check_handle(h));
   std::lock_guard<std::mutex> lock(h->mu);
   if (n < 0 || (n > 0 && (page == nullptr || regions == nullptr || out_ids == nullptr))) return fail(h, MOCR_ERR_INVALID, "bad argument");
-  for (int i0 = 0; i0 < n; i0 += h->max_batch) {
-    const int m = std::min(h->max_batch, n - i0);
-    TRY(stage_regions(h, page, regions + i0, m, channel_order));
-    TRY(preprocess(h));
-    TRY(encode(h));
-    TRY(decode(h, max_length, nullptr));
-    TRY(fetch_ids(h, out_ids + static_cast<size_t>(i0) * max_length, out_lens ? out_lens + i0 : nullptr));
-  }
-  return MOCR_OK;
+  return guarded(h, [&]() -> int {
+    for (int i0 = 0; i0 < n; i0 += h->max_batch) {
+      const int m = std::min(h->max_batch, n - i0);
+      TRY(stage_regions(h, page, regions + i0, m, channel_order));
+      TRY(preprocess(h));
+      TRY(encode(h));
+      TRY(decode(h, max_length, nullptr));
+      TRY(fetch_ids(h, out_ids + static_cast<size_t>(i0) * max_length, out_lens ? out_lens + i0 : nullptr));
+    }
+    return MOCR_OK;
+  });
 }
 
 int mocr_get_region_mask(mocr_handle_t* h, int index, uint8_t* out) {
@@ -1633,19 +1653,19 @@ int mocr_get_region_mask(mocr_handle_t* h, int index, uint8_t* out) {
 int mocr_preprocess(mocr_handle_t* h) {
   TRY(check_handle(h));
   std::lock_guard<std::mutex> lock(h->mu);
-  return preprocess(h);
+  return guarded(h, [&]() -> int { return preprocess(h); });
 }
 
 int mocr_encode(mocr_handle_t* h) {
   TRY(check_handle(h));
   std::lock_guard<std::mutex> lock(h->mu);
-  return encode(h);
+  return guarded(h, [&]() -> int { return encode(h); });
 }
 
 int mocr_decode_greedy(mocr_handle_t* h, int max_length, const int32_t* forced_ids) {
   TRY(check_handle(h));
   std::lock_guard<std::mutex> lock(h->mu);
-  return decode(h, max_length, forced_ids);
+  return guarded(h, [&]() -> int { return decode(h, max_length, forced_ids); });
 }
 
 int mocr_fetch_ids(mocr_handle_t* h, int32_t* out_ids, int32_t* out_lens) {
@@ -1668,19 +1688,21 @@ int mocr_recognize(mocr_handle_t* h, const mocr_crop_t* crops, int n, int channe
   TRY(check_handle(h));
   std::lock_guard<std::mutex> lock(h->mu);
   if (n < 0 || (n > 0 && (crops == nullptr || out_ids == nullptr))) return fail(h, MOCR_ERR_INVALID, "bad argument");
-  for (int i0 = 0; i0 < n; i0 += h->max_batch) {
-    const int m = std::min(h->max_batch, n - i0);
-    if (h->slots > 0 && h->pipeline && m > h->slots && h->taps == 0) {
-      TRY(recognize_pipelined(h, crops + i0, m, channel_order, max_length));
-    } else {
-      TRY(stage_crops(h, crops + i0, m, channel_order));
-      TRY(preprocess(h));
-      TRY(encode(h));
-      TRY(decode(h, max_length, nullptr));
+  return guarded(h, [&]() -> int {
+    for (int i0 = 0; i0 < n; i0 += h->max_batch) {
+      const int m = std::min(h->max_batch, n - i0);
+      if (h->slots > 0 && h->pipeline && m > h->slots && h->taps == 0) {
+        TRY(recognize_pipelined(h, crops + i0, m, channel_order, max_length));
+      } else {
+        TRY(stage_crops(h, crops + i0, m, channel_order));
+        TRY(preprocess(h));
+        TRY(encode(h));
+        TRY(decode(h, max_length, nullptr));
+      }
+      TRY(fetch_ids(h, out_ids + static_cast<size_t>(i0) * max_length, out_lens ? out_lens + i0 : nullptr));
     }
-    TRY(fetch_ids(h, out_ids + static_cast<size_t>(i0) * max_length, out_lens ? out_lens + i0 : nullptr));
-  }
-  return MOCR_OK;
+    return MOCR_OK;
+  });
 }
 
 int decode_beam_device(mocr_handle* h, int beams, int max_length, int ngram, float length_penalty, int early, int32_t* out_ids, int32_t* out_lens,
@@ -1956,7 +1978,7 @@ int mocr_decode_beam(mocr_handle_t* h, int num_beams, int max_length, int no_rep
                      int32_t* out_ids, int32_t* out_lens, float* out_scores) {
   TRY(check_handle(h));
   std::lock_guard<std::mutex> lock(h->mu);
-  return decode_beam(h, num_beams, max_length, no_repeat_ngram_size, length_penalty, early_stopping, out_ids, out_lens, out_scores);
+  return guarded(h, [&]() -> int { return decode_beam(h, num_beams, max_length, no_repeat_ngram_size, length_penalty, early_stopping, out_ids, out_lens, out_scores); });
 }
 
 // Crops / selections -> beam-search hypotheses in ONE call: the handle's mutex is held from staging to the result, so
@@ -1986,8 +2008,8 @@ int mocr_recognize_beam(mocr_handle_t* h, const mocr_crop_t* crops, int n, int c
                         float* out_scores) {
   TRY(check_handle(h));
   std::lock_guard<std::mutex> lock(h->mu);
-  return recognize_beam_impl(h, crops, nullptr, nullptr, n, channel_order, max_length, num_beams, no_repeat_ngram_size, length_penalty,
-                             early_stopping, out_ids, out_lens, out_scores);
+  return guarded(h, [&]() -> int { return recognize_beam_impl(h, crops, nullptr, nullptr, n, channel_order, max_length, num_beams, no_repeat_ngram_size, length_penalty,
+                             early_stopping, out_ids, out_lens, out_scores); });
 }
 
 int mocr_recognize_regions_beam(mocr_handle_t* h, const mocr_crop_t* page, const mocr_region_t* regions, int n, int channel_order,

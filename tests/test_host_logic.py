@@ -154,3 +154,131 @@ def test_generation_config_is_read_from_the_checkpoint_directory(tmp_path):
     (tmp_path / "generation_config.json").write_text(json.dumps({"num_beams": 4, "no_repeat_ngram_size": 3, "early_stopping": True}))
     g = _generation_config(str(tmp_path / "model.safetensors"))
     assert g == {"num_beams": 4, "no_repeat_ngram_size": 3, "length_penalty": 1.0, "early_stopping": True}
+
+
+# ---- the cross-thread micro-batcher, with stub engines (no GPU): batching, fair share, failure isolation, lifetime ----
+
+class _StubEngine:
+    """Stands in for manga_ocr_b200.engine.Engine: ids row = [CLS, marker of the crop, SEP]; a crop whose first pixel is 13
+    makes the whole call fail, like one malformed crop fails a library call."""
+    instances = []
+
+    def __init__(self, weights, device=0, max_batch=64, max_length=300):
+        self.device, self.max_batch, self.max_length = device, max_batch, max_length
+        self.batches = []
+        self.closed = False
+        _StubEngine.instances.append(self)
+
+    def set_option(self, key, value):
+        pass
+
+    def recognize(self, arrays, order=0, max_length=None):
+        import time
+        self.batches.append(len(arrays))
+        time.sleep(0.02)                       # a GPU batch takes a while: callers pile up behind it
+        if any(int(a.flat[0]) == 13 for a in arrays):
+            raise RuntimeError("bad crop in batch")
+        T = max_length or self.max_length
+        ids = np.zeros((len(arrays), T), np.int32)
+        ids[:, 0] = 2
+        for i, a in enumerate(arrays):
+            ids[i, 1] = 5 + int(a.flat[0])
+            ids[i, 2] = 3
+        return ids, np.full(len(arrays), 3, np.int32)
+
+    def close(self):
+        self.closed = True
+
+
+@pytest.fixture
+def stub_ocr(monkeypatch):
+    _StubEngine.instances = []
+    monkeypatch.setattr(O, "Engine", _StubEngine)
+    made = []
+
+    def make(**kw):
+        kw.setdefault("warmup", False)
+        o = O.MangaOcr(weights={"x": np.zeros(1, np.float32)}, **kw)
+        made.append(o)
+        return o
+
+    monkeypatch.setattr(O.W, "complete", lambda w: w)
+    yield make
+    for o in made:
+        o.close()
+
+
+def _img(v):
+    return Image.fromarray(np.full((4, 4, 3), v, np.uint8))
+
+
+def _call_all(ocr, values):
+    import threading
+    out = {}
+
+    def run(i, v):
+        try:
+            out[i] = ocr(_img(v))
+        except Exception as e:      # noqa: BLE001
+            out[i] = e
+
+    ts = [threading.Thread(target=run, args=(i, v)) for i, v in enumerate(values)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    return [out[i] for i in range(len(values))]
+
+
+def test_micro_batcher_gathers_concurrent_callers(stub_ocr):
+    ocr = stub_ocr(devices=[0], max_batch=16, max_length=8, linger_ms=20)
+    vocab = ocr.vocab
+    got = _call_all(ocr, list(range(12)))
+    assert got == [O.ids_to_texts(vocab, np.array([[2, 5 + v, 3, 0]]))[0] for v in range(12)]
+    eng = _StubEngine.instances[0]
+    assert sum(eng.batches) == 12 and max(eng.batches) >= 6, eng.batches      # not twelve batches of one
+
+
+def test_micro_batcher_shares_the_queue_between_gpus(stub_ocr):
+    ocr = stub_ocr(devices=[0, 1], max_batch=64, max_length=8, linger_ms=20)
+    got = _call_all(ocr, [v for v in range(41) if v != 13])
+    assert all(isinstance(g, str) for g in got)
+    a, b = (sum(e.batches) for e in _StubEngine.instances)
+    assert a + b == 40 and min(a, b) >= 8, (a, b)                              # nobody grabbed the whole queue
+
+
+def test_micro_batcher_isolates_a_failing_request(stub_ocr):
+    ocr = stub_ocr(devices=[0], max_batch=16, max_length=8, linger_ms=20)
+    got = _call_all(ocr, [1, 2, 13, 4, 5])
+    assert isinstance(got[2], RuntimeError)
+    assert [isinstance(g, str) for g in got] == [True, True, False, True, True]
+    assert ocr(_img(7)) == got[0][:0] + O.ids_to_texts(ocr.vocab, np.array([[2, 12, 3]]))[0]      # still usable
+    with pytest.raises(ValueError):
+        ocr(Image.fromarray(np.zeros((3, 40000, 3), np.uint8)))                # refused before it is queued
+
+
+def test_instance_lifetime_close_and_collection(stub_ocr):
+    import gc
+    import weakref
+    ocr = stub_ocr(devices=[0], max_batch=4, max_length=8, linger_ms=0)
+    assert isinstance(ocr(_img(3)), str)
+    ocr.close()
+    assert _StubEngine.instances[0].closed and all(not t.is_alive() for t in ocr._threads)
+    with pytest.raises(RuntimeError):
+        ocr(_img(3))
+    ocr.close()                                                                # idempotent
+    # an instance that is dropped without close() is collected: its dispatcher threads hold it weakly
+    _StubEngine.instances = []
+    o2 = O.MangaOcr(weights={"x": np.zeros(1, np.float32)}, devices=[0], max_batch=4, max_length=8, warmup=False)
+    threads = list(o2._threads)
+    ref = weakref.ref(o2)
+    del o2
+    gc.collect()
+    assert ref() is None
+    for t in threads:
+        t.join(timeout=5)
+        assert not t.is_alive()
+    assert _StubEngine.instances[0].closed
+    with stub_ocr(devices=[0], max_batch=4, max_length=8) as o3:               # context manager
+        assert isinstance(o3(_img(1)), str)
+    assert o3._closed
