@@ -913,21 +913,31 @@ __device__ __forceinline__ void cp_async16_zero(void* smem_dst, const void* any_
 // conflict-free.  V rows past the last key are zero-filled (their probabilities are 0, but 0 x garbage
 // could be NaN inside the MMA).  self: the row at index pos is this token's K/V, taken from the QKV buffer
 // and appended to the cache here (modeling_bert.py:190 re-concatenates the whole cache instead).
-template <bool HINT>
+template <bool SELF, bool HINT>
 __device__ __forceinline__ void pd_attn_request_t(uint4* stage, const PdAttnUnit& a, int key_stride, int j0, int gt, uint64_t pol) {
   const int gw = gt >> 5, sub = (gt & 31) >> 3, ch = gt & 7;
-  if (j0 + 32 * gw >= a.n_keys) return;                 // warp-uniform: nothing of this warp's range exists
-  int fresh_j = -1;
-#pragma unroll 1
+  const int kl0 = 32 * gw + sub;                        // this lane's first key of the block; its others follow every 4 keys
+  const int left = a.n_keys - (j0 + 32 * gw);           // keys of this warp's range that exist (warp-uniform)
+  if (left <= 0) return;
+  // (kl & 7) = (sub + 4 i) & 7 = sub + 4 (i & 1): two swizzled chunk positions per lane, fixed strides between the slots
+  uint4* kd0 = stage + kl0 * 8;
+  const int sw0 = ch ^ sub, sw1 = ch ^ (sub + 4);
+  const __nv_bfloat16* ks0 = a.kc + static_cast<size_t>(j0 + kl0) * key_stride;
+  const __nv_bfloat16* vs0 = a.vc + static_cast<size_t>(j0 + kl0) * key_stride;
+  const int mine = left - sub;                          // slot i exists iff 4 i < mine
+  int fresh_i = -1;
+#pragma unroll
   for (int i = 0; i < kPdKeySlots; ++i) {
-    const int kl = 32 * gw + 4 * i + sub;               // key index inside the block
-    const int j = j0 + kl;
-    uint4* kd = stage + kl * 8 + (ch ^ (kl & 7));
+    uint4* kd = kd0 + i * 32 + ((i & 1) ? sw1 : sw0);
     uint4* vd = kd + kPdKeySlots * 128;
-    if (j < a.n_keys) {
-      const bool fresh = j == a.ps;
-      const __nv_bfloat16* ks = fresh ? a.nk : a.kc + static_cast<size_t>(j) * key_stride;
-      const __nv_bfloat16* vs = fresh ? a.nv : a.vc + static_cast<size_t>(j) * key_stride;
+    if (4 * i < mine) {
+      const __nv_bfloat16* ks = ks0 + static_cast<size_t>(4 * i) * key_stride;
+      const __nv_bfloat16* vs = vs0 + static_cast<size_t>(4 * i) * key_stride;
+      if (SELF && j0 + kl0 + 4 * i == a.ps) {           // this token's row comes from the QKV buffer, not from the cache
+        ks = a.nk;
+        vs = a.nv;
+        fresh_i = i;
+      }
       if (HINT) {
         cp_async16_cg_hint(kd, ks, pol);
         cp_async16_cg_hint(vd, vs, pol);
@@ -935,15 +945,15 @@ __device__ __forceinline__ void pd_attn_request_t(uint4* stage, const PdAttnUnit
         cp_async16_cg(kd, ks);
         cp_async16_cg(vd, vs);
       }
-      if (fresh) fresh_j = j;
     } else {
       cp_async16_zero(vd, a.vc);
     }
   }
-  if (fresh_j >= 0) {    // append this token's row to the cache (8 lanes, 16 bytes each, per K and V) once the stream is issued
+  if (SELF && fresh_i >= 0) {    // append this token's row to the cache (8 lanes, 16 bytes each, per K and V) once the stream is issued
     const uint4 kq = ldg_cg16(a.nk), vq = ldg_cg16(a.nv);
-    *reinterpret_cast<uint4*>(const_cast<__nv_bfloat16*>(a.kc) + static_cast<size_t>(fresh_j) * key_stride) = kq;
-    *reinterpret_cast<uint4*>(const_cast<__nv_bfloat16*>(a.vc) + static_cast<size_t>(fresh_j) * key_stride) = vq;
+    const size_t fresh_j = static_cast<size_t>(j0 + kl0 + 4 * fresh_i);
+    *reinterpret_cast<uint4*>(const_cast<__nv_bfloat16*>(a.kc) + fresh_j * key_stride) = kq;
+    *reinterpret_cast<uint4*>(const_cast<__nv_bfloat16*>(a.vc) + fresh_j * key_stride) = vq;
   }
 }
 
@@ -1068,8 +1078,8 @@ __device__ __forceinline__ void pd_attention_stage(Bar& bar, uint8_t* smem, cons
   const bool stream_kv = SELF ? (p.kv_evict_first & 2) != 0 : (p.kv_evict_first & 1) != 0;
   const uint64_t pol = stream_kv ? l2_policy_evict_first() : 0ull;
   auto request = [&](uint4* stage, const PdAttnUnit& a, int j0) {
-    if (stream_kv) pd_attn_request_t<true>(stage, a, key_stride, j0, gt, pol);
-    else pd_attn_request_t<false>(stage, a, key_stride, j0, gt, 0ull);
+    if (stream_kv) pd_attn_request_t<SELF, true>(stage, a, key_stride, j0, gt, pol);
+    else pd_attn_request_t<SELF, false>(stage, a, key_stride, j0, gt, 0ull);
   };
   // cross: which crop the first unit's row decodes is read speculatively before the dependency wait (it changes only when
   // the row finishes and takes the next waiting crop) and checked again after it
