@@ -179,6 +179,7 @@ int mocr_test_encoder_attention(mocr_handle_t* h, int n, const float* qkv /*[n*1
  *            (returned in out_k_row / out_v_row when not NULL); n_ctx <= max_length
  *   mode 0 = cross-attention (modeling_bert.py:210-284) over k/v [n_rows, 197, 768], query as fp32 split-K partials
  *   mode 2 = the same with complete bf16 query rows (the large-batch program)
+ *   mode 3 / 4 = mode 1 / mode 2 through the warp-per-unit attention kernel of the large-batch program
  * mocr_test_stage_gemm: out[n_rows, N] of one small-M GEMM stage; kind 0 bf16, 1 bf16 + GELU, 2 split-K partials (summed + bias),
  *   3 vocabulary arg-max (out = logits, N = 6144), 4 projection + residual + LayerNorm fused in the 16-CTA cluster kernel
  *   (N = K = 768), 5 the same as split-K partials + the LayerNorm row stage. */

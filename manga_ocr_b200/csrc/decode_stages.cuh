@@ -913,7 +913,8 @@ __device__ __forceinline__ void cp_async16_zero(void* smem_dst, const void* any_
 // conflict-free.  V rows past the last key are zero-filled (their probabilities are 0, but 0 x garbage
 // could be NaN inside the MMA).  self: the row at index pos is this token's K/V, taken from the QKV buffer
 // and appended to the cache here (modeling_bert.py:190 re-concatenates the whole cache instead).
-template <bool SELF, bool HINT>
+// KEYS = key rows of the stage's K region (V follows it): 128 in the four-warp kernel, 32 in the warp-per-unit kernel (gt = lane).
+template <bool SELF, bool HINT, int KEYS = 16 * kPdKeySlots>
 __device__ __forceinline__ void pd_attn_request_t(uint4* stage, const PdAttnUnit& a, int key_stride, int j0, int gt, uint64_t pol) {
   const int gw = gt >> 5, sub = (gt & 31) >> 3, ch = gt & 7;
   const int kl0 = 32 * gw + sub;                        // this lane's first key of the block; its others follow every 4 keys
@@ -929,7 +930,7 @@ __device__ __forceinline__ void pd_attn_request_t(uint4* stage, const PdAttnUnit
 #pragma unroll
   for (int i = 0; i < kPdKeySlots; ++i) {
     uint4* kd = kd0 + i * 32 + ((i & 1) ? sw1 : sw0);
-    uint4* vd = kd + kPdKeySlots * 128;
+    uint4* vd = kd + KEYS * 8;
     if (4 * i < mine) {
       const __nv_bfloat16* ks = ks0 + static_cast<size_t>(4 * i) * key_stride;
       const __nv_bfloat16* vs = vs0 + static_cast<size_t>(4 * i) * key_stride;
@@ -1420,6 +1421,209 @@ __global__ void __launch_bounds__(128) pd_attention_kernel(const __grid_constant
   bar.begin(p.prof, st.type * 100);
   pdl_launch_dependents();
   pd_attention_stage<SELF>(bar, pd_smem, p, st);
+}
+// ---- large-batch attention: ONE WARP per (row, head) unit ------------------------------------------------------
+// With hundreds of rows there are thousands of units per stage, and the four-warp form above pays per unit what it
+// was built to shorten per unit: two named barriers, a shared-memory merge of four partial states and a 128-key
+// block granularity that a short self-attention context leaves three quarters empty.  Here a warp owns a unit from
+// its query to its context row: 32-key chunks (K and V, 8 KB) flow through the warp's own two-deep cp.async ring,
+// the online-softmax state never leaves registers, the only synchronisation is __syncwarp, and the first chunk of
+// the warp's next unit is requested while the last chunk of this one is reduced.  Same arithmetic as the four-warp
+// form (m16n8k16 with the query in row 0), one sequential softmax chain per unit: results do not depend on the
+// batch size or on the grid.  (modeling_bert.py:143-207 self, :210-284 cross.)
+constexpr int kPdRowsChunkBytes = 2 * 32 * 128;                     // K and V rows of 32 keys
+constexpr int kPdAttnRowsSmemBytes = 4 * 2 * kPdRowsChunkBytes;     // 4 warps x 2 chunks = 64 KB (three CTAs per SM)
+
+template <bool SELF>
+__global__ void __launch_bounds__(128) pd_attention_rows_kernel(const __grid_constant__ PdParams p, const __grid_constant__ PdStage st) {
+  extern __shared__ __align__(128) uint8_t pd_smem[];
+  StageDep bar;
+  bar.begin(p.prof, st.type * 100 + 1);
+  pdl_launch_dependents();
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, ch = lane & 7;
+  uint4* const ring = reinterpret_cast<uint4*>(pd_smem + w * 2 * kPdRowsChunkBytes);
+  const uint32_t ring_addr = smem_u32(ring);
+  const PdLayer& L = p.layer[st.layer];
+  const __nv_bfloat16* kbase = SELF ? L.self_k : p.crosskv + static_cast<size_t>(st.layer * 2) * kHeads * kEncTokens * kHeadDim;
+  const __nv_bfloat16* vbase = SELF ? L.self_v : p.crosskv + static_cast<size_t>(st.layer * 2 + 1) * kHeads * kEncTokens * kHeadDim;
+  const long long b_stride = SELF ? static_cast<long long>(p.cache_len) * kD : static_cast<long long>(kEncTokens) * 4 * kD;
+  const int key_stride = SELF ? kD : kHeadDim;
+  const int head_stride = SELF ? kHeadDim : kEncTokens * kHeadDim;
+  const int units = p.B * kHeads;
+  const int ustride = gridDim.x * 4;
+  const int u0 = blockIdx.x * 4 + w;
+  const bool stream_kv = SELF ? (p.kv_evict_first & 2) != 0 : (p.kv_evict_first & 1) != 0;
+  const uint64_t pol = stream_kv ? l2_policy_evict_first() : 0ull;
+  const __nv_bfloat16* qsrc = SELF ? p.qkv : st.A;                  // complete bf16 query rows
+  const int q_ld = SELF ? 3 * kD : kD;
+
+  auto make_unit = [&](int u, int fin, int pos, int kvr) {          // pos: self = the row's position; cross = the crop the row decodes
+    PdAttnUnit a;
+    a.b = u / kHeads;
+    a.h = u - a.b * kHeads;
+    a.crop = SELF ? 0 : pos;
+    const int kvb = SELF ? kvr : (pos < 0 ? 0 : pos) / p.kv_div;
+    a.kc = kbase + static_cast<size_t>(kvb) * b_stride + static_cast<size_t>(a.h) * head_stride + ch * 8;
+    a.vc = vbase + static_cast<size_t>(kvb) * b_stride + static_cast<size_t>(a.h) * head_stride + ch * 8;
+    a.nk = a.nv = nullptr;
+    a.ps = -1;
+    a.n_keys = kEncTokens;
+    if (SELF) {
+      a.ps = pos;
+      a.n_keys = pos + 1;
+      a.nk = p.qkv + static_cast<size_t>(a.b) * 3 * kD + kD + a.h * kHeadDim + ch * 8;
+      a.nv = a.nk + kD;
+    }
+    a.skip = fin != 0 && p.forced == nullptr;
+    if (a.skip) a.n_keys = 0;
+    return a;
+  };
+  auto request = [&](int par, const PdAttnUnit& a, int j0) {
+    uint4* stage = ring + par * (kPdRowsChunkBytes / 16);
+    if (stream_kv) pd_attn_request_t<SELF, true, 32>(stage, a, key_stride, j0, lane, pol);
+    else pd_attn_request_t<SELF, false, 32>(stage, a, key_stride, j0, lane, 0ull);
+  };
+  // The query as A fragments, read straight into the row-0 quad (lane t < 4): per 16-dim k-step ks,
+  // a0 = q[16ks + 2t, +1] and a2 = q[16ks + 8 + 2t, +1]; lanes >= 4 keep 0 (rows 1-15 of the A operand).
+  struct QFrag { uint32_t a[4][2]; };
+  auto issue_q = [&](int u, QFrag& f) {
+    const int b = u / kHeads, h = u - b * kHeads;
+    const int* src = reinterpret_cast<const int*>(qsrc + static_cast<size_t>(b) * q_ld + h * kHeadDim) + lane;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      f.a[ks][0] = lane < 4 ? static_cast<uint32_t>(ldg_cg_s32(src + 8 * ks)) : 0u;
+      f.a[ks][1] = lane < 4 ? static_cast<uint32_t>(ldg_cg_s32(src + 8 * ks + 4)) : 0u;
+    }
+  };
+
+  bar.wait();
+  // lane k holds the row state of the warp's k-th unit: one round trip covers (up to) 32 units
+  int s_fin = 0, s_pos = 0, s_kvr = 0;
+  auto load_states = [&](int k0) {
+    const int uk = u0 + (k0 + lane) * ustride;
+    s_fin = 1; s_pos = 0; s_kvr = 0;
+    if (uk < units) {
+      const int b = uk / kHeads;
+      s_fin = ldg_cg_s32(p.finished + b);
+      s_pos = ldg_cg_s32((SELF ? p.pos : p.slot_crop) + b);
+      s_kvr = (SELF && p.kv_row != nullptr) ? ldg_cg_s32(p.kv_row + b) : b;
+    }
+  };
+  load_states(0);
+  QFrag qa{}, q_nxt{};
+  if (u0 < units) issue_q(u0, qa);
+  bool have0 = false;        // chunk 0 of the current unit is already on its way (requested during the previous unit)
+  int par = 0, k = 0;
+  const int t2 = 2 * (lane & 3);
+#pragma unroll 1
+  for (int u = u0; u < units; u += ustride, ++k) {
+    if (k != 0 && (k & 31) == 0) load_states(k);
+    const PdAttnUnit cur = make_unit(u, __shfl_sync(0xffffffffu, s_fin, k & 31), __shfl_sync(0xffffffffu, s_pos, k & 31),
+                                     __shfl_sync(0xffffffffu, s_kvr, k & 31));
+    const int nu = u + ustride;
+    PdAttnUnit nxt = cur;
+    bool nxt_live = false;
+    if (nu < units) {
+      issue_q(nu, q_nxt);
+      if (((k + 1) & 31) != 0) {                  // (its state is in this batch of 32; otherwise it is requested when it starts)
+        nxt = make_unit(nu, __shfl_sync(0xffffffffu, s_fin, (k + 1) & 31), __shfl_sync(0xffffffffu, s_pos, (k + 1) & 31),
+                        __shfl_sync(0xffffffffu, s_kvr, (k + 1) & 31));
+        nxt_live = nxt.n_keys > 0;
+      }
+    }
+    if (cur.n_keys == 0) {                        // a finished row: nothing to read, its context row is not used
+      qa = q_nxt;
+      continue;
+    }
+    if (!have0) {
+      request(par, cur, 0);
+      cp_async_commit();
+    }
+    float m = -INFINITY, l = 0.f;
+    float o[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+#pragma unroll 1
+    for (int j0 = 0; j0 < cur.n_keys; j0 += 32) {
+      const bool last = j0 + 32 >= cur.n_keys;
+      if (!last) request(par ^ 1, cur, j0 + 32);
+      else if (nxt_live) request(par ^ 1, nxt, 0);
+      cp_async_commit();
+      cp_async_wait_group<1>();
+      __syncwarp();
+      const int valid = cur.n_keys - j0;
+      const uint32_t kaddr = ring_addr + par * kPdRowsChunkBytes, vaddr = kaddr + 32 * 128;
+      float sc[4][4];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+        if (8 * nt < valid) {
+          const int kr = 8 * nt + (lane & 7);
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            uint32_t b[4];
+            ldmatrix_x4(b, kaddr + static_cast<uint32_t>(kr * 128 + (((4 * hf + (lane >> 3)) ^ (lane & 7)) << 4)));
+            mma16816(sc[nt], qa.a[2 * hf][0], 0u, qa.a[2 * hf][1], 0u, b[0], b[1]);
+            mma16816(sc[nt], qa.a[2 * hf + 1][0], 0u, qa.a[2 * hf + 1][1], 0u, b[2], b[3]);
+          }
+        }
+      }
+      float bm = -INFINITY;
+      if (valid < 32) {                           // the tail chunk: keys that do not exist score -inf
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          if (8 * nt + t2 >= valid) sc[nt][0] = -INFINITY;
+          if (8 * nt + t2 + 1 >= valid) sc[nt][1] = -INFINITY;
+        }
+      }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) bm = fmaxf(bm, fmaxf(sc[nt][0], sc[nt][1]));
+      bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 1));
+      bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 2));
+      const float mn = fmaxf(m, bm);
+      const float cs = __expf(m - mn);
+      l *= cs;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { o[i][0] *= cs; o[i][1] *= cs; }
+      m = mn;
+      uint32_t pa[2][2];
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        const float p0 = __expf(sc[2 * ks][0] - mn), p1 = __expf(sc[2 * ks][1] - mn);
+        const float p2 = __expf(sc[2 * ks + 1][0] - mn), p3 = __expf(sc[2 * ks + 1][1] - mn);
+        l += (p0 + p1) + (p2 + p3);
+        pa[ks][0] = lane < 4 ? pack_bf16(p0, p1) : 0u;
+        pa[ks][1] = lane < 4 ? pack_bf16(p2, p3) : 0u;
+      }
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        if (16 * ks < valid) {
+          const int kr = 16 * ks + ((lane >> 3) & 1) * 8 + (lane & 7);
+#pragma unroll
+          for (int dp = 0; dp < 4; ++dp) {
+            uint32_t b[4];
+            ldmatrix_x4_trans(b, vaddr + static_cast<uint32_t>(kr * 128 + (((2 * dp + (lane >> 4)) ^ (lane & 7)) << 4)));
+            mma16816(o[2 * dp], pa[ks][0], 0u, pa[ks][1], 0u, b[0], b[1]);
+            mma16816(o[2 * dp + 1], pa[ks][0], 0u, pa[ks][1], 0u, b[2], b[3]);
+          }
+        }
+      }
+      par ^= 1;
+    }
+    // the context row of this (row, head): the row-0 quad holds dims 8 i + 2 t, + 1
+    l += __shfl_xor_sync(0xffffffffu, l, 1);
+    l += __shfl_xor_sync(0xffffffffu, l, 2);
+    if (lane < 4) {
+      const float inv = __fdividef(1.f, l);       // l >= 1
+      uint32_t* dst = reinterpret_cast<uint32_t*>(p.ctx + static_cast<size_t>(cur.b) * kD + cur.h * kHeadDim + t2);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dst[4 * i] = pack_bf16(o[i][0] * inv, o[i][1] * inv);
+    }
+    have0 = nxt_live;
+    qa = q_nxt;
+  }
+  cp_async_wait_group<0>();
+  bar.arrive();
 }
 __global__ void __launch_bounds__(kPdThreads) pd_ln_kernel(const __grid_constant__ PdParams p, const __grid_constant__ PdStage st) {
   StageDep bar;

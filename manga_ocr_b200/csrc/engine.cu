@@ -143,7 +143,8 @@ struct mocr_handle {
   int steps_per_graph = 13; // decode steps captured in one CUDA graph (299 = 23 x 13)
   int fuse_ln = 1;          // decoder projections that feed a LayerNorm as 16-CTA clusters that normalise the rows themselves (0: split-K partials + LayerNorm stage)
   int kv_prefetch = 0;      // 1: a layer's encoder K/V are requested into L2 by the layer's first stage (bulk prefetch before the dependency wait); measured 2.7 us per step SLOWER at 64 rows (the prefetch competes with the weights for L2)
-  int big_attn_grid = 444;  // CTAs of the attention stages in the large-batch program (0 = one per (row, head) unit): 3 resident per SM measured best (444: 399 us per 512-row step, 1184: 416, one per unit: 432)
+  int big_attn_rows = 1;    // large-batch program: attention as one WARP per (row, head) unit (pd_attention_rows_kernel); 0 = the four-warp kernel
+  int big_attn_grid = 384;  // CTAs of the attention stages in the large-batch program (0 = as many as there is work for); warp-per-unit kernel at 512 rows: 384 -> 348 us per step, 444 -> 355, 296 -> 375, 512 -> 405
   int big_bn768 = 32;       // tile width of the large-batch program's N = 768 GEMMs (32 or 64)
   int big_vocab_bn = 64;    // tile width of its vocabulary projection (64 or 128)
   int big_rows = 144;       // more decoder rows than this (measured crossover: 128 rows 207 vs 226 us per step, 160 rows 248 vs 240): the large-batch program (every Linear on the tcgen05 GEMM, 128-row tiles)
@@ -1148,12 +1149,30 @@ int launch_tc_stage(mocr_handle* h, const PdParams& p, const PdStage& st) {
   }
 }
 
+// The attention stage of the per-token program: the four-warp kernel (small program), or one warp per (row, head) unit
+// (large-batch program), on the grid the options give.
+cudaError_t launch_attention_stage(mocr_handle* h, const PdParams& p, const PdStage& st) {
+  const int units = p.B * kHeads;
+  const bool self = st.type == PD_ATTN_SELF;
+  if (p.big && h->big_attn_rows) {
+    const int grid = std::min(h->big_attn_grid > 0 ? h->big_attn_grid : units, (units + 3) / 4);
+    return self ? launch_pdl(h, pd_attention_rows_kernel<true>, grid, 128, kPdAttnRowsSmemBytes, p, st)
+                : launch_pdl(h, pd_attention_rows_kernel<false>, grid, 128, kPdAttnRowsSmemBytes, p, st);
+  }
+  const int want = p.big ? h->big_attn_grid : h->attn_grid;
+  const int grid = want > 0 ? std::min(want, units) : units;
+  return self ? launch_pdl(h, pd_attention_kernel<true>, grid, 128, kPdAttnSmemBytes, p, st)
+              : launch_pdl(h, pd_attention_kernel<false>, grid, 128, kPdAttnSmemBytes, p, st);
+}
+
 // One greedy step as a sequence of stage kernels (decode_stages.cuh), one launch per stage.
 int decode_stage_step(mocr_handle* h, const PdParams& p, bool skip_next = false) {
   static bool done[16] = {};
   if (!done[h->device & 15]) {
     CK(cudaFuncSetAttribute(pd_attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPdAttnSmemBytes));
     CK(cudaFuncSetAttribute(pd_attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPdAttnSmemBytes));
+    CK(cudaFuncSetAttribute(pd_attention_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPdAttnRowsSmemBytes));
+    CK(cudaFuncSetAttribute(pd_attention_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPdAttnRowsSmemBytes));
     CK(cudaFuncSetAttribute(pd_gemm_kernel<48, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pd_gemm_smem_bytes(48)));
     CK(cudaFuncSetAttribute(pd_proj_ln_kernel<8, 3, 1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     if (h->carveout >= 0) {
@@ -1176,8 +1195,6 @@ int decode_stage_step(mocr_handle* h, const PdParams& p, bool skip_next = false)
   // many SMs (8 CTAs of 8 warps made 8 SMs pull 98 KB each at ~75 GB/s per SM: 1.3 us of the stage's 2.6)
   const int row_warps = p.big ? kPdWarps : std::max(1, std::min(h->row_warps, kPdWarps));
   const int row_ctas = (p.B + row_warps - 1) / row_warps;
-  const int attn_grid = p.big ? std::min(p.B * kHeads, h->big_attn_grid > 0 ? h->big_attn_grid : p.B * kHeads)
-                              : (h->attn_grid > 0 ? std::min(h->attn_grid, p.B * kHeads) : p.B * kHeads);
   struct PdlReset { mocr_handle* h; ~PdlReset() { h->pdl_now = 1; } } pdl_reset{h};
   for (int i = 0; i < n_stages; ++i) {
     const PdStage& st = prog[i];
@@ -1205,10 +1222,8 @@ int decode_stage_step(mocr_handle* h, const PdParams& p, bool skip_next = false)
     } else if (st.type == PD_PROJ_LN) {
       const int groups = (p.B + kPlRows - 1) / kPlRows;
       CK(launch_pdl(h, pd_proj_ln_kernel<8, 3, 1>, groups * kPlCluster, 256, pd_proj_ln_smem_bytes(8), p, st));
-    } else if (st.type == PD_ATTN_SELF) {
-      CK(launch_pdl(h, pd_attention_kernel<true>, attn_grid, 128, kPdAttnSmemBytes, p, st));
-    } else if (st.type == PD_ATTN_CROSS) {
-      CK(launch_pdl(h, pd_attention_kernel<false>, attn_grid, 128, kPdAttnSmemBytes, p, st));
+    } else if (st.type == PD_ATTN_SELF || st.type == PD_ATTN_CROSS) {
+      CK(launch_attention_stage(h, p, st));
     } else if (st.type == PD_LN) {
       CK(launch_pdl(h, pd_ln_kernel, row_ctas, 32 * row_warps, 0, p, st));
     } else {
@@ -2134,6 +2149,7 @@ int mocr_set_option(mocr_handle_t* h, const char* key, int value) {
   else if (k == "kv_prefetch") h->kv_prefetch = value != 0;
   else if (k == "big_rows" && value >= 1) h->big_rows = value;
   else if (k == "big_attn_grid" && value >= 0) h->big_attn_grid = value;
+  else if (k == "big_attn_rows") h->big_attn_rows = value != 0;
   else if (k == "big_bn768" && (value == 32 || value == 64)) h->big_bn768 = value;
   else if (k == "big_vocab_bn" && (value == 64 || value == 128)) h->big_vocab_bn = value;
   else if (k == "steps_per_graph" && value >= 1 && value <= 64) h->steps_per_graph = value;
@@ -2236,8 +2252,8 @@ int mocr_time_kernel(mocr_handle_t* h, const char* kernel, int iters, float* ms_
           }
           break;
         case PD_PROJ_LN: le = launch_pdl(h, pd_proj_ln_kernel<8, 3, 1>, ((p.B + kPlRows - 1) / kPlRows) * kPlCluster, 256, pd_proj_ln_smem_bytes(8), p, st); break;
-        case PD_ATTN_SELF: le = launch_pdl(h, pd_attention_kernel<true>, h->attn_grid > 0 ? std::min(h->attn_grid, p.B * kHeads) : p.B * kHeads, 128, kPdAttnSmemBytes, p, st); break;
-        case PD_ATTN_CROSS: le = launch_pdl(h, pd_attention_kernel<false>, h->attn_grid > 0 ? std::min(h->attn_grid, p.B * kHeads) : p.B * kHeads, 128, kPdAttnSmemBytes, p, st); break;
+        case PD_ATTN_SELF:
+        case PD_ATTN_CROSS: le = launch_attention_stage(h, p, st); break;
         default: le = launch_pdl(h, pd_ln_kernel, (p.B + kPdWarps - 1) / kPdWarps, kPdThreads, 0, p, st); break;
       }
       if (le != cudaSuccess) r = fail(h, MOCR_ERR_CUDA, "stage kernel launch failed: %s", cudaGetErrorString(le));
@@ -2395,6 +2411,9 @@ int mocr_test_decode_attention(mocr_handle_t* h, int mode, int n_rows, int n_ctx
                                const float* new_k, const float* new_v, float* out_ctx, float* out_k_row, float* out_v_row) {
   TRY(check_handle(h));
   std::lock_guard<std::mutex> lock(h->mu);
+  const bool rows_kernel = mode >= 3;         // 3: self, 4: cross (bf16 query rows) through the warp-per-unit kernel of the large-batch program
+  if (mode == 3) mode = 1;
+  if (mode == 4) mode = 2;
   const bool self = mode == 1;
   if (mode < 0 || mode > 2 || n_rows < 1 || n_rows > h->max_batch || q == nullptr || k == nullptr || v == nullptr || out_ctx == nullptr)
     return fail(h, MOCR_ERR_INVALID, "bad test_decode_attention argument");
@@ -2413,9 +2432,12 @@ int mocr_test_decode_attention(mocr_handle_t* h, int mode, int n_rows, int n_ctx
   if (!done[h->device & 15]) {
     CK(cudaFuncSetAttribute(pd_attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPdAttnSmemBytes));
     CK(cudaFuncSetAttribute(pd_attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPdAttnSmemBytes));
+    CK(cudaFuncSetAttribute(pd_attention_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPdAttnRowsSmemBytes));
+    CK(cudaFuncSetAttribute(pd_attention_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPdAttnRowsSmemBytes));
     done[h->device & 15] = true;
   }
-  const int grid = h->attn_grid > 0 ? std::min(h->attn_grid, n_rows * kHeads) : n_rows * kHeads;
+  const int grid = rows_kernel ? std::min(h->big_attn_grid > 0 ? h->big_attn_grid : n_rows * kHeads, (n_rows * kHeads + 3) / 4)
+                               : (h->attn_grid > 0 ? std::min(h->attn_grid, n_rows * kHeads) : n_rows * kHeads);
   int r = MOCR_OK;
   auto body = [&]() -> int {
     if (self) {
@@ -2440,7 +2462,8 @@ int mocr_test_decode_attention(mocr_handle_t* h, int mode, int n_rows, int n_ctx
       CK(cudaMemcpyAsync(h->d_qkv, qkv.data(), qkv.size() * 2, cudaMemcpyHostToDevice, h->stream));
       CK(cudaMemcpyAsync(h->d_pos, pos, sizeof(int) * n_rows, cudaMemcpyHostToDevice, h->stream));
       CK(cudaStreamSynchronize(h->stream));
-      CK(launch_pdl(h, pd_attention_kernel<true>, grid, 128, kPdAttnSmemBytes, p, st));
+      if (rows_kernel) CK(launch_pdl(h, pd_attention_rows_kernel<true>, grid, 128, kPdAttnRowsSmemBytes, p, st));
+      else CK(launch_pdl(h, pd_attention_kernel<true>, grid, 128, kPdAttnSmemBytes, p, st));
     } else {
       st.type = PD_ATTN_CROSS;
       // [crop][layer][K|V][head][197][64]
@@ -2474,7 +2497,8 @@ int mocr_test_decode_attention(mocr_handle_t* h, int mode, int n_rows, int n_ctx
         st.bias = d_zero_bias;
       }
       CK(cudaStreamSynchronize(h->stream));
-      CK(launch_pdl(h, pd_attention_kernel<false>, grid, 128, kPdAttnSmemBytes, p, st));
+      if (rows_kernel) CK(launch_pdl(h, pd_attention_rows_kernel<false>, grid, 128, kPdAttnRowsSmemBytes, p, st));
+      else CK(launch_pdl(h, pd_attention_kernel<false>, grid, 128, kPdAttnSmemBytes, p, st));
     }
     ++h->launches;
     std::vector<uint16_t> cb(static_cast<size_t>(n_rows) * kD);

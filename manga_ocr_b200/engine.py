@@ -355,7 +355,7 @@ class Engine:
         pp = None if pos is None else np.ascontiguousarray(pos, np.int32)
         self._ck(self._lib.mocr_test_decode_attention(self._h, mode, n, n_ctx, None if pp is None else pp.ctypes.data_as(POINTER(c_int32)),
                                                       fp(q), fp(k), fp(v), fp(new_k), fp(new_v), fp(ctx), fp(kr), fp(vr)))
-        return (ctx, kr, vr) if mode == 1 else ctx
+        return (ctx, kr, vr) if mode in (1, 3) else ctx
 
     def test_stage_gemm(self, kind: int, A: np.ndarray, Wt: np.ndarray, bias: np.ndarray, resid: Optional[np.ndarray] = None,
                         gamma: Optional[np.ndarray] = None, beta: Optional[np.ndarray] = None, gelu: bool = False):

@@ -99,10 +99,12 @@ def _attn_ref(q, k, v, n_keys):
     return out
 
 
-@pytest.mark.parametrize("n_rows,pos", [(3, [0, 1, 5]), (5, [31, 32, 127, 128, 129]), (4, [255, 256, 257, 298]), (66, None)])
-def test_decode_self_attention_against_torch(engine_dec, n_rows, pos):
+@pytest.mark.parametrize("mode", [1, 3], ids=["four_warp", "warp_per_unit"])
+@pytest.mark.parametrize("n_rows,pos", [(3, [0, 1, 5]), (5, [31, 32, 127, 128, 129]), (6, [30, 33, 63, 64, 65, 96]), (4, [255, 256, 257, 298]), (66, None)])
+def test_decode_self_attention_against_torch(engine_dec, n_rows, pos, mode):
     """One query over 1..299 cached keys (BertSelfAttention with a cache, modeling_bert.py:143-207): every staged-block
-    boundary (32-key warp ranges, 128-key blocks) and the append of this step's K/V row."""
+    boundary (32-key warp ranges / chunks, 128-key blocks) and the append of this step's K/V row; both attention
+    kernels (mode 3 = the warp-per-unit kernel of the large-batch program)."""
     rng = np.random.default_rng(n_rows)
     pos = np.asarray(pos if pos is not None else rng.integers(0, 299, n_rows), np.int32)
     n_ctx = int(pos.max()) + 1
@@ -111,7 +113,7 @@ def test_decode_self_attention_against_torch(engine_dec, n_rows, pos):
     v = rng.standard_normal((n_rows, n_ctx, 768), dtype=np.float32)
     nk = rng.standard_normal((n_rows, 768), dtype=np.float32)
     nv = rng.standard_normal((n_rows, 768), dtype=np.float32)
-    ctx, k_row, v_row = engine_dec.test_decode_attention(1, q, k, v, pos=pos, new_k=nk, new_v=nv)
+    ctx, k_row, v_row = engine_dec.test_decode_attention(mode, q, k, v, pos=pos, new_k=nk, new_v=nv)
     kk, vv = k.copy(), v.copy()
     for b in range(n_rows):
         kk[b, pos[b]] = nk[b]
@@ -121,7 +123,7 @@ def test_decode_self_attention_against_torch(engine_dec, n_rows, pos):
     assert np.array_equal(k_row, _bf16(nk)) and np.array_equal(v_row, _bf16(nv))       # the cache append is exact
 
 
-@pytest.mark.parametrize("mode", [0, 2], ids=["f32_partial_query", "bf16_query"])
+@pytest.mark.parametrize("mode", [0, 2, 4], ids=["f32_partial_query", "bf16_query", "warp_per_unit"])
 def test_decode_cross_attention_against_torch(engine_dec, mode):
     """One query over the 197 encoder keys (BertSelfAttention as cross-attention, modeling_bert.py:210-284), no mask."""
     rng = np.random.default_rng(7 + mode)
