@@ -130,7 +130,9 @@ struct mocr_handle {
   int dec_tc = 1;           // decoder GEMM stages on the encoder's tcgen05 kernel (bit 0: vocabulary, bit 1: FFN1, bit 2: QKV)
   int row_warps = 2;        // warps (= rows) per CTA of the decoder's row-wise stage kernels
   int carveout = -1;        // shared-memory carve-out (percent) forced on every decoder stage kernel; -1: driver default (set before the first decode)
-  int kv_evict_first = 1;   // decoder cross-attention streams the encoder K/V through L2 with an evict-first policy
+  int kv_evict_first = -1;  // L2 evict-first hint on the decoder's K/V reads: bit 0 encoder K/V, bit 1 self-attention cache; -1 = by program:
+                            // small 2 (the encoder K/V of <= 64 rows stay in L2 with the weights: 98.7 -> 94.6 us per step at 32 rows,
+                            // 119.0 -> 118.6 at 64), large 3 (everything streams: 347.5 -> 344.1 at 512 rows)
   int resid_tma = 1;        // encoder residual adds through the TMA reduce-add epilogue (0: per-thread f32 loads/stores)
   int enc_bn768 = 256;      // tile width of the N = 768 encoder GEMMs (128 or 256; 192 would give 2.68 waves instead of 2.007, measured 3 % slower)
   int dec_bn = 32;
@@ -143,6 +145,10 @@ struct mocr_handle {
   int steps_per_graph = 13; // decode steps captured in one CUDA graph (299 = 23 x 13)
   int fuse_ln = 1;          // decoder projections that feed a LayerNorm as 16-CTA clusters that normalise the rows themselves (0: split-K partials + LayerNorm stage)
   int kv_prefetch = 0;      // 1: a layer's encoder K/V are requested into L2 by the layer's first stage (bulk prefetch before the dependency wait); measured 2.7 us per step SLOWER at 64 rows (the prefetch competes with the weights for L2)
+#ifdef MOCR_GEMM_DBG
+  int gemm_dbg = 0;
+#endif
+  int enc_tma_store = 1;    // encoder GEMMs with bf16 outputs (QKV, FFN1): rows leave as TMA stores from a staging tile (GemmArgs::out_tma)
   int big_attn_rows = 1;    // large-batch program: attention as one WARP per (row, head) unit (pd_attention_rows_kernel); 0 = the four-warp kernel
   int big_attn_grid = 384;  // CTAs of the attention stages in the large-batch program (0 = as many as there is work for); warp-per-unit kernel at 512 rows: 384 -> 348 us per step, 444 -> 355, 296 -> 375, 512 -> 405
   int big_bn768 = 32;       // tile width of the large-batch program's N = 768 GEMMs (32 or 64)
@@ -309,6 +315,20 @@ int make_map_f32_out(mocr_handle* h, CUtensorMap* m, const void* base, int rows,
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(h, MOCR_ERR_CUDA, "cuTensorMapEncodeTiled (f32 out) failed (%d) rows=%d cols=%d", (int)r, rows, cols);
+  return MOCR_OK;
+}
+
+// bf16 [rows, cols] view of a GEMM output for the TMA-store epilogue: box 64 columns x 32 rows (one epilogue warp's staging tile)
+int make_map_bf16_out(mocr_handle* h, CUtensorMap* m, const void* base, int rows, int cols) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (enc == nullptr) return fail(h, MOCR_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * 2};
+  cuuint32_t box[2] = {64, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(h, MOCR_ERR_CUDA, "cuTensorMapEncodeTiled (bf16 out) failed (%d) rows=%d cols=%d", (int)r, rows, cols);
   return MOCR_OK;
 }
 
@@ -534,11 +554,18 @@ int gemm(mocr_handle* h, int epi, int bn, const ActBuf& A, Linear& L, int M, Gem
   a.N = L.N;
   a.K = L.K;
   a.bias = L.bias;
+#ifdef MOCR_GEMM_DBG
+  a.dbg = h->gemm_dbg;
+#endif
   const CUtensorMap* mb;
   TRY(linear_map(h, &L, bn, &mb));
   if (epi == EPI_F32_ACCUM) {
     if (a.ldo != L.N || bn > 256 || bn % 64 != 0) return fail(h, MOCR_ERR_INVALID, "accumulating epilogue needs a dense [M, N] output and a 64-column multiple tile");
     TRY(make_map_f32_out(h, &a.tmap_out, a.out, M, L.N));
+  }
+  if ((epi == EPI_BF16 || epi == EPI_BF16_GELU) && h->enc_tma_store && bn % 128 == 0 && a.ldo == L.N) {
+    TRY(make_map_bf16_out(h, &a.tmap_out, a.out, M, L.N));
+    a.out_tma = 1;
   }
   switch (epi) {
     case EPI_BF16: return launch_gemm_bn<EPI_BF16>(h, bn, A.map, *mb, a);
@@ -1013,7 +1040,7 @@ PdParams make_pd_params(mocr_handle* h, int n, int max_length, bool forced, bool
   p.big = n > h->big_rows ? 1 : 0;
   p.n_partials = (p.big || (h->dec_tc & 1)) ? 2 * (kVocab / ((p.big && h->big_vocab_bn == 128) ? 128 : 64)) : kPdVocabTiles;
   p.logits_cur = 0;
-  p.kv_evict_first = h->kv_evict_first;
+  p.kv_evict_first = h->kv_evict_first >= 0 ? h->kv_evict_first : (p.big ? 3 : 2);
   p.fuse_ln = h->fuse_ln;
   p.kv_prefetch = h->kv_prefetch;
   p.eos_id = kSepId;
@@ -2127,7 +2154,7 @@ int mocr_set_option(mocr_handle_t* h, const char* key, int value) {
   const std::string k = key;
   auto bn_ok = [](int v) { return v == 32 || v == 64 || v == 128 || v == 192 || v == 256; };
   if (k == "enc_bn" && bn_ok(value) && kD % value == 0) h->enc_bn = value;
-  else if (k == "enc_bn768" && (value == 128 || value == 256)) h->enc_bn768 = value;
+  else if (k == "enc_bn768" && (value == 128 || value == 192 || value == 256)) h->enc_bn768 = value;
   else if (k == "dec_bn" && bn_ok(value) && kD % value == 0) h->dec_bn = value;
   else if (k == "head_bn" && bn_ok(value) && kVocab % value == 0) h->head_bn = value;
   else if (k == "check_every" && value >= 1) h->check_every = value;
@@ -2138,7 +2165,7 @@ int mocr_set_option(mocr_handle_t* h, const char* key, int value) {
   else if (k == "row_warps" && value >= 1 && value <= 8) h->row_warps = value;
   else if (k == "dec_tc" && value >= 0 && value <= 7) h->dec_tc = value;
   else if (k == "carveout" && value >= -1 && value <= 100) h->carveout = value;
-  else if (k == "kv_evict_first" && value >= 0 && value <= 3) h->kv_evict_first = value;
+  else if (k == "kv_evict_first" && value >= -1 && value <= 3) h->kv_evict_first = value;
   else if (k == "attn_grid" && value >= 0) h->attn_grid = value;
   else if (k == "slots" && value >= 0) h->slots = value;
   else if (k == "stage_threads" && value >= 1 && value <= 64) h->stage_threads = value;
@@ -2150,6 +2177,10 @@ int mocr_set_option(mocr_handle_t* h, const char* key, int value) {
   else if (k == "big_rows" && value >= 1) h->big_rows = value;
   else if (k == "big_attn_grid" && value >= 0) h->big_attn_grid = value;
   else if (k == "big_attn_rows") h->big_attn_rows = value != 0;
+  else if (k == "enc_tma_store") h->enc_tma_store = value != 0;
+#ifdef MOCR_GEMM_DBG
+  else if (k == "gemm_dbg") h->gemm_dbg = value;
+#endif
   else if (k == "big_bn768" && (value == 32 || value == 64)) h->big_bn768 = value;
   else if (k == "big_vocab_bn" && (value == 64 || value == 128)) h->big_vocab_bn = value;
   else if (k == "steps_per_graph" && value >= 1 && value <= 64) h->steps_per_graph = value;

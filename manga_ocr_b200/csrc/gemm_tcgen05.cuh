@@ -48,6 +48,12 @@ struct GemmArgs {
   int tap_steps;
   int pdl;               // 1: launched with programmatic stream serialization (decoder stage): weights are requested before
                          //    griddepcontrol.wait, the activations after it
+  int out_tma;           // EPI_BF16 / EPI_BF16_GELU with BN = 128 or 256: rows leave through tmap_out (bf16 [M, N] view of `out`, box 64 x 32,
+                         //    SWIZZLE_128B) as TMA stores from a staging tile instead of per-lane 16-byte stores
+#ifdef MOCR_GEMM_DBG
+  int dbg;               // timing experiments only (results are garbage): 1 = loads stop after the first ring fill (MMA-side speed),
+                         // 2 = no MMA issued (TMA-side speed), 3 = no epilogue work
+#endif
   alignas(64) CUtensorMap tmap_out;   // EPI_F32_ACCUM: f32 [M, N] view of `out`, box 32 x 32, SWIZZLE_128B
 };
 
@@ -57,14 +63,14 @@ constexpr int kGemmThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogu
 constexpr int kGemmEpiThreads = 256;
 constexpr int kGemmAccumStage = 32 * 128;                      // EPI_F32_ACCUM: one 32-row x 128-byte staging tile per epilogue warp
 constexpr int kGemmAccumSmem = 1024 + 8 * kGemmAccumStage;     // (+ padding that keeps the tiles 1024-byte aligned)
-constexpr int gemm_smem_bytes(int base, int epi) { return base + (epi == 7 ? kGemmAccumSmem : 0); }
+constexpr int gemm_smem_bytes(int base, int epi) { return base + ((epi == 7 || epi == 0 || epi == 1) ? kGemmAccumSmem : 0); }   // staging tiles: EPI_F32_ACCUM, EPI_BF16[_GELU]
 
 template <int BN>
 struct GemmCfg {
   static constexpr int kStageBytesA = kGemmBM * kGemmBK * 2;
   static constexpr int kStageBytesB = BN * kGemmBK * 2;
   static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
-  static constexpr int kStagesFit = (200 * 1024) / kStageBytes;
+  static constexpr int kStagesFit = (192 * 1024) / kStageBytes;      // + 32 KB of epilogue staging tiles + barriers <= 227 KB
   static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
   static constexpr int kTmemCols = 2 * BN <= 32 ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -105,6 +111,57 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, uint32_
     extra = args.pos + static_cast<size_t>(1 + p) * kD;
   }
   (void)bias;
+  if constexpr ((EPI == EPI_BF16 || EPI == EPI_BF16_GELU) && BN % 128 == 0) {
+    if (args.out_tma) {
+      // Two 32-column chunks at a time: 64 bf16 = one 128-byte row of the warp's 32 x 128-byte staging tile (16-byte
+      // pieces XOR-swizzled with the row: conflict-free st.shared.v4, un-swizzled by the map), then ONE TMA store per
+      // warp.  Per-lane row stores cost a warp 32 partial-line transactions per instruction: at 128 x 256 tiles that
+      // (plus the GELU arithmetic) made the epilogue slower than the tile's main loop.
+      const int lane = static_cast<int>(threadIdx.x & 31u);
+      const int row0 = row - lane;
+      const uint32_t dst = smem_u32(stage_w) + static_cast<uint32_t>(lane * 128);
+#pragma unroll 1
+      for (int c = c_lo; c < c_hi; c += 2) {
+        uint32_t v0[32], v1[32];
+        tmem_ld32(taddr + static_cast<uint32_t>(c * 32), v0);
+        tmem_ld32(taddr + static_cast<uint32_t>(c * 32 + 32), v1);
+        tmem_ld_wait();
+        const int col0 = n0 + c * 32;
+        uint32_t pk[32];
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(args.bias + col0 + j));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(args.bias + col0 + 32 + j));
+          float f0 = __uint_as_float(v0[j]) + b0.x, f1 = __uint_as_float(v0[j + 1]) + b0.y;
+          float f2 = __uint_as_float(v0[j + 2]) + b0.z, f3 = __uint_as_float(v0[j + 3]) + b0.w;
+          float g0 = __uint_as_float(v1[j]) + b1.x, g1 = __uint_as_float(v1[j + 1]) + b1.y;
+          float g2 = __uint_as_float(v1[j + 2]) + b1.z, g3 = __uint_as_float(v1[j + 3]) + b1.w;
+          if (EPI == EPI_BF16_GELU) {
+            f0 = gelu_erf_fast(f0); f1 = gelu_erf_fast(f1); f2 = gelu_erf_fast(f2); f3 = gelu_erf_fast(f3);
+            g0 = gelu_erf_fast(g0); g1 = gelu_erf_fast(g1); g2 = gelu_erf_fast(g2); g3 = gelu_erf_fast(g3);
+          }
+          pk[j / 2] = pack_bf16(f0, f1);
+          pk[j / 2 + 1] = pack_bf16(f2, f3);
+          pk[16 + j / 2] = pack_bf16(g0, g1);
+          pk[16 + j / 2 + 1] = pack_bf16(g2, g3);
+        }
+        if (lane == 0) bulk_wait_group_read0();          // the previous pair's tile has been read out
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + static_cast<uint32_t>((j ^ (lane & 7)) << 4)), "r"(pk[4 * j]),
+                       "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
+                       : "memory");
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0 && row0 < args.M) {                // rows >= M are clipped by the map
+          tma_store_2d(&args.tmap_out, stage_w, col0, row0);
+          bulk_commit_group();
+        }
+      }
+      return;
+    }
+  }
 #pragma unroll 1
   for (int c = c_lo; c < c_hi; ++c) {
     uint32_t v[32];
@@ -271,6 +328,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int n0 = (tile % n_tiles) * BN;
       for (int kb = 0; kb < k_blocks; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1u);
+#ifdef MOCR_GEMM_DBG
+        if (args.dbg == 1 && (tile != static_cast<int>(blockIdx.x) || kb >= kStages)) {
+          if (lane == 0) mbar_arrive(&full_bar[stage]);
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          continue;
+        }
+#endif
         if (lane == 0) {
           if (tile == static_cast<int>(blockIdx.x) && kb < pre) {     // B is on its way already
             tma_load_2d(smem_a + stage * Cfg::kStageBytesA, &tmap_a, &full_bar[stage], kb * kGemmBK, m0);
@@ -302,6 +367,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (lane == 0) {
           const uint64_t da = umma_desc_k_sw128(smem_u32(smem_a + stage * Cfg::kStageBytesA));
           const uint64_t db = umma_desc_k_sw128(smem_u32(smem_b + stage * Cfg::kStageBytesB));
+#ifdef MOCR_GEMM_DBG
+          if (args.dbg != 2)
+#endif
 #pragma unroll
           for (int k = 0; k < kGemmBK / 16; ++k) {
             // advance 16 bf16 = 32 B along K inside the 128-B swizzle atom: +2 in 16-B units
@@ -333,12 +401,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       mbar_wait(&acc_full[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * BN);
+#ifdef MOCR_GEMM_DBG
+      if (args.dbg != 3)
+#endif
       gemm_epilogue_tile<BN, EPI>(args, taddr, row, row_ok, n0, nt, n_tiles, half, bias,
                                   smem + kStages * Cfg::kStageBytes + 1024 + (warp - 2) * kGemmAccumStage);
       tc_fence_before();
       mbar_arrive(&acc_empty[as]);
     }
-    if (EPI == EPI_F32_ACCUM && lane == 0) bulk_wait_group0();   // every reduce-add of this warp has landed
+    if ((EPI == EPI_F32_ACCUM || EPI == EPI_BF16 || EPI == EPI_BF16_GELU) && lane == 0) bulk_wait_group0();   // every reduce-add / TMA store of this warp has landed
   }
 
   tc_fence_before();
