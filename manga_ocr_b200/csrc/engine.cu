@@ -1134,6 +1134,9 @@ int launch_gemm_stage_tc(mocr_handle* h, const __nv_bfloat16* a_ptr, int K, Line
   a.K = L.K;
   a.bias = L.bias;
   a.pdl = 1;
+#ifdef MOCR_GEMM_DBG
+  a.dbg = h->gemm_dbg;
+#endif
   const int tiles = ((rows + kGemmBM - 1) / kGemmBM) * (L.N / BN);
   CK(launch_pdl(h, gemm_tcgen05_kernel<BN, EPI>, std::min(tiles, h->sms), kGemmThreads, gemm_smem_bytes(Cfg::kSmemBytes, EPI), ma, *mb, a));
   return MOCR_OK;

@@ -372,6 +372,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #endif
 #pragma unroll
           for (int k = 0; k < kGemmBK / 16; ++k) {
+#ifdef MOCR_GEMM_DBG
+            if (args.dbg == 4 && k > 0) break;           // one MMA per k-block
+#endif
             // advance 16 bf16 = 32 B along K inside the 128-B swizzle atom: +2 in 16-B units
             umma_bf16(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
                       static_cast<uint32_t>((kb | k) != 0));
