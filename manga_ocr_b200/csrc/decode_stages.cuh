@@ -59,6 +59,7 @@ struct PdParams {
   int logits_cur;           // 1: the logits tap holds the CURRENT step only, [B, 6144] (beam mode)
   int kv_evict_first;       // 1: encoder K/V are streamed through L2 with an evict-first policy (the per-step weights stay resident)
   int fuse_ln;              // 1: the projections that feed a LayerNorm run as 16-CTA clusters that normalise the rows themselves
+  int big_accum;             // large-batch program: x += projection in place (TMA reduce-add epilogue), LayerNorm reads x
   int kv_prefetch;          // 1: a layer's encoder K/V are requested into L2 (bulk prefetch) by the layer's first stage
   int big;                  // 1: large-batch program - every Linear on the tcgen05 GEMM (128-row tiles, weights read once for all rows)
   int eos_id;
@@ -1344,8 +1345,13 @@ __host__ __device__ inline int pd_build_program(const PdParams& p, PdStage* prog
     }
     a = PdStage{}; a.type = PD_ATTN_SELF; a.layer = l; prog[n++] = a;
     if (p.big) {
-      prog[n++] = pd_tc_desc(lin0 + PD_LIN_SELF_OUT, 2 /*EPI_F32_RESID*/, p.ctx, kD, kD, nullptr, p.y, kD, p.x);
-      prog[n++] = pd_ln_desc(p.y, 1, nullptr, 0, nullptr, L.ln_self, p.x, p.xb);
+      if (p.big_accum) {
+        prog[n++] = pd_tc_desc(lin0 + PD_LIN_SELF_OUT, 7 /*EPI_F32_ACCUM*/, p.ctx, kD, kD, nullptr, p.x, kD, nullptr);
+        prog[n++] = pd_ln_desc(p.x, 1, nullptr, 0, nullptr, L.ln_self, p.x, p.xb);
+      } else {
+        prog[n++] = pd_tc_desc(lin0 + PD_LIN_SELF_OUT, 2 /*EPI_F32_RESID*/, p.ctx, kD, kD, nullptr, p.y, kD, p.x);
+        prog[n++] = pd_ln_desc(p.y, 1, nullptr, 0, nullptr, L.ln_self, p.x, p.xb);
+      }
     } else if (p.fuse_ln) {
       prog[n++] = pd_proj_ln_desc(p.ctx, kD, L.self_out, 0, p.x, L.ln_self, p.x, p.xb);
     } else {
@@ -1363,8 +1369,13 @@ __host__ __device__ inline int pd_build_program(const PdParams& p, PdStage* prog
     }
     prog[n++] = a;
     if (p.big) {
-      prog[n++] = pd_tc_desc(lin0 + PD_LIN_CROSS_OUT, 2 /*EPI_F32_RESID*/, p.ctx, kD, kD, nullptr, p.y, kD, p.x);
-      prog[n++] = pd_ln_desc(p.y, 1, nullptr, 0, nullptr, L.ln_cross, p.x, p.xb);
+      if (p.big_accum) {
+        prog[n++] = pd_tc_desc(lin0 + PD_LIN_CROSS_OUT, 7 /*EPI_F32_ACCUM*/, p.ctx, kD, kD, nullptr, p.x, kD, nullptr);
+        prog[n++] = pd_ln_desc(p.x, 1, nullptr, 0, nullptr, L.ln_cross, p.x, p.xb);
+      } else {
+        prog[n++] = pd_tc_desc(lin0 + PD_LIN_CROSS_OUT, 2 /*EPI_F32_RESID*/, p.ctx, kD, kD, nullptr, p.y, kD, p.x);
+        prog[n++] = pd_ln_desc(p.y, 1, nullptr, 0, nullptr, L.ln_cross, p.x, p.xb);
+      }
     } else if (p.fuse_ln) {
       prog[n++] = pd_proj_ln_desc(p.ctx, kD, L.cross_out, 0, p.x, L.ln_cross, p.x, p.xb);
     } else {
@@ -1374,8 +1385,13 @@ __host__ __device__ inline int pd_build_program(const PdParams& p, PdStage* prog
     // feed-forward (:330-356)
     if (p.big) {
       prog[n++] = pd_tc_desc(lin0 + PD_LIN_FC1, 1 /*EPI_BF16_GELU*/, p.xb, kD, kFFN, p.ffn, nullptr, kFFN, nullptr);
-      prog[n++] = pd_tc_desc(lin0 + PD_LIN_FC2, 2 /*EPI_F32_RESID*/, p.ffn, kFFN, kD, nullptr, p.y, kD, p.x);
-      prog[n++] = pd_ln_desc(p.y, 1, nullptr, 0, nullptr, L.ln_ffn, p.x, p.xb);
+      if (p.big_accum) {
+        prog[n++] = pd_tc_desc(lin0 + PD_LIN_FC2, 7 /*EPI_F32_ACCUM*/, p.ffn, kFFN, kD, nullptr, p.x, kD, nullptr);
+        prog[n++] = pd_ln_desc(p.x, 1, nullptr, 0, nullptr, L.ln_ffn, p.x, p.xb);
+      } else {
+        prog[n++] = pd_tc_desc(lin0 + PD_LIN_FC2, 2 /*EPI_F32_RESID*/, p.ffn, kFFN, kD, nullptr, p.y, kD, p.x);
+        prog[n++] = pd_ln_desc(p.y, 1, nullptr, 0, nullptr, L.ln_ffn, p.x, p.xb);
+      }
     } else {
       prog[n++] = pd_gemm_desc(PD_GEMM32, PD_BF16_GELU, p.xb, kD, L.fc1, kFFN, 1, p.ffn, nullptr, kFFN);
       prog[n++] = pd_gemm_desc(PD_GEMM16, PD_F32_PARTIAL, p.ffn, kFFN, L.fc2, kD, kPdSplit, nullptr, p.y, kD);

@@ -128,6 +128,7 @@ struct mocr_handle {
   // tile widths (mocr_set_option)
   int enc_bn = 256;
   int dec_tc = 1;           // decoder GEMM stages on the encoder's tcgen05 kernel (bit 0: vocabulary, bit 1: FFN1, bit 2: QKV)
+  int big_row_warps = 2;    // the same in the large-batch program (512 rows: 8 -> 333.0, 4 -> 330.4, 2 -> 329.5 us per step)
   int row_warps = 2;        // warps (= rows) per CTA of the decoder's row-wise stage kernels
   int carveout = -1;        // shared-memory carve-out (percent) forced on every decoder stage kernel; -1: driver default (set before the first decode)
   int kv_evict_first = -1;  // L2 evict-first hint on the decoder's K/V reads: bit 0 encoder K/V, bit 1 self-attention cache; -1 = by program:
@@ -148,12 +149,14 @@ struct mocr_handle {
 #ifdef MOCR_GEMM_DBG
   int gemm_dbg = 0;
 #endif
+  int big_accum = 1;        // large-batch program: the residual projections accumulate into x in place (EPI_F32_ACCUM) instead of y = x + ...
   int enc_tma_store = 1;    // encoder GEMMs with bf16 outputs (QKV, FFN1): rows leave as TMA stores from a staging tile (GemmArgs::out_tma)
   int big_attn_rows = 1;    // large-batch program: attention as one WARP per (row, head) unit (pd_attention_rows_kernel); 0 = the four-warp kernel
   int big_attn_grid = 384;  // CTAs of the attention stages in the large-batch program (0 = as many as there is work for); warp-per-unit kernel at 512 rows: 384 -> 348 us per step, 444 -> 355, 296 -> 375, 512 -> 405
   int big_bn768 = 32;       // tile width of the large-batch program's N = 768 GEMMs (32 or 64)
   int big_vocab_bn = 64;    // tile width of its vocabulary projection (64 or 128)
-  int big_rows = 144;       // more decoder rows than this (measured crossover: 128 rows 207 vs 226 us per step, 160 rows 248 vs 240): the large-batch program (every Linear on the tcgen05 GEMM, 128-row tiles)
+  int big_rows = 112;       // more decoder rows than this: the large-batch program (every Linear on the tcgen05 GEMM, 128-row tiles).  Measured us per step,
+                            // small / large program: 96 rows 157 / 178, 112 rows 184 / 182, 128 rows 199 / 188, 144 rows 244 / 216, 160 rows 248 / 220
   int pipeline = 0;         // with slot refill, 1 (2: equal stream priorities): encode the waiting crops in sub-chunks on a second stream while the decoder
                             // already runs.  Measured on the ragged 512-crop leg: 116 ms (80 ms at equal priorities) against 75 ms with the encoder
                             // serialised in front - the 200 KB GEMM CTAs and the decoder's stage kernels do not share SMs well - so it is off
@@ -1042,6 +1045,7 @@ PdParams make_pd_params(mocr_handle* h, int n, int max_length, bool forced, bool
   p.logits_cur = 0;
   p.kv_evict_first = h->kv_evict_first >= 0 ? h->kv_evict_first : (p.big ? 3 : 2);
   p.fuse_ln = h->fuse_ln;
+  p.big_accum = h->big_accum;
   p.kv_prefetch = h->kv_prefetch;
   p.eos_id = kSepId;
   for (int l = 0; l < kDecLayers; ++l) {
@@ -1134,6 +1138,11 @@ int launch_gemm_stage_tc(mocr_handle* h, const __nv_bfloat16* a_ptr, int K, Line
   a.K = L.K;
   a.bias = L.bias;
   a.pdl = 1;
+  if (EPI == EPI_F32_ACCUM) TRY(make_map_f32_out(h, &a.tmap_out, a.out, rows, L.N));
+  if ((EPI == EPI_BF16 || EPI == EPI_BF16_GELU) && BN % 128 == 0 && h->enc_tma_store && a.ldo == L.N) {
+    TRY(make_map_bf16_out(h, &a.tmap_out, a.out, rows, L.N));
+    a.out_tma = 1;
+  }
 #ifdef MOCR_GEMM_DBG
   a.dbg = h->gemm_dbg;
 #endif
@@ -1171,6 +1180,9 @@ int launch_tc_stage(mocr_handle* h, const PdParams& p, const PdStage& st) {
     case EPI_F32_RESID:
       if (!wide) return launch_gemm_stage_tc<32, EPI_F32_RESID>(h, st.A, st.K, L, p.B, out_f32(st.of, st.ldo, st.resid, kD));
       return launch_gemm_stage_tc<64, EPI_F32_RESID>(h, st.A, st.K, L, p.B, out_f32(st.of, st.ldo, st.resid, kD));
+    case EPI_F32_ACCUM:      // x += A W^T + bias in place (TMA reduce-add: the SM never reads the residual)
+      if (!wide) return launch_gemm_stage_tc<32, EPI_F32_ACCUM>(h, st.A, st.K, L, p.B, out_f32(st.of, st.ldo));
+      return launch_gemm_stage_tc<64, EPI_F32_ACCUM>(h, st.A, st.K, L, p.B, out_f32(st.of, st.ldo));
     case EPI_F32_GELU:
       if (!wide) return launch_gemm_stage_tc<32, EPI_F32_GELU>(h, st.A, st.K, L, p.B, out_f32(st.of, st.ldo));
       return launch_gemm_stage_tc<64, EPI_F32_GELU>(h, st.A, st.K, L, p.B, out_f32(st.of, st.ldo));
@@ -1223,7 +1235,7 @@ int decode_stage_step(mocr_handle* h, const PdParams& p, bool skip_next = false)
   const int n_stages = pd_build_program(p, prog);
   // row-wise stages (LayerNorm, next token): one warp per row; few warps per CTA so that the rows spread over
   // many SMs (8 CTAs of 8 warps made 8 SMs pull 98 KB each at ~75 GB/s per SM: 1.3 us of the stage's 2.6)
-  const int row_warps = p.big ? kPdWarps : std::max(1, std::min(h->row_warps, kPdWarps));
+  const int row_warps = std::max(1, std::min(p.big ? h->big_row_warps : h->row_warps, kPdWarps));
   const int row_ctas = (p.B + row_warps - 1) / row_warps;
   struct PdlReset { mocr_handle* h; ~PdlReset() { h->pdl_now = 1; } } pdl_reset{h};
   for (int i = 0; i < n_stages; ++i) {
@@ -2166,6 +2178,7 @@ int mocr_set_option(mocr_handle_t* h, const char* key, int value) {
   else if (k == "pdl_mask" && value >= 0) h->pdl_mask = value;
   else if (k == "resid_tma") h->resid_tma = value != 0;
   else if (k == "row_warps" && value >= 1 && value <= 8) h->row_warps = value;
+  else if (k == "big_row_warps" && value >= 1 && value <= 8) h->big_row_warps = value;
   else if (k == "dec_tc" && value >= 0 && value <= 7) h->dec_tc = value;
   else if (k == "carveout" && value >= -1 && value <= 100) h->carveout = value;
   else if (k == "kv_evict_first" && value >= -1 && value <= 3) h->kv_evict_first = value;
@@ -2181,6 +2194,7 @@ int mocr_set_option(mocr_handle_t* h, const char* key, int value) {
   else if (k == "big_attn_grid" && value >= 0) h->big_attn_grid = value;
   else if (k == "big_attn_rows") h->big_attn_rows = value != 0;
   else if (k == "enc_tma_store") h->enc_tma_store = value != 0;
+  else if (k == "big_accum") h->big_accum = value != 0;
 #ifdef MOCR_GEMM_DBG
   else if (k == "gemm_dbg") h->gemm_dbg = value;
 #endif

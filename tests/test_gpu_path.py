@@ -100,7 +100,7 @@ def test_decoder_program_variants_match_oracle(engine8, golden_model, oracle12, 
     crops = G.model_inputs()
     T = G.MODEL_T
     ids_ref = golden_model["ids"]
-    defaults = {"fuse_ln": 1, "big_rows": 144, "kv_prefetch": 0, "dec_tc": 1}
+    defaults = {"fuse_ln": 1, "big_rows": 112, "kv_prefetch": 0, "dec_tc": 1}
     _pre(engine8, crops)
     engine8.encode()
     try:

@@ -8,7 +8,7 @@ T = 10
 eng = Engine(W.random_init(0, eos_bias=3.7, gain=3.0), device=0, max_batch=6, max_length=T)
 crops = C.page_batch(5, seed=3)
 eng.set_taps(TAP_PIXELS | TAP_ENCODER | TAP_LOGITS)
-for key, val, back in (("fuse_ln", 1, 1), ("fuse_ln", 0, 1), ("big_rows", 1, 144), ("kv_prefetch", 1, 0)):
+for key, val, back in (("fuse_ln", 1, 1), ("fuse_ln", 0, 1), ("big_rows", 1, 112), ("kv_prefetch", 1, 0)):
     eng.set_option(key, val)
     ids, lens = eng.recognize(crops, max_length=T)
     print(key, val, lens.tolist())
