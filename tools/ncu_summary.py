@@ -53,9 +53,19 @@ def launches(path, header):
         print(f"{us:9.1f} us {100 * us / total:5.1f}%  n={n:4d} avg={us / n:7.2f} us  {name} grid={grid}")
 
 
+def _raw(path):
+    """Rows of `ncu -i <report> --page raw --csv` (or of that CSV saved on the GPU box, when the report itself was too big to bring back)."""
+    if path.endswith(".csv"):
+        with open(path, newline="") as f:
+            out = f.read()
+        out = out[out.find('"ID"'):]
+    else:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    return list(csv.reader(io.StringIO(out)))
+
+
 def full(path, header):
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
-    rd = list(csv.reader(io.StringIO(out)))
+    rd = _raw(path)
     names, units = rd[0], rd[1]
     col = {n: i for i, n in enumerate(names)}
     seen = set()
@@ -74,5 +84,33 @@ def full(path, header):
                 print(f"{m:<88} {row[col[m]]} {units[col[m]]}")
 
 
+def traffic(path, command):
+    """JSON for bench.py's roofline.traffic: DRAM bytes (read + write) per launch, averaged per kernel over the capture."""
+    import json
+    rd = _raw(path)
+    names, units = rd[0], rd[1]
+    col = {n: i for i, n in enumerate(names)}
+
+    def scaled(row, metric, to):
+        v = float(row[col[metric]].replace(",", ""))
+        u = units[col[metric]].lower()
+        f = {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9, "ns": 1e-3, "nsecond": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3,
+             "msecond": 1e3}[u]
+        return v * f
+
+    agg = collections.OrderedDict()
+    for row in rd[2:]:
+        k = row[col["Kernel Name"]].replace("mocr::", "")
+        a = agg.setdefault(k, [0, 0.0, 0.0])
+        a[0] += 1
+        a[1] += scaled(row, "dram__bytes_read.sum", "byte") + scaled(row, "dram__bytes_write.sum", "byte")
+        a[2] += scaled(row, "gpu__time_duration.sum", "us")
+    doc = {"command": command,
+           "note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the captured launches of each kernel (cold cache, serialised)",
+           "kernels": [{"kernel": k, "launches_captured": n, "dram_bytes_per_launch": b / n, "gpu_time_us_per_launch_cold": t / n}
+                       for k, (n, b, t) in agg.items()]}
+    print(json.dumps(doc, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else "")
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else "")
