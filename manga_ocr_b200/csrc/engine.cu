@@ -16,6 +16,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <new>
@@ -150,6 +151,7 @@ struct mocr_handle {
   int gemm_dbg = 0;
 #endif
   int big_accum = 1;        // large-batch program: the residual projections accumulate into x in place (EPI_F32_ACCUM) instead of y = x + ...
+  int stage_chunk = 128;    // crops per staging chunk of a large batch (0 = one piece): see stage_encode
   int enc_tma_store = 1;    // encoder GEMMs with bf16 outputs (QKV, FFN1): rows leave as TMA stores from a staging tile (GemmArgs::out_tma)
   int big_attn_rows = 1;    // large-batch program: attention as one WARP per (row, head) unit (pd_attention_rows_kernel); 0 = the four-warp kernel
   int big_attn_grid = 384;  // CTAs of the attention stages in the large-batch program (0 = as many as there is work for); warp-per-unit kernel at 512 rows: 384 -> 348 us per step, 444 -> 355, 296 -> 375, 512 -> 405
@@ -619,7 +621,10 @@ int table_for(mocr_handle* h, int in_size, mocr_handle::TableRef* out) {
   return MOCR_OK;
 }
 
-int stage_crops(mocr_handle* h, const mocr_crop_t* crops, int n, int order) {
+// chunk > 0 (large batches): the pixels travel in chunks of `chunk` crops on the copy stream, and after_chunk(i0, cnt) is called as
+// soon as a chunk's copies are enqueued (the handle's stream already waits for them): the caller launches that chunk's preprocess
+// and encoder there, so the host-side copy of chunk i+1 overlaps the GPU work on chunk i.
+int stage_crops(mocr_handle* h, const mocr_crop_t* crops, int n, int order, int chunk = 0, const std::function<int(int, int)>* after_chunk = nullptr) {
   if (!h->finalized) return fail(h, MOCR_ERR_INVALID, "weights are not finalized");
   if (n < 1 || n > h->max_batch) return fail(h, MOCR_ERR_CAPACITY, "batch of %d crops, handle capacity is %d", n, h->max_batch);
   if (crops == nullptr) return fail(h, MOCR_ERR_INVALID, "crops is NULL");
@@ -686,54 +691,7 @@ int stage_crops(mocr_handle* h, const mocr_crop_t* crops, int n, int order) {
     off += (rowb * c.height + 15) & ~static_cast<size_t>(15);
   }
   offs[n] = off;
-  // pixels -> pinned arena -> device.  Workers take contiguous runs of crops of about equal bytes; each uploads its run
-  // as soon as it is copied (slices of >= 1 MB), so host copy and H2D overlap and a page batch (100+ MB) is not bound by
-  // one core's memcpy rate.
-  auto copy_run = [&](int lo, int hi) -> cudaError_t {
-    size_t sent = offs[lo];
-    for (int i = lo; i < hi; ++i) {
-      const mocr_crop_t& c = crops[i];
-      const size_t rowb = static_cast<size_t>(c.width) * c.channels;
-      if (static_cast<size_t>(c.stride) == rowb) {
-        memcpy(h->h_arena + offs[i], c.data, rowb * c.height);
-      } else {
-        for (int y = 0; y < c.height; ++y) memcpy(h->h_arena + offs[i] + y * rowb, c.data + static_cast<size_t>(y) * c.stride, rowb);
-      }
-      if (offs[i + 1] - sent >= (1u << 20) || i + 1 == hi) {
-        const cudaError_t e = cudaMemcpyAsync(h->d_arena + sent, h->h_arena + sent, offs[i + 1] - sent, cudaMemcpyHostToDevice, h->stream);
-        if (e != cudaSuccess) return e;
-        sent = offs[i + 1];
-      }
-    }
-    return cudaSuccess;
-  };
-  const int workers = static_cast<int>(std::min<size_t>(h->stage_threads, std::max<size_t>(1, off >> 23)));     // one per 8 MB, at most stage_threads
-  if (workers <= 1) {
-    CK(copy_run(0, n));
-  } else {
-    std::vector<std::thread> pool;
-    std::vector<cudaError_t> errs(workers, cudaSuccess);
-    int lo = 0;
-    for (int w = 0; w < workers; ++w) {
-      const size_t target = off * (w + 1) / workers;
-      int hi = lo;
-      while (hi < n && (offs[hi + 1] <= target || w == workers - 1)) ++hi;
-      if (w == workers - 1) hi = n;
-      const int device = h->device;
-      try {
-        pool.emplace_back([&, w, lo, hi, device]() {
-          cudaSetDevice(device);
-          errs[w] = copy_run(lo, hi);
-        });
-      } catch (...) {          // no thread to be had: this run is copied here (nothing may cross the C ABI as an exception)
-        errs[w] = copy_run(lo, hi);
-      }
-      lo = hi;
-    }
-    for (auto& th : pool) th.join();
-    for (cudaError_t e : errs)
-      if (e != cudaSuccess) return fail(h, MOCR_ERR_CUDA, "crop upload failed: %s", cudaGetErrorString(e));
-  }
+  // resampling tables and descriptors first: a chunk's preprocess may start as soon as its pixels have arrived
   h->pre_pitch = round_up(max_w, 16);
   h->pre_tmp_rows = tmp_rows;
   h->pre_bgr = order == MOCR_BGR ? 1 : 0;
@@ -756,6 +714,66 @@ int stage_crops(mocr_handle* h, const mocr_crop_t* crops, int n, int order) {
   CK(cudaMemcpyAsync(h->d_descs, h->h_descs, sizeof(CropDesc) * n, cudaMemcpyHostToDevice, h->stream));
   h->n = n;
   h->staged_ok = true;
+  // pixels -> pinned arena -> device.  Workers take contiguous runs of crops of about equal bytes; each uploads its run
+  // as soon as it is copied (slices of >= 1 MB), so host copy and H2D overlap and a page batch (100+ MB) is not bound by
+  // one core's memcpy rate.
+  const bool chunked = chunk > 0 && after_chunk != nullptr && n > chunk && h->stream_enc != nullptr;
+  cudaStream_t copy_stream = chunked ? h->stream_enc : h->stream;
+  auto copy_run = [&](int lo, int hi) -> cudaError_t {
+    size_t sent = offs[lo];
+    for (int i = lo; i < hi; ++i) {
+      const mocr_crop_t& c = crops[i];
+      const size_t rowb = static_cast<size_t>(c.width) * c.channels;
+      if (static_cast<size_t>(c.stride) == rowb) {
+        memcpy(h->h_arena + offs[i], c.data, rowb * c.height);
+      } else {
+        for (int y = 0; y < c.height; ++y) memcpy(h->h_arena + offs[i] + y * rowb, c.data + static_cast<size_t>(y) * c.stride, rowb);
+      }
+      if (offs[i + 1] - sent >= (1u << 20) || i + 1 == hi) {
+        const cudaError_t e = cudaMemcpyAsync(h->d_arena + sent, h->h_arena + sent, offs[i + 1] - sent, cudaMemcpyHostToDevice, copy_stream);
+        if (e != cudaSuccess) return e;
+        sent = offs[i + 1];
+      }
+    }
+    return cudaSuccess;
+  };
+  if (chunked) CK(cudaStreamSynchronize(h->stream_enc));
+  for (int c0 = 0; c0 < n; c0 += chunked ? chunk : n) {
+  const int c1 = chunked ? std::min(n, c0 + chunk) : n;
+  const size_t cbytes = offs[c1] - offs[c0];
+  const int workers = static_cast<int>(std::min<size_t>(h->stage_threads, std::max<size_t>(1, cbytes >> 23)));     // one per 8 MB, at most stage_threads
+  if (workers <= 1) {
+    CK(copy_run(c0, c1));
+  } else {
+    std::vector<std::thread> pool;
+    std::vector<cudaError_t> errs(workers, cudaSuccess);
+    int lo = c0;
+    for (int w = 0; w < workers; ++w) {
+      const size_t target = offs[c0] + cbytes * (w + 1) / workers;
+      int hi = lo;
+      while (hi < c1 && (offs[hi + 1] <= target || w == workers - 1)) ++hi;
+      if (w == workers - 1) hi = c1;
+      const int device = h->device;
+      try {
+        pool.emplace_back([&, w, lo, hi, device]() {
+          cudaSetDevice(device);
+          errs[w] = copy_run(lo, hi);
+        });
+      } catch (...) {          // no thread to be had: this run is copied here (nothing may cross the C ABI as an exception)
+        errs[w] = copy_run(lo, hi);
+      }
+      lo = hi;
+    }
+    for (auto& th : pool) th.join();
+    for (cudaError_t e : errs)
+      if (e != cudaSuccess) return fail(h, MOCR_ERR_CUDA, "crop upload failed: %s", cudaGetErrorString(e));
+  }
+  if (chunked) {
+    CK(cudaEventRecord(h->ev_first, copy_stream));
+    CK(cudaStreamWaitEvent(h->stream, h->ev_first, 0));
+    TRY((*after_chunk)(c0, c1 - c0));
+  }
+  }
   return MOCR_OK;
 }
 
@@ -1740,6 +1758,31 @@ int mocr_run_resident(mocr_handle_t* h, int max_length) {
   return decode(h, max_length, nullptr);
 }
 
+// Stage, preprocess and encode m crops.  Batches of at least two chunks (option "stage_chunk", 128 crops: 197 m-tiles fill the
+// encoder GEMMs' waves exactly) are copied chunk by chunk on the copy stream while the encoder already works on the chunks that
+// have arrived; smaller ones go in one piece.
+int stage_encode(mocr_handle* h, const mocr_crop_t* crops, int m, int order) {
+  const int chunk = h->stage_chunk;
+  if (chunk <= 0 || m < 2 * chunk || h->taps != 0) {
+    TRY(stage_crops(h, crops, m, order));
+    TRY(preprocess(h));
+    return encode(h);
+  }
+  struct Restore {
+    mocr_handle* h;
+    ~Restore() { h->sub_i0 = h->sub_n = 0; }
+  } restore{h};
+  const std::function<int(int, int)> after = [h](int i0, int cnt) -> int {
+    h->sub_i0 = i0;
+    h->sub_n = cnt;
+    TRY(preprocess(h));
+    return encode(h);
+  };
+  TRY(stage_crops(h, crops, m, order, chunk, &after));
+  h->sub_i0 = h->sub_n = 0;
+  return MOCR_OK;          // pre_ok / enc_ok were set by the last chunk; every chunk's work is ordered on the handle's stream
+}
+
 int mocr_recognize(mocr_handle_t* h, const mocr_crop_t* crops, int n, int channel_order, int max_length, int32_t* out_ids,
                    int32_t* out_lens) {
   TRY(check_handle(h));
@@ -1751,9 +1794,7 @@ int mocr_recognize(mocr_handle_t* h, const mocr_crop_t* crops, int n, int channe
       if (h->slots > 0 && h->pipeline && m > h->slots && h->taps == 0) {
         TRY(recognize_pipelined(h, crops + i0, m, channel_order, max_length));
       } else {
-        TRY(stage_crops(h, crops + i0, m, channel_order));
-        TRY(preprocess(h));
-        TRY(encode(h));
+        TRY(stage_encode(h, crops + i0, m, channel_order));
         TRY(decode(h, max_length, nullptr));
       }
       TRY(fetch_ids(h, out_ids + static_cast<size_t>(i0) * max_length, out_lens ? out_lens + i0 : nullptr));
@@ -2194,6 +2235,7 @@ int mocr_set_option(mocr_handle_t* h, const char* key, int value) {
   else if (k == "big_attn_grid" && value >= 0) h->big_attn_grid = value;
   else if (k == "big_attn_rows") h->big_attn_rows = value != 0;
   else if (k == "enc_tma_store") h->enc_tma_store = value != 0;
+  else if (k == "stage_chunk" && value >= 0) h->stage_chunk = value;
   else if (k == "big_accum") h->big_accum = value != 0;
 #ifdef MOCR_GEMM_DBG
   else if (k == "gemm_dbg") h->gemm_dbg = value;

@@ -314,3 +314,23 @@ def test_slot_refill_gives_the_same_ids_in_fewer_steps():
         assert np.array_equal(ids, ids_ref) and np.array_equal(lens, lens_ref)
     finally:
         eng.close()
+
+
+def test_chunked_staging_gives_the_same_ids(weights0):
+    """Large batches are staged in chunks on a copy stream, each chunk preprocessed and encoded as it arrives (engine.cu:
+    stage_encode): ids and lengths equal the one-piece path, chunk boundaries inside and at the end of the batch included."""
+    from manga_ocr_b200.engine import Engine
+    crops = C.page_batch(300, seed=21)
+    T = 8
+    eng = Engine(weights0, device=0, max_batch=300, max_length=T)
+    try:
+        eng.set_option("stage_chunk", 0)
+        ids0, lens0 = eng.recognize(crops)
+        for chunk in (128, 100, 150):
+            eng.set_option("stage_chunk", chunk)
+            ids1, lens1 = eng.recognize(crops)
+            assert np.array_equal(ids0, ids1) and np.array_equal(lens0, lens1), chunk
+            ids2, _ = eng.recognize(crops[:257])          # a second batch on the same handle, ragged last chunk
+            assert np.array_equal(ids2, ids0[:257]), chunk
+    finally:
+        eng.close()
