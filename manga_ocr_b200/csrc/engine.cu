@@ -1988,7 +1988,7 @@ int decode_beam_device(mocr_handle* h, int beams, int max_length, int ngram, flo
     // (programmatic dependent launch like the stage kernels: each waits for its predecessor with griddepcontrol.wait)
     CK(launch_pdl(h, beam_topk_dev_kernel, R, 256, 0, d, static_cast<const float*>(h->logits_tap)));
     CK(launch_pdl(h, beam_select_kernel, n, 128, 0, p, d));
-    CK(launch_pdl_grid(h, beam_kv_copy_kernel, dim3(R, 2 * kDecLayers), 256, d, bc, h->max_length));
+    CK(launch_pdl_grid(h, beam_kv_copy_kernel, dim3(R, 2 * kDecLayers, kBeamCopySplit), 256, d, bc, h->max_length));
     h->launches += 3;
     return MOCR_OK;
   };

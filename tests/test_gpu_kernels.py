@@ -19,6 +19,10 @@ GEMM_CASES = [
     (8, 6144, 768, 64, 4), (64, 6144, 768, 128, 4), (3, 6144, 768, 32, 4),
     # 7 = in-place f32 accumulate through the TMA reduce-add epilogue (ragged last tile: rows >= M are clipped by the map)
     (1000, 768, 3072, 256, 7), (1576, 768, 768, 256, 7), (333, 768, 768, 128, 7), (65, 768, 256, 64, 7), (12608, 768, 768, 256, 7),
+    # more tiles than SMs and not a multiple of them: the stream-K work split (boundary tiles finished from a partial of the
+    # neighbouring CTA), every epilogue family; M = 64 x 197 is the headline's encoder
+    (12608, 2304, 768, 256, 0), (12608, 3072, 768, 256, 1), (12608, 768, 3072, 256, 7), (12608, 768, 3072, 128, 7),
+    (20000, 768, 256, 256, 2), (9000, 768, 768, 64, 0),
 ]
 
 
@@ -38,8 +42,10 @@ def test_gemm_against_torch(engine8, M, N, K, bn, epi):
         ref = ref + torch.from_numpy(R).double()
     ref = ref.numpy()
     err = np.abs(got - ref).max()
-    if epi in (0, 1):     # bf16 output: half an ulp of the largest magnitude
-        assert err <= 2.0 ** -8 * max(1.0, np.abs(ref).max()), err
+    if epi in (0, 1):     # bf16 output: half an ulp of the element's binade, plus the fp32 accumulation error that can flip a rounding
+        ulp_half = 2.0 ** (np.floor(np.log2(np.maximum(np.abs(ref), 2.0 ** -20))) - 8)
+        assert (np.abs(got - ref) <= 2.0 * ulp_half + 1e-4).all(), float((np.abs(got - ref) / ulp_half).max())
+        assert err <= 2.0 ** -7 * max(1.0, np.abs(ref).max()), err
     else:                 # fp32 output: fp32 accumulation over K
         assert err <= 1e-3, err
     if epi == 4:
