@@ -442,6 +442,7 @@ def run_b200(args, rank, local_rank, world):
         pe.stage(page, RGB)
         pstream = torch.cuda.ExternalStream(pe.stream, device=local_rank)
         a0 = torch.cuda.Event(enable_timing=True); a1 = torch.cuda.Event(enable_timing=True)
+        pe.run_resident(MAX_LENGTH); pe.sync()     # untimed: the one-piece encoder graph of this batch size (the e2e path stages and encodes in chunks)
         a0.record(pstream); pe.run_resident(MAX_LENGTH); a1.record(pstream); pe.sync()
         dt_max, dev_ms = max_over_ranks(dt, a0.elapsed_time(a1))
         extra["page512"] = {"workload": "configs[2]: 512 mixed-size crops (seed 1003), strong scaling", "crops": total, "n_gpus": world,
