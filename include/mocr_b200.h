@@ -165,7 +165,8 @@ int mocr_get_region_mask(mocr_handle_t* h, int index, uint8_t* out);
 int mocr_get_step_logits(mocr_handle_t* h, float* out /*[n,max_length-1,6144]*/);
 
 /* Kernel-level unit hooks (tests only): run ONE product kernel on caller-supplied host data.
- * epi: 0 bf16, 1 bf16+GELU, 2 f32+residual, 4 arg-max (out = logits), 5 f32+GELU.
+ * epi: 0 bf16, 1 bf16+GELU, 2 f32+residual, 4 arg-max (out = logits), 5 f32+GELU, 7 in-place f32 accumulate (resid = initial out;
+ * bn = 0 selects the cluster K-split kernel of the large-batch decoder program).
  * out = epilogue(A[M,K] * Wt[N,K]^T + bias), inputs rounded to bf16 exactly as the engine stores them.
  * Note the attention hook expects the 1/sqrt(64) scale already folded into q. */
 int mocr_test_gemm(mocr_handle_t* h, int epi, int bn, int M, int N, int K, const float* A, const float* Wt, const float* bias,

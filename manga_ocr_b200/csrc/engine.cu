@@ -30,6 +30,7 @@
 #include "decode_stages.cuh"
 #include "encoder_attn_tc.cuh"
 #include "gemm_tcgen05.cuh"
+#include "gemm_ksplit.cuh"
 #include "preprocess.cuh"
 #include "region_mask.cuh"
 #include "beam_search.h"
@@ -150,6 +151,7 @@ struct mocr_handle {
 #ifdef MOCR_GEMM_DBG
   int gemm_dbg = 0;
 #endif
+  int big_ksplit = 1;       // ... and split their K dimension over clusters of four CTAs (gemm_ksplit.cuh) while tiles x 4 <= SMs
   int big_accum = 1;        // large-batch program: the residual projections accumulate into x in place (EPI_F32_ACCUM) instead of y = x + ...
   int stage_chunk = 128;    // crops per staging chunk of a large batch (0 = one piece): see stage_encode
   int enc_tma_store = 1;    // encoder GEMMs with bf16 outputs (QKV, FFN1): rows leave as TMA stores from a staging tile (GemmArgs::out_tma)
@@ -1169,6 +1171,31 @@ int launch_gemm_stage_tc(mocr_handle* h, const __nv_bfloat16* a_ptr, int K, Line
   return MOCR_OK;
 }
 
+// The residual projections of the large-batch program with K split over clusters of four CTAs (gemm_ksplit.cuh).
+int launch_gemm_ksplit(mocr_handle* h, const __nv_bfloat16* a_ptr, int K, Linear& L, int rows, float* x) {
+  static bool attr_done[16] = {};
+  if (!attr_done[h->device & 15]) {
+    CK(cudaFuncSetAttribute(gemm_ksplit_accum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kKsSmemBytes));
+    attr_done[h->device & 15] = true;
+  }
+  CUtensorMap ma;
+  TRY(make_map(h, &ma, a_ptr, rows, K, kGemmBM));
+  const CUtensorMap* mb;
+  TRY(linear_map(h, &L, kKsBN, &mb));
+  GemmArgs a{};
+  a.M = rows;
+  a.N = L.N;
+  a.K = L.K;
+  a.bias = L.bias;
+  a.out = x;
+  a.ldo = L.N;
+  a.pdl = 1;
+  TRY(make_map_f32_out(h, &a.tmap_out, x, rows, L.N));
+  const int tiles = ((rows + kGemmBM - 1) / kGemmBM) * (L.N / kKsBN);
+  CK(launch_pdl(h, gemm_ksplit_accum_kernel, tiles * kKsSplit, kKsThreads, kKsSmemBytes, ma, *mb, a));
+  return MOCR_OK;
+}
+
 Linear* dec_linear(mocr_handle* h, int lin) {
   if (lin == PD_LIN_HEAD_T) return &h->head_t;
   if (lin == PD_LIN_HEAD_DEC) return &h->head_dec;
@@ -1199,6 +1226,11 @@ int launch_tc_stage(mocr_handle* h, const PdParams& p, const PdStage& st) {
       if (!wide) return launch_gemm_stage_tc<32, EPI_F32_RESID>(h, st.A, st.K, L, p.B, out_f32(st.of, st.ldo, st.resid, kD));
       return launch_gemm_stage_tc<64, EPI_F32_RESID>(h, st.A, st.K, L, p.B, out_f32(st.of, st.ldo, st.resid, kD));
     case EPI_F32_ACCUM:      // x += A W^T + bias in place (TMA reduce-add: the SM never reads the residual)
+      // (measured at 512 rows: FFN2, K = 3072, 17.4 -> 11.2 us; the K = 768 projections 6.6 -> 8.4 us: the cluster's fixed costs
+      //  - two cluster barriers, the exchange - outweigh nine saved k-blocks, so only long K goes this way)
+      if (h->big_ksplit && st.K >= 2048 && st.N % kKsBN == 0 && st.K % (kGemmBK * kKsSplit) == 0 &&
+          ((p.B + kGemmBM - 1) / kGemmBM) * (st.N / kKsBN) * kKsSplit <= h->sms)
+        return launch_gemm_ksplit(h, st.A, st.K, L, p.B, st.of);
       if (!wide) return launch_gemm_stage_tc<32, EPI_F32_ACCUM>(h, st.A, st.K, L, p.B, out_f32(st.of, st.ldo));
       return launch_gemm_stage_tc<64, EPI_F32_ACCUM>(h, st.A, st.K, L, p.B, out_f32(st.of, st.ldo));
     case EPI_F32_GELU:
@@ -2237,6 +2269,7 @@ int mocr_set_option(mocr_handle_t* h, const char* key, int value) {
   else if (k == "enc_tma_store") h->enc_tma_store = value != 0;
   else if (k == "stage_chunk" && value >= 0) h->stage_chunk = value;
   else if (k == "big_accum") h->big_accum = value != 0;
+  else if (k == "big_ksplit") h->big_ksplit = value != 0;
 #ifdef MOCR_GEMM_DBG
   else if (k == "gemm_dbg") h->gemm_dbg = value;
 #endif
@@ -2373,7 +2406,8 @@ int mocr_test_gemm(mocr_handle_t* h, int epi, int bn, int M, int N, int K, const
                    const float* resid, float* out, int32_t* out_argmax) {
   TRY(check_handle(h));
   std::lock_guard<std::mutex> lock(h->mu);
-  if (M < 1 || N < 1 || K < 1 || A == nullptr || Wt == nullptr || bias == nullptr || out == nullptr || N % bn != 0 || K % kGemmBK != 0)
+  if (M < 1 || N < 1 || K < 1 || A == nullptr || Wt == nullptr || bias == nullptr || out == nullptr || (bn != 0 && N % bn != 0) || K % kGemmBK != 0 ||
+      (bn == 0 && epi != EPI_F32_ACCUM))
     return fail(h, MOCR_ERR_INVALID, "bad test_gemm argument");
   if (epi == EPI_PATCH) return fail(h, MOCR_ERR_INVALID, "EPI_PATCH is covered by the encoder test");
   const int Mp = round_up(M, kGemmBM);
@@ -2413,7 +2447,7 @@ int mocr_test_gemm(mocr_handle_t* h, int epi, int bn, int M, int N, int K, const
       if (resid == nullptr) return fail(h, MOCR_ERR_INVALID, "resid is NULL");
       CK(cudaMemcpy(d_out, resid, mn * sizeof(float), cudaMemcpyHostToDevice));
     }
-    const int parts = 2 * (N / bn);
+    const int parts = bn > 0 ? 2 * (N / bn) : 0;
     if (epi == EPI_ARGMAX) {
       CK(cudaMalloc(&d_pm, static_cast<size_t>(M) * parts * sizeof(float)));
       CK(cudaMalloc(&d_pi, static_cast<size_t>(M) * parts * sizeof(int)));
@@ -2425,7 +2459,15 @@ int mocr_test_gemm(mocr_handle_t* h, int epi, int bn, int M, int N, int K, const
       g.step = static_cast<const int*>(d_step);
       g.tap_steps = 1;
     }
-    TRY(gemm(h, epi, bn, a, L, M, g));
+    if (epi == EPI_F32_ACCUM && bn == 0) {     // the cluster K-split kernel of the large-batch decoder program
+      if (N % kKsBN != 0 || K % (kGemmBK * kKsSplit) != 0) return fail(h, MOCR_ERR_INVALID, "K-split GEMM needs N %% 128 == 0 and K %% 256 == 0");
+      h->pdl_now = 0;
+      const int kr = launch_gemm_ksplit(h, a.p, K, L, M, static_cast<float*>(d_out));
+      h->pdl_now = 1;
+      TRY(kr);
+    } else {
+      TRY(gemm(h, epi, bn, a, L, M, g));
+    }
     CK(cudaStreamSynchronize(h->stream));
     if (epi == EPI_BF16 || epi == EPI_BF16_GELU) {
       std::vector<uint16_t> ob(mn);

@@ -23,6 +23,9 @@ GEMM_CASES = [
     # neighbouring CTA), every epilogue family; M = 64 x 197 is the headline's encoder
     (12608, 2304, 768, 256, 0), (12608, 3072, 768, 256, 1), (12608, 768, 3072, 256, 7), (12608, 768, 3072, 128, 7),
     (20000, 768, 256, 256, 2), (9000, 768, 768, 64, 0),
+    # bn = 0: the cluster K-split kernel of the large-batch decoder program (gemm_ksplit.cuh): four CTAs per 128 x 128 tile, partial
+    # chunks exchanged through distributed shared memory, fixed-order sum, TMA reduce-add into the residual
+    (512, 768, 3072, 0, 7), (512, 768, 768, 0, 7), (300, 768, 768, 0, 7), (130, 768, 3072, 0, 7), (1, 768, 768, 0, 7),
 ]
 
 
