@@ -158,7 +158,8 @@ struct mocr_handle {
   int big_attn_rows = 1;    // large-batch program: attention as one WARP per (row, head) unit (pd_attention_rows_kernel); 0 = the four-warp kernel
   int big_attn_grid = 384;  // CTAs of the attention stages in the large-batch program (0 = as many as there is work for); warp-per-unit kernel at 512 rows: 384 -> 348 us per step, 444 -> 355, 296 -> 375, 512 -> 405
   int big_bn768 = 32;       // tile width of the large-batch program's N = 768 GEMMs (32 or 64)
-  int big_vocab_bn = 64;    // tile width of its vocabulary projection (64 or 128)
+  int big_vocab_bn = 0;     // tile width of its vocabulary projection: 64, 128, 256, or 0 = by row count (about 96 tiles: 64 columns per 128-row
+                            // m-tile; us per step 64 / 128 / 256: 128 rows 178.6 / 180.7 / 183.0, 256 rows 227.3 / 224.7 / 227.5, 512 rows 317.5 / 314.1 / 312.6)
   int big_rows = 112;       // more decoder rows than this: the large-batch program (every Linear on the tcgen05 GEMM, 128-row tiles).  Measured us per step,
                             // small / large program: 96 rows 157 / 178, 112 rows 184 / 182, 128 rows 199 / 188, 144 rows 244 / 216, 160 rows 248 / 220
   int pipeline = 0;         // with slot refill, 1 (2: equal stream priorities): encode the waiting crops in sub-chunks on a second stream while the decoder
@@ -1050,6 +1051,13 @@ PdLinear pd_lin(const Linear& L) { return PdLinear{L.w, L.bias}; }
 PdLn pd_ln(const LnParams& l) { return PdLn{l.g, l.b}; }
 
 // n = decoder rows, n_crops = crops they work through (0: one crop per row)
+// tile width of the large-batch program's vocabulary projection for n rows
+int big_vocab_tile(const mocr_handle* h, int n) {
+  if (h->big_vocab_bn != 0) return h->big_vocab_bn;
+  const int m_tiles = (n + kGemmBM - 1) / kGemmBM;
+  return m_tiles <= 1 ? 64 : (m_tiles <= 3 ? 128 : 256);
+}
+
 PdParams make_pd_params(mocr_handle* h, int n, int max_length, bool forced, bool tap, int n_crops = 0) {
   PdParams p{};
   p.B = n;
@@ -1061,7 +1069,7 @@ PdParams make_pd_params(mocr_handle* h, int n, int max_length, bool forced, bool
   p.cache_len = h->max_length;
   p.kv_div = 1;
   p.big = n > h->big_rows ? 1 : 0;
-  p.n_partials = (p.big || (h->dec_tc & 1)) ? 2 * (kVocab / ((p.big && h->big_vocab_bn == 128) ? 128 : 64)) : kPdVocabTiles;
+  p.n_partials = (p.big || (h->dec_tc & 1)) ? 2 * (kVocab / (p.big ? big_vocab_tile(h, n) : 64)) : kPdVocabTiles;
   p.logits_cur = 0;
   p.kv_evict_first = h->kv_evict_first >= 0 ? h->kv_evict_first : (p.big ? 3 : 2);
   p.fuse_ln = h->fuse_ln;
@@ -1302,7 +1310,9 @@ int decode_stage_step(mocr_handle* h, const PdParams& p, bool skip_next = false)
         a.logits = p.logits;
         a.step = p.logits_cur ? h->d_zero : p.pos;          // beam mode taps the current step only: [B, 6144]
         a.tap_steps = p.logits_cur ? 1 : p.max_len - 1;
-        if (p.big && h->big_vocab_bn == 128) TRY((launch_gemm_stage_tc<128, EPI_ARGMAX>(h, st.A, kD, h->head_dec, p.B, a)));
+        const int vbn = p.big ? big_vocab_tile(h, p.B) : 64;
+        if (vbn == 256) TRY((launch_gemm_stage_tc<256, EPI_ARGMAX>(h, st.A, kD, h->head_dec, p.B, a)));
+        else if (vbn == 128) TRY((launch_gemm_stage_tc<128, EPI_ARGMAX>(h, st.A, kD, h->head_dec, p.B, a)));
         else TRY((launch_gemm_stage_tc<64, EPI_ARGMAX>(h, st.A, kD, h->head_dec, p.B, a)));
       } else {
         const int nt = st.type == PD_GEMM16 ? 16 : (st.type == PD_GEMM32 ? 32 : 48);
@@ -2274,7 +2284,7 @@ int mocr_set_option(mocr_handle_t* h, const char* key, int value) {
   else if (k == "gemm_dbg") h->gemm_dbg = value;
 #endif
   else if (k == "big_bn768" && (value == 32 || value == 64)) h->big_bn768 = value;
-  else if (k == "big_vocab_bn" && (value == 64 || value == 128)) h->big_vocab_bn = value;
+  else if (k == "big_vocab_bn" && (value == 0 || value == 64 || value == 128 || value == 256)) h->big_vocab_bn = value;
   else if (k == "steps_per_graph" && value >= 1 && value <= 64) h->steps_per_graph = value;
   else if (k == "decode_prof") h->decode_prof = value != 0;
   else return fail(h, MOCR_ERR_INVALID, "unknown option or bad value: %s=%d", key, value);
@@ -2369,7 +2379,10 @@ int mocr_time_kernel(mocr_handle_t* h, const char* kernel, int iters, float* ms_
             ga.part_idx = p.part_idx;
             ga.step = p.pos;
             ga.tap_steps = p.max_len - 1;
-            r = launch_gemm_stage_tc<64, EPI_ARGMAX>(h, st.A, kD, h->head_dec, p.B, ga);
+            const int vbn = p.big ? big_vocab_tile(h, p.B) : 64;
+            if (vbn == 256) r = launch_gemm_stage_tc<256, EPI_ARGMAX>(h, st.A, kD, h->head_dec, p.B, ga);
+            else if (vbn == 128) r = launch_gemm_stage_tc<128, EPI_ARGMAX>(h, st.A, kD, h->head_dec, p.B, ga);
+            else r = launch_gemm_stage_tc<64, EPI_ARGMAX>(h, st.A, kD, h->head_dec, p.B, ga);
           } else {
             le = launch_pdl(h, pd_gemm_kernel<48, 1>, (st.N / 48) * st.ksplit, 128 * kPdStageKS, pd_gemm_smem_bytes(48), p, st);
           }
