@@ -259,22 +259,40 @@ __global__ void __launch_bounds__(128) beam_select_kernel(const __grid_constant_
     if (rank < beams) s_midx[rank] = tid;
   }
   __syncthreads();
-  // ---- token rows (read the old parity, write the new one)
-  for (int j = 0; j < beams; ++j) {
-    const int i = s_midx[j];
-    int* dst = fin_new + static_cast<size_t>(row0 + j) * T;
-    if (i < beams) {
-      const int* src = fin_old + static_cast<size_t>(row0 + i) * T;
-      for (int c = tid; c < T; c += blockDim.x) dst[c] = src[c];
-    } else {
-      const int k = i - beams;
-      const int* src = run_old + static_cast<size_t>(row0 + s_top_beam[k]) * T;
-      for (int c = tid; c < T; c += blockDim.x) dst[c] = c == cur_len ? s_top_tok[k] : src[c];
+  // ---- token rows (read the old parity, write the new one): one warp per row, the whole row in registers before the first
+  //      store (row after row with interleaved loads and stores, every piece waited for the previous stores: ~24 dependent
+  //      L2 round trips per step)
+  for (int rowi = warp; rowi < 2 * beams; rowi += blockDim.x >> 5) {
+    const int j = rowi >> 1;
+    const int* src;
+    int* dst;
+    int tok = -1;                                   // token written at position cur_len (-1: plain copy)
+    if ((rowi & 1) == 0) {                          // finished set, slot j
+      const int i = s_midx[j];
+      dst = fin_new + static_cast<size_t>(row0 + j) * T;
+      if (i < beams) {
+        src = fin_old + static_cast<size_t>(row0 + i) * T;
+      } else {
+        src = run_old + static_cast<size_t>(row0 + s_top_beam[i - beams]) * T;
+        tok = s_top_tok[i - beams];
+      }
+    } else {                                        // running beam j
+      const int k = s_sel[j];
+      src = run_old + static_cast<size_t>(row0 + s_top_beam[k]) * T;
+      dst = run_new + static_cast<size_t>(row0 + j) * T;
+      tok = s_top_tok[k];
     }
-    const int k = s_sel[j];
-    const int* rsrc = run_old + static_cast<size_t>(row0 + s_top_beam[k]) * T;
-    int* rdst = run_new + static_cast<size_t>(row0 + j) * T;
-    for (int c = tid; c < T; c += blockDim.x) rdst[c] = c == cur_len ? s_top_tok[k] : rsrc[c];
+    int v[16];                                      // T <= 512
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int c = lane + 32 * i;
+      v[i] = c < T ? src[c] : 0;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int c = lane + 32 * i;
+      if (c < T) dst[c] = (tok >= 0 && c == cur_len) ? tok : v[i];
+    }
   }
   // ---- every running row of the crop consumes its next token at position cur_len (one warp per row)
   {
