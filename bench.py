@@ -531,7 +531,7 @@ def run_b200(args, rank, local_rank, world):
                              "call_threads": n_threads, "call_crops_per_s": n_stream / dt_call, "call_s": dt_call,
                              "call_first_char_equal_to_batch": same1 / n_stream, "call_strings_equal_to_batch": same / n_stream, "h2d_bytes": int(sum(c.nbytes for c in scrops)),
                              "note": "__call__ blocks its caller until that crop is decoded: 50 threads bound the crops in flight to 50 "
-                                     "(<= 50 / GPUs per batch), whatever the engine could take. The batch call decodes >144 rows per GPU on the large-batch program "
+                                     "(<= 50 / GPUs per batch), whatever the engine could take. The batch call decodes >112 rows per GPU on the large-batch program "
                                      "(tcgen05 GEMMs), the small batches of __call__ on the mma.sync program: with random-init weights (top-2 margins "
                                      "of ~1e-2) the two roundings part at a near-tie somewhere in 299 tokens for most crops, hence the low "
                                      "whole-string agreement; parity of each program with the oracle is what tests/ pins"}

@@ -296,12 +296,19 @@ class MangaOcr:
         so that callers arriving together share a batch, then take this GPU's share of what is queued (with several
         GPUs nobody grabs the whole queue).  None = closed and drained."""
         if self.linger_s > 0 and 0 < len(self._queue) < self.max_batch and not self._closed:
-            deadline = time.monotonic() + self.linger_s
+            # A lone caller waits linger_s.  While requests keep arriving (a pool of workers resubmitting after the previous
+            # batch: 50 Python threads need a few ms to come back) every arrival extends the wait by a third of linger_s,
+            # up to 4 x linger_s in total - otherwise the burst is served as two half batches, each a full decode long.
+            now = time.monotonic()
+            deadline, cap, seen = now + self.linger_s, now + 4.0 * self.linger_s, len(self._queue)
             while len(self._queue) < self.max_batch and not self._closed:
-                left = deadline - time.monotonic()
+                left = min(deadline, cap) - time.monotonic()
                 if left <= 0:
                     break
                 self._cv.wait(left)
+                if len(self._queue) > seen:
+                    seen = len(self._queue)
+                    deadline = max(deadline, time.monotonic() + self.linger_s / 3.0)
         if not self._queue:
             return None
         share = -(-len(self._queue) // max(1, len(self.engines) - self._busy))     # ceil(queued / idle GPUs)

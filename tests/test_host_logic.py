@@ -239,6 +239,31 @@ def test_micro_batcher_gathers_concurrent_callers(stub_ocr):
     assert sum(eng.batches) == 12 and max(eng.batches) >= 6, eng.batches      # not twelve batches of one
 
 
+def test_micro_batcher_linger_extends_while_callers_keep_arriving(stub_ocr):
+    """Callers that trickle in (a worker pool resubmitting: one every 5 ms for 40 ms, linger 30 ms) still share one batch: every
+    arrival extends the wait by a third of the linger; a lone caller is not held longer than the linger."""
+    import threading
+    import time
+    ocr = stub_ocr(devices=[0], max_batch=16, max_length=8, linger_ms=30)
+    out = {}
+
+    def run(i):
+        time.sleep(0.005 * i)
+        out[i] = ocr(_img(i))
+
+    ts = [threading.Thread(target=run, args=(i,)) for i in range(9)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    eng = _StubEngine.instances[0]
+    assert sum(eng.batches) == 9 and max(eng.batches) >= 7, eng.batches        # 9 arrivals over 40 ms: not cut off after 30 ms
+    n_before = len(eng.batches)
+    t0 = time.monotonic()
+    ocr(_img(3))
+    assert time.monotonic() - t0 < 0.2 and len(eng.batches) == n_before + 1    # alone: one linger, not the 4x cap
+
+
 def test_micro_batcher_shares_the_queue_between_gpus(stub_ocr):
     ocr = stub_ocr(devices=[0, 1], max_batch=64, max_length=8, linger_ms=20)
     got = _call_all(ocr, [v for v in range(41) if v != 13])
