@@ -39,3 +39,20 @@ growth = after[-1] - after[0]
 print("after-close in-use per cycle (MB):", [round(a / 2**20) for a in after], "growth:", round(growth / 2**20, 1))
 assert growth < 8 * 2**20
 print("stress ok")
+
+# ---- large batches: the large-batch program (> 112 rows), chunked staging (>= 256 crops), several passes (> max_batch), slot refill
+big_pool = C.page_batch(160, seed=7)
+after = []
+for cycle in range(3):
+    eng = Engine(w, device=0, max_batch=300, max_length=40)
+    for it in range(12):
+        n = int(rng.integers(100, 700))
+        idx = rng.integers(0, len(big_pool), n)
+        eng.set_option("slots", 64 if it % 3 == 2 else 0)
+        ids, lens = eng.recognize([big_pool[i] for i in idx])
+        assert ids.shape == (n, 40) and (ids[:, 0] == 2).all() and (lens >= 1).all()
+    eng.close()
+    after.append(free0 - torch.cuda.mem_get_info()[0])
+    print(f"large cycle {cycle}: after close {round(after[-1] / 2**20)} MB in use, {time.time() - t0:.0f} s", flush=True)
+assert after[-1] - after[0] < 8 * 2**20
+print("ok")
