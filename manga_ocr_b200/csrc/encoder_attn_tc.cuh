@@ -93,26 +93,35 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q /*box 64 
   {
     mbar_wait(bar_s, 0);                               // S is complete: Q and K have been read, their memory is free for P
     tc_fence_after();
-    // ---- pass 1: row maximum over the 197 valid keys
+    // A warp whose 32 query rows all lie past the 197th token (the last warp of the second tile) has nothing to compute: its P rows
+    // may hold anything (an output row depends on its own P row only, and these are never stored).
+    const bool warp_live = t * 128 + (warp & 3) * 32 < kEncTokens;
+    // ---- pass 1: row maximum over the 197 valid keys (two TMEM loads in flight per wait)
     float mx = -INFINITY;
+    if (warp_live) {
 #pragma unroll 1
-    for (int c = 0; c < 7; ++c) {
-      uint32_t v[32];
-      tmem_ld32(ts + static_cast<uint32_t>(c * 32), v);
-      tmem_ld_wait();
+      for (int c = 0; c < 7; c += 2) {
+        uint32_t v[32], w2[32];
+        tmem_ld32(ts + static_cast<uint32_t>(c * 32), v);
+        if (c + 1 < 7) tmem_ld32(ts + static_cast<uint32_t>(c * 32 + 32), w2);
+        tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (c * 32 + j < kEncTokens) mx = fmaxf(mx, __uint_as_float(v[j]));
+        for (int j = 0; j < 32; ++j)
+          if (c * 32 + j < kEncTokens) mx = fmaxf(mx, __uint_as_float(v[j]));
+        if (c + 1 < 7) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c * 32 + 32 + j < kEncTokens) mx = fmaxf(mx, __uint_as_float(w2[j]));
+        }
+      }
     }
     // ---- pass 2: p = exp(s - max), row sum, P (bf16) into the swizzled K-major A-operand layout
     const float mxl = mx * kLog2e;
     float sum = 0.f;
     uint8_t* prow = sPt + r * 128;
-#pragma unroll 1
-    for (int c = 0; c < 7; ++c) {
-      uint32_t v[32];
-      tmem_ld32(ts + static_cast<uint32_t>(c * 32), v);
-      tmem_ld_wait();
+    // one 32-key chunk: exp, row sum, 4 x 8 bf16 (16 B) into the P tile; key k lives in atom k / 64, chunk (k % 64) / 8, XOR-swizzled
+    // with row % 8
+    auto emit_chunk = [&](const uint32_t (&v)[32], int c) {
       float p[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
@@ -120,7 +129,6 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q /*box 64 
         p[j] = c * 32 + j < kEncTokens ? e : 0.f;
         sum += p[j];
       }
-      // 32 keys = 4 chunks of 8 bf16 (16 B); key k lives in atom k / 64, chunk (k % 64) / 8, XOR-swizzled with row % 8
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const int k0 = c * 32 + g * 8;
@@ -133,6 +141,17 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q /*box 64 
           const int atom = k0 >> 6, chunk = (k0 & 63) >> 3;
           *reinterpret_cast<uint4*>(prow + atom * (128 * 128) + ((chunk ^ (r & 7)) << 4)) = w;
         }
+      }
+    };
+    if (warp_live) {
+#pragma unroll 1
+      for (int c = 0; c < 7; c += 2) {                 // two TMEM loads in flight per wait
+        uint32_t v[32], w2[32];
+        tmem_ld32(ts + static_cast<uint32_t>(c * 32), v);
+        if (c + 1 < 7) tmem_ld32(ts + static_cast<uint32_t>(c * 32 + 32), w2);
+        tmem_ld_wait();
+        emit_chunk(v, c);
+        if (c + 1 < 7) emit_chunk(w2, c + 1);
       }
     }
     fence_proxy_async_smem();                          // generic-proxy writes of P -> visible to the tensor core
@@ -155,7 +174,7 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q /*box 64 
     mbar_wait(bar_o, 0);
     tc_fence_after();
     // ---- epilogue: O / sum -> bf16 -> ctx[row, head * 64 ..]
-    const float inv = __fdividef(1.0f, sum);           // sum >= 1 (the maximum contributes exp(0))
+    const float inv = warp_live ? __fdividef(1.0f, sum) : 0.f;   // sum >= 1 (the maximum contributes exp(0))
     uint32_t o0[32], o1[32];
     tmem_ld32(ts, o0);
     tmem_ld32(ts + 32, o1);
