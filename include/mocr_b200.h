@@ -194,6 +194,23 @@ int mocr_test_stage_gemm(mocr_handle_t* h, int kind, int n_rows, int N, int K, c
  * of int32 written (or needed when out is NULL), negative on error. */
 int mocr_resample_table(int in_size, int32_t* ksize, int32_t* out, int capacity);
 
+/* ---- admission into a running decode ------------------------------------------------------
+ * The reference decodes one crop per call (reference/src/ui/main_window.py:9801) from up to 50 worker threads
+ * (:608-611, :4317-4327); a batch API makes late callers wait for the whole batch in flight.  A session keeps `rows`
+ * decoder rows stepping and admits crops while it runs: mocr_session_add stages, preprocesses, encodes and publishes
+ * n crops (n <= free slots; out_slots[n] = the slot of each, 0 <= slot < max_batch), an idle row picks each of them
+ * up (the admission runs on a second stream: decode steps already launched keep running meanwhile);
+ * mocr_session_run launches `steps` greedy steps and, when out_lens is not NULL, waits for them and returns
+ * out_lens[max_batch]: > 0 for a slot whose crop has finished (its id count), 0 for running or unused slots (out_lens
+ * NULL = launch only; steps 0 = wait and read only: launch, admit, then poll); mocr_session_fetch copies the id rows of finished slots
+ * (out_ids [n, max_length], PAD-filled) and, with release != 0, frees the slots for reuse.  ids per crop equal
+ * mocr_recognize's.  Other compute entry points of the handle fail while a session is active. */
+int mocr_session_begin(mocr_handle_t* h, int channel_order, int max_length, int rows);
+int mocr_session_add(mocr_handle_t* h, const mocr_crop_t* crops, int n, int32_t* out_slots);
+int mocr_session_run(mocr_handle_t* h, int steps, int32_t* out_lens);
+int mocr_session_fetch(mocr_handle_t* h, const int32_t* slots, int n, int32_t* out_ids, int release);
+int mocr_session_end(mocr_handle_t* h);
+
 /* ---- plumbing --------------------------------------------------------------------------- */
 
 void* mocr_stream(mocr_handle_t* h);            /* the cudaStream_t all work is launched on   */

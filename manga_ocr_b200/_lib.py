@@ -73,6 +73,11 @@ _SIGNATURES = {
     "mocr_beam_banned": (c_int, [c_void_p, c_int, POINTER(c_int32), c_int]),
     "mocr_beam_step": (c_int, [c_void_p, POINTER(c_float), POINTER(c_int32), POINTER(c_int32), POINTER(c_int32)]),
     "mocr_beam_result": (c_int, [c_void_p, POINTER(c_int32), POINTER(c_int32), POINTER(c_float)]),
+    "mocr_session_begin": (c_int, [c_void_p, c_int, c_int, c_int]),
+    "mocr_session_add": (c_int, [c_void_p, POINTER(mocr_crop_t), c_int, POINTER(c_int32)]),
+    "mocr_session_run": (c_int, [c_void_p, c_int, POINTER(c_int32)]),
+    "mocr_session_fetch": (c_int, [c_void_p, POINTER(c_int32), c_int, POINTER(c_int32), c_int]),
+    "mocr_session_end": (c_int, [c_void_p]),
     "mocr_stage_crops": (c_int, [c_void_p, POINTER(mocr_crop_t), c_int, c_int]),
     "mocr_stage_regions": (c_int, [c_void_p, POINTER(mocr_crop_t), POINTER(mocr_region_t), c_int, c_int]),
     "mocr_get_region_mask": (c_int, [c_void_p, c_int, POINTER(c_uint8)]),

@@ -69,6 +69,9 @@ struct PdParams {
   EmbedWeights emb;
   const __nv_bfloat16* crosskv;   // [crop][layer][K|V][head][197][64]
   // state
+  const int* queue_slots;   // session mode (admission into a running decode): ring [n_crops] of crop SLOTS in publication order; the queue
+                            // counters then count publications, and publication i decodes into slot queue_slots[i % n_crops]
+  int idle_start;           // session mode: every row starts idle (no crop is ready yet)
   int ext_queue;            // 1: the queue is initialised and fed by the host's encoder stream (crops become ready while the decode runs)
   int n_crops;              // crops of this decode (>= B: with more crops than rows, a row that finishes takes the next waiting crop)
   int* ids;                 // [n_crops, max_len]
@@ -572,7 +575,7 @@ __device__ __forceinline__ int pd_pop_waiting_crop(const PdParams& p) {      // 
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(avail) : "l"(p.queue + 1) : "memory");
     if (static_cast<int>(head) >= avail) return -1;
     const unsigned int seen = atomicCAS(reinterpret_cast<unsigned int*>(p.queue), head, head + 1u);
-    if (seen == head) return static_cast<int>(head);
+    if (seen == head) return p.queue_slots != nullptr ? ldg_cg_s32(p.queue_slots + head % static_cast<unsigned int>(p.n_crops)) : static_cast<int>(head);
     head = seen;
   }
 }
@@ -605,7 +608,7 @@ __device__ __forceinline__ void pd_next_token_stage(Bar& bar, const PdParams& p,
     const bool was_finished = fin0 != 0;
     if (was_finished && (p.forced == nullptr || ps >= p.max_len - 1)) {
       // an idle row (its crop is done and nothing was waiting then): crops whose encoder K/V arrive later are picked up here
-      if (p.forced == nullptr && p.n_crops > p.B) {
+      if (p.forced == nullptr && (p.n_crops > p.B || p.queue_slots != nullptr)) {
         int c = lane == 0 ? pd_pop_waiting_crop(p) : 0;
         c = __shfl_sync(0xffffffffu, c, 0);
         if (c >= 0) {
@@ -642,7 +645,7 @@ __device__ __forceinline__ void pd_next_token_stage(Bar& bar, const PdParams& p,
       if (fin && !was_finished) {            // the crop is complete
         p.lens[crop] = np + 1 < p.max_len ? np + 1 : p.max_len;
         atomicAdd(p.queue + 2, 1);
-        if (p.forced == nullptr && p.n_crops > p.B) next_crop = pd_pop_waiting_crop(p);
+        if (p.forced == nullptr && (p.n_crops > p.B || p.queue_slots != nullptr)) next_crop = pd_pop_waiting_crop(p);
       }
       if (next_crop >= 0) {                  // the slot goes to the next waiting crop
         p.slot_crop[r] = next_crop;
@@ -1668,6 +1671,14 @@ __global__ void __launch_bounds__(kPdThreads) pd_begin_kernel(const __grid_const
     for (int i = lane; i < p.max_len; i += 32) p.ids[static_cast<size_t>(c) * p.max_len + i] = i == 0 ? 2 : 0;
     if (lane == 0) p.lens[c] = p.max_len <= 1 ? 1 : 0;
     if (c >= p.B) continue;
+    if (p.idle_start) {          // session mode: the row waits for a published crop
+      if (lane == 0) {
+        p.slot_crop[c] = 0;
+        p.pos[c] = 0;
+        p.finished[c] = 1;
+      }
+      continue;
+    }
     if (lane == 0) {
       p.slot_crop[c] = c;
       p.pos[c] = 0;
@@ -1690,6 +1701,28 @@ __global__ void pd_publish_kernel(int* queue, int head, int ready) {
   } else {
     __threadfence();
     atomicMax(queue + 1, ready);
+  }
+}
+
+// Session mode (admission into a running decode): crops whose encoder K/V have just been written into the given SLOTS become
+// available to idle rows.  The slots' id rows and lengths are reset here (a slot is reused once the host has fetched its previous
+// result), then the slot numbers enter the ring in publication order and the "ready" counter moves.  One CTA of 256 threads.
+struct PdSlotList {
+  int n;
+  int slot[64];
+};
+__global__ void __launch_bounds__(256) pd_publish_slots_kernel(int* queue, int* ring, int cap, int first_pub, int* ids, int* lens, int max_len,
+                                                               const PdSlotList l) {
+  for (int i = threadIdx.x; i < l.n * max_len; i += blockDim.x) {
+    const int k = i / max_len, c = i - k * max_len;
+    ids[static_cast<size_t>(l.slot[k]) * max_len + c] = c == 0 ? 2 : 0;
+  }
+  if (threadIdx.x < l.n) lens[l.slot[threadIdx.x]] = 0;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < l.n; ++i) ring[(first_pub + i) % cap] = l.slot[i];
+    __threadfence();
+    atomicMax(queue + 1, first_pub + l.n);
   }
 }
 

@@ -153,6 +153,15 @@ struct mocr_handle {
 #endif
   int big_ksplit = 1;       // ... and split their K dimension over clusters of four CTAs (gemm_ksplit.cuh) while tiles x 4 <= SMs
   int big_accum = 1;        // large-batch program: the residual projections accumulate into x in place (EPI_F32_ACCUM) instead of y = x + ...
+  // ---- session (admission into a running decode; mocr_session_*)
+  bool sess_on = false;
+  int sess_T = 0, sess_rows = 0, sess_order = 0;
+  long long sess_published = 0;          // publications so far (the device queue counts them)
+  std::vector<char> sess_used;           // slot occupied (published, result not yet released)
+  PdParams sess_p{};
+  cudaGraphExec_t sess_exec = nullptr;
+  int64_t sess_per_step = 0;
+  int* d_ring = nullptr;                 // [max_batch] slots in publication order
   int stage_chunk = 128;    // crops per staging chunk of a large batch (0 = one piece): see stage_encode
   int enc_tma_store = 1;    // encoder GEMMs with bf16 outputs (QKV, FFN1): rows leave as TMA stores from a staging tile (GemmArgs::out_tma)
   int big_attn_rows = 1;    // large-batch program: attention as one WARP per (row, head) unit (pd_attention_rows_kernel); 0 = the four-warp kernel
@@ -627,9 +636,13 @@ int table_for(mocr_handle* h, int in_size, mocr_handle::TableRef* out) {
 // chunk > 0 (large batches): the pixels travel in chunks of `chunk` crops on the copy stream, and after_chunk(i0, cnt) is called as
 // soon as a chunk's copies are enqueued (the handle's stream already waits for them): the caller launches that chunk's preprocess
 // and encoder there, so the host-side copy of chunk i+1 overlaps the GPU work on chunk i.
-int stage_crops(mocr_handle* h, const mocr_crop_t* crops, int n, int order, int chunk = 0, const std::function<int(int, int)>* after_chunk = nullptr) {
+// desc_base (session mode): the crops take descriptor / crop indices [desc_base, desc_base + n) instead of [0, n).
+int stage_crops(mocr_handle* h, const mocr_crop_t* crops, int n, int order, int chunk = 0, const std::function<int(int, int)>* after_chunk = nullptr,
+                int desc_base = -1) {
+  if (h->sess_on != (desc_base >= 0)) return fail(h, MOCR_ERR_INVALID, h->sess_on ? "a session is active on this handle (mocr_session_end first)" : "no session is active");
+  if (desc_base < 0) desc_base = 0;
   if (!h->finalized) return fail(h, MOCR_ERR_INVALID, "weights are not finalized");
-  if (n < 1 || n > h->max_batch) return fail(h, MOCR_ERR_CAPACITY, "batch of %d crops, handle capacity is %d", n, h->max_batch);
+  if (n < 1 || desc_base + n > h->max_batch) return fail(h, MOCR_ERR_CAPACITY, "batch of %d crops, handle capacity is %d", n, h->max_batch);
   if (crops == nullptr) return fail(h, MOCR_ERR_INVALID, "crops is NULL");
   h->staged_ok = h->pre_ok = h->enc_ok = h->dec_ok = false;
   h->region_mask_off.clear();
@@ -663,7 +676,7 @@ int stage_crops(mocr_handle* h, const mocr_crop_t* crops, int n, int order, int 
   for (int i = 0; i < n; ++i) {
     const mocr_crop_t& c = crops[i];
     const size_t rowb = static_cast<size_t>(c.width) * c.channels;
-    CropDesc& d = h->h_descs[i];
+    CropDesc& d = h->h_descs[desc_base + i];
     d.offset = static_cast<long long>(off);
     d.h = c.height;
     d.w = c.width;
@@ -714,7 +727,7 @@ int stage_crops(mocr_handle* h, const mocr_crop_t* crops, int n, int order, int 
     // h_coefs is pageable: the copy above is staged synchronously by the runtime, safe to reuse
     h->d_coefs_used = h->h_coefs.size();
   }
-  CK(cudaMemcpyAsync(h->d_descs, h->h_descs, sizeof(CropDesc) * n, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->d_descs + desc_base, h->h_descs + desc_base, sizeof(CropDesc) * n, cudaMemcpyHostToDevice, h->stream));
   h->n = n;
   h->staged_ok = true;
   // pixels -> pinned arena -> device.  Workers take contiguous runs of crops of about equal bytes; each uploads its run
@@ -789,6 +802,7 @@ int stage_regions(mocr_handle* h, const mocr_crop_t* page, const mocr_region_t* 
   if (!h->finalized) return fail(h, MOCR_ERR_INVALID, "weights are not finalized");
   if (n < 1 || n > h->max_batch) return fail(h, MOCR_ERR_CAPACITY, "batch of %d regions, handle capacity is %d", n, h->max_batch);
   if (page == nullptr || regions == nullptr) return fail(h, MOCR_ERR_INVALID, "page or regions is NULL");
+  if (h->sess_on) return fail(h, MOCR_ERR_INVALID, "a session is active on this handle (mocr_session_end first)");
   const mocr_crop_t& pg = *page;
   if (pg.data == nullptr || pg.height < 1 || pg.width < 1 || (pg.channels != 1 && pg.channels != 3 && pg.channels != 4) ||
       pg.stride < pg.width * pg.channels)
@@ -1360,7 +1374,7 @@ int decode_step_graph(mocr_handle* h, const PdParams& pdp, bool forced, bool tap
   if (!h->use_graph) return MOCR_OK;
   const int n = pdp.n_crops, rows = pdp.B, max_length = pdp.max_len;
   const uint64_t key = (static_cast<uint64_t>(n) << 40) | (static_cast<uint64_t>(rows) << 20) | (static_cast<uint64_t>(max_length) << 8) |
-                       (forced ? 2u : 0u) | (tap ? 1u : 0u);
+                       (pdp.queue_slots != nullptr ? 4u : 0u) | (forced ? 2u : 0u) | (tap ? 1u : 0u);
   const int spg = std::max(1, std::min(h->steps_per_graph, max_length - 1));
   auto it = h->graphs.find(key);
   if (it != h->graphs.end()) {
@@ -1447,6 +1461,7 @@ int decode_loop(mocr_handle* h, const PdParams& pdp, bool forced, cudaGraphExec_
 }
 
 int decode(mocr_handle* h, int max_length, const int32_t* forced_ids) {
+  if (h->sess_on) return fail(h, MOCR_ERR_INVALID, "a session is active on this handle (mocr_session_end first)");
   if (!h->enc_ok) return fail(h, MOCR_ERR_INVALID, "encode has not run on the staged crops");
   if (max_length < 2 || max_length > h->max_length)
     return fail(h, MOCR_ERR_CAPACITY, "max_length %d outside [2, %d]", max_length, h->max_length);
@@ -1843,6 +1858,157 @@ int mocr_recognize(mocr_handle_t* h, const mocr_crop_t* crops, int n, int channe
     }
     return MOCR_OK;
   });
+}
+
+// ---- admission into a running decode (include/mocr_b200.h: mocr_session_*) ------------------------------------------
+// A session keeps `rows` decoder rows stepping; crops are added while it runs: each takes a free SLOT (crop index: encoder K/V,
+// id row, length), is preprocessed and encoded between two step chunks and published to the device queue, where the first idle
+// row picks it up (pd_next_kernel).  The host reads the slots' lengths after every chunk, fetches the rows that finished and
+// releases their slots for reuse: no batch boundary, a caller waits for its own crop only.  ids per crop are those of
+// mocr_recognize (rows are independent).
+
+int session_end(mocr_handle* h) {
+  h->sess_on = false;
+  h->sub_i0 = h->sub_n = 0;
+  h->staged_ok = h->pre_ok = h->enc_ok = h->dec_ok = false;
+  cudaStreamSynchronize(h->stream_enc);
+  cudaStreamSynchronize(h->stream);
+  return MOCR_OK;
+}
+
+int mocr_session_begin(mocr_handle_t* h, int channel_order, int max_length, int rows) {
+  TRY(check_handle(h));
+  std::lock_guard<std::mutex> lock(h->mu);
+  return guarded(h, [&]() -> int {
+    if (!h->finalized) return fail(h, MOCR_ERR_INVALID, "weights are not finalized");
+    if (h->sess_on) return fail(h, MOCR_ERR_INVALID, "a session is already active");
+    if (h->taps != 0) return fail(h, MOCR_ERR_INVALID, "sessions do not run with parity taps");
+    if (max_length < 2 || max_length > h->max_length) return fail(h, MOCR_ERR_CAPACITY, "max_length %d outside [2, %d]", max_length, h->max_length);
+    if (rows < 1 || rows > h->max_batch) return fail(h, MOCR_ERR_CAPACITY, "%d decoder rows, handle capacity is %d", rows, h->max_batch);
+    if (h->d_ring == nullptr) {
+      TRY(dmalloc(h, &h->d_ring, static_cast<size_t>(h->max_batch)));
+      CK(cudaMemsetAsync(h->d_ring, 0, sizeof(int) * h->max_batch, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    h->staged_ok = h->pre_ok = h->enc_ok = h->dec_ok = false;
+    pd_publish_kernel<<<1, 1, 0, h->stream>>>(h->d_queue, 0, 0);                     // (the graph's warm-up step must find an empty queue)
+    CK(cudaGetLastError());
+    PdParams p = make_pd_params(h, rows, max_length, false, false, h->max_batch);
+    p.queue_slots = h->d_ring;
+    p.ext_queue = 1;
+    p.idle_start = 1;
+    TRY(decode_step_graph(h, p, false, false, &h->sess_exec, &h->sess_per_step));     // (its warm-up step runs on throw-away state)
+    TRY(decode_begin(h, p));                                                         // every row idle, every id row [CLS] PAD ...
+    pd_publish_kernel<<<1, 1, 0, h->stream>>>(h->d_queue, 0, 0);                     // nothing published, nothing finished
+    CK(cudaGetLastError());
+    ++h->launches;
+    h->sess_p = p;
+    h->sess_T = max_length;
+    h->sess_rows = rows;
+    h->sess_order = channel_order;
+    h->sess_published = 0;
+    h->sess_used.assign(static_cast<size_t>(h->max_batch), 0);
+    h->sess_on = true;
+    return MOCR_OK;
+  });
+}
+
+int mocr_session_add(mocr_handle_t* h, const mocr_crop_t* crops, int n, int32_t* out_slots) {
+  TRY(check_handle(h));
+  std::lock_guard<std::mutex> lock(h->mu);
+  return guarded(h, [&]() -> int {
+    if (!h->sess_on) return fail(h, MOCR_ERR_INVALID, "no session is active");
+    if (n < 1 || crops == nullptr || out_slots == nullptr) return fail(h, MOCR_ERR_INVALID, "bad argument");
+    int n_free = 0;
+    for (char u : h->sess_used) n_free += u ? 0 : 1;
+    if (n > n_free) return fail(h, MOCR_ERR_CAPACITY, "%d crops added, %d slots are free", n, n_free);
+    // Everything an admission launches - pixel upload, preprocess, the encoder, the publication - goes to the (lower-priority)
+    // encoder stream: the decode steps already queued on the handle's stream keep running meanwhile, and the rows pick the new
+    // crops up at their next next-token stage.  The encoder touches nothing the decoder reads except the K/V slots being added.
+    struct Restore {
+      mocr_handle* h;
+      cudaStream_t s;
+      ~Restore() { h->stream = s; h->sub_i0 = h->sub_n = 0; }
+    } restore{h, h->stream};
+    h->stream = h->stream_enc;
+    int done = 0;
+    while (done < n) {
+      // the next run of free slots: one staging + encoder pass per run (crop indices of a pass are contiguous)
+      int s0 = 0;
+      while (h->sess_used[s0]) ++s0;
+      int len = 0;
+      while (s0 + len < h->max_batch && !h->sess_used[s0 + len] && len < std::min(n - done, 64)) ++len;
+      TRY(stage_crops(h, crops + done, len, h->sess_order, 0, nullptr, s0));
+      h->sub_i0 = s0;
+      h->sub_n = len;
+      TRY(preprocess(h));
+      TRY(encode_launches(h));             // (not through the per-size graph cache: run lengths and offsets vary freely)
+      PdSlotList l{};
+      l.n = len;
+      for (int i = 0; i < len; ++i) l.slot[i] = s0 + i;
+      pd_publish_slots_kernel<<<1, 256, 0, h->stream>>>(h->d_queue, h->d_ring, h->max_batch, static_cast<int>(h->sess_published), h->d_ids,
+                                                        h->d_lens, h->sess_T, l);
+      CK(cudaGetLastError());
+      ++h->launches;
+      h->sess_published += len;
+      for (int i = 0; i < len; ++i) {
+        h->sess_used[s0 + i] = 1;
+        out_slots[done + i] = s0 + i;
+      }
+      done += len;
+    }
+    return MOCR_OK;
+  });
+}
+
+int mocr_session_run(mocr_handle_t* h, int steps, int32_t* out_lens) {
+  TRY(check_handle(h));
+  std::lock_guard<std::mutex> lock(h->mu);
+  return guarded(h, [&]() -> int {
+    if (!h->sess_on) return fail(h, MOCR_ERR_INVALID, "no session is active");
+    if (steps < 0 || (steps == 0 && out_lens == nullptr)) return fail(h, MOCR_ERR_INVALID, "bad argument");
+    const int spg = h->sess_exec != nullptr ? std::max(1, std::min(h->steps_per_graph, h->sess_T - 1)) : 1;
+    for (int ran = 0; ran < steps; ran += spg) {
+      if (h->sess_exec != nullptr) {
+        CK(cudaGraphLaunch(h->sess_exec, h->stream));
+        h->launches += h->sess_per_step;
+      } else {
+        TRY(decode_stage_step(h, h->sess_p));
+      }
+    }
+    if (out_lens == nullptr) return MOCR_OK;       // launch only: the caller admits crops meanwhile and polls with steps = 0
+    CK(cudaMemcpyAsync(h->h_flags, h->d_lens, sizeof(int) * h->max_batch, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < h->max_batch; ++i) out_lens[i] = h->sess_used[i] ? h->h_flags[i] : 0;
+    return MOCR_OK;
+  });
+}
+
+int mocr_session_fetch(mocr_handle_t* h, const int32_t* slots, int n, int32_t* out_ids, int release) {
+  TRY(check_handle(h));
+  std::lock_guard<std::mutex> lock(h->mu);
+  return guarded(h, [&]() -> int {
+    if (!h->sess_on) return fail(h, MOCR_ERR_INVALID, "no session is active");
+    if (n < 0 || (n > 0 && (slots == nullptr || out_ids == nullptr))) return fail(h, MOCR_ERR_INVALID, "bad argument");
+    for (int i = 0; i < n; ++i) {
+      if (slots[i] < 0 || slots[i] >= h->max_batch || !h->sess_used[slots[i]]) return fail(h, MOCR_ERR_INVALID, "slot %d is not in use", slots[i]);
+      CK(cudaMemcpyAsync(out_ids + static_cast<size_t>(i) * h->sess_T, h->d_ids + static_cast<size_t>(slots[i]) * h->sess_T, sizeof(int) * h->sess_T,
+                         cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (release)     // a released slot reads "not finished" from now on (its next occupant is published from the encoder stream)
+      for (int i = 0; i < n; ++i) CK(cudaMemsetAsync(h->d_lens + slots[i], 0, sizeof(int), h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (release)
+      for (int i = 0; i < n; ++i) h->sess_used[slots[i]] = 0;
+    return MOCR_OK;
+  });
+}
+
+int mocr_session_end(mocr_handle_t* h) {
+  TRY(check_handle(h));
+  std::lock_guard<std::mutex> lock(h->mu);
+  if (!h->sess_on) return fail(h, MOCR_ERR_INVALID, "no session is active");
+  return session_end(h);
 }
 
 int decode_beam_device(mocr_handle* h, int beams, int max_length, int ngram, float length_penalty, int early, int32_t* out_ids, int32_t* out_lens,

@@ -176,6 +176,41 @@ class Engine:
         del keep
         return ids, lens
 
+    # ---- admission into a running decode (include/mocr_b200.h: mocr_session_*)
+    def session_begin(self, rows: int, order: int = RGB, max_length: Optional[int] = None) -> None:
+        self._sess_T = max_length or self.max_length
+        self._ck(self._lib.mocr_session_begin(self._h, order, self._sess_T, rows))
+
+    def session_add(self, crops: Sequence[np.ndarray]) -> np.ndarray:
+        """Stage, encode and publish crops to the running session; returns the slot of each (n <= free slots)."""
+        arr, keep = _as_crop_array(crops)
+        slots = np.zeros((len(crops),), np.int32)
+        self._ck(self._lib.mocr_session_add(self._h, arr, len(crops), slots.ctypes.data_as(POINTER(c_int32))))
+        del keep
+        return slots
+
+    def session_run(self, steps: int, wait: bool = True) -> Optional[np.ndarray]:
+        """`steps` greedy steps of every active row.  wait=True: returns lens [max_batch], > 0 where a slot's crop has finished;
+        wait=False launches only (admit crops meanwhile, then session_run(0) waits and reads)."""
+        if not wait:
+            self._ck(self._lib.mocr_session_run(self._h, steps, None))
+            return None
+        lens = np.zeros((self.max_batch,), np.int32)
+        self._ck(self._lib.mocr_session_run(self._h, steps, lens.ctypes.data_as(POINTER(c_int32))))
+        return lens
+
+    def session_fetch(self, slots: Sequence[int], release: bool = True) -> np.ndarray:
+        """ids [n, max_length] of finished slots; release=True frees the slots for new crops."""
+        sl = np.ascontiguousarray(slots, np.int32)
+        ids = np.zeros((len(sl), self._sess_T), np.int32)
+        if len(sl):
+            self._ck(self._lib.mocr_session_fetch(self._h, sl.ctypes.data_as(POINTER(c_int32)), len(sl), ids.ctypes.data_as(POINTER(c_int32)),
+                                                  1 if release else 0))
+        return ids
+
+    def session_end(self) -> None:
+        self._ck(self._lib.mocr_session_end(self._h))
+
     def stage(self, crops: Sequence[np.ndarray], order: int = RGB) -> None:
         arr, keep = _as_crop_array(crops)
         self._ck(self._lib.mocr_stage_crops(self._h, arr, len(crops), order))

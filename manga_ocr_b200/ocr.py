@@ -11,6 +11,7 @@ reference never batches: upstream runs ``x[None]``), one dispatcher thread per G
 from __future__ import annotations
 
 import glob
+import contextlib
 import os
 import threading
 import time
@@ -136,7 +137,7 @@ class MangaOcr:
                  devices: Optional[Sequence[int]] = None, max_batch: int = 64, max_length: int = MAX_LENGTH,
                  warmup: bool = True, num_beams: Optional[int] = None, no_repeat_ngram_size: Optional[int] = None,
                  length_penalty: Optional[float] = None, early_stopping=None, linger_ms: Optional[float] = None,
-                 slots: Optional[int] = None):
+                 slots: Optional[int] = None, admission: Optional[bool] = None):
         if force_cpu:
             raise RuntimeError("manga_ocr_b200 has no CPU path (force_cpu=True is not supported); it needs a B200 GPU")
         gen = dict(GREEDY)
@@ -201,10 +202,23 @@ class MangaOcr:
         self._cv = threading.Condition()
         self._closed = False
         self._busy = 0                     # dispatchers currently running a batch
+        # __call__ traffic: admission into a running decode (greedy only; engine sessions, include/mocr_b200.h mocr_session_*): a
+        # caller's crop joins the rows that are already stepping and is answered when ITS crop finishes.  admission=False (or
+        # MOCR_ADMISSION=0) keeps the batch dispatcher: callers that arrive together share a batch and wait for all of it.
+        if admission is None:
+            admission = os.environ.get("MOCR_ADMISSION", "1") != "0"
+        self.admission = bool(admission) and int(gen["num_beams"]) <= 1
+        self.session_rows = max(1, min(max_batch, int(slots) if slots else 64))
+        self._engine_locks = [threading.Lock() for _ in self.engines]      # a session owns its engine; batch callers wait for it to drain
+        self._batch_waiting = [0] * len(self.engines)
         self.linger_s = float(os.environ.get("MOCR_LINGER_MS", "1.5")) * 1e-3 if linger_ms is None else linger_ms * 1e-3
         ref = weakref.ref(self)
-        self._threads = [threading.Thread(target=MangaOcr._dispatch, args=(ref, e, self._cv), name=f"mocr-gpu{e.device}", daemon=True)
-                         for e in self.engines]
+        if self.admission:
+            self._threads = [threading.Thread(target=MangaOcr._dispatch_session, args=(ref, k, e, self._cv), name=f"mocr-gpu{e.device}", daemon=True)
+                             for k, e in enumerate(self.engines)]
+        else:
+            self._threads = [threading.Thread(target=MangaOcr._dispatch, args=(ref, e, self._cv), name=f"mocr-gpu{e.device}", daemon=True)
+                             for e in self.engines]
         for t in self._threads:
             t.start()
         if warmup:   # upstream runs one example image through the model inside __init__
@@ -253,7 +267,11 @@ class MangaOcr:
             return engine.recognize_regions_beam(arr, regs, order, self.max_length, int(g["num_beams"]), int(g["no_repeat_ngram_size"]),
                                                  float(g["length_penalty"]), g["early_stopping"])[0]
 
-        return ids_to_texts(self.vocab, self._sharded(len(regions), lambda k, lo, hi: run(self.engines[k], regions[lo:hi])))
+        def work(k: int, lo: int, hi: int) -> np.ndarray:
+            with self._engine_excl(k):
+                return run(self.engines[k], regions[lo:hi])
+
+        return ids_to_texts(self.vocab, self._sharded(len(regions), work))
 
     def _engine_ids(self, engine: Engine, arrays: Sequence[np.ndarray], order: int) -> np.ndarray:
         g = self.generation
@@ -263,7 +281,24 @@ class MangaOcr:
                                      float(g["length_penalty"]), g["early_stopping"])[0]
 
     def recognize_ids(self, arrays: Sequence[np.ndarray], order: int = RGB) -> np.ndarray:
-        return self._sharded(len(arrays), lambda k, lo, hi: self._engine_ids(self.engines[k], arrays[lo:hi], order))
+        def work(k: int, lo: int, hi: int) -> np.ndarray:
+            with self._engine_excl(k):
+                return self._engine_ids(self.engines[k], arrays[lo:hi], order)
+
+        return self._sharded(len(arrays), work)
+
+    @contextlib.contextmanager
+    def _engine_excl(self, k: int):
+        """Engine k for a batch call: a running admission session stops admitting, drains and hands the engine over."""
+        with self._cv:
+            self._batch_waiting[k] += 1
+        try:
+            with self._engine_locks[k]:
+                yield
+        finally:
+            with self._cv:
+                self._batch_waiting[k] -= 1
+                self._cv.notify_all()
 
     def _sharded(self, n: int, work) -> np.ndarray:
         """Host-side job splitter: contiguous blocks of the n units, one worker thread per GPU, no collective."""
@@ -355,6 +390,75 @@ class MangaOcr:
                 with cv:
                     self._busy -= 1
             del self, batch
+
+    @staticmethod
+    def _dispatch_session(ref, k: int, engine: Engine, cv: threading.Condition) -> None:
+        """__call__ traffic of one GPU with admission: while requests are in flight the engine runs a session - queued
+        requests are staged, encoded and published between two chunks of decode steps, finished crops are answered at once."""
+        steps = 13                                  # decode steps between two admissions / result polls (one CUDA graph)
+        while True:
+            with cv:
+                self = ref()
+                if self is None:
+                    return
+                if not self._queue or self._batch_waiting[k] > 0:
+                    if self._closed and not self._queue:
+                        return
+                    del self
+                    cv.wait(0.25)
+                    continue
+                lock = self._engine_locks[k]
+            del self
+            with lock:
+                inflight: Dict[int, _Request] = {}
+                try:
+                    self = ref()
+                    if self is None:
+                        return
+                    engine.session_begin(self.session_rows, RGB, self.max_length)
+                    capacity = self.max_batch
+                    try:
+                        while True:
+                            with cv:
+                                reqs = []
+                                free = capacity - len(inflight)
+                                if self._queue and free > 0 and self._batch_waiting[k] == 0:
+                                    share = -(-len(self._queue) // len(self.engines))          # leave work for the other GPUs
+                                    reqs = [self._queue.popleft() for _ in range(min(free, share, 64))]
+                                if not reqs and not inflight:
+                                    break
+                            launched = bool(inflight)
+                            if launched:
+                                engine.session_run(steps, wait=False)       # the rows in flight keep stepping while crops are admitted
+                            if reqs:
+                                try:
+                                    for r, s in zip(reqs, engine.session_add([r.crop for r in reqs])):
+                                        inflight[int(s)] = r
+                                except BaseException:       # noqa: BLE001 - one bad crop must not fail its neighbours
+                                    for r in reqs:
+                                        try:
+                                            inflight[int(engine.session_add([r.crop])[0])] = r
+                                        except BaseException as e:   # noqa: BLE001
+                                            r.error = e
+                                            r.event.set()
+                            if inflight:
+                                lens = engine.session_run(0 if launched else steps)
+                                done = [s for s in inflight if lens[s] > 0]
+                                if done:
+                                    texts = ids_to_texts(self.vocab, engine.session_fetch(done, release=True))
+                                    for s, t in zip(done, texts):
+                                        r = inflight.pop(s)
+                                        r.text = t
+                                        r.event.set()
+                    finally:
+                        engine.session_end()
+                except BaseException as e:          # noqa: BLE001 - the engine failed: every request in flight gets the error
+                    for r in inflight.values():
+                        r.error = e
+                        r.event.set()
+                    inflight.clear()
+                finally:
+                    self = None
 
     def close(self) -> None:
         with self._cv:

@@ -2,6 +2,7 @@
 (path / PIL / ValueError), concurrent callers (the app's worker threads) and the full-size
 batch-64 x max_length-300 configuration checked through size-independent properties."""
 import threading
+import time
 
 import numpy as np
 import pytest
@@ -12,10 +13,12 @@ from manga_ocr_b200 import crops as C
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def ocr16(weights0):
+@pytest.fixture(scope="module", params=[True, False], ids=["admission", "batch_dispatcher"])
+def ocr16(weights0, request):
+    """__call__ traffic served by admission into a running decode (the default for greedy decoding) and by the batch dispatcher."""
     from manga_ocr_b200.ocr import MangaOcr
-    o = MangaOcr(weights=weights0, devices=[0], max_batch=16, max_length=12)
+    o = MangaOcr(weights=weights0, devices=[0], max_batch=16, max_length=12, admission=request.param)
+    assert o.admission == request.param
     yield o
     o.close()
 
@@ -226,7 +229,11 @@ def test_instance_is_collected_without_close(weights0):
     threads = list(ocr._threads)
     ref = weakref.ref(ocr)
     del ocr
-    gc.collect()
+    for _ in range(200):          # (a dispatcher may still be closing the session that served the call)
+        gc.collect()
+        if ref() is None:
+            break
+        time.sleep(0.01)
     assert ref() is None
     for t in threads:
         t.join(timeout=5)

@@ -334,3 +334,48 @@ def test_chunked_staging_gives_the_same_ids(weights0):
             assert np.array_equal(ids2, ids0[:257]), chunk
     finally:
         eng.close()
+
+
+def test_session_admission_gives_the_same_ids():
+    """Admission into a running decode (include/mocr_b200.h mocr_session_*): crops added while other rows are stepping, more
+    crops than slots over time (slots are reused), fewer decoder rows than slots - every crop's ids equal mocr_recognize's."""
+    from manga_ocr_b200 import weights as W
+    from manga_ocr_b200.engine import Engine, MocrError
+    w = W.random_init(0, gain=3.0, eos_bias=3.7)          # ragged lengths: rows finish at different steps
+    T = 24
+    crops = C.page_batch(40, seed=5)
+    eng = Engine(w, device=0, max_batch=16, max_length=T)
+    try:
+        ref = np.concatenate([eng.recognize(crops[i:i + 16])[0] for i in range(0, 40, 16)])
+        eng.session_begin(rows=6, max_length=T)
+        with pytest.raises(MocrError):
+            eng.recognize(crops[:2])                        # the handle is the session's
+        pending = list(range(40))
+        inflight, got = {}, {}
+        rounds = 0
+        while pending or inflight:
+            free = 16 - len(inflight)
+            take = min(free, len(pending), 1 + rounds % 5)  # trickle: 1..5 crops per round
+            if take:
+                idx = [pending.pop(0) for _ in range(take)]
+                for i, s in zip(idx, eng.session_add([crops[i] for i in idx])):
+                    assert int(s) not in inflight
+                    inflight[int(s)] = i
+            lens = eng.session_run(3)
+            done = [s for s in inflight if lens[s] > 0]
+            ids = eng.session_fetch(done)
+            for s, row in zip(done, ids):
+                i = inflight.pop(s)
+                got[i] = row
+                assert lens[s] == (row != 0).sum()
+            rounds += 1
+            assert rounds < 2000
+        eng.session_end()
+        for i in range(40):
+            assert np.array_equal(got[i], ref[i]), i
+        ids2, _ = eng.recognize(crops[:5])                  # the handle is usable again
+        assert np.array_equal(ids2, ref[:5])
+        with pytest.raises(MocrError):
+            eng.session_run(1)
+    finally:
+        eng.close()

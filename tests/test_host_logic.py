@@ -186,6 +186,55 @@ class _StubEngine:
             ids[i, 2] = 3
         return ids, np.full(len(arrays), 3, np.int32)
 
+    # ---- sessions (admission into a running decode): a crop finishes `need` calls of session_run after it was added; need =
+    #      1 + (first pixel % 3), so crops added together finish at different times
+    def session_begin(self, rows, order=0, max_length=None):
+        assert not getattr(self, "sess", None), "session already active"
+        self.sess = {"T": max_length or self.max_length, "slots": {}, "rows": rows}
+        self.sessions = getattr(self, "sessions", 0) + 1
+        self.adds = getattr(self, "adds", [])
+
+    def session_add(self, arrays):
+        import time
+        time.sleep(0.002)
+        if any(int(a.flat[0]) == 13 for a in arrays):
+            raise RuntimeError("bad crop in batch")
+        free = [s for s in range(self.max_batch) if s not in self.sess["slots"]]
+        assert len(arrays) <= len(free)
+        self.adds.append(len(arrays))
+        out = []
+        for a, s in zip(arrays, free):
+            self.sess["slots"][s] = [int(a.flat[0]), 1 + int(a.flat[0]) % 3]
+            out.append(s)
+        return np.asarray(out, np.int32)
+
+    def session_run(self, steps, wait=True):
+        import time
+        if not wait:                               # launch only: the tick is accounted for by the poll that follows
+            self.pending = True
+            return None
+        assert steps > 0 or getattr(self, "pending", False), "poll without a launch"
+        self.pending = False
+        time.sleep(0.005)
+        lens = np.zeros((self.max_batch,), np.int32)
+        for s, st in self.sess["slots"].items():
+            st[1] -= 1
+            if st[1] <= 0:
+                lens[s] = 3
+        return lens
+
+    def session_fetch(self, slots, release=True):
+        ids = np.zeros((len(slots), self.sess["T"]), np.int32)
+        for i, s in enumerate(slots):
+            ids[i, :3] = (2, 5 + self.sess["slots"][s][0], 3)
+            if release:
+                del self.sess["slots"][s]
+        return ids
+
+    def session_end(self):
+        assert not self.sess["slots"], "session ended with crops in flight"
+        self.sess = None
+
     def close(self):
         self.closed = True
 
@@ -198,6 +247,7 @@ def stub_ocr(monkeypatch):
 
     def make(**kw):
         kw.setdefault("warmup", False)
+        kw.setdefault("admission", False)          # the batch dispatcher unless a test asks for sessions
         o = O.MangaOcr(weights={"x": np.zeros(1, np.float32)}, **kw)
         made.append(o)
         return o
@@ -307,3 +357,47 @@ def test_instance_lifetime_close_and_collection(stub_ocr):
     with stub_ocr(devices=[0], max_batch=4, max_length=8) as o3:               # context manager
         assert isinstance(o3(_img(1)), str)
     assert o3._closed
+
+
+# ---- admission into a running decode (MangaOcr(admission=True), the default for greedy decoding), with stub engines ----
+
+def test_admission_answers_each_caller_when_its_crop_finishes(stub_ocr):
+    ocr = stub_ocr(devices=[0], max_batch=8, max_length=8, admission=True)
+    vocab = ocr.vocab
+    got = _call_all(ocr, list(range(12)) + [20, 21])            # more callers than slots: slots are reused
+    assert got == [O.ids_to_texts(vocab, np.array([[2, 5 + v, 3, 0]]))[0] for v in list(range(12)) + [20, 21]]
+    eng = _StubEngine.instances[0]
+    assert sum(eng.adds) == 14 and eng.sess is None                            # everything admitted, the session ended when idle
+    assert ocr(_img(4)) == O.ids_to_texts(vocab, np.array([[2, 9, 3]]))[0]      # a new session starts on demand
+    assert eng.sessions >= 2
+
+
+def test_admission_isolates_a_failing_request_and_yields_to_batch_calls(stub_ocr):
+    import threading
+    ocr = stub_ocr(devices=[0], max_batch=8, max_length=8, admission=True)
+    got = _call_all(ocr, [1, 2, 13, 4, 5])
+    assert isinstance(got[2], RuntimeError)
+    assert [isinstance(g, str) for g in got] == [True, True, False, True, True]
+    # a batch call on the same engine waits for the session to drain and runs between sessions
+    out = {}
+    ts = [threading.Thread(target=lambda i=i: out.__setitem__(i, ocr(_img(i)))) for i in range(6)]
+    for t in ts:
+        t.start()
+    texts = ocr.recognize_batch([np.full((4, 4, 3), 7, np.uint8), np.full((4, 4, 3), 8, np.uint8)])
+    for t in ts:
+        t.join()
+    assert texts == [O.ids_to_texts(ocr.vocab, np.array([[2, 12, 3]]))[0], O.ids_to_texts(ocr.vocab, np.array([[2, 13, 3]]))[0]]
+    assert all(isinstance(out[i], str) for i in range(6))
+    assert _StubEngine.instances[0].sess is None
+
+
+def test_admission_shares_callers_between_gpus_and_closes_cleanly(stub_ocr):
+    ocr = stub_ocr(devices=[0, 1], max_batch=16, max_length=8, admission=True)
+    got = _call_all(ocr, [v for v in range(41) if v != 13])
+    assert all(isinstance(g, str) for g in got)
+    a, b = (sum(e.adds) for e in _StubEngine.instances)
+    assert a + b == 40 and min(a, b) >= 5, (a, b)
+    ocr.close()
+    assert all(e.closed and e.sess is None for e in _StubEngine.instances)
+    with pytest.raises(RuntimeError):
+        ocr(_img(1))
