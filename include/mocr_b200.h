@@ -200,9 +200,11 @@ int mocr_resample_table(int in_size, int32_t* ksize, int32_t* out, int capacity)
  * decoder rows stepping and admits crops while it runs: mocr_session_add stages, preprocesses, encodes and publishes
  * n crops (n <= free slots; out_slots[n] = the slot of each, 0 <= slot < max_batch), an idle row picks each of them
  * up (the admission runs on a second stream: decode steps already launched keep running meanwhile);
- * mocr_session_run launches `steps` greedy steps and, when out_lens is not NULL, waits for them and returns
- * out_lens[max_batch]: > 0 for a slot whose crop has finished (its id count), 0 for running or unused slots (out_lens
- * NULL = launch only; steps 0 = wait and read only: launch, admit, then poll); mocr_session_fetch copies the id rows of finished slots
+ * mocr_session_run launches `steps` greedy steps followed by a snapshot of the slots' lengths (at most two snapshots may
+ * be pending) and, when out_lens is not NULL, waits for the OLDEST pending snapshot and returns it as
+ * out_lens[max_batch]: > 0 for a slot whose crop has finished (its id count), 0 for running or unused slots.  out_lens
+ * NULL = launch only; steps 0 = read only: "launch, admit, launch, read" keeps one chunk queued while the host works.
+ * mocr_session_fetch copies the id rows of finished slots
  * (out_ids [n, max_length], PAD-filled) and, with release != 0, frees the slots for reuse.  ids per crop equal
  * mocr_recognize's.  Other compute entry points of the handle fail while a session is active. */
 int mocr_session_begin(mocr_handle_t* h, int channel_order, int max_length, int rows);

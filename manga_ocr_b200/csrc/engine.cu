@@ -162,6 +162,10 @@ struct mocr_handle {
   cudaGraphExec_t sess_exec = nullptr;
   int64_t sess_per_step = 0;
   int* d_ring = nullptr;                 // [max_batch] slots in publication order
+  int* h_sess_lens[2] = {nullptr, nullptr};   // pinned [max_batch]: two length snapshots in flight
+  cudaEvent_t sess_ev[2] = {nullptr, nullptr};
+  long long snap_enq = 0, snap_read = 0;      // snapshots enqueued / handed to the caller
+  std::vector<long long> sess_min_snap;       // per slot: the first snapshot that may speak for its current occupant
   int stage_chunk = 128;    // crops per staging chunk of a large batch (0 = one piece): see stage_encode
   int enc_tma_store = 1;    // encoder GEMMs with bf16 outputs (QKV, FFN1): rows leave as TMA stores from a staging tile (GemmArgs::out_tma)
   int big_attn_rows = 1;    // large-batch program: attention as one WARP per (row, head) unit (pd_attention_rows_kernel); 0 = the four-warp kernel
@@ -1700,6 +1704,10 @@ int mocr_destroy(mocr_handle_t* h) {
     if (h->d_beam_dev) cudaFree(h->d_beam_dev);
     if (h->h_beam_ctl) cudaFreeHost(h->h_beam_ctl);
     if (h->logits_tap) cudaFree(h->logits_tap);
+    for (int i = 0; i < 2; ++i) {
+      if (h->h_sess_lens[i]) cudaFreeHost(h->h_sess_lens[i]);
+      if (h->sess_ev[i]) cudaEventDestroy(h->sess_ev[i]);
+    }
     if (h->d_arena) cudaFree(h->d_arena);
     if (h->h_arena) cudaFreeHost(h->h_arena);
     if (h->d_coefs) cudaFree(h->d_coefs);
@@ -1872,6 +1880,7 @@ int session_end(mocr_handle* h) {
   h->sub_i0 = h->sub_n = 0;
   h->staged_ok = h->pre_ok = h->enc_ok = h->dec_ok = false;
   cudaStreamSynchronize(h->stream_enc);
+  cudaStreamSynchronize(h->stream_enc_hi);
   cudaStreamSynchronize(h->stream);
   return MOCR_OK;
 }
@@ -1908,6 +1917,12 @@ int mocr_session_begin(mocr_handle_t* h, int channel_order, int max_length, int 
     h->sess_order = channel_order;
     h->sess_published = 0;
     h->sess_used.assign(static_cast<size_t>(h->max_batch), 0);
+    h->sess_min_snap.assign(static_cast<size_t>(h->max_batch), 0);
+    h->snap_enq = h->snap_read = 0;
+    for (int i = 0; i < 2; ++i) {
+      if (h->h_sess_lens[i] == nullptr) CK(cudaMallocHost(reinterpret_cast<void**>(&h->h_sess_lens[i]), sizeof(int) * h->max_batch));
+      if (h->sess_ev[i] == nullptr) CK(cudaEventCreateWithFlags(&h->sess_ev[i], cudaEventDisableTiming));
+    }
     h->sess_on = true;
     return MOCR_OK;
   });
@@ -1953,6 +1968,7 @@ int mocr_session_add(mocr_handle_t* h, const mocr_crop_t* crops, int n, int32_t*
       h->sess_published += len;
       for (int i = 0; i < len; ++i) {
         h->sess_used[s0 + i] = 1;
+        h->sess_min_snap[s0 + i] = h->snap_enq;      // snapshots enqueued before this point may still show the previous occupant
         out_slots[done + i] = s0 + i;
       }
       done += len;
@@ -1976,10 +1992,24 @@ int mocr_session_run(mocr_handle_t* h, int steps, int32_t* out_lens) {
         TRY(decode_stage_step(h, h->sess_p));
       }
     }
-    if (out_lens == nullptr) return MOCR_OK;       // launch only: the caller admits crops meanwhile and polls with steps = 0
-    CK(cudaMemcpyAsync(h->h_flags, h->d_lens, sizeof(int) * h->max_batch, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    for (int i = 0; i < h->max_batch; ++i) out_lens[i] = h->sess_used[i] ? h->h_flags[i] : 0;
+    // A snapshot of the slots' lengths follows every chunk of steps; up to two are in flight, so the host can read the snapshot of
+    // chunk k (an event wait, not a stream sync) while chunk k + 1 is already queued: the GPU never waits for the host.
+    auto enqueue_snapshot = [&]() -> int {
+      if (h->snap_enq - h->snap_read >= 2) return fail(h, MOCR_ERR_INVALID, "two length snapshots are pending: read one first");
+      const int k = static_cast<int>(h->snap_enq & 1);
+      CK(cudaMemcpyAsync(h->h_sess_lens[k], h->d_lens, sizeof(int) * h->max_batch, cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaEventRecord(h->sess_ev[k], h->stream));
+      ++h->snap_enq;
+      return MOCR_OK;
+    };
+    if (steps > 0) TRY(enqueue_snapshot());
+    if (out_lens == nullptr) return MOCR_OK;       // launch only: the caller admits crops meanwhile and reads later (steps = 0)
+    if (h->snap_enq == h->snap_read) TRY(enqueue_snapshot());
+    const long long j = h->snap_read;              // the oldest unread snapshot
+    CK(cudaEventSynchronize(h->sess_ev[j & 1]));
+    const int* lens = h->h_sess_lens[j & 1];
+    for (int i = 0; i < h->max_batch; ++i) out_lens[i] = (h->sess_used[i] && j >= h->sess_min_snap[i]) ? lens[i] : 0;
+    ++h->snap_read;
     return MOCR_OK;
   });
 }
@@ -1990,14 +2020,17 @@ int mocr_session_fetch(mocr_handle_t* h, const int32_t* slots, int n, int32_t* o
   return guarded(h, [&]() -> int {
     if (!h->sess_on) return fail(h, MOCR_ERR_INVALID, "no session is active");
     if (n < 0 || (n > 0 && (slots == nullptr || out_ids == nullptr))) return fail(h, MOCR_ERR_INVALID, "bad argument");
+    // The rows of finished slots are final: they are copied on a side stream, without waiting for the decode steps that are queued
+    // on the handle's stream.  A released slot's length is zeroed here, synchronously, before the slot can be handed out again
+    // (its next occupant is published from the encoder stream; snapshots enqueued before that are ignored for it).
+    cudaStream_t side = h->stream_enc_hi;
     for (int i = 0; i < n; ++i) {
       if (slots[i] < 0 || slots[i] >= h->max_batch || !h->sess_used[slots[i]]) return fail(h, MOCR_ERR_INVALID, "slot %d is not in use", slots[i]);
       CK(cudaMemcpyAsync(out_ids + static_cast<size_t>(i) * h->sess_T, h->d_ids + static_cast<size_t>(slots[i]) * h->sess_T, sizeof(int) * h->sess_T,
-                         cudaMemcpyDeviceToHost, h->stream));
+                         cudaMemcpyDeviceToHost, side));
+      if (release) CK(cudaMemsetAsync(h->d_lens + slots[i], 0, sizeof(int), side));
     }
-    if (release)     // a released slot reads "not finished" from now on (its next occupant is published from the encoder stream)
-      for (int i = 0; i < n; ++i) CK(cudaMemsetAsync(h->d_lens + slots[i], 0, sizeof(int), h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaStreamSynchronize(side));
     if (release)
       for (int i = 0; i < n; ++i) h->sess_used[slots[i]] = 0;
     return MOCR_OK;

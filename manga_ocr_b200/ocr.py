@@ -417,6 +417,7 @@ class MangaOcr:
                         return
                     engine.session_begin(self.session_rows, RGB, self.max_length)
                     capacity = self.max_batch
+                    pending = 0                     # length snapshots enqueued and not yet read (at most two)
                     try:
                         while True:
                             with cv:
@@ -427,9 +428,12 @@ class MangaOcr:
                                     reqs = [self._queue.popleft() for _ in range(min(free, share, 64))]
                                 if not reqs and not inflight:
                                     break
+                            # launch a chunk, admit, launch the first chunk of a session that was idle, then read the length snapshot of
+                            # the chunk BEFORE the one just launched: one chunk is always queued while the host works
                             launched = bool(inflight)
                             if launched:
-                                engine.session_run(steps, wait=False)       # the rows in flight keep stepping while crops are admitted
+                                engine.session_run(steps, wait=False)
+                                pending += 1
                             if reqs:
                                 try:
                                     for r, s in zip(reqs, engine.session_add([r.crop for r in reqs])):
@@ -441,8 +445,12 @@ class MangaOcr:
                                         except BaseException as e:   # noqa: BLE001
                                             r.error = e
                                             r.event.set()
-                            if inflight:
-                                lens = engine.session_run(0 if launched else steps)
+                            if inflight and not launched:
+                                engine.session_run(steps, wait=False)
+                                pending += 1
+                            if pending >= 2:
+                                lens = engine.session_run(0)
+                                pending -= 1
                                 done = [s for s in inflight if lens[s] > 0]
                                 if done:
                                     texts = ids_to_texts(self.vocab, engine.session_fetch(done, release=True))

@@ -373,6 +373,36 @@ def test_session_admission_gives_the_same_ids():
         eng.session_end()
         for i in range(40):
             assert np.array_equal(got[i], ref[i]), i
+        # the dispatcher's pipelined form: a chunk is launched before the snapshot of the previous one is read, slots are reused
+        # while older snapshots (that still show their previous occupant's length) are in flight
+        eng.session_begin(rows=16, max_length=T)
+        pending_snaps, pending, inflight, got = 0, list(range(40)) * 2, {}, {}
+        order = []
+        while pending or inflight:
+            launched = bool(inflight)
+            if launched:
+                eng.session_run(2, wait=False)
+                pending_snaps += 1
+            take = min(16 - len(inflight), len(pending), 7)
+            if take:
+                idx = [pending.pop(0) for _ in range(take)]
+                for i, s in zip(idx, eng.session_add([crops[i] for i in idx])):
+                    inflight[int(s)] = (i, len(order))
+                    order.append(i)
+            if inflight and not launched:
+                eng.session_run(2, wait=False)
+                pending_snaps += 1
+            if pending_snaps >= 2:
+                lens = eng.session_run(0)
+                pending_snaps -= 1
+                done = [s for s in inflight if lens[s] > 0]
+                for s, row in zip(done, eng.session_fetch(done)):
+                    i, k = inflight.pop(s)
+                    got[k] = (i, row, int(lens[s]))
+        eng.session_end()
+        assert len(got) == 80
+        for k, (i, row, n) in got.items():
+            assert np.array_equal(row, ref[i]) and n == (ref[i] != 0).sum(), (k, i)
         ids2, _ = eng.recognize(crops[:5])                  # the handle is usable again
         assert np.array_equal(ids2, ref[:5])
         with pytest.raises(MocrError):

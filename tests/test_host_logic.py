@@ -210,11 +210,14 @@ class _StubEngine:
 
     def session_run(self, steps, wait=True):
         import time
-        if not wait:                               # launch only: the tick is accounted for by the poll that follows
-            self.pending = True
+        if not wait:                               # launch only (+ a length snapshot): read later with session_run(0)
+            self.pending = getattr(self, "pending", 0) + 1
+            assert self.pending <= 2, "more than two snapshots pending"
             return None
-        assert steps > 0 or getattr(self, "pending", False), "poll without a launch"
-        self.pending = False
+        if steps > 0:
+            self.pending = getattr(self, "pending", 0) + 1
+        assert getattr(self, "pending", 0) > 0, "poll without a launch"
+        self.pending -= 1
         time.sleep(0.005)
         lens = np.zeros((self.max_batch,), np.int32)
         for s, st in self.sess["slots"].items():
@@ -234,6 +237,7 @@ class _StubEngine:
     def session_end(self):
         assert not self.sess["slots"], "session ended with crops in flight"
         self.sess = None
+        self.pending = 0
 
     def close(self):
         self.closed = True
