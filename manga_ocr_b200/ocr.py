@@ -415,7 +415,15 @@ class MangaOcr:
                     self = ref()
                     if self is None:
                         return
-                    engine.session_begin(self.session_rows, RGB, self.max_length)
+                    try:
+                        engine.session_begin(self.session_rows, RGB, self.max_length)
+                    except BaseException:       # noqa: BLE001 - no session to be had (e.g. parity taps are set on the engine):
+                        # the callers that are waiting are served as one batch instead, with its per-request failure isolation
+                        with cv:
+                            batch = [self._queue.popleft() for _ in range(min(len(self._queue), self.max_batch))]
+                        if batch:
+                            self._run_requests(engine, batch)
+                        continue
                     capacity = self.max_batch
                     pending = 0                     # length snapshots enqueued and not yet read (at most two)
                     try:

@@ -189,6 +189,8 @@ class _StubEngine:
     # ---- sessions (admission into a running decode): a crop finishes `need` calls of session_run after it was added; need =
     #      1 + (first pixel % 3), so crops added together finish at different times
     def session_begin(self, rows, order=0, max_length=None):
+        if getattr(self, "refuse_sessions", False):
+            raise RuntimeError("sessions do not run with parity taps")
         assert not getattr(self, "sess", None), "session already active"
         self.sess = {"T": max_length or self.max_length, "slots": {}, "rows": rows}
         self.sessions = getattr(self, "sessions", 0) + 1
@@ -405,3 +407,13 @@ def test_admission_shares_callers_between_gpus_and_closes_cleanly(stub_ocr):
     assert all(e.closed and e.sess is None for e in _StubEngine.instances)
     with pytest.raises(RuntimeError):
         ocr(_img(1))
+
+
+def test_admission_falls_back_to_a_batch_when_no_session_can_start(stub_ocr):
+    """An engine that refuses sessions (parity taps set, as __graft_entry__.smoke() does) must not leave callers waiting."""
+    ocr = stub_ocr(devices=[0], max_batch=8, max_length=8, admission=True)
+    _StubEngine.instances[0].refuse_sessions = True
+    got = _call_all(ocr, [1, 2, 13, 4])
+    assert [isinstance(g, str) for g in got] == [True, True, False, True]
+    _StubEngine.instances[0].refuse_sessions = False
+    assert isinstance(ocr(_img(3)), str)
