@@ -2671,6 +2671,9 @@ int mocr_test_gemm(mocr_handle_t* h, int epi, int bn, int M, int N, int K, const
       g.step = static_cast<const int*>(d_step);
       g.tap_steps = 1;
     }
+    // the set-up above went through the legacy default stream (cudaMemset / cudaMemcpy), which does not order against the handle's
+    // non-blocking stream: without this, a 150 MB memset of `out` can still be running when the GEMM writes it
+    CK(cudaDeviceSynchronize());
     if (epi == EPI_F32_ACCUM && bn == 0) {     // the cluster K-split kernel of the large-batch decoder program
       if (N % kKsBN != 0 || K % (kGemmBK * kKsSplit) != 0) return fail(h, MOCR_ERR_INVALID, "K-split GEMM needs N %% 128 == 0 and K %% 256 == 0");
       h->pdl_now = 0;
@@ -2915,6 +2918,7 @@ int mocr_test_stage_gemm(mocr_handle_t* h, int kind, int n_rows, int N, int K, c
         CK(cudaMemcpy(d_res, resid, mn * sizeof(float), cudaMemcpyHostToDevice));
       }
     }
+    CK(cudaDeviceSynchronize());      // (legacy-stream set-up above vs the handle's non-blocking stream)
     PdParams p = make_pd_params(h, n_rows, h->max_length, false, false);
     p.n_partials = kPdVocabTiles;
     if (kind == 3) {
