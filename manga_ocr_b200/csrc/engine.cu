@@ -2918,7 +2918,6 @@ int mocr_test_stage_gemm(mocr_handle_t* h, int kind, int n_rows, int N, int K, c
         CK(cudaMemcpy(d_res, resid, mn * sizeof(float), cudaMemcpyHostToDevice));
       }
     }
-    CK(cudaDeviceSynchronize());      // (legacy-stream set-up above vs the handle's non-blocking stream)
     PdParams p = make_pd_params(h, n_rows, h->max_length, false, false);
     p.n_partials = kPdVocabTiles;
     if (kind == 3) {
@@ -2928,6 +2927,7 @@ int mocr_test_stage_gemm(mocr_handle_t* h, int kind, int n_rows, int N, int K, c
       p.logits_cur = 1;
       if (N != kVocab) return fail(h, MOCR_ERR_INVALID, "arg-max stage test runs at N = %d", kVocab);
     }
+    CK(cudaDeviceSynchronize());      // (legacy-stream set-up above vs the handle's non-blocking stream)
     const PdLinear lin{d_w, d_bias};
     const PdLn ln{d_g, d_b};
     if (kind == 4) {
