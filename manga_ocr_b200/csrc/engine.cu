@@ -1937,6 +1937,26 @@ int mocr_session_add(mocr_handle_t* h, const mocr_crop_t* crops, int n, int32_t*
     int n_free = 0;
     for (char u : h->sess_used) n_free += u ? 0 : 1;
     if (n > n_free) return fail(h, MOCR_ERR_CAPACITY, "%d crops added, %d slots are free", n, n_free);
+    {
+      // all or nothing: every crop is checked before the first run of slots is published (a failure must not leave crops of an
+      // earlier run decoding into slots the caller never learns about)
+      int max_w = 0, tmp_rows = kPreStripRows;
+      for (int i = 0; i < n; ++i) {
+        const mocr_crop_t& c = crops[i];
+        if (c.data == nullptr || c.height < 1 || c.width < 1 || (c.channels != 1 && c.channels != 3 && c.channels != 4) ||
+            c.stride < c.width * c.channels)
+          return fail(h, MOCR_ERR_INVALID, "crop %d is malformed (h=%d w=%d stride=%d channels=%d)", i, c.height, c.width, c.stride, c.channels);
+        if (c.height > 32768 || c.width > 32768) return fail(h, MOCR_ERR_CAPACITY, "crop %d is larger than 32768 px", i);
+        max_w = std::max(max_w, c.width);
+        if (c.height != kImage) {
+          mocr_handle::TableRef t;
+          TRY(table_for(h, c.height, &t));
+          tmp_rows = std::max(tmp_rows, t.strip_rows);
+        }
+      }
+      const size_t smem = pre_smem_bytes(round_up(max_w, 16), tmp_rows);
+      if (smem > 200 * 1024) return fail(h, MOCR_ERR_CAPACITY, "crop extents need %zu B of shared memory (limit 204800)", smem);
+    }
     // Everything an admission launches - pixel upload, preprocess, the encoder, the publication - goes to the (lower-priority)
     // encoder stream: the decode steps already queued on the handle's stream keep running meanwhile, and the rows pick the new
     // crops up at their next next-token stage.  The encoder touches nothing the decoder reads except the K/V slots being added.
