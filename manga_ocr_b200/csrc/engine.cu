@@ -138,8 +138,6 @@ struct mocr_handle {
                             // 119.0 -> 118.6 at 64), large 3 (everything streams: 347.5 -> 344.1 at 512 rows)
   int resid_tma = 1;        // encoder residual adds through the TMA reduce-add epilogue (0: per-thread f32 loads/stores)
   int enc_bn768 = 256;      // tile width of the N = 768 encoder GEMMs (128 or 256; 192 would give 2.68 waves instead of 2.007, measured 3 % slower)
-  int dec_bn = 32;
-  int head_bn = 64;
   int check_every = 26;
   int use_graph = 1;
   int use_pdl = 1;          // programmatic dependent launch between the decoder's stage kernels
@@ -2472,8 +2470,6 @@ int mocr_set_option(mocr_handle_t* h, const char* key, int value) {
   auto bn_ok = [](int v) { return v == 32 || v == 64 || v == 128 || v == 192 || v == 256; };
   if (k == "enc_bn" && bn_ok(value) && kD % value == 0) h->enc_bn = value;
   else if (k == "enc_bn768" && (value == 128 || value == 192 || value == 256)) h->enc_bn768 = value;
-  else if (k == "dec_bn" && bn_ok(value) && kD % value == 0) h->dec_bn = value;
-  else if (k == "head_bn" && bn_ok(value) && kVocab % value == 0) h->head_bn = value;
   else if (k == "check_every" && value >= 1) h->check_every = value;
   else if (k == "use_graph") h->use_graph = value != 0;
   else if (k == "use_pdl") h->use_pdl = value != 0;
