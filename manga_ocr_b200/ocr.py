@@ -395,7 +395,7 @@ class MangaOcr:
     def _dispatch_session(ref, k: int, engine: Engine, cv: threading.Condition) -> None:
         """__call__ traffic of one GPU with admission: while requests are in flight the engine runs a session - queued
         requests are staged, encoded and published between two chunks of decode steps, finished crops are answered at once."""
-        steps = 13                                  # decode steps between two admissions / result polls (one CUDA graph)
+        steps = int(os.environ.get("MOCR_SESSION_STEPS", "13"))   # decode steps between two admissions / result polls (13 = one CUDA graph)
         while True:
             with cv:
                 self = ref()
