@@ -396,6 +396,7 @@ class MangaOcr:
         """__call__ traffic of one GPU with admission: while requests are in flight the engine runs a session - queued
         requests are staged, encoded and published between two chunks of decode steps, finished crops are answered at once."""
         steps = int(os.environ.get("MOCR_SESSION_STEPS", "13"))   # decode steps between two admissions / result polls (13 = one CUDA graph)
+        few = int(os.environ.get("MOCR_SESSION_FEW", "8"))        # at most this many crops in flight: answer latency before queue depth
         while True:
             with cv:
                 self = ref()
@@ -456,7 +457,9 @@ class MangaOcr:
                             if inflight and not launched:
                                 engine.session_run(steps, wait=False)
                                 pending += 1
-                            if pending >= 2:
+                            # (with only a few crops in flight the snapshot of the chunk just launched is read instead: a short text is
+                            #  answered one chunk earlier, and an idle GPU between two chunks costs nothing then)
+                            if pending >= 2 or (pending == 1 and len(inflight) <= few):
                                 lens = engine.session_run(0)
                                 pending -= 1
                                 done = [s for s in inflight if lens[s] > 0]

@@ -296,15 +296,15 @@ def test_micro_batcher_gathers_concurrent_callers(stub_ocr):
 
 
 def test_micro_batcher_linger_extends_while_callers_keep_arriving(stub_ocr):
-    """Callers that trickle in (a worker pool resubmitting: one every 5 ms for 40 ms, linger 30 ms) still share one batch: every
+    """Callers that trickle in (a worker pool resubmitting: one every 8 ms for 64 ms, linger 60 ms) still share one batch: every
     arrival extends the wait by a third of the linger; a lone caller is not held longer than the linger."""
     import threading
     import time
-    ocr = stub_ocr(devices=[0], max_batch=16, max_length=8, linger_ms=30)
+    ocr = stub_ocr(devices=[0], max_batch=16, max_length=8, linger_ms=60)
     out = {}
 
     def run(i):
-        time.sleep(0.005 * i)
+        time.sleep(0.008 * i)
         out[i] = ocr(_img(i))
 
     ts = [threading.Thread(target=run, args=(i,)) for i in range(9)]
@@ -313,11 +313,11 @@ def test_micro_batcher_linger_extends_while_callers_keep_arriving(stub_ocr):
     for t in ts:
         t.join()
     eng = _StubEngine.instances[0]
-    assert sum(eng.batches) == 9 and max(eng.batches) >= 7, eng.batches        # 9 arrivals over 40 ms: not cut off after 30 ms
+    assert sum(eng.batches) == 9 and max(eng.batches) >= 8, eng.batches        # 9 arrivals over 64 ms: not cut off after 60 ms (8 of them are in by then)
     n_before = len(eng.batches)
     t0 = time.monotonic()
     ocr(_img(3))
-    assert time.monotonic() - t0 < 0.2 and len(eng.batches) == n_before + 1    # alone: one linger, not the 4x cap
+    assert time.monotonic() - t0 < 0.2 and len(eng.batches) == n_before + 1    # alone: one linger (60 ms), not the 4x cap (240 ms)
 
 
 def test_micro_batcher_shares_the_queue_between_gpus(stub_ocr):
