@@ -103,10 +103,12 @@ def _generation_config(weights_path: Optional[str]) -> Dict:
 
 def image_to_array(img) -> np.ndarray:
     """PIL image -> the uint8 array the engine reads.  The luma conversion itself
-    (``img.convert("L")``) happens on the GPU; modes whose ``convert("L")`` is not the plain
-    ITU-R 601 map of their RGB bytes are first expanded to RGB by Pillow."""
+    (``img.convert("L")``, the upstream wrapper's first step) happens on the GPU for the modes
+    whose ``convert("L")`` is the ITU-R 601 map of their RGB bytes (RGB, and RGBA: Pillow ignores
+    alpha there); every other mode (P, 1, LA, CMYK, I, I;16, F, YCbCr - whose L is its Y plane,
+    not the luma of its RGB expansion - ...) is converted by Pillow itself, exactly as upstream."""
     if img.mode not in ("RGB", "L", "RGBA"):
-        img = img.convert("RGB")
+        img = img.convert("L")
     a = np.asarray(img)
     if a.dtype != np.uint8:
         a = a.astype(np.uint8)

@@ -115,6 +115,52 @@ def test_free_running_ids_b64_t300_margin_rule(engine64, oracle300):
     assert np.array_equal(ids16, ids[16:32])
 
 
+def test_large_batch_program_t300_matches_oracle(weights0, engine64, oracle300):
+    """The LARGE-BATCH decoder program at the headline length.  Above 112 rows (the page batch, the 512-row tall leg, the
+    stream leg) every decoder Linear runs on the tcgen05 kernel and attention on the warp-per-unit kernel (32-key chunks, 299
+    cached keys = 10 chunks): 144 mixed crops are decoded freely for 299 steps with it; rows of that batch must equal the
+    same crops decoded by the same program in a batch of 16 (rows are independent inside a program), the program's
+    teacher-forced logits are held to the oracle's at every step, and every token of the checked rows is the oracle's
+    arg-max or a near-tie of it (modeling_bert.py:143-284, 379-421; generation/utils.py:2743-2805)."""
+    from manga_ocr_b200.engine import Engine, TAP_LOGITS
+    crops = C.page_batch(128, seed=1003) + C.tall_batch(16, seed=1004)
+    big = Engine(weights0, device=0, max_batch=144, max_length=T)
+    try:
+        ids144, lens144 = _free_run(big, crops)                # 144 rows > 112: the large-batch program by default
+        assert big.last_steps == T - 1
+    finally:
+        big.close()
+    assert ids144.shape == (144, T) and (lens144 == T).all() and (ids144[:, 0] == 2).all()
+    engine64.set_option("big_rows", 1)                         # the same program at 16 rows
+    try:
+        for lo in (0, 128):
+            sub = crops[lo:lo + 16]
+            ids16, _ = _free_run(engine64, sub)
+            assert np.array_equal(ids16, ids144[lo:lo + 16]), lo
+            engine64.set_taps(TAP_LOGITS)
+            try:
+                engine64.decode(T, forced_ids=ids16)
+                logits = engine64.step_logits()                # [16, 299, 6144]
+            finally:
+                engine64.set_taps(0)
+            ref = oracle300.teacher_forced_logits(sub, ids16)
+            err_t = np.abs(logits - ref).max(axis=(0, 2))
+            print(f"large-batch program, rows {lo}..{lo + 15}: teacher-forced logits max-abs per step",
+                  {t: float(f"{err_t[t]:.3e}") for t in REPORT_STEPS}, "overall", float(err_t.max()), "at t =", int(err_t.argmax()))
+            assert err_t.max() <= LOGIT_TOL, (lo, float(err_t.max()), int(err_t.argmax()))
+            assert err_t[200:].mean() <= 3 * max(err_t[:100].mean(), 2e-3)          # no growth with the number of cached keys
+            am = ref.argmax(-1)
+            got = ids16[:, 1:].astype(np.int64)
+            mism = got != am
+            if mism.any():
+                top = np.take_along_axis(ref, am[..., None], -1)[..., 0]
+                mine = np.take_along_axis(ref, got[..., None], -1)[..., 0]
+                assert ((top - mine)[mism] <= LOGIT_TOL).all(), (lo, float((top - mine)[mism].max()))
+            print(f"   token agreement with the oracle arg-max: {float(1.0 - mism.mean()):.4f}")
+    finally:
+        engine64.set_option("big_rows", 112)
+
+
 def test_ragged_eos_t300_matches_oracle_generate():
     """Weights with a raised EOS bias: rows stop at different steps (some beyond the first 128-key block); the ids,
     the EOS stop and the PAD fill must be the oracle's generate() result up to near-ties."""

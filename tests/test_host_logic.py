@@ -89,14 +89,20 @@ def test_image_to_array_modes():
     assert np.array_equal(O.image_to_array(Image.fromarray(rgb)), rgb)
     assert O.image_to_array(Image.fromarray(rgb[..., 0])).shape == (9, 7)
     assert O.image_to_array(Image.fromarray(rgb).convert("RGBA")).shape == (9, 7, 4)
-    p = Image.fromarray(rgb).convert("P")
-    a = O.image_to_array(p)
-    assert a.shape == (9, 7, 3)
-    # the engine's luma of the expanded RGB equals Pillow's own convert("L") of the palette image
+    # what reaches the engine has the L plane upstream's img.convert("L") gives, for every Pillow mode: RGB / RGBA bytes go to
+    # the GPU's luma conversion, the other modes are converted by Pillow itself (YCbCr -> L is the Y plane, NOT the luma of the
+    # image's RGB expansion: 42 % of the pixels differ by 1)
     from oracle.preprocess_np import rgb_to_l
-    assert np.array_equal(rgb_to_l(a), np.asarray(p.convert("L")))
-    one = Image.fromarray(rgb[..., 0] > 128)
-    assert np.array_equal(rgb_to_l(O.image_to_array(one)), np.asarray(one.convert("L")))
+    base = Image.fromarray(rng.integers(0, 256, (33, 21, 3), dtype=np.uint8))
+    imgs = [base.convert(m) for m in ("RGB", "RGBA", "L", "P", "PA", "1", "LA", "CMYK", "YCbCr", "HSV", "I", "F", "RGBX")]
+    imgs.append(Image.fromarray(rng.integers(0, 65536, (33, 21), dtype=np.uint16)))              # I;16
+    imgs.append(Image.fromarray(rng.integers(-500, 70000, (33, 21)).astype(np.int32)))           # I, out of the uint8 range
+    imgs.append(Image.fromarray((rng.random((33, 21)) * 600 - 100).astype(np.float32)))          # F, likewise
+    for im in imgs:
+        a = O.image_to_array(im)
+        assert a.dtype == np.uint8 and a.shape[:2] == (33, 21), im.mode
+        plane = a if a.ndim == 2 else rgb_to_l(a[..., :3])
+        assert np.array_equal(plane, np.asarray(im.convert("L"))), im.mode
 
 
 def test_shard_bounds_cover_exactly():
