@@ -1711,6 +1711,10 @@ struct PdSlotList {
   int n;
   int slot[64];
 };
+// The slot list as a device table (the cross-K/V epilogue of the admission's encoder pass scatters crop c into block slot[c]).
+__global__ void pd_slot_map_kernel(int* map, const PdSlotList l) {
+  if (threadIdx.x < l.n) map[threadIdx.x] = l.slot[threadIdx.x];
+}
 __global__ void __launch_bounds__(256) pd_publish_slots_kernel(int* queue, int* ring, int cap, int first_pub, int* ids, int* lens, int max_len,
                                                                const PdSlotList l) {
   for (int i = threadIdx.x; i < l.n * max_len; i += blockDim.x) {

@@ -23,6 +23,7 @@
 #include <string>
 #include <thread>
 #include <unordered_map>
+#include <chrono>
 #include <vector>
 
 #include "../../include/mocr_b200.h"
@@ -117,7 +118,12 @@ struct mocr_handle {
   int sms = 148;
   cudaStream_t stream = nullptr;
   cudaStream_t stream_enc = nullptr;  // lower priority: encoder of the crops that are still waiting while the decoder already runs (slot refill)
-  cudaStream_t stream_enc_hi = nullptr;   // the same at the decoder's priority (option pipeline = 2)
+  cudaStream_t stream_enc_hi = nullptr;   // the same at the decoder's priority (option pipeline = 2; admissions with sess_enc_hi = 1)
+  cudaStream_t stream_fetch = nullptr;    // finished id rows of a session (mocr_session_fetch)
+  int* d_sess_map = nullptr;              // [64] cache block of each crop of the admission being encoded
+  const int* enc_crop_map = nullptr;      // set while an admission's encoder pass is launched
+  cudaEvent_t ev_staged = nullptr;        // the last admission's pixels and descriptors have been consumed (its preprocess has run)
+  int sess_enc_hi = 0;                    // admissions of a session run at the decoder's stream priority
   cudaEvent_t ev_first = nullptr;     // first sub-chunk encoded and published
   std::mutex mu;
   std::string error;
@@ -176,6 +182,7 @@ struct mocr_handle {
   int pipeline = 0;         // with slot refill, 1 (2: equal stream priorities): encode the waiting crops in sub-chunks on a second stream while the decoder
                             // already runs.  Measured on the ragged 512-crop leg: 116 ms (80 ms at equal priorities) against 75 ms with the encoder
                             // serialised in front - the 200 KB GEMM CTAs and the decoder's stage kernels do not share SMs well - so it is off
+  double prof_add[4] = {0, 0, 0, 0};   // MOCR_SESSION_PROF: seconds in mocr_session_add (wait for the previous pass, staging, launches) and passes
   int sub_i0 = 0, sub_n = 0;   // sub-range of the staged crops that preprocess / encode work on (sub_n = 0: all of them)
   int beam_device = 1;      // beam search with the selection on the device and the steps in a CUDA graph (0: host bookkeeping, one round trip per step)
   int beam_steps_per_graph = 8;
@@ -660,7 +667,12 @@ int stage_crops(mocr_handle* h, const mocr_crop_t* crops, int n, int order, int 
     max_w = std::max(max_w, c.width);
   }
   // the previous batch may still be reading the arena / tables
-  CK(cudaStreamSynchronize(h->stream));
+  {
+    const auto t0 = std::chrono::steady_clock::now();
+    if (h->sess_on) CK(cudaEventSynchronize(h->ev_staged));    // (an admission: the previous one's encoder pass may still run - only its preprocess reads them)
+    else CK(cudaStreamSynchronize(h->stream));
+    h->prof_add[0] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  }
   if (total > h->arena_cap) {
     if (h->h_arena) cudaFreeHost(h->h_arena);
     if (h->d_arena) cudaFree(h->d_arena);
@@ -1015,7 +1027,11 @@ int encode_launches(mocr_handle* h) {
   }
   TRY(layernorm(h, h->hres, M, h->enc_ln, h->enc_out.p, (h->taps & MOCR_TAP_ENCODER) ? h->enc_f32 : nullptr));   // :455
   // cross-attention K/V of both decoder layers, once per crop (modeling_bert.py:252-267)
-  TRY(gemm(h, EPI_CROSSKV, bn, h->enc_out, h->cross_kv, M, out_bf16(h->crosskv + static_cast<size_t>(i0) * kEncTokens * 4 * kD, 4 * kD)));
+  {
+    GemmArgs a = out_bf16(h->crosskv + static_cast<size_t>(i0) * kEncTokens * 4 * kD, 4 * kD);
+    a.crop_map = h->enc_crop_map;        // an admission's crops go to the cache blocks of their slots
+    TRY(gemm(h, EPI_CROSSKV, bn, h->enc_out, h->cross_kv, M, a));
+  }
   return MOCR_OK;
 }
 
@@ -1584,6 +1600,7 @@ int create_impl(mocr_handle* h) {
     CK(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, hi));
     CK(cudaStreamCreateWithPriority(&h->stream_enc, cudaStreamNonBlocking, lo));
     CK(cudaStreamCreateWithPriority(&h->stream_enc_hi, cudaStreamNonBlocking, hi));
+    CK(cudaStreamCreateWithPriority(&h->stream_fetch, cudaStreamNonBlocking, hi));
     CK(cudaEventCreateWithFlags(&h->ev_first, cudaEventDisableTiming));
   }
   const int B = h->max_batch, T = h->max_length;
@@ -1717,7 +1734,9 @@ int mocr_destroy(mocr_handle_t* h) {
     if (h->h_queue) cudaFreeHost(h->h_queue);
     if (h->stream_enc) cudaStreamDestroy(h->stream_enc);
     if (h->stream_enc_hi) cudaStreamDestroy(h->stream_enc_hi);
+    if (h->stream_fetch) cudaStreamDestroy(h->stream_fetch);
     if (h->ev_first) cudaEventDestroy(h->ev_first);
+    if (h->ev_staged) cudaEventDestroy(h->ev_staged);
     if (h->stream) cudaStreamDestroy(h->stream);
   }
   delete h;
@@ -1875,10 +1894,15 @@ int mocr_recognize(mocr_handle_t* h, const mocr_crop_t* crops, int n, int channe
 
 int session_end(mocr_handle* h) {
   h->sess_on = false;
+  if (getenv("MOCR_SESSION_PROF") != nullptr && h->prof_add[3] > 0)
+    fprintf(stderr, "[mocr] session: %.0f encoder passes; in mocr_session_add: %.1f ms waiting for the previous pass, %.1f ms staging, %.1f ms launching\n",
+            h->prof_add[3], h->prof_add[0] * 1e3, h->prof_add[1] * 1e3, h->prof_add[2] * 1e3);
+  h->prof_add[0] = h->prof_add[1] = h->prof_add[2] = h->prof_add[3] = 0;
   h->sub_i0 = h->sub_n = 0;
   h->staged_ok = h->pre_ok = h->enc_ok = h->dec_ok = false;
   cudaStreamSynchronize(h->stream_enc);
   cudaStreamSynchronize(h->stream_enc_hi);
+  cudaStreamSynchronize(h->stream_fetch);
   cudaStreamSynchronize(h->stream);
   return MOCR_OK;
 }
@@ -1896,6 +1920,8 @@ int mocr_session_begin(mocr_handle_t* h, int channel_order, int max_length, int 
       TRY(dmalloc(h, &h->d_ring, static_cast<size_t>(h->max_batch)));
       CK(cudaMemsetAsync(h->d_ring, 0, sizeof(int) * h->max_batch, h->stream));
     }
+    if (h->d_sess_map == nullptr) TRY(dmalloc(h, &h->d_sess_map, 64));
+    if (h->ev_staged == nullptr) CK(cudaEventCreateWithFlags(&h->ev_staged, cudaEventDisableTiming));
     CK(cudaStreamSynchronize(h->stream));
     h->staged_ok = h->pre_ok = h->enc_ok = h->dec_ok = false;
     pd_publish_kernel<<<1, 1, 0, h->stream>>>(h->d_queue, 0, 0);                     // (the graph's warm-up step must find an empty queue)
@@ -1963,31 +1989,46 @@ int mocr_session_add(mocr_handle_t* h, const mocr_crop_t* crops, int n, int32_t*
       cudaStream_t s;
       ~Restore() { h->stream = s; h->sub_i0 = h->sub_n = 0; }
     } restore{h, h->stream};
-    h->stream = h->stream_enc;
+    h->stream = h->sess_enc_hi ? h->stream_enc_hi : h->stream_enc;
     int done = 0;
     while (done < n) {
-      // the next run of free slots: one staging + encoder pass per run (crop indices of a pass are contiguous)
-      int s0 = 0;
-      while (h->sess_used[s0]) ++s0;
-      int len = 0;
-      while (s0 + len < h->max_batch && !h->sess_used[s0 + len] && len < std::min(n - done, 64)) ++len;
-      TRY(stage_crops(h, crops + done, len, h->sess_order, 0, nullptr, s0));
-      h->sub_i0 = s0;
-      h->sub_n = len;
-      TRY(preprocess(h));
-      TRY(encode_launches(h));             // (not through the per-size graph cache: run lengths and offsets vary freely)
+      // ONE staging + encoder pass for the crops (64 at a time): they take whichever slots are free - the pass works on its own
+      // contiguous activations, only the cross-K/V epilogue and the publication go by slot (one pass per run of adjacent free slots
+      // cost 1.3-1.6 passes of ~1 ms per admission, each waiting for the one before)
+      const int len = std::min(n - done, 64);
       PdSlotList l{};
       l.n = len;
-      for (int i = 0; i < len; ++i) l.slot[i] = s0 + i;
+      for (int i = 0, s0 = 0; i < len; ++i, ++s0) {
+        while (h->sess_used[s0]) ++s0;
+        l.slot[i] = s0;
+      }
+      const auto t0 = std::chrono::steady_clock::now();
+      const double w0 = h->prof_add[0];
+      TRY(stage_crops(h, crops + done, len, h->sess_order, 0, nullptr, 0));
+      const auto t1 = std::chrono::steady_clock::now();
+      h->sub_i0 = 0;
+      h->sub_n = len;
+      TRY(preprocess(h));
+      CK(cudaEventRecord(h->ev_staged, h->stream));
+      pd_slot_map_kernel<<<1, 64, 0, h->stream>>>(h->d_sess_map, l);
+      CK(cudaGetLastError());
+      ++h->launches;
+      h->enc_crop_map = h->d_sess_map;
+      const int re = encode_launches(h);       // (not through the per-size graph cache: the pass runs next to the decode steps)
+      h->enc_crop_map = nullptr;
+      TRY(re);
+      h->prof_add[1] += std::chrono::duration<double>(t1 - t0).count() - (h->prof_add[0] - w0);
+      h->prof_add[2] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
+      h->prof_add[3] += 1;
       pd_publish_slots_kernel<<<1, 256, 0, h->stream>>>(h->d_queue, h->d_ring, h->max_batch, static_cast<int>(h->sess_published), h->d_ids,
                                                         h->d_lens, h->sess_T, l);
       CK(cudaGetLastError());
       ++h->launches;
       h->sess_published += len;
       for (int i = 0; i < len; ++i) {
-        h->sess_used[s0 + i] = 1;
-        h->sess_min_snap[s0 + i] = h->snap_enq;      // snapshots enqueued before this point may still show the previous occupant
-        out_slots[done + i] = s0 + i;
+        h->sess_used[l.slot[i]] = 1;
+        h->sess_min_snap[l.slot[i]] = h->snap_enq;      // snapshots enqueued before this point may still show the previous occupant
+        out_slots[done + i] = l.slot[i];
       }
       done += len;
     }
@@ -2041,7 +2082,7 @@ int mocr_session_fetch(mocr_handle_t* h, const int32_t* slots, int n, int32_t* o
     // The rows of finished slots are final: they are copied on a side stream, without waiting for the decode steps that are queued
     // on the handle's stream.  A released slot's length is zeroed here, synchronously, before the slot can be handed out again
     // (its next occupant is published from the encoder stream; snapshots enqueued before that are ignored for it).
-    cudaStream_t side = h->stream_enc_hi;
+    cudaStream_t side = h->stream_fetch;
     for (int i = 0; i < n; ++i) {
       if (slots[i] < 0 || slots[i] >= h->max_batch || !h->sess_used[slots[i]]) return fail(h, MOCR_ERR_INVALID, "slot %d is not in use", slots[i]);
       CK(cudaMemcpyAsync(out_ids + static_cast<size_t>(i) * h->sess_T, h->d_ids + static_cast<size_t>(slots[i]) * h->sess_T, sizeof(int) * h->sess_T,
@@ -2466,6 +2507,7 @@ int mocr_set_option(mocr_handle_t* h, const char* key, int value) {
   TRY(check_handle(h));
   std::lock_guard<std::mutex> lock(h->mu);
   if (key == nullptr) return fail(h, MOCR_ERR_INVALID, "key is NULL");
+  if (h->sess_on) return fail(h, MOCR_ERR_INVALID, "options cannot change while a session is active (its CUDA graph is in use)");
   const std::string k = key;
   auto bn_ok = [](int v) { return v == 32 || v == 64 || v == 128 || v == 192 || v == 256; };
   if (k == "enc_bn" && bn_ok(value) && kD % value == 0) h->enc_bn = value;
@@ -2500,6 +2542,7 @@ int mocr_set_option(mocr_handle_t* h, const char* key, int value) {
 #endif
   else if (k == "big_bn768" && (value == 32 || value == 64)) h->big_bn768 = value;
   else if (k == "big_vocab_bn" && (value == 0 || value == 64 || value == 128 || value == 256)) h->big_vocab_bn = value;
+  else if (k == "sess_enc_hi") h->sess_enc_hi = value != 0;
   else if (k == "steps_per_graph" && value >= 1 && value <= 64) h->steps_per_graph = value;
   else if (k == "decode_prof") h->decode_prof = value != 0;
   else return fail(h, MOCR_ERR_INVALID, "unknown option or bad value: %s=%d", key, value);

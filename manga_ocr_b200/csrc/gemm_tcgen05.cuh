@@ -46,6 +46,7 @@ struct GemmArgs {
   float* logits;         // EPI_ARGMAX: optional f32 tap for parity tests (may be null):
   const int* step;       //   row r writes logits[(r * tap_steps + step[r]) * N ...]
   int tap_steps;
+  const int* crop_map;  // EPI_CROSSKV: optional, cache block of the batch's crop c is crop_map[c] (null: c) - admissions into free slots of a session
   int pdl;               // 1: launched with programmatic stream serialization (decoder stage): weights are requested before
                          //    griddepcontrol.wait, the activations after it
   int out_tma;           // EPI_BF16 / EPI_BF16_GELU with BN = 128 or 256: rows leave through tmap_out (bf16 [M, N] view of `out`, box 64 x 32,
@@ -188,9 +189,10 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, uint32_
           // column = (layer * 2 + kv) * 768 + head * 64 + d  ->  cache[crop][layer][kv][head][token][64]: every
           // (crop, layer, head) K or V block is one contiguous 25 KB stream for the decoder's attention
           const int crop = row / kEncTokens, tok = row - crop * kEncTokens;
+          const int block = args.crop_map != nullptr ? args.crop_map[crop] : crop;
           const int lkv = col0 / kD, hd = col0 - lkv * kD;
           dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(args.out) +
-                                         ((static_cast<size_t>(crop) * 4 + lkv) * kHeads + hd / kHeadDim) * (kEncTokens * kHeadDim) +
+                                         ((static_cast<size_t>(block) * 4 + lkv) * kHeads + hd / kHeadDim) * (kEncTokens * kHeadDim) +
                                          static_cast<size_t>(tok) * kHeadDim + (hd & (kHeadDim - 1)));
         }
 #pragma unroll

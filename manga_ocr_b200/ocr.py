@@ -213,6 +213,7 @@ class MangaOcr:
         self.session_rows = max(1, min(max_batch, int(slots) if slots else 64))
         self._engine_locks = [threading.Lock() for _ in self.engines]      # a session owns its engine; batch callers wait for it to drain
         self._batch_waiting = [0] * len(self.engines)
+        self._session_prof = {} if os.environ.get("MOCR_SESSION_PROF") else None     # dispatcher phase times (seconds, count)
         self.linger_s = float(os.environ.get("MOCR_LINGER_MS", "1.5")) * 1e-3 if linger_ms is None else linger_ms * 1e-3
         ref = weakref.ref(self)
         if self.admission:
@@ -429,8 +430,18 @@ class MangaOcr:
                         continue
                     capacity = self.max_batch
                     pending = 0                     # length snapshots enqueued and not yet read (at most two)
+                    prof = self._session_prof       # None, or {phase: [seconds, count]} (MOCR_SESSION_PROF=1: tools/call_latency.py)
+                    clock = time.perf_counter
+
+                    def lap(name, t0, n=1):
+                        if prof is not None:
+                            e = prof.setdefault(name, [0.0, 0])
+                            e[0] += clock() - t0
+                            e[1] += n
+                        return clock()
                     try:
                         while True:
+                            t0 = clock()
                             with cv:
                                 reqs = []
                                 free = capacity - len(inflight)
@@ -439,12 +450,14 @@ class MangaOcr:
                                     reqs = [self._queue.popleft() for _ in range(min(free, share, 64))]
                                 if not reqs and not inflight:
                                     break
+                            t0 = lap("take", t0)
                             # launch a chunk, admit, launch the first chunk of a session that was idle, then read the length snapshot of
                             # the chunk BEFORE the one just launched: one chunk is always queued while the host works
                             launched = bool(inflight)
                             if launched:
                                 engine.session_run(steps, wait=False)
                                 pending += 1
+                                t0 = lap("launch", t0)
                             if reqs:
                                 try:
                                     for r, s in zip(reqs, engine.session_add([r.crop for r in reqs])):
@@ -456,14 +469,17 @@ class MangaOcr:
                                         except BaseException as e:   # noqa: BLE001
                                             r.error = e
                                             r.event.set()
+                                t0 = lap("admit", t0, len(reqs))
                             if inflight and not launched:
                                 engine.session_run(steps, wait=False)
                                 pending += 1
+                                t0 = lap("launch", t0)
                             # (with only a few crops in flight the snapshot of the chunk just launched is read instead: a short text is
                             #  answered one chunk earlier, and an idle GPU between two chunks costs nothing then)
                             if pending >= 2 or (pending == 1 and len(inflight) <= few):
                                 lens = engine.session_run(0)
                                 pending -= 1
+                                t0 = lap("snapshot", t0)
                                 done = [s for s in inflight if lens[s] > 0]
                                 if done:
                                     texts = ids_to_texts(self.vocab, engine.session_fetch(done, release=True))
@@ -471,6 +487,7 @@ class MangaOcr:
                                         r = inflight.pop(s)
                                         r.text = t
                                         r.event.set()
+                                    lap("answer", t0, len(done))
                     finally:
                         engine.session_end()
                 except BaseException as e:          # noqa: BLE001 - the engine failed: every request in flight gets the error
