@@ -123,7 +123,7 @@ struct mocr_handle {
   int* d_sess_map = nullptr;              // [64] cache block of each crop of the admission being encoded
   const int* enc_crop_map = nullptr;      // set while an admission's encoder pass is launched
   cudaEvent_t ev_staged = nullptr;        // the last admission's pixels and descriptors have been consumed (its preprocess has run)
-  int sess_enc_hi = 0;                    // admissions of a session run at the decoder's stream priority
+  int sess_enc_hi = 1;                    // admissions of a session run at the decoder's stream priority
   cudaEvent_t ev_first = nullptr;     // first sub-chunk encoded and published
   std::mutex mu;
   std::string error;
@@ -1043,7 +1043,7 @@ int encode(mocr_handle* h) {
     TRY(encode_launches(h));
   } else {
     const uint64_t key = (static_cast<uint64_t>(h->sub_n > 0 ? h->sub_n : h->n) << 32) | (static_cast<uint64_t>(h->sub_n > 0 ? h->sub_i0 : 0) << 8) |
-                         ((h->taps & MOCR_TAP_ENCODER) ? 1u : 0u);
+                         ((h->taps & MOCR_TAP_ENCODER) ? 1u : 0u) | (h->enc_crop_map != nullptr ? 2u : 0u);
     auto it = h->enc_graphs.find(key);
     if (it == h->enc_graphs.end()) {
       const int64_t l0 = h->launches;
@@ -1062,7 +1062,7 @@ int encode(mocr_handle* h) {
       if (ce != cudaSuccess) return fail(h, MOCR_ERR_CUDA, "encoder stream capture failed: %s", cudaGetErrorString(ce));
       CK(cudaGraphInstantiate(&exec, graph, 0));
       cudaGraphDestroy(graph);
-      if (h->enc_graphs.size() >= 64) {
+      if (h->enc_graphs.size() >= 160) {
         for (auto& g : h->enc_graphs) cudaGraphExecDestroy(g.second.exec);
         h->enc_graphs.clear();
       }
@@ -2014,7 +2014,9 @@ int mocr_session_add(mocr_handle_t* h, const mocr_crop_t* crops, int n, int32_t*
       CK(cudaGetLastError());
       ++h->launches;
       h->enc_crop_map = h->d_sess_map;
-      const int re = encode_launches(h);       // (not through the per-size graph cache: the pass runs next to the decode steps)
+      // (a pass always works on activations [0, len) and the same map: up to 4 crops - a lone caller's latency is mostly these 88
+      //  launches - it is replayed from a graph per crop count; larger counts are launched directly, a capture costs ~7 ms once each)
+      const int re = len <= 4 ? encode(h) : encode_launches(h);
       h->enc_crop_map = nullptr;
       TRY(re);
       h->prof_add[1] += std::chrono::duration<double>(t1 - t0).count() - (h->prof_add[0] - w0);
@@ -2026,8 +2028,7 @@ int mocr_session_add(mocr_handle_t* h, const mocr_crop_t* crops, int n, int32_t*
       ++h->launches;
       h->sess_published += len;
       for (int i = 0; i < len; ++i) {
-        h->sess_used[l.slot[i]] = 1;
-        h->sess_min_snap[l.slot[i]] = h->snap_enq;      // snapshots enqueued before this point may still show the previous occupant
+        h->sess_used[l.slot[i]] = 1;               // (which snapshots may speak for the slot was settled when it was released)
         out_slots[done + i] = l.slot[i];
       }
       done += len;
@@ -2091,7 +2092,14 @@ int mocr_session_fetch(mocr_handle_t* h, const int32_t* slots, int n, int32_t* o
     }
     CK(cudaStreamSynchronize(side));
     if (release)
-      for (int i = 0; i < n; ++i) h->sess_used[slots[i]] = 0;
+      for (int i = 0; i < n; ++i) {
+        h->sess_used[slots[i]] = 0;
+        // The length was zeroed synchronously just now: a snapshot enqueued from here on is taken after that and shows 0 or the next
+        // occupant's length; one enqueued earlier may already have been taken with this occupant's length in it and must not speak
+        // for the next one.  (Counting from the next ADMISSION instead cost short texts a whole chunk: the snapshot that follows
+        // the chunk they are decoded in is usually enqueued before they are admitted.)
+        h->sess_min_snap[slots[i]] = h->snap_enq;
+      }
     return MOCR_OK;
   });
 }

@@ -8,7 +8,7 @@ import numpy as np
 from PIL import Image
 from manga_ocr_b200 import crops as C, weights as W
 from manga_ocr_b200.ocr import MangaOcr
-n = 256
+n = 1024
 crops = [Image.fromarray(c) for c in C.bubble_batch(64, seed=1002)] * (n // 64)
 w = W.random_init(0, eos_bias=4.2, gain=3.0)
 counts = [int(a) for a in sys.argv[1:] if "=" not in a] or [1, 4, 15, 50]
