@@ -403,9 +403,42 @@ def test_session_admission_gives_the_same_ids():
         assert len(got) == 80
         for k, (i, row, n) in got.items():
             assert np.array_equal(row, ref[i]) and n == (ref[i] != 0).sum(), (k, i)
+        # one admission into NON-ADJACENT free slots: a single encoder pass whose cross-K/V rows are scattered through the slot
+        # map; the occupants of the slots in between keep their K/V (their rows are still decoding when the pass runs)
+        eng.session_begin(rows=16, max_length=T)
+        first = [int(x) for x in eng.session_add(crops[:8])]
+        assert first == list(range(8))
+        held = {}
+        for _ in range(T):
+            lens = eng.session_run(1)
+            for sl in (1, 3, 6):
+                if sl not in held and lens[sl] > 0:
+                    held[sl] = eng.session_fetch([sl])[0]          # released as soon as it ends, the others keep stepping
+            if len(held) == 3:
+                break
+        assert len(held) == 3
+        second = [int(x) for x in eng.session_add(crops[8:11])]
+        assert second == [1, 3, 6]
+        rows_a, rows_b = {}, {}
+        for _ in range(2 * T):
+            lens = eng.session_run(1)
+            for sl in range(8):
+                if lens[sl] > 0 and sl not in rows_b and (sl in (1, 3, 6) or sl not in rows_a):
+                    (rows_b if sl in (1, 3, 6) else rows_a)[sl] = eng.session_fetch([sl], release=False)[0]
+            if len(rows_a) == 5 and len(rows_b) == 3:
+                break
+        eng.session_end()
+        for sl in range(8):
+            assert np.array_equal(held[sl] if sl in held else rows_a[sl], ref[sl]), sl
+        for k, sl in enumerate((1, 3, 6)):
+            assert np.array_equal(rows_b[sl], ref[8 + k]), sl
         ids2, _ = eng.recognize(crops[:5])                  # the handle is usable again
         assert np.array_equal(ids2, ref[:5])
         with pytest.raises(MocrError):
             eng.session_run(1)
+        eng.session_begin(rows=4, max_length=T)
+        with pytest.raises(MocrError):
+            eng.set_option("steps_per_graph", 5)            # the session's graph is in use
+        eng.session_end()
     finally:
         eng.close()
