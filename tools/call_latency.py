@@ -11,20 +11,21 @@ from manga_ocr_b200.ocr import MangaOcr
 n = 1024
 crops = [Image.fromarray(c) for c in C.bubble_batch(64, seed=1002)] * (n // 64)
 w = W.random_init(0, eos_bias=4.2, gain=3.0)
+devices = [int(x) for x in os.environ.get("MOCR_DEVICES", "0").split(",")]      # MOCR_DEVICES=0,1: one process, two GPUs
 counts = [int(a) for a in sys.argv[1:] if "=" not in a] or [1, 4, 15, 50]
 for cfg in [a for a in sys.argv[1:] if "=" in a] or ["steps=13"]:
     opts = dict(kv.split("=") for kv in cfg.split(","))
     steps = int(opts.pop("steps", 13))
     os.environ["MOCR_SESSION_STEPS"] = str(steps)
-    ocr = MangaOcr(weights=w, devices=[0], max_batch=64, max_length=300, warmup=True)
+    ocr = MangaOcr(weights=w, devices=devices, max_batch=64, max_length=300, warmup=True)
     for _ in range(50):                     # (the warm-up call's session may still be closing: options are refused until it has)
         try:
-            ocr.engines[0].set_option("steps_per_graph", steps)
+            for e in ocr.engines: e.set_option("steps_per_graph", steps)
             break
         except Exception:
             time.sleep(0.02)
     for k, v in opts.items():
-        ocr.engines[0].set_option(k, int(v))
+        for e in ocr.engines: e.set_option(k, int(v))
     for threads in counts:
         for rep in range(2):
             it = iter(range(n)); lock = threading.Lock(); lat = []
