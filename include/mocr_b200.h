@@ -198,7 +198,8 @@ int mocr_resample_table(int in_size, int32_t* ksize, int32_t* out, int capacity)
  * The reference decodes one crop per call (reference/src/ui/main_window.py:9801) from up to 50 worker threads
  * (:608-611, :4317-4327); a batch API makes late callers wait for the whole batch in flight.  A session keeps `rows`
  * decoder rows stepping and admits crops while it runs: mocr_session_add stages, preprocesses, encodes and publishes
- * n crops (n <= free slots; out_slots[n] = the slot of each, 0 <= slot < max_batch), an idle row picks each of them
+ * n crops (n <= free slots; out_slots[n] = the slot of each, 0 <= slot < max_batch, not necessarily adjacent: the crops of one
+ * call are encoded in one pass whichever slots are free), an idle row picks each of them
  * up (the admission runs on a second stream: decode steps already launched keep running meanwhile);
  * mocr_session_run launches `steps` greedy steps followed by a snapshot of the slots' lengths (at most two snapshots may
  * be pending) and, when out_lens is not NULL, waits for the OLDEST pending snapshot and returns it as
@@ -219,7 +220,7 @@ void* mocr_stream(mocr_handle_t* h);            /* the cudaStream_t all work is 
 int mocr_sync(mocr_handle_t* h);
 int64_t mocr_launch_count(mocr_handle_t* h);    /* kernels launched by this handle so far     */
 int mocr_last_steps(mocr_handle_t* h);          /* decode steps executed by the last decode   */
-int mocr_set_option(mocr_handle_t* h, const char* key, int value);
+int mocr_set_option(mocr_handle_t* h, const char* key, int value);   /* tuning switches; fails while a session is active */
 /* Times `iters` back-to-back launches of one named kernel of the path on the handle's stream
  * with CUDA events, on the current batch state (used by bench.py for the roofline line). */
 int mocr_time_kernel(mocr_handle_t* h, const char* kernel, int iters, float* ms_per_launch, double* algo_bytes,

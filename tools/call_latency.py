@@ -17,7 +17,8 @@ for cfg in [a for a in sys.argv[1:] if "=" in a] or ["steps=13"]:
     opts = dict(kv.split("=") for kv in cfg.split(","))
     steps = int(opts.pop("steps", 13))
     os.environ["MOCR_SESSION_STEPS"] = str(steps)
-    ocr = MangaOcr(weights=w, devices=devices, max_batch=64, max_length=300, warmup=True)
+    rows = int(opts.pop("rows", 0))         # decoder rows of the session (0: 64)
+    ocr = MangaOcr(weights=w, devices=devices, max_batch=64, max_length=300, warmup=True, slots=rows or None)
     for _ in range(50):                     # (the warm-up call's session may still be closing: options are refused until it has)
         try:
             for e in ocr.engines: e.set_option("steps_per_graph", steps)
