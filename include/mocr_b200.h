@@ -212,6 +212,11 @@ int mocr_session_begin(mocr_handle_t* h, int channel_order, int max_length, int 
 int mocr_session_add(mocr_handle_t* h, const mocr_crop_t* crops, int n, int32_t* out_slots);
 int mocr_session_run(mocr_handle_t* h, int steps, int32_t* out_lens);
 int mocr_session_fetch(mocr_handle_t* h, const int32_t* slots, int n, int32_t* out_ids, int release);
+/* The chunks launched from here on step only the first `rows` decoder rows (rounded up to a row count the session has a step
+ * program for: 16, or the session's own; that count is returned).  A lightly loaded session steps faster on fewer rows (92 vs
+ * 119 us per step).  Growing is always allowed - rows above the current count are idle by construction; shrinking only while no
+ * slot is in use.  A session begins on all its rows. */
+int mocr_session_rows(mocr_handle_t* h, int rows);
 int mocr_session_end(mocr_handle_t* h);
 
 /* ---- plumbing --------------------------------------------------------------------------- */

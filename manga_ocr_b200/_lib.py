@@ -78,6 +78,7 @@ _SIGNATURES = {
     "mocr_session_run": (c_int, [c_void_p, c_int, POINTER(c_int32)]),
     "mocr_session_fetch": (c_int, [c_void_p, POINTER(c_int32), c_int, POINTER(c_int32), c_int]),
     "mocr_session_end": (c_int, [c_void_p]),
+    "mocr_session_rows": (c_int, [c_void_p, c_int]),
     "mocr_stage_crops": (c_int, [c_void_p, POINTER(mocr_crop_t), c_int, c_int]),
     "mocr_stage_regions": (c_int, [c_void_p, POINTER(mocr_crop_t), POINTER(mocr_region_t), c_int, c_int]),
     "mocr_get_region_mask": (c_int, [c_void_p, c_int, POINTER(c_uint8)]),

@@ -163,6 +163,10 @@ struct mocr_handle {
   long long sess_published = 0;          // publications so far (the device queue counts them)
   std::vector<char> sess_used;           // slot occupied (published, result not yet released)
   PdParams sess_p{};
+  PdParams sess_p_small{};                // the same session on its first kSessSmallRows rows only (mocr_session_rows)
+  cudaGraphExec_t sess_exec_small = nullptr;
+  int64_t sess_per_step_small = 0;
+  int sess_rows_now = 0;                  // rows the following chunks step
   cudaGraphExec_t sess_exec = nullptr;
   int64_t sess_per_step = 0;
   int* d_ring = nullptr;                 // [max_batch] slots in publication order
@@ -1892,6 +1896,8 @@ int mocr_recognize(mocr_handle_t* h, const mocr_crop_t* crops, int n, int channe
 // releases their slots for reuse: no batch boundary, a caller waits for its own crop only.  ids per crop are those of
 // mocr_recognize (rows are independent).
 
+constexpr int kSessSmallRows = 16;
+
 int session_end(mocr_handle* h) {
   h->sess_on = false;
   if (getenv("MOCR_SESSION_PROF") != nullptr && h->prof_add[3] > 0)
@@ -1926,11 +1932,25 @@ int mocr_session_begin(mocr_handle_t* h, int channel_order, int max_length, int 
     h->staged_ok = h->pre_ok = h->enc_ok = h->dec_ok = false;
     pd_publish_kernel<<<1, 1, 0, h->stream>>>(h->d_queue, 0, 0);                     // (the graph's warm-up step must find an empty queue)
     CK(cudaGetLastError());
+    if (h->graphs.size() + 2 >= 64) {       // (the two programs of this session must not evict each other from the cache)
+      for (auto& g : h->graphs) cudaGraphExecDestroy(g.second.exec);
+      h->graphs.clear();
+    }
     PdParams p = make_pd_params(h, rows, max_length, false, false, h->max_batch);
     p.queue_slots = h->d_ring;
     p.ext_queue = 1;
     p.idle_start = 1;
     TRY(decode_step_graph(h, p, false, false, &h->sess_exec, &h->sess_per_step));     // (its warm-up step runs on throw-away state)
+    h->sess_exec_small = nullptr;
+    if (rows > kSessSmallRows) {       // the program of a lightly loaded session (mocr_session_rows): same state, fewer rows per step
+      PdParams ps = make_pd_params(h, kSessSmallRows, max_length, false, false, h->max_batch);
+      ps.queue_slots = h->d_ring;
+      ps.ext_queue = 1;
+      ps.idle_start = 1;
+      TRY(decode_step_graph(h, ps, false, false, &h->sess_exec_small, &h->sess_per_step_small));
+      h->sess_p_small = ps;
+    }
+    h->sess_rows_now = rows;
     TRY(decode_begin(h, p));                                                         // every row idle, every id row [CLS] PAD ...
     pd_publish_kernel<<<1, 1, 0, h->stream>>>(h->d_queue, 0, 0);                     // nothing published, nothing finished
     CK(cudaGetLastError());
@@ -2043,13 +2063,15 @@ int mocr_session_run(mocr_handle_t* h, int steps, int32_t* out_lens) {
   return guarded(h, [&]() -> int {
     if (!h->sess_on) return fail(h, MOCR_ERR_INVALID, "no session is active");
     if (steps < 0 || (steps == 0 && out_lens == nullptr)) return fail(h, MOCR_ERR_INVALID, "bad argument");
-    const int spg = h->sess_exec != nullptr ? std::max(1, std::min(h->steps_per_graph, h->sess_T - 1)) : 1;
+    const bool small = h->sess_rows_now < h->sess_rows;
+    const cudaGraphExec_t exec = small ? h->sess_exec_small : h->sess_exec;
+    const int spg = exec != nullptr ? std::max(1, std::min(h->steps_per_graph, h->sess_T - 1)) : 1;
     for (int ran = 0; ran < steps; ran += spg) {
-      if (h->sess_exec != nullptr) {
-        CK(cudaGraphLaunch(h->sess_exec, h->stream));
-        h->launches += h->sess_per_step;
+      if (exec != nullptr) {
+        CK(cudaGraphLaunch(exec, h->stream));
+        h->launches += small ? h->sess_per_step_small : h->sess_per_step;
       } else {
-        TRY(decode_stage_step(h, h->sess_p));
+        TRY(decode_stage_step(h, small ? h->sess_p_small : h->sess_p));
       }
     }
     // A snapshot of the slots' lengths follows every chunk of steps; up to two are in flight, so the host can read the snapshot of
@@ -2072,6 +2094,19 @@ int mocr_session_run(mocr_handle_t* h, int steps, int32_t* out_lens) {
     ++h->snap_read;
     return MOCR_OK;
   });
+}
+
+int mocr_session_rows(mocr_handle_t* h, int rows) {
+  TRY(check_handle(h));
+  std::lock_guard<std::mutex> lock(h->mu);
+  if (!h->sess_on) return fail(h, MOCR_ERR_INVALID, "no session is active");
+  if (rows < 1 || rows > h->sess_rows) return fail(h, MOCR_ERR_CAPACITY, "%d rows, the session has %d", rows, h->sess_rows);
+  const int want = (rows <= kSessSmallRows && h->sess_rows > kSessSmallRows) ? kSessSmallRows : h->sess_rows;
+  if (want < h->sess_rows_now)       // rows above the new count must be idle: certain only when no crop is in the session
+    for (char u : h->sess_used)
+      if (u) return fail(h, MOCR_ERR_INVALID, "the row count of a session shrinks only while no slot is in use");
+  h->sess_rows_now = want;
+  return want;
 }
 
 int mocr_session_fetch(mocr_handle_t* h, const int32_t* slots, int n, int32_t* out_ids, int release) {

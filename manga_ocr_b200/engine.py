@@ -208,6 +208,14 @@ class Engine:
                                                   1 if release else 0))
         return ids
 
+    def session_rows(self, rows: int) -> int:
+        """The following chunks step only the first `rows` decoder rows (rounded up to 16 or the session's count; returned).
+        Growing is always allowed, shrinking only while no slot is in use."""
+        rc = self._lib.mocr_session_rows(self._h, int(rows))
+        if rc < 0:
+            self._ck(rc)
+        return int(rc)
+
     def session_end(self) -> None:
         self._ck(self._lib.mocr_session_end(self._h))
 

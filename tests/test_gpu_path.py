@@ -442,3 +442,50 @@ def test_session_admission_gives_the_same_ids():
         eng.session_end()
     finally:
         eng.close()
+
+
+def test_session_row_count_grows_with_the_load():
+    """mocr_session_rows: a session of 40 rows steps its first 16 rows while lightly loaded and all of them later; the state is
+    shared (crops admitted under one program finish under the other), ids per crop equal mocr_recognize's; shrinking is refused
+    while slots are in use."""
+    from manga_ocr_b200 import weights as W
+    from manga_ocr_b200.engine import Engine, MocrError
+    w = W.random_init(0, gain=3.0, eos_bias=3.7)
+    T = 24
+    crops = C.page_batch(40, seed=5)
+    eng = Engine(w, device=0, max_batch=40, max_length=T)
+    try:
+        ref, _ = eng.recognize(crops)
+        eng.session_begin(rows=40, max_length=T)
+        assert eng.session_rows(16) == 16
+        slots = {int(s): i for i, s in enumerate(eng.session_add(crops[:10]))}
+        got = {}
+
+        def collect(lens):
+            done = [s for s in slots if lens[s] > 0]
+            for s, row in zip(done, eng.session_fetch(done)):
+                got[slots.pop(s)] = row
+        collect(eng.session_run(3))                       # (3 steps requested = one graph of 13: the short texts end here)
+        with pytest.raises(MocrError):
+            eng.session_rows(41)
+        assert eng.session_rows(40) == 40                 # more load: every row steps from the next chunk on
+        if slots:
+            with pytest.raises(MocrError):
+                eng.session_rows(16)                      # crops are in flight
+        for i, s in enumerate(eng.session_add(crops[10:])):
+            slots[int(s)] = 10 + i
+        for _ in range(8):
+            collect(eng.session_run(3))
+            if not slots:
+                break
+        assert not slots and len(got) == 40
+        assert eng.session_rows(16) == 16                 # idle again: back to the small program, and it still works
+        slots = {int(s): 3 + i for i, s in enumerate(eng.session_add(crops[3:6]))}
+        for _ in range(4):
+            collect(eng.session_run(3))
+        eng.session_end()
+        assert not slots
+        for i in range(40):
+            assert np.array_equal(got[i], ref[i]), i
+    finally:
+        eng.close()

@@ -216,6 +216,15 @@ class _StubEngine:
             out.append(s)
         return np.asarray(out, np.int32)
 
+    def session_rows(self, rows):
+        assert getattr(self, "sess", None) is not None
+        now = 16 if rows <= 16 < self.sess["rows"] else self.sess["rows"]
+        if now < self.sess.get("rows_now", self.sess["rows"]):
+            assert not self.sess["slots"], "the row count shrinks only while no slot is in use"
+        self.sess["rows_now"] = now
+        self.row_counts = getattr(self, "row_counts", []) + [now]
+        return now
+
     def session_run(self, steps, wait=True):
         import time
         if not wait:                               # launch only (+ a length snapshot): read later with session_run(0)
@@ -413,6 +422,25 @@ def test_admission_shares_callers_between_gpus_and_closes_cleanly(stub_ocr):
     assert all(e.closed and e.sess is None for e in _StubEngine.instances)
     with pytest.raises(RuntimeError):
         ocr(_img(1))
+
+
+def test_admission_session_starts_on_16_rows_and_grows_with_the_load(stub_ocr):
+    """A session steps only its first 16 decoder rows while at most 16 crops are in flight and all 64 once more arrive; the row
+    count never shrinks while slots are in use (the stub asserts it), and the next session starts small again."""
+    ocr = stub_ocr(devices=[0], max_batch=64, max_length=8, admission=True)
+    eng = _StubEngine.instances[0]
+    got = _call_all(ocr, [1, 2, 3, 4])
+    assert all(isinstance(g, str) for g in got)
+    assert set(eng.row_counts) == {16}                            # a few callers: never grown
+    eng.row_counts = []
+    got = _call_all(ocr, [v for v in range(60) if v != 13])
+    assert all(isinstance(g, str) for g in got)
+    assert eng.row_counts[0] == 16 and 64 in eng.row_counts       # 59 callers at once: grown
+    for a, b in zip(eng.row_counts, eng.row_counts[1:]):
+        assert not (a == 64 and b == 64)                          # once per session
+    small = stub_ocr(devices=[0], max_batch=8, max_length=8, admission=True)
+    assert isinstance(small(_img(2)), str)
+    assert not getattr(_StubEngine.instances[-1], "row_counts", [])      # a session of at most 16 rows has one program
 
 
 def test_admission_falls_back_to_a_batch_when_no_session_can_start(stub_ocr):
