@@ -122,6 +122,8 @@ struct mocr_handle {
   cudaStream_t stream_fetch = nullptr;    // finished id rows of a session (mocr_session_fetch)
   int* d_sess_map = nullptr;              // [64] cache block of each crop of the admission being encoded
   const int* enc_crop_map = nullptr;      // set while an admission's encoder pass is launched
+  cudaEvent_t ev_published = nullptr;     // the last admission's crops are in the device queue
+  bool sess_wait_pub = false;             // the next chunk starts after that publication (the session was empty: no row to hold up)
   cudaEvent_t ev_staged = nullptr;        // the last admission's pixels and descriptors have been consumed (its preprocess has run)
   int sess_enc_hi = 1;                    // admissions of a session run at the decoder's stream priority
   cudaEvent_t ev_first = nullptr;     // first sub-chunk encoded and published
@@ -1741,6 +1743,7 @@ int mocr_destroy(mocr_handle_t* h) {
     if (h->stream_fetch) cudaStreamDestroy(h->stream_fetch);
     if (h->ev_first) cudaEventDestroy(h->ev_first);
     if (h->ev_staged) cudaEventDestroy(h->ev_staged);
+    if (h->ev_published) cudaEventDestroy(h->ev_published);
     if (h->stream) cudaStreamDestroy(h->stream);
   }
   delete h;
@@ -1928,6 +1931,8 @@ int mocr_session_begin(mocr_handle_t* h, int channel_order, int max_length, int 
     }
     if (h->d_sess_map == nullptr) TRY(dmalloc(h, &h->d_sess_map, 64));
     if (h->ev_staged == nullptr) CK(cudaEventCreateWithFlags(&h->ev_staged, cudaEventDisableTiming));
+    if (h->ev_published == nullptr) CK(cudaEventCreateWithFlags(&h->ev_published, cudaEventDisableTiming));
+    h->sess_wait_pub = false;
     CK(cudaStreamSynchronize(h->stream));
     h->staged_ok = h->pre_ok = h->enc_ok = h->dec_ok = false;
     pd_publish_kernel<<<1, 1, 0, h->stream>>>(h->d_queue, 0, 0);                     // (the graph's warm-up step must find an empty queue)
@@ -1981,6 +1986,7 @@ int mocr_session_add(mocr_handle_t* h, const mocr_crop_t* crops, int n, int32_t*
     int n_free = 0;
     for (char u : h->sess_used) n_free += u ? 0 : 1;
     if (n > n_free) return fail(h, MOCR_ERR_CAPACITY, "%d crops added, %d slots are free", n, n_free);
+    const bool was_empty = n_free == static_cast<int>(h->sess_used.size());
     {
       // all or nothing: every crop is checked before the first run of slots is published (a failure must not leave crops of an
       // earlier run decoding into slots the caller never learns about)
@@ -2047,12 +2053,16 @@ int mocr_session_add(mocr_handle_t* h, const mocr_crop_t* crops, int n, int32_t*
       CK(cudaGetLastError());
       ++h->launches;
       h->sess_published += len;
+      CK(cudaEventRecord(h->ev_published, h->stream));
       for (int i = 0; i < len; ++i) {
         h->sess_used[l.slot[i]] = 1;               // (which snapshots may speak for the slot was settled when it was released)
         out_slots[done + i] = l.slot[i];
       }
       done += len;
     }
+    // An empty session has no row to hold up: its next chunk starts when these crops are in the queue instead of stepping idle rows
+    // while the encoder pass runs (a lone caller's text then has the whole chunk to end in)
+    h->sess_wait_pub = was_empty;
     return MOCR_OK;
   });
 }
@@ -2063,6 +2073,10 @@ int mocr_session_run(mocr_handle_t* h, int steps, int32_t* out_lens) {
   return guarded(h, [&]() -> int {
     if (!h->sess_on) return fail(h, MOCR_ERR_INVALID, "no session is active");
     if (steps < 0 || (steps == 0 && out_lens == nullptr)) return fail(h, MOCR_ERR_INVALID, "bad argument");
+    if (steps > 0 && h->sess_wait_pub) {
+      CK(cudaStreamWaitEvent(h->stream, h->ev_published, 0));
+      h->sess_wait_pub = false;
+    }
     const bool small = h->sess_rows_now < h->sess_rows;
     const cudaGraphExec_t exec = small ? h->sess_exec_small : h->sess_exec;
     const int spg = exec != nullptr ? std::max(1, std::min(h->steps_per_graph, h->sess_T - 1)) : 1;
