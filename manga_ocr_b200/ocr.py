@@ -400,6 +400,7 @@ class MangaOcr:
         requests are staged, encoded and published between two chunks of decode steps, finished crops are answered at once."""
         steps = int(os.environ.get("MOCR_SESSION_STEPS", "13"))   # decode steps between two admissions / result polls (13 = one CUDA graph)
         few = int(os.environ.get("MOCR_SESSION_FEW", "8"))        # at most this many crops in flight: answer latency before queue depth
+        settle = float(os.environ.get("MOCR_SESSION_SETTLE_MS", "0.3")) * 1e-3    # wait this long for the callers just answered to call again
         while True:
             with cv:
                 self = ref()
@@ -444,8 +445,33 @@ class MangaOcr:
                             e[1] += n
                         return clock()
                     try:
+                        answered = 0                # callers answered in the previous round (they are about to call again)
                         while True:
                             t0 = clock()
+                            # launch a chunk, take what is queued and admit it, launch the first chunk of a session that was idle, then
+                            # read the length snapshot of the chunk BEFORE the one just launched: one chunk is always queued while the
+                            # host works
+                            launched = bool(inflight)
+                            if launched:
+                                if small and len(inflight) + len(self._queue) > 16:
+                                    engine.session_rows(self.session_rows)
+                                    small = False
+                                engine.session_run(steps, wait=False)
+                                pending += 1
+                                t0 = lap("launch", t0)
+                                if answered and settle > 0:
+                                    # The callers that were answered a moment ago need a few hundred microseconds to come back with their
+                                    # next crop; taking the queue right away would miss them by that much and cost them a whole chunk.
+                                    # The chunk just launched keeps the GPU busy meanwhile.
+                                    with cv:
+                                        end = clock() + settle
+                                        while len(self._queue) < answered and not self._closed:
+                                            left = end - clock()
+                                            if left <= 0:
+                                                break
+                                            cv.wait(left)
+                                    t0 = lap("settle", t0)
+                            answered = 0
                             with cv:
                                 reqs = []
                                 free = capacity - len(inflight)
@@ -458,13 +484,6 @@ class MangaOcr:
                                 engine.session_rows(self.session_rows)
                                 small = False
                             t0 = lap("take", t0)
-                            # launch a chunk, admit, launch the first chunk of a session that was idle, then read the length snapshot of
-                            # the chunk BEFORE the one just launched: one chunk is always queued while the host works
-                            launched = bool(inflight)
-                            if launched:
-                                engine.session_run(steps, wait=False)
-                                pending += 1
-                                t0 = lap("launch", t0)
                             if reqs:
                                 try:
                                     for r, s in zip(reqs, engine.session_add([r.crop for r in reqs])):
@@ -494,6 +513,7 @@ class MangaOcr:
                                         r = inflight.pop(s)
                                         r.text = t
                                         r.event.set()
+                                    answered = len(done)
                                     lap("answer", t0, len(done))
                     finally:
                         engine.session_end()
