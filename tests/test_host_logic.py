@@ -443,6 +443,37 @@ def test_admission_session_starts_on_16_rows_and_grows_with_the_load(stub_ocr):
     assert not getattr(_StubEngine.instances[-1], "row_counts", [])      # a session of at most 16 rows has one program
 
 
+def test_admission_serves_a_worker_pool_that_resubmits(stub_ocr):
+    """The app's shape: a few worker threads, each calling again as soon as it has its answer.  The dispatcher launches the next
+    chunk, gives the callers it has just answered a moment to come back, and admits them in the same round; every call gets its
+    own text and the session ends when the pool is done."""
+    import threading
+    ocr = stub_ocr(devices=[0], max_batch=8, max_length=8, admission=True)
+    out, lock = {}, threading.Lock()
+
+    def worker(w):
+        for j in range(6):
+            v = (7 * w + j) % 12
+            t = ocr(_img(v))
+            with lock:
+                out[(w, j)] = (v, t)
+
+    ts = [threading.Thread(target=worker, args=(w,)) for w in range(4)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=30)
+    assert len(out) == 24
+    for v, t in out.values():
+        assert t == O.ids_to_texts(ocr.vocab, np.array([[2, 5 + v, 3, 0]]))[0]
+    eng = _StubEngine.instances[0]
+    assert sum(eng.adds) == 24 and max(eng.adds) <= 4
+    deadline = __import__("time").monotonic() + 2
+    while eng.sess is not None and __import__("time").monotonic() < deadline:
+        __import__("time").sleep(0.01)
+    assert eng.sess is None
+
+
 def test_admission_falls_back_to_a_batch_when_no_session_can_start(stub_ocr):
     """An engine that refuses sessions (parity taps set, as __graft_entry__.smoke() does) must not leave callers waiting."""
     ocr = stub_ocr(devices=[0], max_batch=8, max_length=8, admission=True)
