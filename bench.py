@@ -517,13 +517,19 @@ def run_b200(args, rank, local_rank, world):
                       return
                   out[i] = socr(imgs[i])
 
-          ts = [threading.Thread(target=caller) for _ in range(n_threads)]
-          t0 = time.perf_counter()
-          for t in ts:
-              t.start()
-          for t in ts:
-              t.join()
-          dt_call = time.perf_counter() - t0
+          def run_calls():
+              ts = [threading.Thread(target=caller) for _ in range(n_threads)]
+              t0 = time.perf_counter()
+              for t in ts:
+                  t.start()
+              for t in ts:
+                  t.join()
+              return time.perf_counter() - t0
+
+          nxt[0] = max(0, n_stream - 64 * world)        # warm (like the batch call above): the session's graphs, the encoder graphs
+          run_calls()                                   # of small admissions, the dispatcher threads - 64 crops per GPU, untimed
+          nxt[0] = 0
+          dt_call = run_calls()
           same = sum(a == b for a, b in zip(out, texts))
           same1 = sum(a[:1] == b[:1] for a, b in zip(out, texts))
           extra["stream"] = {"workload": "configs[4]: crop stream (config-3 distribution, seed 1005), one process driving every GPU", "crops": n_stream,
