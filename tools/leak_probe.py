@@ -1,3 +1,4 @@
+"""Device memory after create / use / destroy cycles of a handle (a leak shows as a shrinking free figure):  python tools/leak_probe.py [full|create]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
