@@ -84,7 +84,8 @@ class Vocab:
         """(per-token post-processed strings, mask of tokens that need the context-aware path, UTF-32 code unit
         per single-character token (0: none), mask of tokens whose only context dependence is the dot rules)."""
         if getattr(self, "_fast", None) is None:
-            slow = np.array([any(ch in _TRIGGERS or ch.isspace() for ch in t) for t in self.tokens], bool)
+            # (a token that starts with "##" is glued to its predecessor by decode(): context-dependent as well)
+            slow = np.array([t.startswith("##") or any(ch in _TRIGGERS or ch.isspace() for ch in t) for t in self.tokens], bool)
             tz = [t if s else h2z(t) for t, s in zip(self.tokens, slow)]
             dots = np.array([s and len(t) == 1 and t in _DOT_TRIGGERS for t, s in zip(self.tokens, slow)], bool)
             # code unit of every token whose (post-processed, or raw for the dot characters) form is ONE character
@@ -93,8 +94,11 @@ class Vocab:
         return self._fast
 
     def decode(self, ids: Iterable[int]) -> str:
-        """``tokenizer.decode(ids, skip_special_tokens=True)``."""
-        return " ".join(self._kept_tokens(ids))
+        """``tokenizer.decode(ids, skip_special_tokens=True)`` of the character-level ``BertJapaneseTokenizer``:
+        the kept tokens joined by spaces, every " ##" removed (a word-piece continuation is glued to its
+        predecessor; a leading one keeps its hashes) and the ends stripped
+        (transformers/models/bert_japanese/tokenization_bert_japanese.py:256-261)."""
+        return " ".join(self._kept_tokens(ids)).replace(" ##", "").strip()
 
 
 # --- jaconv.h2z(ascii=True, digit=True, kana=True) restated -----------------
@@ -157,7 +161,8 @@ _DOT_TRIGGERS = set("…・.")      # ... of which these only take part in the e
 
 def ids_to_text(vocab: Vocab, ids: Iterable[int]) -> str:
     """``post_process(tokenizer.decode(ids, skip_special_tokens=True))``.  The reference joins the
-    tokens with spaces and then strips ALL whitespace; concatenating directly is the same string.
+    tokens with spaces, drops every " ##" and then strips ALL whitespace; for tokens that do not start
+    with "##" concatenating directly is the same string.
     Fast path: when no token of the row contains a context-dependent character (dots, ellipsis,
     half-width voiced marks) or whitespace, post_process acts on every character independently and
     the per-token results are precomputed."""
@@ -170,7 +175,7 @@ def ids_to_text(vocab: Vocab, ids: Iterable[int]) -> str:
             if not fast[1][kept].any():
                 tz = fast[0]
                 return "".join([tz[i] for i in kept.tolist()])
-    return post_process("".join(vocab._kept_tokens(ids)))
+    return post_process(vocab.decode(ids))
 
 
 def ids_to_texts(vocab: Vocab, ids: np.ndarray) -> List[str]:

@@ -124,9 +124,20 @@ def post_process(text: str) -> str:
     return _h2z(text)
 
 
+class _CharTokenizer:
+    """The one attribute ``BertJapaneseTokenizer.convert_tokens_to_string`` reads (the real tokenizer cannot be built here:
+    its word tokenizer needs fugashi / unidic, absent offline - SURVEY.md section 8c)."""
+    subword_tokenizer_type = "character"
+
+
 def decode_ids(tokens: Sequence[str], ids: Iterable[int]) -> str:
+    """``tokenizer.decode(ids, skip_special_tokens=True)``: the special ids are dropped and the kept tokens go through
+    transformers' OWN ``BertJapaneseTokenizer.convert_tokens_to_string`` (tokenization_bert_japanese.py:256-261: joined by
+    spaces, " ##" removed, stripped) - called, not restated."""
+    from transformers.models.bert_japanese.tokenization_bert_japanese import BertJapaneseTokenizer
     specials = {PAD_ID, UNK_ID, CLS_ID, SEP_ID, MASK_ID}
-    return " ".join(tokens[int(i)] for i in ids if int(i) not in specials)
+    kept = [tokens[int(i)] for i in ids if int(i) not in specials]
+    return BertJapaneseTokenizer.convert_tokens_to_string(_CharTokenizer(), kept)
 
 
 class ReferenceMangaOcr:

@@ -81,3 +81,40 @@ def test_batch_conversion_equals_per_row_conversion():
     ids[9:20, 1:] = rng.choice(plain, size=(11, 299))          # rows that stay on the vectorised path
     assert ids_to_texts(v, ids) == [ids_to_text(v, r) for r in ids]
     assert ids_to_texts(v, ids[:0]) == []
+
+
+def test_decode_glues_wordpiece_continuations_like_transformers():
+    """tokenizer.decode(skip_special_tokens=True) of BertJapaneseTokenizer is `" ".join(tokens).replace(" ##", "").strip()`
+    (transformers/models/bert_japanese/tokenization_bert_japanese.py:256-261): a token that starts with "##" is glued to
+    its predecessor, a leading one keeps its hashes.  Checked against transformers' own function, on a vocabulary that has
+    such tokens (a real vocab.txt may), through every conversion path of the product."""
+    from transformers.models.bert_japanese.tokenization_bert_japanese import BertJapaneseTokenizer
+
+    class Char:
+        subword_tokenizer_type = "character"
+
+    from oracle.reference_ocr import post_process as oracle_post_process
+    base = Vocab.synthetic()
+    v = Vocab(base.tokens[:-6] + ["##あ", "##b", "##", "###c", "#x", "a b"])
+    tok = {t: i for i, t in enumerate(v.tokens)}
+    rows = [
+        ["あ", "##あ", "い"], ["##あ", "い"], ["a", "###c"], ["a", "##"], ["#", "#", "x"], ["#", "#x"], ["a", "##b", ".", ".", "##あ"],
+        ["a b", "##b"], ["[CLS]", "##b", "[SEP]"], ["ｶ", "##あ", "ﾞ"], ["##", "##"], [],
+    ]
+    T = 8
+    ids = np.zeros((len(rows), T), np.int32)
+    for r, toks in enumerate(rows):
+        ids[r, :len(toks)] = [tok[t] for t in toks]
+    want = []
+    for r, toks in enumerate(rows):
+        kept = [v.tokens[i] for i in ids[r] if i not in v.special_ids]
+        decoded = BertJapaneseTokenizer.convert_tokens_to_string(Char(), kept)
+        assert v.decode(ids[r]) == decoded == v.decode(ids[r].tolist())
+        want.append(oracle_post_process(decoded))
+    assert [ids_to_text(v, r) for r in ids] == want
+    assert ids_to_texts(v, ids) == want
+    assert want[0] == "ああい" and want[1] == "＃＃あい" and want[2] == "a＃c".replace("a", "ａ").replace("c", "ｃ")
+    # rows without such tokens stay on the vectorised path and are unchanged by the rule
+    rng = np.random.default_rng(3)
+    plain = rng.integers(5, len(base.tokens) - 6, size=(6, 40)).astype(np.int32)
+    assert ids_to_texts(v, plain) == ids_to_texts(base, plain) == [ids_to_text(base, r) for r in plain]
