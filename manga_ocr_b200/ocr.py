@@ -78,12 +78,25 @@ GREEDY = {"num_beams": 1, "no_repeat_ngram_size": 0, "length_penalty": 1.0, "ear
 def _generation_config(weights_path: Optional[str]) -> Dict:
     """``generate()`` reads the checkpoint's generation settings: ``generation_config.json`` WHOLESALE when the file
     exists (transformers builds the GenerationConfig from it alone), else the legacy generation fields of
-    ``config.json``.  The shipped kha-white/manga-ocr-base is believed to carry num_beams=4, no_repeat_ngram_size=3,
-    length_penalty=2.0, early_stopping=true; without a file the path is greedy (BASELINE)."""
-    import json
+    ``config.json`` - the top-level ones and, attribute by attribute where the top level has none, those of its
+    ``decoder`` sub-config (``GenerationConfig.from_model_config``, transformers/generation/configuration_utils.py;
+    checked against transformers 5.5.0 itself by tests/test_host_logic.py.  4.x compared with 1 / 0 / 1.0 / False instead
+    of None when it decided whether the top level had "set" a field).  The shipped kha-white/manga-ocr-base is believed
+    to carry num_beams=4, no_repeat_ngram_size=3, length_penalty=2.0, early_stopping=true (SURVEY.md section 8c);
+    without a file the path is greedy (BASELINE)."""
     gen = dict(GREEDY)
+    for k, v in _generation_fields(weights_path, list(gen)).items():
+        if v is not None:
+            gen[k] = v
+    return gen
+
+
+def _generation_fields(weights_path: Optional[str], keys: Sequence[str]) -> Dict:
+    """{key: value or None} as generate() would resolve them for the checkpoint of ``weights_path`` (see _generation_config)."""
+    import json
+    out = {k: None for k in keys}
     if not weights_path:
-        return gen
+        return out
     d = weights_path if os.path.isdir(weights_path) else os.path.dirname(weights_path)
     for fn in ("generation_config.json", "config.json"):
         fp = os.path.join(d, fn)
@@ -94,11 +107,36 @@ def _generation_config(weights_path: Optional[str]) -> Dict:
                 cfg = json.load(f)
         except (OSError, ValueError):
             continue
-        for k in gen:
+        if not isinstance(cfg, dict):
+            continue
+        sub = {}
+        if fn == "config.json":
+            sub = next((cfg[n] for n in ("decoder", "generator", "text_config") if isinstance(cfg.get(n), dict) and cfg[n]), {})
+        for k in keys:
             if cfg.get(k) is not None:
-                gen[k] = cfg[k]
+                out[k] = cfg[k]
+            elif sub.get(k) is not None:
+                out[k] = sub[k]
         break                      # the first file that exists decides; they are not merged
-    return gen
+    return out
+
+
+# Generation settings that change what generate() returns and that this engine does not implement, with their neutral values.
+# A checkpoint that carries one of them would silently decode differently here: the constructor refuses it instead
+# (MOCR_IGNORE_GENERATION_EXTRAS=1 overrides).  Sampling-only knobs (temperature, top_k, top_p ...) matter only with do_sample.
+_UNSUPPORTED_GENERATION = {
+    "do_sample": (False,), "num_beam_groups": (1,), "diversity_penalty": (0, 0.0), "repetition_penalty": (1, 1.0),
+    "encoder_repetition_penalty": (1, 1.0), "encoder_no_repeat_ngram_size": (0,), "min_length": (0,), "min_new_tokens": (0,),
+    "max_new_tokens": (), "bad_words_ids": ([],), "force_words_ids": ([],), "suppress_tokens": ([],), "begin_suppress_tokens": ([],),
+    "forced_bos_token_id": (), "forced_eos_token_id": (), "num_return_sequences": (1,), "penalty_alpha": (0, 0.0),
+    "exponential_decay_length_penalty": (), "sequence_bias": ({}, []), "renormalize_logits": (False,), "constraints": ([],),
+}
+
+
+def _unsupported_generation_settings(weights_path: Optional[str]) -> Dict:
+    """{key: value} of the checkpoint's generation settings this engine would not honour (empty: none)."""
+    found = _generation_fields(weights_path, list(_UNSUPPORTED_GENERATION))
+    return {k: v for k, v in found.items() if v is not None and v not in _UNSUPPORTED_GENERATION[k]}
 
 
 def image_to_array(img) -> np.ndarray:
@@ -160,6 +198,12 @@ class MangaOcr:
                         "(nothing is downloaded), or use 'random[:seed[:eos_bias]]' for random-init weights")
                 weights = W.load_weights(found[0])
                 gen = _generation_config(found[0])
+                extras = _unsupported_generation_settings(found[0])
+                if extras and os.environ.get("MOCR_IGNORE_GENERATION_EXTRAS", "0") != "1":
+                    raise NotImplementedError(
+                        f"the checkpoint's generation settings {extras} are not implemented by this engine (it does greedy and beam "
+                        "search with no_repeat_ngram_size / length_penalty / early_stopping); its output would differ from "
+                        "generate()'s.  MOCR_IGNORE_GENERATION_EXTRAS=1 decodes without them")
                 if vocab is None and found[1]:
                     vocab = Vocab.from_file(found[1])
         else:

@@ -162,6 +162,88 @@ def test_generation_config_is_read_from_the_checkpoint_directory(tmp_path):
     assert g == {"num_beams": 4, "no_repeat_ngram_size": 3, "length_penalty": 1.0, "early_stopping": True}
 
 
+def test_generation_config_resolution_equals_transformers(tmp_path):
+    """The generation settings the product reads from a checkpoint directory are the ones transformers' own generate() would
+    use for it: a tiny VisionEncoderDecoderModel is saved, its json files are edited into every combination (generation_config.json
+    alone / flagged _from_model_config / next to legacy fields in config.json; legacy fields at the top level, in the decoder
+    sub-config, in both; none) and `model._prepare_generation_config()` of the reloaded model is the reference
+    (transformers/generation/utils.py, configuration_utils.py::from_model_config)."""
+    import json
+    import warnings
+    from transformers import BertConfig, ViTConfig, VisionEncoderDecoderConfig, VisionEncoderDecoderModel
+    from manga_ocr_b200.ocr import _generation_config
+    enc = ViTConfig(hidden_size=32, num_hidden_layers=1, num_attention_heads=2, intermediate_size=64, image_size=32, patch_size=16)
+    dec = BertConfig(hidden_size=32, num_hidden_layers=1, num_attention_heads=2, intermediate_size=64, vocab_size=50, is_decoder=True,
+                     add_cross_attention=True)
+    d = tmp_path / "ckpt"
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = VisionEncoderDecoderModel(VisionEncoderDecoderConfig.from_encoder_decoder_configs(enc, dec))
+        m.generation_config.decoder_start_token_id, m.generation_config.eos_token_id, m.generation_config.pad_token_id = 2, 3, 0
+        m.save_pretrained(str(d))
+    cfg0 = json.loads((d / "config.json").read_text())
+    base = {"decoder_start_token_id": 2, "eos_token_id": 3, "pad_token_id": 0}
+    beams = {"num_beams": 4, "no_repeat_ngram_size": 3, "early_stopping": True}
+
+    def with_decoder(extra_top, extra_dec):
+        c = json.loads(json.dumps(cfg0))
+        c.update(extra_top)
+        c["decoder"].update(extra_dec)
+        return c
+
+    cases = {                                      # name: (generation_config.json or None, config.json)
+        "generation_config alone": ({**base, **beams}, cfg0),
+        "generation_config wins over legacy fields, wholesale": ({**base, **beams}, with_decoder({"num_beams": 2, "length_penalty": 1.5}, {})),
+        "generation_config flagged _from_model_config": ({**base, **beams, "_from_model_config": True}, with_decoder({"num_beams": 2}, {})),
+        "legacy fields at the top level": (None, with_decoder({"num_beams": 2, "length_penalty": 1.5}, {})),
+        "legacy fields in the decoder sub-config": (None, with_decoder({}, {"num_beams": 3, "no_repeat_ngram_size": 2, "length_penalty": 2.0,
+                                                                            "early_stopping": True})),
+        "top level first, decoder per missing attribute": (None, with_decoder({"num_beams": 5}, {"num_beams": 3, "no_repeat_ngram_size": 2})),
+        "no generation fields": (None, cfg0),
+    }
+    for name, (gen_json, cfg_json) in cases.items():
+        (d / "config.json").write_text(json.dumps(cfg_json))
+        if gen_json is None:
+            (d / "generation_config.json").unlink(missing_ok=True)
+        else:
+            (d / "generation_config.json").write_text(json.dumps(gen_json))
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            gc, _ = VisionEncoderDecoderModel.from_pretrained(str(d))._prepare_generation_config(None)
+        want = {"num_beams": gc.num_beams or 1, "no_repeat_ngram_size": gc.no_repeat_ngram_size or 0,
+                "length_penalty": 1.0 if gc.length_penalty is None else gc.length_penalty, "early_stopping": gc.early_stopping or False}
+        assert _generation_config(str(d)) == want, (name, _generation_config(str(d)), want)
+        assert _generation_config(str(d / "model.safetensors")) == want, name
+
+
+def test_unsupported_generation_settings_are_refused_not_ignored(tmp_path, monkeypatch):
+    """A checkpoint whose generation settings ask for something this engine does not implement (repetition penalty, sampling,
+    bad words ...) must not decode silently differently from generate(): the constructor raises (the app treats any exception as
+    "engine unavailable", main_window.py:3396-3398); neutral values, as old config.json files spell them out, are fine."""
+    import json
+    d = tmp_path / "ckpt"
+    d.mkdir()
+    (d / "model.safetensors").write_bytes(b"x")
+    neutral = {"do_sample": False, "num_beam_groups": 1, "diversity_penalty": 0.0, "repetition_penalty": 1.0, "min_length": 0,
+               "bad_words_ids": None, "num_return_sequences": 1, "encoder_no_repeat_ngram_size": 0, "temperature": 1.0, "top_k": 50,
+               "forced_eos_token_id": None, "suppress_tokens": None, "max_length": 20, "num_beams": 4, "no_repeat_ngram_size": 3}
+    (d / "config.json").write_text(json.dumps({"model_type": "vision-encoder-decoder", "decoder": neutral}))
+    assert O._unsupported_generation_settings(str(d)) == {}
+    assert O._generation_config(str(d))["num_beams"] == 4
+    (d / "generation_config.json").write_text(json.dumps({"num_beams": 4, "repetition_penalty": 1.2, "bad_words_ids": [[7]], "min_length": 0}))
+    assert O._unsupported_generation_settings(str(d / "model.safetensors")) == {"repetition_penalty": 1.2, "bad_words_ids": [[7]]}
+    _StubEngine.instances = []
+    monkeypatch.setattr(O, "Engine", _StubEngine)
+    monkeypatch.setattr(O.W, "complete", lambda w: w)
+    monkeypatch.setattr(O.W, "load_weights", lambda path: {"x": np.zeros(1, np.float32)})
+    with pytest.raises(NotImplementedError, match="repetition_penalty"):
+        O.MangaOcr(str(d), warmup=False)
+    monkeypatch.setenv("MOCR_IGNORE_GENERATION_EXTRAS", "1")
+    ocr = O.MangaOcr(str(d), warmup=False)
+    assert ocr.generation["num_beams"] == 4
+    ocr.close()
+
+
 # ---- the cross-thread micro-batcher, with stub engines (no GPU): batching, fair share, failure isolation, lifetime ----
 
 class _StubEngine:
