@@ -33,3 +33,33 @@ def test_oracle_rejects_bad_argument(oracle12):
     import pytest
     with pytest.raises(ValueError):
         oracle12(12345)
+
+
+def test_checkpoints_written_by_transformers_load_with_the_product_loaders(oracle12, weights0, tmp_path):
+    """Row N4 as far as it can be checked offline: a checkpoint directory written by transformers itself (save_pretrained of the
+    full-size VisionEncoderDecoderModel: config.json, generation_config.json, model.safetensors) and a 4.x-style pytorch_model.bin
+    (torch.save of the state dict with the `position_ids` buffer and an UNTIED LM-head copy) go through the product's torch-free
+    readers: every parameter the engine uses arrives bit-exactly, buffers and the dead pooler are tolerated, an untied head is kept."""
+    import warnings
+    import torch
+    from manga_ocr_b200 import weights as W
+    from manga_ocr_b200.ocr import GREEDY, _find_checkpoint, _generation_config, _unsupported_generation_settings
+    d = tmp_path / "ckpt"
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        oracle12.model.save_pretrained(str(d))
+    assert _find_checkpoint(str(d)) == (str(d / "model.safetensors"), None)
+    got = W.complete(W.load_weights(str(d / "model.safetensors")))
+    for k, v in weights0.items():
+        assert np.array_equal(got[k], v), k
+    assert _generation_config(str(d)) == GREEDY and _unsupported_generation_settings(str(d)) == {}
+    sd = {k: v.clone() for k, v in oracle12.model.state_dict().items()}
+    sd["decoder.bert.embeddings.position_ids"] = torch.arange(512)[None]
+    head = sd["decoder.bert.embeddings.word_embeddings.weight"].clone() + 0.5
+    sd["decoder.cls.predictions.decoder.weight"] = head
+    torch.save(sd, str(tmp_path / "pytorch_model.bin"))
+    got = W.complete(W.load_weights(str(tmp_path / "pytorch_model.bin")))
+    for k, v in weights0.items():
+        if k != "decoder.cls.predictions.decoder.weight":
+            assert np.array_equal(got[k], v), k
+    assert np.array_equal(got["decoder.cls.predictions.decoder.weight"], head.numpy())
