@@ -130,6 +130,8 @@ _UNSUPPORTED_GENERATION = {
     "max_new_tokens": (), "bad_words_ids": ([],), "force_words_ids": ([],), "suppress_tokens": ([],), "begin_suppress_tokens": ([],),
     "forced_bos_token_id": (), "forced_eos_token_id": (), "num_return_sequences": (1,), "penalty_alpha": (0, 0.0),
     "exponential_decay_length_penalty": (), "sequence_bias": ({}, []), "renormalize_logits": (False,), "constraints": ([],),
+    # the token ids the kernels are built around (start = [CLS] 2, stop = [SEP] 3, fill = [PAD] 0): a checkpoint that names others
+    "decoder_start_token_id": (2,), "eos_token_id": (3, [3]), "pad_token_id": (0,),
 }
 
 

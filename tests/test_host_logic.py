@@ -232,6 +232,11 @@ def test_unsupported_generation_settings_are_refused_not_ignored(tmp_path, monke
     assert O._generation_config(str(d))["num_beams"] == 4
     (d / "generation_config.json").write_text(json.dumps({"num_beams": 4, "repetition_penalty": 1.2, "bad_words_ids": [[7]], "min_length": 0}))
     assert O._unsupported_generation_settings(str(d / "model.safetensors")) == {"repetition_penalty": 1.2, "bad_words_ids": [[7]]}
+    (d / "generation_config.json").write_text(json.dumps({"decoder_start_token_id": 2, "eos_token_id": 3, "pad_token_id": 0}))
+    assert O._unsupported_generation_settings(str(d)) == {}
+    (d / "generation_config.json").write_text(json.dumps({"decoder_start_token_id": 101, "eos_token_id": [3, 102]}))
+    assert O._unsupported_generation_settings(str(d)) == {"decoder_start_token_id": 101, "eos_token_id": [3, 102]}
+    (d / "generation_config.json").write_text(json.dumps({"num_beams": 4, "repetition_penalty": 1.2, "bad_words_ids": [[7]], "min_length": 0}))
     _StubEngine.instances = []
     monkeypatch.setattr(O, "Engine", _StubEngine)
     monkeypatch.setattr(O.W, "complete", lambda w: w)
