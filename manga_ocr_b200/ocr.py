@@ -141,6 +141,58 @@ def _unsupported_generation_settings(weights_path: Optional[str]) -> Dict:
     return {k: v for k, v in found.items() if v is not None and v not in _UNSUPPORTED_GENERATION[k]}
 
 
+# Hyper-parameters of config.json that change the arithmetic without changing a tensor shape (shapes are checked by
+# weights.complete): what the kernels implement (model constants).  A key that is absent has this value
+# by the library's default.
+_ARCHITECTURE = {
+    "encoder": {"model_type": ("vit",), "hidden_act": ("gelu",), "layer_norm_eps": (1e-12,), "num_attention_heads": (12,),
+                "patch_size": (16,), "image_size": (224, [224, 224]), "qkv_bias": (True,), "num_channels": (3,)},
+    "decoder": {"model_type": ("bert",), "hidden_act": ("gelu",), "layer_norm_eps": (1e-12,), "num_attention_heads": (12,),
+                "position_embedding_type": ("absolute",), "is_decoder": (True,), "add_cross_attention": (True,)},
+}
+
+
+_PREPROCESSOR = {
+    "do_resize": (True,), "do_rescale": (True,), "do_normalize": (True,), "resample": (2,), "rescale_factor": (1 / 255,),
+    "size": (224, [224, 224], {"height": 224, "width": 224}), "image_mean": ([0.5, 0.5, 0.5], 0.5), "image_std": ([0.5, 0.5, 0.5], 0.5),
+    "do_center_crop": (False,), "do_convert_rgb": (False,),
+}
+
+
+def _unsupported_architecture(weights_path: Optional[str]) -> Dict:
+    """{"encoder.hidden_act": "gelu_new", ...}: fields of the checkpoint's config.json the kernels do not implement (empty: none,
+    or no config.json next to the weights)."""
+    import json
+    if not weights_path:
+        return {}
+    d = weights_path if os.path.isdir(weights_path) else os.path.dirname(weights_path)
+    try:
+        with open(os.path.join(d, "config.json"), encoding="utf-8") as f:
+            cfg = json.load(f)
+    except (OSError, ValueError):
+        return {}
+    bad = {}
+    for part, want in _ARCHITECTURE.items():
+        sub = cfg.get(part) if isinstance(cfg, dict) else None
+        if not isinstance(sub, dict):
+            continue
+        for k, ok in want.items():
+            if sub.get(k) is not None and sub[k] not in ok:
+                bad[f"{part}.{k}"] = sub[k]
+    # preprocessor_config.json (what ViTImageProcessor.from_pretrained would read): the preprocess kernel is Pillow's bilinear
+    # resize to 224 x 224, x / 255, (x - 0.5) / 0.5 and nothing else
+    try:
+        with open(os.path.join(d, "preprocessor_config.json"), encoding="utf-8") as f:
+            pre = json.load(f)
+    except (OSError, ValueError):
+        pre = None
+    if isinstance(pre, dict):
+        for k, ok in _PREPROCESSOR.items():
+            if pre.get(k) is not None and pre[k] not in ok:
+                bad[f"preprocessor.{k}"] = pre[k]
+    return bad
+
+
 def image_to_array(img) -> np.ndarray:
     """PIL image -> the uint8 array the engine reads.  The luma conversion itself
     (``img.convert("L")``, the upstream wrapper's first step) happens on the GPU for the modes
@@ -200,6 +252,10 @@ class MangaOcr:
                         "(nothing is downloaded), or use 'random[:seed[:eos_bias]]' for random-init weights")
                 weights = W.load_weights(found[0])
                 gen = _generation_config(found[0])
+                arch = _unsupported_architecture(found[0])
+                if arch:
+                    raise NotImplementedError(f"the checkpoint's config.json asks for {arch}: the kernels implement ViT-base/16-224 (erf-GELU, "
+                                              "LayerNorm eps 1e-12, qkv bias) + a 12-head BERT decoder with absolute positions only")
                 extras = _unsupported_generation_settings(found[0])
                 if extras and os.environ.get("MOCR_IGNORE_GENERATION_EXTRAS", "0") != "1":
                     raise NotImplementedError(

@@ -53,6 +53,32 @@ def test_checkpoints_written_by_transformers_load_with_the_product_loaders(oracl
     for k, v in weights0.items():
         assert np.array_equal(got[k], v), k
     assert _generation_config(str(d)) == GREEDY and _unsupported_generation_settings(str(d)) == {}
+    # the config.json transformers wrote for this architecture is accepted; one that changes the arithmetic without changing a
+    # shape (another activation, another LayerNorm epsilon, relative positions) is named
+    import json
+    from manga_ocr_b200.ocr import _unsupported_architecture
+    assert _unsupported_architecture(str(d / "model.safetensors")) == {}
+    cfg = json.loads((d / "config.json").read_text())
+    cfg["encoder"]["hidden_act"] = "gelu_new"
+    cfg["decoder"]["layer_norm_eps"] = 1e-5
+    cfg["decoder"]["position_embedding_type"] = "relative_key"
+    # ... and the preprocessor_config.json transformers' own ViT image processor (PIL backend, the oracle's) writes is accepted,
+    # one with another resampling filter or other statistics is named
+    from transformers.models.vit.image_processing_pil_vit import ViTImageProcessorPil
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ViTImageProcessorPil(image_mean=[0.5, 0.5, 0.5], image_std=[0.5, 0.5, 0.5]).save_pretrained(str(d))
+    assert (d / "preprocessor_config.json").exists()
+    assert _unsupported_architecture(str(d)) == {}, json.loads((d / "preprocessor_config.json").read_text())
+    (tmp_path / "other").mkdir()
+    pre = json.loads((d / "preprocessor_config.json").read_text())
+    pre.update({"resample": 3, "image_mean": [0.485, 0.456, 0.406]})
+    (tmp_path / "other" / "preprocessor_config.json").write_text(json.dumps(pre))
+    (tmp_path / "other" / "config.json").write_text(json.dumps(cfg))
+    assert _unsupported_architecture(str(tmp_path / "other")) == {"encoder.hidden_act": "gelu_new", "decoder.layer_norm_eps": 1e-5,
+                                                                   "decoder.position_embedding_type": "relative_key",
+                                                                   "preprocessor.resample": 3,
+                                                                   "preprocessor.image_mean": [0.485, 0.456, 0.406]}
     sd = {k: v.clone() for k, v in oracle12.model.state_dict().items()}
     sd["decoder.bert.embeddings.position_ids"] = torch.arange(512)[None]
     head = sd["decoder.bert.embeddings.word_embeddings.weight"].clone() + 0.5
