@@ -36,7 +36,12 @@ def _hub_snapshots(name: str) -> List[str]:
     """Snapshot directories of ``name`` in the local Hugging Face cache, the one ``refs/main`` points to first.
     Nothing is ever downloaded: the reference relies on ``from_pretrained`` fetching the checkpoint, this engine needs
     it on disk already."""
-    home = os.environ.get("HF_HUB_CACHE") or os.path.join(os.environ.get("HF_HOME", os.path.expanduser("~/.cache/huggingface")), "hub")
+    # the cache directory as huggingface_hub resolves it (huggingface_hub/constants.py): HF_HUB_CACHE, its legacy alias
+    # HUGGINGFACE_HUB_CACHE, else $HF_HOME/hub with HF_HOME defaulting to $XDG_CACHE_HOME/huggingface (~/.cache/huggingface)
+    env = os.environ
+    hf_home = env.get("HF_HOME") or os.path.join(env.get("XDG_CACHE_HOME") or "~/.cache", "huggingface")
+    home = env.get("HF_HUB_CACHE") or env.get("HUGGINGFACE_HUB_CACHE") or os.path.join(hf_home, "hub")
+    home = os.path.expandvars(os.path.expanduser(home))
     repo = os.path.join(home, "models--" + name.replace("/", "--"))
     snaps = sorted(glob.glob(os.path.join(repo, "snapshots", "*")))
     try:

@@ -148,6 +148,32 @@ def test_gather_ids_gloo_world2(n_total):
     assert all(res)
 
 
+def test_hub_cache_resolution_equals_huggingface_hub(tmp_path, monkeypatch):
+    """MangaOcr() with no argument finds kha-white/manga-ocr-base where from_pretrained would look for it offline: the snapshot
+    `refs/main` names, in the cache directory huggingface_hub resolves from HF_HUB_CACHE / HUGGINGFACE_HUB_CACHE / HF_HOME /
+    XDG_CACHE_HOME - compared with huggingface_hub.snapshot_download(local_files_only=True) on a synthetic cache."""
+    import huggingface_hub as hh
+    root = tmp_path / "cache" / "huggingface" / "hub"
+    repo = root / "models--kha-white--manga-ocr-base"
+    for rev in ("0aaa", "1bbb", "2ccc"):
+        (repo / "snapshots" / rev).mkdir(parents=True)
+        (repo / "snapshots" / rev / "model.safetensors").write_bytes(b"x")
+        (repo / "snapshots" / rev / "config.json").write_text("{}")
+    (repo / "refs").mkdir()
+    (repo / "refs" / "main").write_text("1bbb")
+    want = hh.snapshot_download("kha-white/manga-ocr-base", cache_dir=str(root), local_files_only=True)
+    assert want.endswith("1bbb")
+    for var in ("HF_HUB_CACHE", "HUGGINGFACE_HUB_CACHE", "HF_HOME", "XDG_CACHE_HOME", "MOCR_WEIGHTS"):
+        monkeypatch.delenv(var, raising=False)
+    for var, value in (("HF_HUB_CACHE", root), ("HUGGINGFACE_HUB_CACHE", root), ("HF_HOME", root.parent), ("XDG_CACHE_HOME", root.parent.parent)):
+        monkeypatch.setenv(var, str(value))
+        assert O._find_checkpoint("kha-white/manga-ocr-base") == (os.path.join(want, "model.safetensors"), None), var
+        monkeypatch.delenv(var)
+    monkeypatch.setenv("HF_HUB_CACHE", str(tmp_path / "empty"))
+    monkeypatch.setenv("HF_HOME", str(root.parent))                    # HF_HUB_CACHE wins over HF_HOME, as in huggingface_hub
+    assert O._find_checkpoint("kha-white/manga-ocr-base") is None
+
+
 def test_generation_config_is_read_from_the_checkpoint_directory(tmp_path):
     """generate() uses the checkpoint's generation settings; no file -> greedy."""
     import json
