@@ -18,7 +18,7 @@ from __future__ import annotations
 
 import os
 import re
-from typing import Iterable, List, Sequence
+from typing import Optional, Iterable, List, Sequence
 
 import numpy as np
 
@@ -51,10 +51,11 @@ def _synthetic_tokens() -> List[str]:
 class Vocab:
     """id -> token table of a character-level vocabulary (one token per id)."""
 
-    def __init__(self, tokens: Sequence[str]):
+    def __init__(self, tokens: Sequence[str], special_ids: Optional[Iterable[int]] = None):
         self.tokens = list(tokens)
         # ids whose token is [..]-bracketed specials are dropped on decode
-        self.special_ids = frozenset(i for i, t in enumerate(self.tokens) if t in SPECIAL_TOKENS)
+        self.special_ids = (frozenset(i for i, t in enumerate(self.tokens) if t in SPECIAL_TOKENS) if special_ids is None
+                            else frozenset(int(i) for i in special_ids))
         self._special_mask = np.zeros(len(self.tokens), bool)
         self._special_mask[list(self.special_ids)] = True
 
@@ -64,8 +65,17 @@ class Vocab:
 
     @classmethod
     def from_file(cls, path: str) -> "Vocab":
+        """``vocab.txt`` as ``BertJapaneseTokenizer`` reads it (tokenization_bert_japanese.py ``load_vocab`` and the
+        ``ids_to_tokens`` table built from it): one token per line, "\n" stripped; of a token that occurs on several lines only
+        the LAST line keeps it, the earlier ids decode to "[UNK]" - and are not special: ``skip_special_tokens`` goes by id, and
+        the special ids are the ones the five special token strings map to.  Checked against the tokenizer itself in
+        tests/test_text.py."""
         with open(path, encoding="utf-8") as f:
-            return cls([line.rstrip("\n") for line in f])
+            lines = [line.rstrip("\n") for line in f.readlines()]
+        last = {t: i for i, t in enumerate(lines)}
+        tokens = [t if last[t] == i else "[UNK]" for i, t in enumerate(lines)]
+        special = {last.get(t, last.get("[UNK]")) for t in SPECIAL_TOKENS}
+        return cls(tokens, special_ids=[i for i in special if i is not None])
 
     def _kept_tokens(self, ids: Iterable[int]) -> List[str]:
         n = len(self.tokens)

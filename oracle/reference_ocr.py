@@ -124,20 +124,31 @@ def post_process(text: str) -> str:
     return _h2z(text)
 
 
-class _CharTokenizer:
-    """The one attribute ``BertJapaneseTokenizer.convert_tokens_to_string`` reads (the real tokenizer cannot be built here:
-    its word tokenizer needs fugashi / unidic, absent offline - SURVEY.md section 8c)."""
-    subword_tokenizer_type = "character"
+_TOKENIZERS: Dict[int, object] = {}
+
+
+def real_tokenizer(tokens: Sequence[str]):
+    """transformers' OWN ``BertJapaneseTokenizer`` over ``tokens`` (written out as a vocab.txt and read back by the class, as
+    for a checkpoint).  ``AutoTokenizer`` cannot build the checkpoint's tokenizer offline - its word tokenizer is MeCab and
+    needs fugashi / unidic - but ``decode`` never runs the word tokenizer: with
+    ``word_tokenizer_type="basic"`` the class constructs here, and id -> text is the library's own code path
+    (``convert_ids_to_tokens(skip_special_tokens=True)`` -> ``convert_tokens_to_string``, tokenization_bert_japanese.py:250-261)."""
+    import os
+    import tempfile
+    from transformers.models.bert_japanese.tokenization_bert_japanese import BertJapaneseTokenizer
+    key = hash(tuple(tokens))
+    if key not in _TOKENIZERS:
+        with tempfile.TemporaryDirectory() as d:
+            path = os.path.join(d, "vocab.txt")
+            with open(path, "w", encoding="utf-8", newline="\n") as f:
+                f.write("\n".join(tokens) + "\n")
+            _TOKENIZERS[key] = BertJapaneseTokenizer(path, word_tokenizer_type="basic", subword_tokenizer_type="character")
+    return _TOKENIZERS[key]
 
 
 def decode_ids(tokens: Sequence[str], ids: Iterable[int]) -> str:
-    """``tokenizer.decode(ids, skip_special_tokens=True)``: the special ids are dropped and the kept tokens go through
-    transformers' OWN ``BertJapaneseTokenizer.convert_tokens_to_string`` (tokenization_bert_japanese.py:256-261: joined by
-    spaces, " ##" removed, stripped) - called, not restated."""
-    from transformers.models.bert_japanese.tokenization_bert_japanese import BertJapaneseTokenizer
-    specials = {PAD_ID, UNK_ID, CLS_ID, SEP_ID, MASK_ID}
-    kept = [tokens[int(i)] for i in ids if int(i) not in specials]
-    return BertJapaneseTokenizer.convert_tokens_to_string(_CharTokenizer(), kept)
+    """``tokenizer.decode(ids, skip_special_tokens=True)`` - called on the real tokenizer class, not restated."""
+    return real_tokenizer(tokens).decode([int(i) for i in ids], skip_special_tokens=True)
 
 
 class ReferenceMangaOcr:

@@ -118,3 +118,40 @@ def test_decode_glues_wordpiece_continuations_like_transformers():
     rng = np.random.default_rng(3)
     plain = rng.integers(5, len(base.tokens) - 6, size=(6, 40)).astype(np.int32)
     assert ids_to_texts(v, plain) == ids_to_texts(base, plain) == [ids_to_text(base, r) for r in plain]
+
+
+def test_vocab_file_and_decode_equal_the_real_tokenizer(tmp_path):
+    """vocab.txt -> id table -> tokenizer.decode(skip_special_tokens=True) -> post_process, the product's against transformers' own
+    BertJapaneseTokenizer built on the same file (word tokenizer "basic": decode never runs it, and MeCab is absent offline).  The
+    file has what a real one may have: "##" continuation tokens, a multi-character token, a token on two lines (only the last
+    line keeps it, the earlier id decodes to "[UNK]" and is NOT special), a space token, an empty line, out-of-range ids."""
+    import warnings
+    from transformers.models.bert_japanese.tokenization_bert_japanese import BertJapaneseTokenizer
+    from oracle.reference_ocr import post_process as oracle_post_process
+    base = Vocab.synthetic().tokens[:300]
+    lines = base + ["##あ", "##b", "a b", "x", "x", " ", "", "'", "n't", ".", "[MASK]", "ｶ", "ﾞ"]
+    path = tmp_path / "vocab.txt"
+    path.write_text("\n".join(lines) + "\n", encoding="utf-8")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        tk = BertJapaneseTokenizer(str(path), word_tokenizer_type="basic", subword_tokenizer_type="character")
+    v = Vocab.from_file(str(path))
+    assert len(v.tokens) == len(lines)
+    assert v.special_ids == frozenset(tk.all_special_ids)
+    assert [v.tokens[i] for i in range(len(lines))] == tk.convert_ids_to_tokens(list(range(len(lines))))
+    rng = np.random.default_rng(11)
+    ids = rng.integers(0, len(lines), size=(60, 40)).astype(np.int32)
+    ids[:, 0] = 2
+    ids[3, 5:] = 0
+    ids[4, 1:9] = [300, 301, 302, 303, 304, 305, 306, 307]
+    ids[5, 1:4] = [311, 312, 300]                      # ｶ ﾞ ##あ
+    ids[6, 1:3] = [4, 310]                             # the first [MASK] line lost the token to the second one
+    want = [oracle_post_process(tk.decode(row.tolist(), skip_special_tokens=True)) for row in ids]
+    for row, w in zip(ids, want):
+        assert v.decode(row) == tk.decode(row.tolist(), skip_special_tokens=True)
+        assert ids_to_text(v, row) == w
+    assert ids_to_texts(v, ids) == want
+    wide = ids.copy()
+    wide[7, 3] = len(lines) + 5                        # an id beyond the table: "[UNK]", kept (the check is by id)
+    assert ids_to_text(v, wide[7]) == oracle_post_process(tk.decode(wide[7].tolist(), skip_special_tokens=True))
+    assert ids_to_texts(v, wide)[7] == ids_to_text(v, wide[7])
