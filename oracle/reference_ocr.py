@@ -14,7 +14,10 @@ it calls:
   * ``VisionEncoderDecoderModel.generate(x[None], max_length=300)`` greedy
     (transformers/generation/utils.py:2658-2810; ViT: models/vit/modeling_vit.py:428-458;
     BERT decoder: models/bert/modeling_bert.py:856-910)
-  * ``tokenizer.decode(skip_special_tokens=True)`` + ``post_process``.
+  * ``tokenizer.decode(skip_special_tokens=True)``: transformers' own ``BertJapaneseTokenizer`` (``real_tokenizer``; it
+    constructs offline with the basic word tokenizer, which decode never runs);
+  * ``post_process`` + ``jaconv.h2z``: RESTATED from their published behaviour (both packages are absent offline) -
+    this last step is "parity unpinned" against upstream.
 
 fp32, eager, batch 1 per call exactly like the reference.  Nothing in
 ``manga_ocr_b200`` imports this file.
