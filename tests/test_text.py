@@ -155,3 +155,31 @@ def test_vocab_file_and_decode_equal_the_real_tokenizer(tmp_path):
     wide[7, 3] = len(lines) + 5                        # an id beyond the table: "[UNK]", kept (the check is by id)
     assert ids_to_text(v, wide[7]) == oracle_post_process(tk.decode(wide[7].tolist(), skip_special_tokens=True))
     assert ids_to_texts(v, wide)[7] == ids_to_text(v, wide[7])
+
+
+def test_h2z_tables_against_unicode_compatibility_mappings():
+    """An authority that is neither restatement: Unicode's own compatibility mappings (unicodedata, NFKC).  Half-width katakana
+    letters and punctuation widen to exactly their NFKC form; a letter followed by a (semi-)voiced mark composes to the NFKC
+    composition for every pair jaconv converts; widened ASCII narrows back to the original under NFKC - except the four look-alikes
+    jaconv's table substitutes (” ’ ￥ ‘), which is what sets it apart from a plain block shift."""
+    import unicodedata
+    from manga_ocr_b200.text import H2Z_ASCII_SPECIAL, h2z
+    from oracle.reference_ocr import _h2z as oracle_h2z
+
+    def nfkc(t):
+        return unicodedata.normalize("NFKC", t)
+    for cp in list(range(0xFF66, 0xFF9E)) + [0xFF61, 0xFF62, 0xFF63, 0xFF64, 0xFF65]:       # ｦ..ﾝ and ｡｢｣､･
+        ch = chr(cp)
+        assert h2z(ch) == nfkc(ch) == oracle_h2z(ch), hex(cp)
+    voiced = "ｶｷｸｹｺｻｼｽｾｿﾀﾁﾂﾃﾄﾊﾋﾌﾍﾎｳ"
+    for base in voiced:
+        assert h2z(base + "ﾞ") == nfkc(base + "ﾞ") == oracle_h2z(base + "ﾞ") and len(h2z(base + "ﾞ")) == 1, base
+    for base in "ﾊﾋﾌﾍﾎ":
+        assert h2z(base + "ﾟ") == nfkc(base + "ﾟ") == oracle_h2z(base + "ﾟ") and len(h2z(base + "ﾟ")) == 1, base
+    assert h2z("ｱﾞ") == "ア゛" == oracle_h2z("ｱﾞ")             # no composition outside jaconv's list: the mark widens on its own
+    for cp in range(0x21, 0x7F):
+        ch = chr(cp)
+        if ch in H2Z_ASCII_SPECIAL:
+            assert nfkc(h2z(ch)) != ch                          # the look-alikes are not compatibility forms of the ASCII character
+        else:
+            assert nfkc(h2z(ch)) == ch and h2z(ch) == chr(cp + 0xFEE0), hex(cp)
