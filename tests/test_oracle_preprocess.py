@@ -53,3 +53,38 @@ def test_coefficients_sum_to_one():
         assert (cnt >= 1).all() and (xmin >= 0).all() and (xmin + cnt <= n).all()
         s = kk.sum(axis=1)
         assert np.abs(s - (1 << P.PRECISION_BITS)).max() <= cnt.max()   # rounding of each tap
+
+
+def test_torchvision_backend_delta_is_small_and_reported():
+    """Informational ("preprocess-backend trap"): parity is defined against the PIL backend
+    (`ViTImageProcessorPil`, what the reference's transformers 4.x stack ran); under transformers 5.x the name `ViTImageProcessor` is
+    the torchvision backend, whose antialiased resize rounds differently.  The difference a user of a 5.x reference install would
+    see against this engine: at most one uint8 step on a fraction of a percent of the pixels (DESIGN.md section 2 has the
+    model-level effect: encoder rel-L2 2.4e-4, identical ids)."""
+    import warnings
+    pytest = __import__("pytest")
+    pytest.importorskip("torchvision")
+    from PIL import Image
+    from transformers import ViTImageProcessor
+    from transformers.models.vit.image_processing_pil_vit import ViTImageProcessorPil
+    from manga_ocr_b200 import crops as C
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        pil = ViTImageProcessorPil(image_mean=[0.5] * 3, image_std=[0.5] * 3)
+        tv = ViTImageProcessor(image_mean=[0.5] * 3, image_std=[0.5] * 3)
+    if type(tv).__module__ == type(pil).__module__:
+        pytest.skip("this transformers build has one backend only")
+    total = differing = 0
+    worst = 0.0
+    for c in C.bubble_batch(6, seed=1002) + C.page_batch(6, seed=1003) + C.tall_batch(3, seed=1004):
+        img = Image.fromarray(c).convert("L").convert("RGB")
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            a = pil(img, return_tensors="np").pixel_values[0]
+            b = np.asarray(tv(img, return_tensors="pt").pixel_values[0])
+        d = np.abs(a - b)
+        total += d.size
+        differing += int((d > 1e-6).sum())
+        worst = max(worst, float(d.max()))
+    print(f"torchvision vs PIL backend: {differing / total:.4%} of the pixel values differ, max {worst * 127.5:.2f} uint8 steps")
+    assert worst <= 2.0 / 127.5 + 1e-6 and differing / total < 0.05
