@@ -62,7 +62,6 @@ def test_torchvision_backend_delta_is_small_and_reported():
     see against this engine: at most one uint8 step on a fraction of a percent of the pixels (DESIGN.md section 2 has the
     model-level effect: encoder rel-L2 2.4e-4, identical ids)."""
     import warnings
-    pytest = __import__("pytest")
     pytest.importorskip("torchvision")
     from PIL import Image
     from transformers import ViTImageProcessor
