@@ -316,7 +316,7 @@ class MangaOcr:
         # MOCR_ADMISSION=0) keeps the batch dispatcher: callers that arrive together share a batch and wait for all of it.
         if admission is None:
             admission = os.environ.get("MOCR_ADMISSION", "1") != "0"
-        self.admission = bool(admission) and int(gen["num_beams"]) <= 1
+        self.admission = bool(admission) and int(gen["num_beams"]) <= 1 and int(gen["no_repeat_ngram_size"]) <= 0
         self.session_rows = max(1, min(max_batch, int(slots) if slots else 64))
         self._engine_locks = [threading.Lock() for _ in self.engines]      # a session owns its engine; batch callers wait for it to drain
         self._batch_waiting = [0] * len(self.engines)
@@ -371,11 +371,10 @@ class MangaOcr:
         regions = list(regions)
 
         def run(engine: Engine, regs: Sequence) -> np.ndarray:
-            g = self.generation
-            if int(g["num_beams"]) <= 1:
+            b = self._beam_args()
+            if b is None:
                 return engine.recognize_regions(arr, regs, order, self.max_length)[0]
-            return engine.recognize_regions_beam(arr, regs, order, self.max_length, int(g["num_beams"]), int(g["no_repeat_ngram_size"]),
-                                                 float(g["length_penalty"]), g["early_stopping"])[0]
+            return engine.recognize_regions_beam(arr, regs, order, self.max_length, *b)[0]
 
         def work(k: int, lo: int, hi: int) -> np.ndarray:
             with self._engine_excl(k):
@@ -384,11 +383,23 @@ class MangaOcr:
         return ids_to_texts(self.vocab, self._sharded(len(regions), work))
 
     def _engine_ids(self, engine: Engine, arrays: Sequence[np.ndarray], order: int) -> np.ndarray:
-        g = self.generation
-        if int(g["num_beams"]) <= 1:
+        b = self._beam_args()
+        if b is None:
             return engine.recognize(arrays, order, self.max_length)[0]
-        return engine.recognize_beam(arrays, order, self.max_length, int(g["num_beams"]), int(g["no_repeat_ngram_size"]),
-                                     float(g["length_penalty"]), g["early_stopping"])[0]
+        return engine.recognize_beam(arrays, order, self.max_length, *b)[0]
+
+    def _beam_args(self):
+        """None for the plain greedy path, else (num_beams, no_repeat_ngram_size, length_penalty, early_stopping) of the search
+        entry points.  generate() applies ``no_repeat_ngram_size`` in greedy mode too (NoRepeatNGramLogitsProcessor,
+        generation/utils.py): the arg-max kernels have no ban list, but a ONE-beam search that stops at its first finished
+        hypothesis follows the banned arg-max token by token and ends where greedy decoding ends - the same ids
+        (tests/test_beam_host.py pins that against generate(num_beams=1, no_repeat_ngram_size=n))."""
+        g = self.generation
+        if int(g["num_beams"]) > 1:
+            return int(g["num_beams"]), int(g["no_repeat_ngram_size"]), float(g["length_penalty"]), g["early_stopping"]
+        if int(g["no_repeat_ngram_size"]) > 0:
+            return 1, int(g["no_repeat_ngram_size"]), 1.0, True
+        return None
 
     def recognize_ids(self, arrays: Sequence[np.ndarray], order: int = RGB) -> np.ndarray:
         def work(k: int, lo: int, hi: int) -> np.ndarray:
