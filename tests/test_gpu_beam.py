@@ -129,9 +129,9 @@ def test_manga_ocr_front_end_runs_the_checkpoint_generation_config(beam_setup, t
         assert ocr(Image.fromarray(crops[1])) == want[1]
     finally:
         ocr.close()
-    greedy = MangaOcr(str(tmp_path), max_batch=16, max_length=T, warmup=False, num_beams=1)
+    greedy = MangaOcr(str(tmp_path), max_batch=16, max_length=T, warmup=False, num_beams=1, no_repeat_ngram_size=0)
     try:
-        assert greedy.generation["num_beams"] == 1
+        assert greedy.generation["num_beams"] == 1 and greedy._beam_args() is None      # the plain arg-max path
         assert greedy.recognize_batch(crops[:2]) == ids_to_texts(Vocab.synthetic(), eng.recognize(crops[:2], max_length=T)[0])
     finally:
         greedy.close()
