@@ -587,6 +587,31 @@ def test_admission_serves_a_worker_pool_that_resubmits(stub_ocr):
     assert eng.sess is None
 
 
+def test_ngram_ban_with_one_beam_goes_to_the_one_beam_search(stub_ocr):
+    """generate() applies no_repeat_ngram_size in greedy mode too; the arg-max path has no ban list, so such settings are served by
+    the search entry points with ONE beam and early_stopping=True (= greedy decoding with the ban, tests/test_beam_host.py), on
+    every entry point, and __call__ traffic uses the batch dispatcher (sessions are arg-max only)."""
+    calls = []
+
+    def recognize_beam(self, arrays, order, max_length, *beam_args):
+        calls.append(beam_args)
+        return self.recognize(arrays, order, max_length)
+
+    _StubEngine.recognize_beam = recognize_beam
+    try:
+        ocr = stub_ocr(devices=[0], max_batch=8, max_length=8, admission=None, num_beams=1, no_repeat_ngram_size=3)
+        assert ocr._beam_args() == (1, 3, 1.0, True) and not ocr.admission
+        assert len(ocr.recognize_batch([np.full((4, 4, 3), 7, np.uint8)])) == 1
+        assert isinstance(ocr(_img(5)), str)
+        assert calls == [(1, 3, 1.0, True)] * 2
+        plain = stub_ocr(devices=[0], max_batch=8, max_length=8, admission=None)
+        assert plain._beam_args() is None and plain.admission
+        four = stub_ocr(devices=[0], max_batch=8, max_length=8, num_beams=4, no_repeat_ngram_size=3, length_penalty=2.0, early_stopping=True)
+        assert four._beam_args() == (4, 3, 2.0, True) and not four.admission
+    finally:
+        del _StubEngine.recognize_beam
+
+
 def test_admission_falls_back_to_a_batch_when_no_session_can_start(stub_ocr):
     """An engine that refuses sessions (parity taps set, as __graft_entry__.smoke() does) must not leave callers waiting."""
     ocr = stub_ocr(devices=[0], max_batch=8, max_length=8, admission=True)
